@@ -1,0 +1,66 @@
+"""ctypes binding of liboetr_b200.so (include/oetr_b200.h).  The CUDA library is mandatory: importing this
+module never falls back to another implementation, and every entry point raises when the library is missing."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboetr_b200.so")
+
+OETR_OK, OETR_E_ARG, OETR_E_SHAPE, OETR_E_ARCH, OETR_E_CUDA, OETR_E_NOMEM = 0, -1, -2, -3, -4, -5
+ATTN_LINEAR, ATTN_FULL = 0, 1
+PREC_FP32, PREC_FP16 = 0, 1
+
+EXPORTS = (
+    "oetr_abi_version", "oetr_last_error", "oetr_packed_weight_count", "oetr_create", "oetr_destroy",
+    "oetr_workspace_bytes", "oetr_forward", "oetr_last_launch_count", "oetr_forward_host",
+    "oetr_selftest_tcgen05",
+)
+
+
+class OetrError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("liboetr_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the in-tree library and declare the prototypes of include/oetr_b200.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise OetrError(OETR_E_ARCH, "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                     "(there is no CPU or PyTorch fallback for the hot path)" % path)
+    lib = ctypes.CDLL(path)
+    c = ctypes
+    f32p, vp = c.POINTER(c.c_float), c.c_void_p
+    lib.oetr_abi_version.restype = c.c_int
+    lib.oetr_last_error.restype = c.c_char_p
+    lib.oetr_packed_weight_count.restype = c.c_size_t
+    lib.oetr_create.restype = c.c_int
+    lib.oetr_create.argtypes = [vp, c.c_size_t, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(vp)]
+    lib.oetr_destroy.restype = c.c_int
+    lib.oetr_destroy.argtypes = [vp]
+    lib.oetr_workspace_bytes.restype = c.c_int
+    lib.oetr_workspace_bytes.argtypes = [vp, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_size_t)]
+    lib.oetr_forward.restype = c.c_int
+    lib.oetr_forward.argtypes = [vp, vp, vp] + [c.c_int] * 10 + [vp] * 6 + [vp, c.c_size_t, vp]
+    lib.oetr_last_launch_count.restype = c.c_int
+    lib.oetr_last_launch_count.argtypes = [vp]
+    lib.oetr_forward_host.restype = c.c_int
+    lib.oetr_forward_host.argtypes = [vp, vp, vp] + [c.c_int] * 10 + [vp, vp, vp]
+    lib.oetr_selftest_tcgen05.restype = c.c_int
+    lib.oetr_selftest_tcgen05.argtypes = [f32p, c.c_int]
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def check(rc, lib=None):
+    if rc != OETR_OK:
+        lib = lib or load_library()
+        raise OetrError(rc, (lib.oetr_last_error() or b"").decode("utf-8", "replace"))

@@ -1,0 +1,446 @@
+// C ABI of liboetr_b200.so (declared in include/oetr_b200.h): handle management, workspace carving and the
+// stream-ordered orchestration of the hot path.  No torch types, no exceptions across the boundary.
+#include "../../include/oetr_b200.h"
+#include "oetr_common.cuh"
+#include "tc_path.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace oetr;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? OETR_E_NOMEM : OETR_E_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                          \
+    } while (0)
+
+struct oetr_handle {
+    int attn_mode = 0, prec = 0, max_h = 0, max_w = 0, device = 0;
+    WLayout L;
+    float* d_w = nullptr;      // packed fp32 weights (canonical order)
+    float* d_w9 = nullptr;     // heatmap_conv.0.weight repacked per tap: [9][256 out][256 in]
+    float* d_pe = nullptr;     // PositionEncodingSine table, channel-last: [max_h][max_w][256]
+    TcWeights tc;              // fp16 UMMA operand images (FP16 path only)
+    int last_launches = 0;
+    // staging owned by the handle for oetr_forward_host only
+    float *st_feat1 = nullptr, *st_feat2 = nullptr, *st_boxes = nullptr;
+    void* st_ws = nullptr;
+    size_t st_feat1_n = 0, st_feat2_n = 0, st_boxes_n = 0, st_ws_n = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// small setup kernels
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_repack_conv(const float* __restrict__ w, float* __restrict__ w9) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // over [tap][o][c]
+    if (idx >= 9 * C * C) return;
+    const int c = idx % C, o = (idx / C) % C, tap = idx / (C * C);
+    w9[idx] = w[((size_t)o * C + c) * 9 + tap];
+}
+// token-major positional rows of an (hf,wf) map: out[l][:] = pe[l / wf][l % wf][:]   (models/utils.py:200-205)
+__global__ void k_gather_pos(const float* __restrict__ pe, int max_w, int wf, int L, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L * (C / 4)) return;
+    const int c4 = idx % (C / 4), l = idx / (C / 4);
+    reinterpret_cast<float4*>(out)[idx] =
+        reinterpret_cast<const float4*>(pe)[((size_t)(l / wf) * max_w + (l % wf)) * (C / 4) + c4];
+}
+
+// PositionEncodingSine (src/models/utils.py:185-198) incl. the precedence quirk: div_term = exp(-2k), k=0..63.
+static void build_pe_host(std::vector<float>& pe, int max_h, int max_w) {
+    pe.assign((size_t)max_h * max_w * C, 0.f);
+    const float factor = std::floor((float)(-std::log(10000.0) / C) / 2.0f);    // == -1.0f
+    for (int k = 0; k < C / 4; ++k) {
+        const float div = (float)std::exp((double)((float)(2 * k) * factor));   // fp32 exp of fp32 arg
+        for (int y = 0; y < max_h; ++y)
+            for (int x = 0; x < max_w; ++x) {
+                float* p = &pe[((size_t)y * max_w + x) * C + 4 * k];
+                const float ax = (float)(x + 1) * div, ay = (float)(y + 1) * div;   // fp32 products
+                p[0] = (float)std::sin((double)ax);
+                p[1] = (float)std::cos((double)ax);
+                p[2] = (float)std::sin((double)ay);
+                p[3] = (float)std::cos((double)ay);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+    template <typename T> T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+struct Workspace {
+    float *X, *T, *Q, *KF, *V, *O, *H, *kvs, *pos;
+    float *dt, *du, *dqk, *dq, *dk, *dv, *dob, *dh, *dkvs;
+    TcWorkspace tc;
+    size_t bytes;
+};
+Workspace carve(void* base, const oetr_handle* h, int B, int L1, int L2) {
+    Workspace w{};
+    Carver c(base);
+    const size_t R = (size_t)B * (L1 + L2);
+    w.X = c.take<float>(R * C); w.T = c.take<float>(R * C); w.Q = c.take<float>(R * C);
+    w.KF = c.take<float>(R * C); w.V = c.take<float>(R * C); w.O = c.take<float>(R * C);
+    w.H = c.take<float>(R * FF);
+    w.kvs = c.take<float>((size_t)2 * B * KVS);
+    w.pos = c.take<float>((size_t)(L1 + L2) * C);
+    const size_t D = (size_t)2 * B * C;
+    w.dt = c.take<float>(D); w.du = c.take<float>(D); w.dqk = c.take<float>(D); w.dq = c.take<float>(D);
+    w.dk = c.take<float>(D); w.dv = c.take<float>(D); w.dob = c.take<float>(D); w.dh = c.take<float>(2 * D);
+    w.dkvs = c.take<float>((size_t)2 * B * KVS);
+    if (h->prec == OETR_PREC_FP16) tc_carve(c.off, base, B, L1, L2, w.tc);
+    w.bytes = (c.off + 255) & ~size_t(255);
+    return w;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 orchestration
+// ---------------------------------------------------------------------------------------------------------
+static void encoder_fp32(const oetr_handle* h, const Workspace& w, int B, int L1, int L2, cudaStream_t s,
+                         LaunchCounter& lc) {
+    const float* W = h->d_w;
+    const int R1 = B * L1, R2 = B * L2, R = R1 + R2;
+    float* const pos1 = w.pos;
+    float* const pos2 = w.pos + (size_t)L1 * C;
+    auto ln_both = [&](const float* g, const float* b, bool with_pos, float* out) {
+        ln_pos(w.X, g, b, with_pos ? pos1 : nullptr, L1, out, R1, s, lc);
+        ln_pos(w.X + (size_t)R1 * C, g, b, with_pos ? pos2 : nullptr, L2, out + (size_t)R1 * C, R2, s, lc);
+    };
+    const bool linear = h->attn_mode == OETR_ATTN_LINEAR;
+    for (int i = 0; i < N_ENC; ++i) {
+        const EncW& e = h->L.enc[i];
+        // key/value side: ONE normalised source (+pos) feeds k_proj and v_proj (transformer.py:119-126)
+        ln_both(W + e.lnkv_g, W + e.lnkv_b, true, w.T);
+        gemm_nt(w.T, C, W + e.wk, C, nullptr, w.KF, C, R, C, C, linear ? ACT_ELU1 : ACT_NONE, 0, s, lc);
+        gemm_nt(w.T, C, W + e.wv, C, nullptr, w.V, C, R, C, C, ACT_NONE, 0, s, lc);
+        if (linear) {
+            kv_reduce(w.KF, w.V, w.kvs, B, L1, s, lc);
+            kv_reduce(w.KF + (size_t)R1 * C, w.V + (size_t)R1 * C, w.kvs + (size_t)B * KVS, B, L2, s, lc);
+        }
+        // query side
+        ln_both(W + e.lnq_g, W + e.lnq_b, true, w.T);
+        gemm_nt(w.T, C, W + e.wq, C, nullptr, w.Q, C, R, C, C, linear ? ACT_ELU1 : ACT_NONE, 0, s, lc);
+        const bool cross = (i & 1) != 0;   // ['self','cross']*4; cross layers read the partner's PRE-update state
+        if (linear) {
+            const float* kv_for_1 = w.kvs + (cross ? (size_t)B * KVS : 0);
+            const float* kv_for_2 = w.kvs + (cross ? 0 : (size_t)B * KVS);
+            linattn_apply(w.Q, kv_for_1, w.O, R1, L1, s, lc);
+            linattn_apply(w.Q + (size_t)R1 * C, kv_for_2, w.O + (size_t)R1 * C, R2, L2, s, lc);
+        } else {
+            const size_t o2 = (size_t)R1 * C;
+            if (!cross) {
+                full_attention(w.Q, w.KF, w.V, w.O, B, L1, L1, s, lc);
+                full_attention(w.Q + o2, w.KF + o2, w.V + o2, w.O + o2, B, L2, L2, s, lc);
+            } else {
+                full_attention(w.Q, w.KF + o2, w.V + o2, w.O, B, L1, L2, s, lc);
+                full_attention(w.Q + o2, w.KF, w.V, w.O + o2, B, L2, L1, s, lc);
+            }
+        }
+        gemm_nt(w.O, C, W + e.wm, C, nullptr, w.X, C, R, C, C, ACT_NONE, 1, s, lc);          // x += merge(att)
+        ln_both(W + e.ln2_g, W + e.ln2_b, false, w.T);
+        gemm_nt(w.T, C, W + e.w1, C, nullptr, w.H, FF, R, FF, C, ACT_GELU, 0, s, lc);
+        gemm_nt(w.H, FF, W + e.w2, FF, nullptr, w.X, C, R, C, FF, ACT_NONE, 1, s, lc);        // x += mlp
+    }
+}
+
+// Query decoder (transformer.py:224-284,361-381) for both image sets stacked as rows [0,B) | [B,2B).
+// `decoder_kv` supplies the cross-attention summaries of decoder layer j in w.dkvs.
+template <class KvFn>
+static void decoder_fp32(const oetr_handle* h, const Workspace& w, int B, cudaStream_t s, LaunchCounter& lc,
+                         KvFn decoder_kv) {
+    const float* W = h->d_w;
+    const int D2 = 2 * B;
+    const float* qe = W + h->L.qe1;                       // qe1 | qe2 are adjacent in the blob
+    cudaMemsetAsync(w.dt, 0, (size_t)D2 * C * sizeof(float), s);
+    for (int j = 0; j < N_DEC; ++j) {
+        const DecW& d = h->L.dec[j];
+        // self-attention over the single query token
+        ln_pos(w.dt, W + d.ln1_g, W + d.ln1_b, nullptr, 1, w.du, D2, s, lc);
+        ln_pos(w.du, nullptr, nullptr, qe, -B, w.dqk, D2, s, lc);               // u + query_embed{1,2}
+        gemm_nt(w.dqk, C, W + d.sa.wq, C, W + d.sa.bq, w.dq, C, D2, C, C, ACT_ELU1, 0, s, lc);
+        gemm_nt(w.dqk, C, W + d.sa.wk, C, W + d.sa.bk, w.dk, C, D2, C, C, ACT_ELU1, 0, s, lc);
+        gemm_nt(w.du, C, W + d.sa.wv, C, W + d.sa.bv, w.dv, C, D2, C, C, ACT_NONE, 0, s, lc);
+        kv_reduce(w.dk, w.dv, w.dkvs, D2, 1, s, lc);
+        linattn_apply(w.dq, w.dkvs, w.dob, D2, 1, s, lc);
+        gemm_nt(w.dob, C, W + d.sa.wm, C, nullptr, w.dt, C, D2, C, C, ACT_NONE, 1, s, lc);
+        // cross-attention into the encoder memory: k = memory+pos, v = memory (no LN, no pos on v)
+        ln_pos(w.dt, W + d.ln2_g, W + d.ln2_b, qe, -B, w.dqk, D2, s, lc);
+        gemm_nt(w.dqk, C, W + d.ca.wq, C, W + d.ca.bq, w.dq, C, D2, C, C, ACT_ELU1, 0, s, lc);
+        decoder_kv(j);
+        linattn_apply(w.dq, w.dkvs, w.dob, D2, 1, s, lc);
+        gemm_nt(w.dob, C, W + d.ca.wm, C, nullptr, w.dt, C, D2, C, C, ACT_NONE, 1, s, lc);
+        // feed-forward
+        ln_pos(w.dt, W + d.ln3_g, W + d.ln3_b, nullptr, 1, w.du, D2, s, lc);
+        gemm_nt(w.du, C, W + d.w1, C, nullptr, w.dh, FF, D2, FF, C, ACT_RELU, 0, s, lc);
+        gemm_nt(w.dh, FF, W + d.w2, FF, nullptr, w.dt, C, D2, C, FF, ACT_NONE, 1, s, lc);
+    }
+}
+
+static void decoder_kv_fp32(const oetr_handle* h, const Workspace& w, int j, int B, int L1, int L2,
+                            cudaStream_t s, LaunchCounter& lc) {
+    const float* W = h->d_w;
+    const DecW& d = h->L.dec[j];
+    const int R1 = B * L1, R2 = B * L2, R = R1 + R2;
+    ln_pos(w.X, nullptr, nullptr, w.pos, L1, w.T, R1, s, lc);
+    ln_pos(w.X + (size_t)R1 * C, nullptr, nullptr, w.pos + (size_t)L1 * C, L2, w.T + (size_t)R1 * C, R2, s, lc);
+    gemm_nt(w.T, C, W + d.ca.wk, C, W + d.ca.bk, w.KF, C, R, C, C, ACT_ELU1, 0, s, lc);
+    gemm_nt(w.X, C, W + d.ca.wv, C, W + d.ca.bv, w.V, C, R, C, C, ACT_NONE, 0, s, lc);
+    kv_reduce(w.KF, w.V, w.dkvs, B, L1, s, lc);
+    kv_reduce(w.KF + (size_t)R1 * C, w.V + (size_t)R1 * C, w.dkvs + (size_t)B * KVS, B, L2, s, lc);
+}
+
+// conv3x3 as 9 shifted GEMMs accumulating into Y (bias added by the first tap)
+static void head_conv_fp32(const oetr_handle* h, const Workspace& w, int B, int hf1, int wf1, int hf2, int wf2,
+                           const float* G, float* Gs, float* Y, cudaStream_t s, LaunchCounter& lc) {
+    const int R1 = B * hf1 * wf1, R2 = B * hf2 * wf2, R = R1 + R2;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        shift_tokens(G, Gs, B, hf1, wf1, dy, dx, s, lc);
+        shift_tokens(G + (size_t)R1 * C, Gs + (size_t)R1 * C, B, hf2, wf2, dy, dx, s, lc);
+        gemm_nt(Gs, C, h->d_w9 + (size_t)tap * C * C, C, tap == 0 ? h->d_w + h->L.hm_b0 : nullptr, Y, C, R, C, C,
+                ACT_NONE, tap == 0 ? 0 : 1, s, lc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// exported functions
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int oetr_abi_version(void) { return OETR_ABI_VERSION; }
+const char* oetr_last_error(void) { return g_err; }
+size_t oetr_packed_weight_count(void) { return make_layout().total; }
+
+int oetr_create(const float* weights, size_t n_floats, int weights_on_device, int attention_mode,
+                int operand_precision, int max_h, int max_w, oetr_handle** out) {
+    if (!weights || !out) return fail(OETR_E_ARG, "oetr_create: null argument");
+    *out = nullptr;
+    if (attention_mode != OETR_ATTN_LINEAR && attention_mode != OETR_ATTN_FULL)
+        return fail(OETR_E_ARG, "oetr_create: attention_mode %d not in {0 linear, 1 full}", attention_mode);
+    if (operand_precision != OETR_PREC_FP32 && operand_precision != OETR_PREC_FP16)
+        return fail(OETR_E_ARG, "oetr_create: operand_precision %d not in {0 fp32, 1 fp16}", operand_precision);
+    if (max_h < 1 || max_w < 1 || max_h > 1024 || max_w > 1024)
+        return fail(OETR_E_SHAPE, "oetr_create: max_shape (%d,%d) out of range", max_h, max_w);
+    const WLayout L = make_layout();
+    if (n_floats != L.total)
+        return fail(OETR_E_ARG, "oetr_create: expected %zu packed floats, got %zu", L.total, n_floats);
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(OETR_E_ARCH, "oetr_create: device %d is sm_%d%d; this library is sm_100a-only (no fallback)",
+                    dev, prop.major, prop.minor);
+    if (operand_precision == OETR_PREC_FP16 && attention_mode == OETR_ATTN_FULL)
+        return fail(OETR_E_ARG, "oetr_create: full attention is implemented on the fp32 path only (round 1)");
+    oetr_handle* h = new (std::nothrow) oetr_handle();
+    if (!h) return fail(OETR_E_NOMEM, "oetr_create: host allocation failed");
+    h->attn_mode = attention_mode; h->prec = operand_precision; h->max_h = max_h; h->max_w = max_w;
+    h->device = dev; h->L = L;
+    auto bail = [&](int code) { oetr_destroy(h); return code; };
+#define CUH(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return bail(fail(e_ == cudaErrorMemoryAllocation ? OETR_E_NOMEM : OETR_E_CUDA, "%s: %s", #call, \
+                             cudaGetErrorString(e_)));                                              \
+    } while (0)
+    CUH(cudaMalloc(&h->d_w, L.total * sizeof(float)));
+    CUH(cudaMemcpy(h->d_w, weights, L.total * sizeof(float),
+                   weights_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    CUH(cudaMalloc(&h->d_w9, (size_t)9 * C * C * sizeof(float)));
+    k_repack_conv<<<(9 * C * C + 255) / 256, 256>>>(h->d_w + L.hm_w0, h->d_w9);
+    std::vector<float> pe;
+    build_pe_host(pe, max_h, max_w);
+    CUH(cudaMalloc(&h->d_pe, pe.size() * sizeof(float)));
+    CUH(cudaMemcpy(h->d_pe, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (operand_precision == OETR_PREC_FP16) {
+        char msg[256] = "";
+        if (tc_prepare_weights(h->d_w, L, h->tc, msg, sizeof(msg)) != 0)
+            return bail(fail(OETR_E_CUDA, "oetr_create: %s", msg));
+    }
+    CUH(cudaDeviceSynchronize());
+#undef CUH
+    *out = h;
+    return OETR_OK;
+}
+
+int oetr_destroy(oetr_handle* h) {
+    if (!h) return OETR_OK;
+    cudaFree(h->d_w); cudaFree(h->d_w9); cudaFree(h->d_pe);
+    tc_free_weights(h->tc);
+    cudaFree(h->st_feat1); cudaFree(h->st_feat2); cudaFree(h->st_boxes); cudaFree(h->st_ws);
+    delete h;
+    return OETR_OK;
+}
+
+static int check_shapes(const oetr_handle* h, int batch, int hf1, int wf1, int hf2, int wf2) {
+    if (!h) return fail(OETR_E_ARG, "null handle");
+    if (batch < 0) return fail(OETR_E_ARG, "batch %d < 0", batch);
+    if (hf1 < 1 || wf1 < 1 || hf2 < 1 || wf2 < 1 || hf1 > h->max_h || hf2 > h->max_h || wf1 > h->max_w ||
+        wf2 > h->max_w)
+        return fail(OETR_E_SHAPE, "feature maps (%d,%d),(%d,%d) outside [1,(%d,%d)] (PositionEncodingSine max_shape)",
+                    hf1, wf1, hf2, wf2, h->max_h, h->max_w);
+    return OETR_OK;
+}
+
+int oetr_workspace_bytes(const oetr_handle* h, int batch, int hf1, int wf1, int hf2, int wf2, size_t* out) {
+    if (!out) return fail(OETR_E_ARG, "oetr_workspace_bytes: null out");
+    int rc = check_shapes(h, batch, hf1, wf1, hf2, wf2);
+    if (rc) return rc;
+    *out = carve(nullptr, h, batch, hf1 * wf1, hf2 * wf2).bytes + 256;
+    return OETR_OK;
+}
+
+int oetr_last_launch_count(const oetr_handle* h) { return h ? h->last_launches : 0; }
+
+int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int batch, int hf1, int wf1, int hf2,
+                 int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp, float* boxes1, float* boxes2,
+                 float* dbg_hs, float* dbg_memory, float* dbg_cxy, float* dbg_tlbr, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    int rc = check_shapes(h, batch, hf1, wf1, hf2, wf2);
+    if (rc) return rc;
+    if (batch == 0) { h->last_launches = 0; return OETR_OK; }              // empty batch: nothing to do
+    if (!feat1 || !feat2 || !boxes1 || !boxes2 || !workspace)
+        return fail(OETR_E_ARG, "oetr_forward: null buffer");
+    if (img_h1 < hf1 || img_h2 < hf2 || img_w1 < 1 || img_w2 < 1)
+        return fail(OETR_E_SHAPE, "oetr_forward: image sizes (%d,%d),(%d,%d) smaller than the feature maps", img_h1,
+                    img_w1, img_h2, img_w2);
+    if (reinterpret_cast<uintptr_t>(workspace) & 255)
+        return fail(OETR_E_ARG, "oetr_forward: workspace must be 256-byte aligned");
+    const int B = batch, L1 = hf1 * wf1, L2 = hf2 * wf2;
+    const Workspace w = carve(workspace, h, B, L1, L2);
+    if (w.bytes > workspace_bytes)
+        return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes, w.bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LaunchCounter lc;
+    const int R1 = B * L1, R2 = B * L2;
+    const float* W = h->d_w;
+
+    // positional rows for both geometries (PositionEncodingSine.forward slice, models/utils.py:200-205)
+    k_gather_pos<<<(L1 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf1, L1, w.pos); lc.n++;
+    k_gather_pos<<<(L2 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf2, L2, w.pos + (size_t)L1 * C); lc.n++;
+
+    if (h->prec == OETR_PREC_FP32) {
+        nchw_to_tokens(feat1, w.X, B, L1, s, lc);
+        nchw_to_tokens(feat2, w.X + (size_t)R1 * C, B, L2, s, lc);
+        encoder_fp32(h, w, B, L1, L2, s, lc);
+        decoder_fp32(h, w, B, s, lc, [&](int j) { decoder_kv_fp32(h, w, j, B, L1, L2, s, lc); });
+    } else {
+        // tcgen05 encoder + decoder K/V summaries; leaves token-major memory in w.X
+        char msg[256] = "";
+        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_pe, h->max_w, w.X,
+                       w.dkvs, s, lc, msg, sizeof(msg)) != 0)
+            return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
+        decoder_fp32(h, w, B, s, lc, [&](int j) {
+            cudaMemcpyAsync(w.dkvs, w.tc.dec_kvs + (size_t)j * 2 * B * KVS, (size_t)2 * B * KVS * sizeof(float),
+                            cudaMemcpyDeviceToDevice, s);
+        });
+    }
+    // memory = encoder output (w.X), hs = decoder output (w.dt)
+    if (dbg_memory) cudaMemcpyAsync(dbg_memory, w.X, (size_t)(R1 + R2) * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (dbg_hs) cudaMemcpyAsync(dbg_hs, w.dt, (size_t)2 * B * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+
+    // head: heat = memory * <memory, hs>; conv3x3 (+bias) -> Y ; then the row-wise tail per image
+    float *G = w.T, *Gs = w.Q, *Y = w.O;
+    heat_scale(w.X, w.dt, G, R1, L1, s, lc);
+    heat_scale(w.X + (size_t)R1 * C, w.dt + (size_t)B * C, G + (size_t)R1 * C, R2, L2, s, lc);
+    head_conv_fp32(h, w, B, hf1, wf1, hf2, wf2, G, Gs, Y, s, lc);
+    HeadParams p{};
+    p.gn_g = W + h->L.hm_gn_g; p.gn_b = W + h->L.hm_gn_b; p.w3 = W + h->L.hm_w3; p.b3 = W + h->L.hm_b3;
+    p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;
+    p.batch = B; p.clamp = clamp;
+    p.Y = Y; p.hs = w.dt; p.hf = hf1; p.wf = wf1; p.img_h = img_h1; p.img_w = img_w1;
+    p.boxes = boxes1; p.dbg_cxy = dbg_cxy; p.dbg_tlbr = dbg_tlbr;
+    head_finalize(p, s, lc);
+    p.Y = Y + (size_t)R1 * C; p.hs = w.dt + (size_t)B * C; p.hf = hf2; p.wf = wf2; p.img_h = img_h2; p.img_w = img_w2;
+    p.boxes = boxes2; p.dbg_cxy = dbg_cxy ? dbg_cxy + 2 * B : nullptr; p.dbg_tlbr = dbg_tlbr ? dbg_tlbr + 4 * B : nullptr;
+    head_finalize(p, s, lc);
+
+    h->last_launches = lc.n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(OETR_E_CUDA, "oetr_forward: launch failed: %s", cudaGetErrorString(e));
+    return OETR_OK;
+}
+
+static int grow(float** p, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    cudaFree(*p); *p = nullptr; *have = 0;
+    if (cudaMalloc(p, need * sizeof(float)) != cudaSuccess) return -1;
+    *have = need;
+    return 0;
+}
+
+int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat2_host, int batch, int hf1, int wf1,
+                      int hf2, int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp,
+                      float* boxes1_host, float* boxes2_host, void* stream) {
+    int rc = check_shapes(h, batch, hf1, wf1, hf2, wf2);
+    if (rc) return rc;
+    if (batch == 0) return OETR_OK;
+    if (!feat1_host || !feat2_host || !boxes1_host || !boxes2_host) return fail(OETR_E_ARG, "oetr_forward_host: null buffer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n1 = (size_t)batch * C * hf1 * wf1, n2 = (size_t)batch * C * hf2 * wf2;
+    size_t ws = 0;
+    rc = oetr_workspace_bytes(h, batch, hf1, wf1, hf2, wf2, &ws);
+    if (rc) return rc;
+    if (grow(&h->st_feat1, &h->st_feat1_n, n1) || grow(&h->st_feat2, &h->st_feat2_n, n2) ||
+        grow(&h->st_boxes, &h->st_boxes_n, (size_t)batch * 8))
+        return fail(OETR_E_NOMEM, "oetr_forward_host: staging allocation failed");
+    if (h->st_ws_n < ws) {
+        cudaFree(h->st_ws); h->st_ws = nullptr; h->st_ws_n = 0;
+        if (cudaMalloc(&h->st_ws, ws) != cudaSuccess) return fail(OETR_E_NOMEM, "oetr_forward_host: workspace allocation failed");
+        h->st_ws_n = ws;
+    }
+    CU(cudaMemcpyAsync(h->st_feat1, feat1_host, n1 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->st_feat2, feat2_host, n2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = oetr_forward(h, h->st_feat1, h->st_feat2, batch, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp,
+                      h->st_boxes, h->st_boxes + (size_t)batch * 4, nullptr, nullptr, nullptr, nullptr, h->st_ws,
+                      h->st_ws_n, stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(boxes1_host, h->st_boxes, (size_t)batch * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(boxes2_host, h->st_boxes + (size_t)batch * 4, (size_t)batch * 4 * sizeof(float),
+                       cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OETR_OK;
+}
+
+int oetr_selftest_tcgen05(float* errs_host, int n_errs) {
+    if (!errs_host || n_errs < 1) return fail(OETR_E_ARG, "oetr_selftest_tcgen05: bad arguments");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(OETR_E_ARCH, "oetr_selftest_tcgen05: device is sm_%d%d", prop.major, prop.minor);
+    char msg[256] = "";
+    if (tc_selftest(errs_host, n_errs, msg, sizeof(msg)) != 0) return fail(OETR_E_CUDA, "oetr_selftest_tcgen05: %s", msg);
+    return OETR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// Interface of the tcgen05 (OETR_PREC_FP16) path: fp16 UMMA operand images of the weights, its workspace
+// slice, the encoder driver and the building-block self-test.  Implemented in tc_kernels.cu.
+#pragma once
+#include "oetr_common.cuh"
+
+namespace oetr {
+
+struct TcWeights {
+    __half* enc_img = nullptr;     // per encoder layer: the chunk stream the layer kernels consume (see tc_kernels.cu)
+    __half* dec_img = nullptr;     // decoder cross-attention k/v projection chunk streams (2 layers)
+    size_t enc_layer_halfs = 0, dec_layer_halfs = 0;
+};
+
+struct TcWorkspace {
+    float* xt = nullptr;           // tile-blocked fp32 residual stream [tiles][64][128][4]
+    float* post = nullptr;         // tile-blocked positional rows per geometry
+    float* kv_part = nullptr;      // per-tile linear-attention partial summaries [tiles][KVS]
+    float* dec_kvs = nullptr;      // [2 decoder layers][2B][KVS] cross-attention summaries
+};
+
+void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w);
+int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char* msg, size_t msg_len);
+void tc_free_weights(TcWeights& w);
+// runs the 8 encoder layers and the decoder's cross-attention K/V summaries; writes token-major memory to X_out
+int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
+               const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* d_pe, int max_w,
+               float* X_out, float* dkvs_scratch, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
+int tc_selftest(float* errs_host, int n_errs, char* msg, size_t msg_len);
+
+}  // namespace oetr

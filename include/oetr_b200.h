@@ -1,0 +1,144 @@
+/*
+ * oetr_b200.h -- C ABI of the B200-native OETR hot path (liboetr_b200.so).
+ *
+ * The reference (TencentYoutuResearch/ImageMatching-OETR) is pure Python/PyTorch and has no FFI; this header is
+ * the drop-in boundary a maintainer binds with ctypes.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross this boundary.
+ *   - every function returns an int status (0 = OETR_OK, <0 = error); oetr_last_error() gives the message of
+ *     the last failing call on the calling thread.  No exception ever crosses the boundary.
+ *   - all device pointers are caller-owned (e.g. torch allocations); the handle owns only its private copy of
+ *     the weights (and the constant position-encoding table derived at create time).
+ *   - oetr_forward is asynchronous and stream-ordered: no hidden synchronisation, no allocation.
+ *   - the library targets sm_100a only; on any other device oetr_create fails with OETR_E_ARCH (there is no
+ *     fallback path, CPU or otherwise).
+ */
+#ifndef OETR_B200_H_
+#define OETR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OETR_API __attribute__((visibility("default")))
+#else
+#define OETR_API
+#endif
+
+#define OETR_ABI_VERSION 1
+
+/* status codes */
+#define OETR_OK        0
+#define OETR_E_ARG    (-1)   /* null pointer / bad enum / bad size                                         */
+#define OETR_E_SHAPE  (-2)   /* feature-map shape outside what the reference supports (1..100 per side)    */
+#define OETR_E_ARCH   (-3)   /* current device is not sm_100                                               */
+#define OETR_E_CUDA   (-4)   /* a CUDA runtime call failed (message in oetr_last_error)                    */
+#define OETR_E_NOMEM  (-5)   /* device allocation failed / workspace too small                             */
+
+/* attention_mode: which attention the encoder layers use.
+ *   LINEAR = src/models/linear_attention.py:16-50 (what OETR ships: src/model.py:82-84 never passes a mode)
+ *   FULL   = src/models/linear_attention.py:53-87 (QueryTransformer(attention_mode='full'), encoder only) */
+#define OETR_ATTN_LINEAR 0
+#define OETR_ATTN_FULL   1
+
+/* operand_precision: arithmetic of the dense contractions.
+ *   FP32 = CUDA-core fp32 FMA everywhere (reference-grade, slow)
+ *   FP16 = tcgen05 tensor-core MMA, fp16 operands / fp32 TMEM accumulation for the encoder GEMMs and the
+ *          linear-attention contractions; everything row-wise (LayerNorm, elu, GELU, softmax, GroupNorm)
+ *          stays fp32.  (plain bf16 operands miss the 1e-3 parity bar, SURVEY.md finding 3.) */
+#define OETR_PREC_FP32 0
+#define OETR_PREC_FP16 1
+
+typedef struct oetr_handle oetr_handle;
+
+/* Number of fp32 values in the packed weight blob, in the canonical order below.  (6 443 525)            */
+OETR_API size_t oetr_packed_weight_count(void);
+
+/*
+ * Create a handle from the packed hot-path weights (fp32, host OR device pointer, copied).
+ * Replaces: OETR.__init__'s construction of QueryTransformer / tlbr_reg / heatmap_conv / query_embed* /
+ * PositionEncodingSine (src/model.py:58-86) + load_state_dict (dloc/core/overlaps/oetr.py:36-42).
+ *
+ * Canonical order of `weights` (each tensor row-major with the shape torch's state_dict gives it):
+ *   for i in 0..7,  prefix "transformer.encoder.<i>.":
+ *       q_proj.weight[256,256] k_proj.weight[256,256] v_proj.weight[256,256] merge.weight[256,256]
+ *       mlp.0.weight[512,256] mlp.2.weight[256,512]
+ *       pre_norm_q.weight[256] pre_norm_q.bias[256] pre_norm_kv.weight[256] pre_norm_kv.bias[256]
+ *       norm2.weight[256] norm2.bias[256]
+ *   for j in 0..1,  prefix "transformer.decoder.layers.<j>.":
+ *       for a in (self_attn, multihead_attn):
+ *           a.q_proj.weight[256,256] a.q_proj.bias[256] a.k_proj.weight a.k_proj.bias a.v_proj.weight a.v_proj.bias
+ *           a.merge.weight[256,256]
+ *       mlp.0.weight[512,256] mlp.2.weight[256,512]
+ *       norm1.weight norm1.bias norm2.weight norm2.bias norm3.weight norm3.bias        (each [256])
+ *   query_embed1.weight[256] query_embed2.weight[256]
+ *   tlbr_reg.0.weight[256,256] tlbr_reg.2.weight[4,256] tlbr_reg.2.bias[4]
+ *   heatmap_conv.0.weight[256,256,3,3] heatmap_conv.0.bias[256] heatmap_conv.1.weight[256] heatmap_conv.1.bias[256]
+ *   heatmap_conv.3.weight[256] heatmap_conv.3.bias[1]
+ * (The decoder layers' unused q_proj/k_proj/v_proj/merge are not part of the blob.)
+ *
+ * max_h/max_w: PositionEncodingSine max_shape (cfg.NECK.MAX_SHAPE, src/config/default.py:25-28); 100,100.
+ */
+OETR_API int oetr_create(const float* weights, size_t n_floats, int weights_on_device,
+                int attention_mode, int operand_precision, int max_h, int max_w,
+                oetr_handle** out);
+
+OETR_API int oetr_destroy(oetr_handle* h);
+
+/* Bytes of caller-provided device scratch oetr_forward needs for this problem size. */
+OETR_API int oetr_workspace_bytes(const oetr_handle* h, int batch, int hf1, int wf1, int hf2, int wf2, size_t* out);
+
+/*
+ * The hot path.  Replaces OETR.feature_correlation + center_estimation + size_regression +
+ * box_tlbr_to_xyxy (src/model.py:240-250; forward's unclamped variant :193-211 when clamp == 0).
+ *
+ *   feat1 [batch,256,hf1,wf1], feat2 [batch,256,hf2,wf2]  fp32 NCHW device (output of input_proj2)
+ *   img_h*, img_w*: model-input image sizes in pixels (src/model.py:230-233); stride = img_h / hf (integer)
+ *   boxes1, boxes2 [batch,4] fp32 device, xyxy pixels
+ *   dbg_* : nullable device outputs of the stage boundaries, for parity tests:
+ *       dbg_hs     [2][batch][256]          decoder outputs hs1 | hs2
+ *       dbg_memory [batch*L1 + batch*L2][256]  encoder outputs memory1 | memory2 (token-major)
+ *       dbg_cxy    [2][batch][2]            soft-argmax centres (x,y)
+ *       dbg_tlbr   [2][batch][4]            sigmoid(top,left,bottom,right)
+ *   workspace: >= oetr_workspace_bytes(...) bytes, 256-byte aligned, device
+ *   stream: a cudaStream_t (as void*); 0 = legacy default stream
+ */
+OETR_API int oetr_forward(oetr_handle* h,
+                 const float* feat1, const float* feat2,
+                 int batch, int hf1, int wf1, int hf2, int wf2,
+                 int img_h1, int img_w1, int img_h2, int img_w2,
+                 int clamp,
+                 float* boxes1, float* boxes2,
+                 float* dbg_hs, float* dbg_memory, float* dbg_cxy, float* dbg_tlbr,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the last oetr_forward on this handle launched (bench.py's gpu_launches). */
+OETR_API int oetr_last_launch_count(const oetr_handle* h);
+
+/* Convenience for hosts without a CUDA runtime binding of their own (used by the host-buffer e2e path):
+ *   host feats (pinned or pageable) -> device, forward, boxes -> host; synchronises `stream` before return.
+ *   Device staging buffers are owned by the handle and grown on demand (the only entry point that allocates). */
+OETR_API int oetr_forward_host(oetr_handle* h,
+                      const float* feat1_host, const float* feat2_host,
+                      int batch, int hf1, int wf1, int hf2, int wf2,
+                      int img_h1, int img_w1, int img_h2, int img_w2,
+                      int clamp, float* boxes1_host, float* boxes2_host, void* stream);
+
+/* tcgen05 / TMEM / bulk-TMA self-test of the building blocks the FP16 path relies on (descriptor encodings,
+ * swizzled operand images, TMEM accumulate).  Writes one max-abs-error per sub-test into errs[0..n_errs).
+ * Returns OETR_OK when the kernels ran (inspect errs for the numeric outcome). */
+OETR_API int oetr_selftest_tcgen05(float* errs_host, int n_errs);
+
+OETR_API const char* oetr_last_error(void);
+OETR_API int oetr_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* OETR_B200_H_ */

@@ -1,0 +1,42 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Build liboetr_b200.so (nvcc cross-compiles without a GPU) if it is not there yet."""
+    from oetr_b200 import cabi
+    if not os.path.exists(cabi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return cabi.LIB_PATH
+
+
+def load_case(name):
+    """(weights dict, feat1, feat2, case tuple, golden npz) for a tests/golden case."""
+    from cases import CASES
+    from oetr_b200 import weights
+    b, fm1, fm2, hw1, hw2, attention, wseed, fseed = CASES[name]
+    W = weights.synthetic_hot_path_weights(wseed)
+    f1 = weights.synthetic_features(b, *fm1, seed=fseed, tag="feat1")
+    f2 = weights.synthetic_features(b, *fm2, seed=fseed, tag="feat2")
+    golden = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    return W, f1, f2, CASES[name], golden
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

@@ -1,0 +1,158 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle and the committed reference outputs.
+
+Tolerances (north star: boxes within 1e-3 relative of the fp32 reference):
+  fp32 path : box error / image side < 2e-5   (fp32 summation-order noise; the reference's own fp32-vs-fp64 gap
+              is ~2e-6), intermediates < 5e-5 relative
+  fp16 path : box error / image side < 1e-3   (the stated bar), memory/hs < 3e-3 relative (max-norm)
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, MEMORY_STRIDE
+from conftest import load_case, rel_err
+from oracle import oetr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+import oetr_b200  # noqa: E402
+from oetr_b200 import cabi, weights  # noqa: E402
+
+TOL = {"fp32": dict(box=2e-5, mid=5e-5), "fp16": dict(box=1e-3, mid=3e-3)}
+
+
+def _run(W, f1, f2, hw1, hw2, attention, precision, clamp):
+    hot = oetr_b200.OverlapHotPath(W, attention=attention, precision=precision)
+    b1, b2, dbg = hot.forward(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(), hw1, hw2, clamp=clamp,
+                              debug=True)
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in dbg.items()}
+    out["box1"], out["box2"] = b1.cpu().numpy(), b2.cpu().numpy()
+    out["launches"] = hot.last_launch_count
+    hot.close()
+    return out
+
+
+def _cases(precision):
+    return [n for n in sorted(CASES) if precision == "fp32" or CASES[n][5] == "linear"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_stage_parity_with_oracle_and_golden(name, precision):
+    if name not in _cases(precision):
+        pytest.skip("full attention runs on the fp32 path only in round 1")
+    W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case(name)
+    want = orc.hot_path(W, f1, f2, hw1, hw2, attention=attention)
+    got = _run(W, f1, f2, hw1, hw2, attention, precision, clamp=False)
+    tol = TOL[precision]
+    assert got["launches"] > 0
+    for k in ("memory1", "memory2", "hs1", "hs2", "tlbr1", "tlbr2"):
+        assert rel_err(got[k], want[k]) < tol["mid"], (k, rel_err(got[k], want[k]))
+    for i, hw in ((1, hw1), (2, hw2)):
+        side = max(hw)
+        assert np.abs(got["cxy%d" % i] - want["cxy%d" % i]).max() / side < tol["box"]
+        assert np.abs(got["box%d" % i] - want["box%d_raw" % i]).max() / side < tol["box"]
+        # committed outputs of the real reference (fp32 as shipped)
+        assert np.abs(got["box%d" % i] - g["box%d_raw" % i]).max() / side < tol["box"] + 2e-5
+        assert rel_err(got["memory%d" % i][:, ::MEMORY_STRIDE], g["memory%d_sub" % i]) < tol["mid"] + 2e-5
+    clamped = _run(W, f1, f2, hw1, hw2, attention, precision, clamp=True)
+    for i, hw in ((1, hw1), (2, hw2)):
+        assert np.abs(clamped["box%d" % i] - g["box%d" % i]).max() / max(hw) < tol["box"] + 2e-5
+        assert clamped["box%d" % i].min() >= 0 and clamped["box%d" % i][:, 0::2].max() <= hw[1]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_edge_shapes(precision):
+    W = weights.synthetic_hot_path_weights(0)
+    # 1x1 maps, a single row, a non-multiple-of-anything map, and the PositionEncodingSine maximum (100x100)
+    for b, fm1, fm2 in ((1, (1, 1), (1, 1)), (2, (1, 9), (3, 1)), (1, (7, 13), (11, 5)), (1, (100, 100), (2, 2))):
+        hw1, hw2 = (fm1[0] * 32, fm1[1] * 32), (fm2[0] * 32, fm2[1] * 32)
+        f1 = weights.synthetic_features(b, *fm1, seed=5, tag="e1")
+        f2 = weights.synthetic_features(b, *fm2, seed=5, tag="e2")
+        want = orc.hot_path(W, f1, f2, hw1, hw2)
+        got = _run(W, f1, f2, hw1, hw2, "linear", precision, clamp=False)
+        for i, hw in ((1, hw1), (2, hw2)):
+            err = np.abs(got["box%d" % i] - want["box%d_raw" % i]).max() / max(hw)
+            assert err < TOL[precision]["box"], (fm1, fm2, i, err)
+
+
+def test_empty_batch_and_error_codes():
+    W = weights.synthetic_hot_path_weights(0)
+    hot = oetr_b200.OverlapHotPath(W, precision="fp32")
+    e = torch.empty(0, 256, 4, 4, device="cuda")
+    b1, b2 = hot.forward(e, e, (128, 128), (128, 128))
+    assert b1.shape == (0, 4) and b2.shape == (0, 4)
+    with pytest.raises(cabi.OetrError) as ei:
+        big = torch.zeros(1, 256, 101, 2, device="cuda")
+        hot.forward(big, big, (3232, 64), (3232, 64))
+    assert ei.value.code == cabi.OETR_E_SHAPE
+    with pytest.raises(ValueError):
+        hot.forward(torch.zeros(1, 128, 4, 4, device="cuda"), torch.zeros(1, 128, 4, 4, device="cuda"), (128, 128),
+                    (128, 128))
+    need = ctypes.c_size_t()
+    lib = cabi.load_library()
+    assert lib.oetr_workspace_bytes(hot._handle, 1, 4, 4, 4, 4, ctypes.byref(need)) == 0 and need.value > 0
+    f = torch.zeros(1, 256, 4, 4, device="cuda")
+    out = torch.zeros(1, 4, device="cuda")
+    small = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.oetr_forward(hot._handle, p(f), p(f), 1, 4, 4, 4, 4, 128, 128, 128, 128, 1, p(out), p(out), None, None,
+                          None, None, p(small), small.numel(), None)
+    assert rc == cabi.OETR_E_NOMEM
+    hot.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_full_size_properties(precision):
+    """BASELINE config 2 (batch 32, 640x640 -> 20x20 maps): size-independent properties."""
+    W = weights.synthetic_hot_path_weights(0)
+    b = 32
+    f1 = torch.from_numpy(weights.synthetic_features(b, 20, 20, seed=9, tag="p1")).cuda()
+    f2 = torch.from_numpy(weights.synthetic_features(b, 20, 20, seed=9, tag="p2")).cuda()
+    hot = oetr_b200.OverlapHotPath(W, precision=precision)
+    a1, a2 = hot.forward(f1, f2, (640, 640), (640, 640), clamp=False)
+    # determinism
+    c1, c2 = hot.forward(f1, f2, (640, 640), (640, 640), clamp=False)
+    assert torch.equal(a1, c1) and torch.equal(a2, c2)
+    # pairs are independent: permuting the batch permutes the boxes, and a sub-batch reproduces its rows
+    perm = torch.randperm(b, generator=torch.Generator().manual_seed(0)).cuda()
+    p1, p2 = hot.forward(f1[perm], f2[perm], (640, 640), (640, 640), clamp=False)
+    assert torch.allclose(p1, a1[perm], rtol=0, atol=1e-3) and torch.allclose(p2, a2[perm], rtol=0, atol=1e-3)
+    s1, s2 = hot.forward(f1[5:8], f2[5:8], (640, 640), (640, 640), clamp=False)
+    assert torch.allclose(s1, a1[5:8], rtol=0, atol=1e-3) and torch.allclose(s2, a2[5:8], rtol=0, atol=1e-3)
+    # image-size linearity of the box assembly: doubling the declared image size doubles stride and extents
+    d1, _ = hot.forward(f1, f2, (1280, 1280), (1280, 1280), clamp=False)
+    assert torch.allclose(d1, 2 * a1, rtol=1e-5, atol=1e-3)
+    # oracle on a 4-pair sample of the same batch
+    want = orc.hot_path(W, f1[:4].cpu().numpy(), f2[:4].cpu().numpy(), (640, 640), (640, 640))
+    assert np.abs(a1[:4].cpu().numpy() - want["box1_raw"]).max() / 640 < TOL[precision]["box"]
+    assert np.abs(a2[:4].cpu().numpy() - want["box2_raw"]).max() / 640 < TOL[precision]["box"]
+    # host-buffer entry point gives the same boxes
+    h1, h2 = hot.forward_host(f1.cpu().numpy(), f2.cpu().numpy(), (640, 640), (640, 640), clamp=False)
+    assert np.array_equal(h1, a1.cpu().numpy()) and np.array_equal(h2, a2.cpu().numpy())
+    hot.close()
+
+
+def test_swap_symmetry():
+    """With identical query embeddings the model is symmetric in its two inputs: swapping them swaps the boxes."""
+    W = weights.synthetic_hot_path_weights(0)
+    W["query_embed2.weight"] = W["query_embed1.weight"].copy()
+    f1 = torch.from_numpy(weights.synthetic_features(2, 9, 12, seed=3, tag="s1")).cuda()
+    f2 = torch.from_numpy(weights.synthetic_features(2, 10, 7, seed=3, tag="s2")).cuda()
+    hot = oetr_b200.OverlapHotPath(W, precision="fp32")
+    a1, a2 = hot.forward(f1, f2, (288, 384), (320, 224), clamp=False)
+    b1, b2 = hot.forward(f2, f1, (320, 224), (288, 384), clamp=False)
+    assert torch.allclose(a1, b2, rtol=0, atol=1e-3) and torch.allclose(a2, b1, rtol=0, atol=1e-3)
+    hot.close()
+
+
+def test_selftest_tcgen05_building_blocks():
+    lib = cabi.load_library()
+    errs = (ctypes.c_float * 16)()
+    cabi.check(lib.oetr_selftest_tcgen05(errs, 16), lib)
+    vals = list(errs)
+    print("tcgen05 selftest errors:", vals)
+    assert all(v == v and v < 2e-3 for v in vals[:8]), vals

@@ -1,0 +1,58 @@
+"""Pins the CPU oracle (oracle/oetr_oracle.py) to outputs of the UNMODIFIED reference modules
+(tests/golden/*.npz, made by tests/golden/make_golden.py in the build container)."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, MEMORY_STRIDE
+from conftest import ROOT, load_case, rel_err
+from oracle import oetr_oracle as orc
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_fp64(name):
+    W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case(name)
+    o = orc.hot_path(W, f1, f2, hw1, hw2, attention=attention)
+    # every stage boundary against the reference run in double precision: agreement at fp64 noise level
+    for k in ("hs1", "hs2", "cxy1", "cxy2", "tlbr1", "tlbr2", "box1_raw", "box2_raw"):
+        assert rel_err(o[k], g[k + "_f64"]) < 1e-7, k
+    assert rel_err(o["memory1"][:, ::MEMORY_STRIDE], g["memory1_sub_f64"]) < 1e-7
+    # and against the reference as shipped (fp32): its own rounding noise is the only difference
+    for k in ("hs1", "hs2", "tlbr1", "tlbr2"):
+        assert rel_err(o[k], g[k]) < 2e-5, k
+    for k, side in (("box1", max(hw1)), ("box2", max(hw2)), ("box1_raw", max(hw1)), ("box2_raw", max(hw2))):
+        assert np.abs(o[k] - g[k]).max() / side < 2e-5, k
+    for i in (1, 2):
+        m = o["memory%d" % i]
+        assert rel_err(m[:, ::MEMORY_STRIDE], g["memory%d_sub" % i]) < 2e-5
+        assert np.allclose(m.sum(axis=(1, 2)), g["memory%d_sum" % i], rtol=0, atol=1e-4 * g["memory%d_abs" % i].max())
+
+
+def test_clamp_semantics():
+    # forward_dummy clamps (models/utils.py:16-28), forward does not (model.py:193-211)
+    W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case("full_ragged")
+    o = orc.hot_path(W, f1, f2, hw1, hw2, attention=attention)
+    assert (g["box1_raw"] < 0).any() or (g["box1_raw"] > max(hw1)).any(), "case must exercise clamping"
+    assert np.array_equal(o["box1"], np.stack([np.clip(o["box1_raw"][:, 0], 0, hw1[1]),
+                                               np.clip(o["box1_raw"][:, 1], 0, hw1[0]),
+                                               np.clip(o["box1_raw"][:, 2], 0, hw1[1]),
+                                               np.clip(o["box1_raw"][:, 3], 0, hw1[0])], axis=1))
+
+
+def test_pe_table_matches_reference():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pe_table.npz"))
+    pe = orc.pe_table((100, 100), dtype=np.float32)
+    assert np.abs(pe[:, ::9, ::7] - g["pe_sub"]).max() < 1e-6
+    assert np.abs(pe[:, :3, :3] - g["pe_corner"]).max() < 1e-6
+    # the precedence quirk: frequencies are exp(-2k), so channel group k=1 already decays by e^-2
+    assert abs(pe[4, 0, 0] - np.sin(np.exp(-2.0))) < 1e-6
+
+
+def test_fp16_rounding_model_is_close_but_not_identical():
+    # the operand-rounding model used to bound the tensor-core path stays within the 1e-3 parity bar at 640x640
+    W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case("b2_640")
+    exact = orc.hot_path(W, f1, f2, hw1, hw2)
+    q = orc.hot_path(W, f1, f2, hw1, hw2, rnd=orc.round_fp16)
+    d = np.abs(q["box1_raw"] - exact["box1_raw"]).max() / max(hw1)
+    assert 1e-6 < d < 1e-3
