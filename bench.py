@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the OETR hot path (feature-correlation transformer + overlap-box head) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one pass of the hot path over one batch of synthetic input: 32 pairs of 640x640 images, i.e. two
+[32,256,20,20] fp32 feature maps (BASELINE.json configs[1]); with N GPUs every rank runs its own batch (weak
+scaling, replicated weights) and the boxes are all-gathered (configs[2]).  One JSON line is printed by rank 0.
+
+  value          pairs/s, inputs resident in HBM, CUDA-event time of exactly K steps, max over ranks
+  e2e            the same metric through the C-ABI host-buffer entry point (oetr_forward_host): pinned host
+                 features -> H2D -> hot path -> D2H boxes, every step, wall clock
+  roofline       dominant kernel (k_tc_layer, one launch per encoder layer): algorithmic FLOPs / launch over the
+                 CUDA-event launch duration measured inside the timed region, against the measured bf16/fp16
+                 tensor peak (MEASURED_PEAKS.json, sustained figure: the kernel is timed inside a long step)
+  cpu_baseline   the numpy port of the reference algorithm (oracle/) on the host cores, bounded sample
+  --impl reference   times that same CPU implementation as the reference arm (the reference itself is pure
+                 Python under /root/reference, which does not exist on the GPU box; the port is pinned to it by
+                 tests/golden)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image-pairs/sec at 640x640"
+FEAT_HW = 20                     # 640 / 32
+IMG = 640
+PAIRS_PER_GPU = 32
+N_ROTATE = 8                     # input batches cycled so that a step never finds its inputs in L2
+
+# algorithmic FLOPs (multiply-add = 2), per token, of one k_tc_layer launch:
+#   q_proj 2*256^2 + merge 2*256^2 + MLP 2*(2*256*512) + Q.KV 2*8*32*32
+FLOPS_LAYER_PER_TOKEN = 2 * 256 * 256 * 2 + 2 * 2 * 256 * 512 + 2 * 8 * 32 * 32
+# whole hot path per pair at L=400: 8.32 GFLOP
+FLOPS_PER_PAIR = 8.32e9
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json, sustained)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(int(r[0]))
+                mx = max(mx, int(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_pairs_per_s(n_pairs, reps):
+    """Time the numpy port (fp32, all BLAS threads) on `n_pairs` pairs of the bench workload."""
+    from oetr_b200 import weights
+    from oracle import oetr_oracle as orc
+    W = weights.synthetic_hot_path_weights(0)
+    f1 = weights.synthetic_features(n_pairs, FEAT_HW, FEAT_HW, seed=21, tag="cpu1")
+    f2 = weights.synthetic_features(n_pairs, FEAT_HW, FEAT_HW, seed=21, tag="cpu2")
+    orc.hot_path(W, f1[:1], f2[:1], (IMG, IMG), (IMG, IMG), dtype=np.float32)      # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.hot_path(W, f1, f2, (IMG, IMG), (IMG, IMG), dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return n_pairs * reps / dt, dt
+
+
+def _host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return max(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path, one bounded sample (2 pairs) per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 2
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_port_pairs_per_s(n, 1)
+    pps, dt = cpu_port_pairs_per_s(n, args.steps)
+    cores = _host_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": pps, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch=32 640x640 pairs (hot path on [*,256,20,20] feature maps); CPU sample of "
+                               "%d pairs per step" % n},
+        "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d pairs x %d steps, numpy fp32 port of the reference algorithm" % (n, args.steps)},
+        "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import oetr_b200
+    from oetr_b200 import weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = PAIRS_PER_GPU, args.steps, args.warmup
+
+    Wts = weights.synthetic_hot_path_weights(0)
+    hot = oetr_b200.OverlapHotPath(Wts, attention="linear", precision=args.precision, device=dev)
+    # N_ROTATE different resident input batches (8 x 26 MB > 126 MB L2)
+    base1 = weights.synthetic_features(B, FEAT_HW, FEAT_HW, seed=100 + rank, tag="b1")
+    base2 = weights.synthetic_features(B, FEAT_HW, FEAT_HW, seed=100 + rank, tag="b2")
+    feats = []
+    for i in range(N_ROTATE):
+        feats.append((torch.from_numpy(np.roll(base1, i, axis=0)).to(dev), torch.from_numpy(np.roll(base2, i, axis=0)).to(dev)))
+    gathered = torch.empty(world * B, 2, 4, device=dev) if world > 1 else None
+
+    def step(i):
+        f1, f2 = feats[i % N_ROTATE]
+        b1, b2 = hot.forward(f1, f2, (IMG, IMG), (IMG, IMG), clamp=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, torch.stack([b1, b2], dim=1))
+        return b1, b2
+
+    for i in range(Wm):
+        step(i)
+    torch.cuda.synchronize()
+    hot.poll_error()
+    if world > 1:
+        dist.barrier()
+    hot.profile(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(K):
+            step(Wm + i)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    layer_ms, n_layer = hot.profile_read()
+    hot.profile(False)
+    launches = hot.last_launch_count * K
+    hot.poll_error()
+
+    # e2e: host buffers through the C ABI, H2D + D2H inside the timed region
+    h1 = torch.from_numpy(base1).pin_memory()
+    h2 = torch.from_numpy(base2).pin_memory()
+    for _ in range(2):
+        hot.forward_host(h1.numpy(), h2.numpy(), (IMG, IMG), (IMG, IMG))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eb1, eb2 = hot.forward_host(h1.numpy(), h2.numpy(), (IMG, IMG), (IMG, IMG))
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t[0].item(), t[1].item()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # parity spot check of the timed configuration against the CPU port (2 pairs)
+    from oracle import oetr_oracle as orc
+    want = orc.hot_path(Wts, base1[:2], base2[:2], (IMG, IMG), (IMG, IMG), clamp=False)
+    g1, g2 = hot.forward(feats[0][0][:2], feats[0][1][:2], (IMG, IMG), (IMG, IMG), clamp=False)
+    torch.cuda.synchronize()
+    perr = max(np.abs(g1.cpu().numpy() - want["box1_raw"]).max(), np.abs(g2.cpu().numpy() - want["box2_raw"]).max()) / IMG
+
+    peak, peak_src = _peaks()
+    tokens = B * 2 * FEAT_HW * FEAT_HW
+    roof = None
+    if n_layer:
+        ach = FLOPS_LAYER_PER_TOKEN * tokens / (layer_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_tc_layer", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "launch_ms": layer_ms, "launches_timed": n_layer,
+                "share_of_step": layer_ms * 8 / (ms / K),
+                "whole_path_tflops": FLOPS_PER_PAIR * B * K / (ms * 1e-3) / 1e12}
+    else:
+        ach = FLOPS_PER_PAIR * B * K / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "whole hot path (fp32 CUDA-core path has no single dominant kernel)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src}
+    cpu_pps, cpu_dt = cpu_port_pairs_per_s(2, 4)
+    value = world * B * K / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate" if args.precision == "fp16" else "f32", "data": "synthetic",
+        "config": {"workload": "batch=32 640x640 pairs per GPU: hot path (8-layer correlation transformer + "
+                               "decoder + overlap head) on two [32,256,20,20] fp32 feature maps",
+                   "pairs_per_gpu": B, "precision": args.precision, "attention": "linear",
+                   "l2": "inputs rotate over %d resident batches (%.0f MB > 126 MB L2)" % (
+                       N_ROTATE, N_ROTATE * 2 * base1.nbytes / 1e6),
+                   "parallelism": "batch shards, replicated weights, all-gather of boxes" if world > 1 else "1 GPU"},
+        "clocks": clk.summary(),
+        "e2e": {"value": world * B * K / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * base1.nbytes),
+                "d2h_bytes_per_step": int(B * 8 * 4), "api": "oetr_forward_host (C ABI, pinned host buffers)"},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu_pps, "unit": "pairs/s", "cores": _host_threads(), "kind": "port",
+                         "sample": "2 pairs x 4 runs of the numpy fp32 port (%.1f s)" % cpu_dt},
+        "parity": {"box_err_over_image_side": float(perr), "bar": 1e-3, "pairs_checked": 2},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("OETR_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,8 @@ struct oetr_handle {
     float* d_w9 = nullptr;     // heatmap_conv.0.weight repacked per tap: [9][256 out][256 in]
     float* d_pe = nullptr;     // PositionEncodingSine table, channel-last: [max_h][max_w][256]
     TcWeights tc;              // fp16 UMMA operand images (FP16 path only)
+    KernelProfiler prof;       // optional CUDA-event brackets around the dominant kernel
+    int* d_flag = nullptr;     // raised by a device-side mbarrier wait that timed out (protocol bug guard)
     int last_launches = 0;
     // staging owned by the handle for oetr_forward_host only
     float *st_feat1 = nullptr, *st_feat2 = nullptr, *st_boxes = nullptr;
@@ -281,6 +283,8 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
     build_pe_host(pe, max_h, max_w);
     CUH(cudaMalloc(&h->d_pe, pe.size() * sizeof(float)));
     CUH(cudaMemcpy(h->d_pe, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUH(cudaMalloc(&h->d_flag, sizeof(int)));
+    CUH(cudaMemset(h->d_flag, 0, sizeof(int)));
     if (operand_precision == OETR_PREC_FP16) {
         char msg[256] = "";
         if (tc_prepare_weights(h->d_w, L, h->tc, msg, sizeof(msg)) != 0)
@@ -294,8 +298,9 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
 
 int oetr_destroy(oetr_handle* h) {
     if (!h) return OETR_OK;
-    cudaFree(h->d_w); cudaFree(h->d_w9); cudaFree(h->d_pe);
+    cudaFree(h->d_w); cudaFree(h->d_w9); cudaFree(h->d_pe); cudaFree(h->d_flag);
     tc_free_weights(h->tc);
+    for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
     cudaFree(h->st_feat1); cudaFree(h->st_feat2); cudaFree(h->st_boxes); cudaFree(h->st_ws);
     delete h;
     return OETR_OK;
@@ -320,6 +325,42 @@ int oetr_workspace_bytes(const oetr_handle* h, int batch, int hf1, int wf1, int 
 }
 
 int oetr_last_launch_count(const oetr_handle* h) { return h ? h->last_launches : 0; }
+
+int oetr_profile_enable(oetr_handle* h, int enable) {
+    if (!h) return fail(OETR_E_ARG, "null handle");
+    h->prof.on = enable != 0;
+    h->prof.used = 0;
+    return OETR_OK;
+}
+
+int oetr_profile_read(oetr_handle* h, float* avg_ms, int* n_launches) {
+    if (!h || !avg_ms || !n_launches) return fail(OETR_E_ARG, "oetr_profile_read: null argument");
+    CU(cudaDeviceSynchronize());
+    double total = 0.0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < h->prof.used; i += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->prof.ev[i], h->prof.ev[i + 1]));
+        total += ms;
+        ++n;
+    }
+    *avg_ms = n ? (float)(total / n) : 0.f;
+    *n_launches = n;
+    h->prof.used = 0;
+    return OETR_OK;
+}
+
+int oetr_poll_error(oetr_handle* h) {
+    if (!h) return fail(OETR_E_ARG, "null handle");
+    CU(cudaDeviceSynchronize());
+    int flag = 0;
+    CU(cudaMemcpy(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(h->d_flag, 0, sizeof(int));
+        return fail(OETR_E_CUDA, "a device-side mbarrier wait timed out (pipeline protocol error); results are invalid");
+    }
+    return OETR_OK;
+}
 
 int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int batch, int hf1, int wf1, int hf2,
                  int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp, float* boxes1, float* boxes2,
@@ -357,7 +398,7 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
         // tcgen05 encoder + decoder K/V summaries; leaves token-major memory in w.X
         char msg[256] = "";
         if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_pe, h->max_w, w.X,
-                       w.dkvs, s, lc, msg, sizeof(msg)) != 0)
+                       h->d_flag, &h->prof, s, lc, msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
         decoder_fp32(h, w, B, s, lc, [&](int j) {
             cudaMemcpyAsync(w.dkvs, w.tc.dec_kvs + (size_t)j * 2 * B * KVS, (size_t)2 * B * KVS * sizeof(float),
@@ -428,6 +469,12 @@ int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat
     CU(cudaMemcpyAsync(boxes2_host, h->st_boxes + (size_t)batch * 4, (size_t)batch * 4 * sizeof(float),
                        cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    int flag = 0;
+    CU(cudaMemcpy(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(h->d_flag, 0, sizeof(int));
+        return fail(OETR_E_CUDA, "a device-side mbarrier wait timed out (pipeline protocol error); results are invalid");
+    }
     return OETR_OK;
 }
 

@@ -3,6 +3,8 @@
 #pragma once
 #include "oetr_common.cuh"
 
+#include <vector>
+
 namespace oetr {
 
 struct TcWeights {
@@ -18,13 +20,30 @@ struct TcWorkspace {
     float* dec_kvs = nullptr;      // [2 decoder layers][2B][KVS] cross-attention summaries
 };
 
+// CUDA-event bracket around every launch of the dominant kernel (k_tc_layer); read back by bench.py through
+// oetr_profile_read.  Events are recorded on the launching stream, consecutive pairs = (begin, end).
+struct KernelProfiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    void mark(cudaStream_t s) {
+        if (!on) return;
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+            ev.push_back(e);
+        }
+        cudaEventRecord(ev[used++], s);
+    }
+};
+
 void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w);
 int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char* msg, size_t msg_len);
 void tc_free_weights(TcWeights& w);
 // runs the 8 encoder layers and the decoder's cross-attention K/V summaries; writes token-major memory to X_out
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* d_pe, int max_w,
-               float* X_out, float* dkvs_scratch, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
+               float* X_out, int* timeout_flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
 int tc_selftest(float* errs_host, int n_errs, char* msg, size_t msg_len);
 
 }  // namespace oetr

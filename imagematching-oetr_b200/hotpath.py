@@ -51,6 +51,19 @@ class OverlapHotPath:
             self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def profile(self, enable=True):
+        cabi.check(self._lib.oetr_profile_enable(self._handle, int(bool(enable))), self._lib)
+
+    def profile_read(self):
+        """(average k_tc_layer launch duration in ms, launches) since the last read; synchronises."""
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        cabi.check(self._lib.oetr_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)), self._lib)
+        return ms.value, n.value
+
+    def poll_error(self):
+        """Synchronise and raise if an earlier forward failed asynchronously (tests / debugging)."""
+        cabi.check(self._lib.oetr_poll_error(self._handle), self._lib)
+
     @property
     def last_launch_count(self):
         return self._lib.oetr_last_launch_count(self._handle)

@@ -121,6 +121,17 @@ OETR_API int oetr_forward(oetr_handle* h,
 /* Number of kernels the last oetr_forward on this handle launched (bench.py's gpu_launches). */
 OETR_API int oetr_last_launch_count(const oetr_handle* h);
 
+/* Measurement hook (bench.py's roofline leg): when enabled, every launch of the dominant kernel of the FP16 path
+ * (k_tc_layer, one per encoder layer) is bracketed by CUDA events on the launching stream.  oetr_profile_read
+ * synchronises, returns the average launch duration since the last read and the number of launches, and resets. */
+OETR_API int oetr_profile_enable(oetr_handle* h, int enable);
+OETR_API int oetr_profile_read(oetr_handle* h, float* avg_ms, int* n_launches);
+
+/* Synchronises the device and reports (and clears) asynchronous failures of earlier oetr_forward calls on this
+ * handle: the tcgen05 kernels bound every mbarrier wait, so a pipeline protocol error surfaces here as
+ * OETR_E_CUDA instead of hanging the GPU.  Intended for tests and debugging; not needed on the hot path. */
+OETR_API int oetr_poll_error(oetr_handle* h);
+
 /* Convenience for hosts without a CUDA runtime binding of their own (used by the host-buffer e2e path):
  *   host feats (pinned or pageable) -> device, forward, boxes -> host; synchronises `stream` before return.
  *   Device staging buffers are owned by the handle and grown on demand (the only entry point that allocates). */
