@@ -723,7 +723,7 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
 // expected outputs are plain matrix products computed on the host:
 //   errs[0] v-projection path + KV summary (K-major GEMM, MN-major KV MMA)   [with LBO = slab stride]
 //   errs[1] Ksum (N=16 ones-product)
-//   errs[2] same as 0 with LBO/SBO swapped (expected to FAIL; tells which convention the hardware uses)
+//   errs[2] unused (0)
 //   errs[3] full layer kernel vs host fp32 emulation of the same tile
 //   errs[4] timeout flag raised by any mbarrier wait (0 = none)
 int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
@@ -793,7 +793,7 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
             kv_ref[(size_t)im * KVS + h * HD * HD + d * HD + e] += kf * (double)h16((float)vh[((size_t)im * L + l) * C + h * HD + e]);
     }
     std::vector<float> part((size_t)2 * KVS);
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 1; ++variant) {   // (the swapped LBO/SBO probe addressed out of range on B200: convention settled)
         KvParams kp{};
         kp.g = g; kp.feat1 = d_feat; kp.feat2 = d_feat + (size_t)C * L; kp.xt = d_xt; kp.post1 = d_post; kp.post2 = d_post;
         kp.ln_g = nullptr; kp.ln_b = nullptr; kp.bk = nullptr; kp.bv = nullptr; kp.pos_on_v = 1; kp.wimg = d_img;
@@ -811,8 +811,8 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
         double scale = 0;
         for (int i = 0; i < NH * HD * HD; ++i) scale = std::max(scale, std::abs(kv_ref[i]));
         if (variant == 0) { errs[0] = (float)(e_kv / scale); if (n_errs > 1) errs[1] = (float)(e_ks / L); }
-        else if (n_errs > 2) errs[2] = (float)(e_kv / scale);
     }
+    if (n_errs > 2) errs[2] = 0.f;
     // layer kernel (self layer) with the variant-0 summaries: host emulation with the same rounding points
     if (n_errs > 3) {
         KvParams kp{};
