@@ -1,18 +1,29 @@
 // tcgen05 / TMEM / bulk-TMA kernels of the OETR encoder (OETR_PREC_FP16 path).
 //
-// Work decomposition: one CTA = one tile of 128 tokens of one image; 10 warps:
-//   warps 0-7  "row" warps: thread <-> (token row, half of the 256 channels).  They own every row-wise step
-//              (LayerNorm, +pos, elu+1, 1/Z, GELU, fp32->fp16 operand images) and read/write TMEM
-//   warp 8     weight producer: streams pre-swizzled 16 KB fp16 weight chunks global->shared with cp.async.bulk
-//              through a 4-stage mbarrier ring
-//   warp 9     MMA issuer: one lane issues tcgen05.mma (M=128, fp16 x fp16 -> fp32 in TMEM)
-// The fp32 residual stream of the tile lives in TMEM columns [0,256): the merge and MLP-down GEMMs accumulate
-// straight into it (x += ...), so the residual adds cost nothing.  Columns [256,512) are the scratch accumulator.
+// Arithmetic.  Plain fp16 (or tf32/bf16) operands miss the 1e-3 box-parity bar by 2-4x (measured, DESIGN.md
+// section 3), so every contraction is a 3-term split product on the tensor cores:
+//       a = a_hi + a_lo,  w = w_hi + w_lo   (fp16 each)      a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo
+// accumulated in fp32 in TMEM (the dropped a_lo.w_lo term is ~2^-22 relative).  Everything row-wise (LayerNorm,
+// elu+1, 1/Z, GELU, residual adds) is fp32 on the CUDA cores.
 //
-// Two kernels per encoder layer (reference src/models/transformer.py:104-142, linear_attention.py:22-50):
-//   k_tc_kv     source side: LN_kv(+pos) -> v,k projections -> elu+1 -> per-tile KV = K^T V and Ksum
-//   k_tc_layer  query side : LN_q(+pos) -> q projection -> elu+1, Z -> Q.KV -> merge (+=x) -> LN2 -> MLP (+=x)
-// Per-tile KV partials are summed by the consumer, which keeps the reduction order fixed (deterministic).
+// Work decomposition: one CTA = one tile of 128 tokens of one image; 18 warps:
+//   warps 0-15  "row" warps: thread <-> (token row, one quarter of the columns).  Warp w owns TMEM lanes
+//               32*(w%4).. and the 32-column chunks {w/4, w/4+4}.  The fp32 residual stream of the tile lives in
+//               their REGISTERS (64 per thread) for the whole kernel.
+//   warp 16     weight producer: streams pre-swizzled 16 KB fp16 stages global->shared with cp.async.bulk
+//               through a 4-stage mbarrier ring (2 MB per encoder layer per CTA, L2 resident)
+//   warp 17     MMA issuer: one lane issues tcgen05.mma M=128 N=256 K=16 (fp16 x fp16 -> fp32)
+// TMEM holds two 128x256 fp32 accumulators S0 | S1 (all 512 columns).  Shared memory holds ONE operand image
+// of the tile (hi and lo, 128 KB), written by the row warps in two column passes so that the next GEMM starts
+// on the first half while the second half is still being produced.
+//
+// One kernel, k_enc, runs per encoder layer: the query phase of layer i followed by the source ("kv") phase
+// of layer i+1 (reference src/models/transformer.py:104-142, linear_attention.py:22-50):
+//   kv phase : LN_kv(x)+pos -> v, k projections -> elu(k)+1 -> per-tile KV = K^T V and Ksum (tensor cores)
+//   k_fold   : per image: sums the tile partials (fixed order, deterministic) and folds the summary into the
+//              merge projection:  M_img = blockdiag_h(KV_h) . Wm^T.  Linear attention followed by `merge` is
+//              then ONE GEMM per tile with per-image weights:  msg = (phi(q)/Z) . M_img^T
+//   q phase  : LN_q(x)+pos -> q -> phi(q)/Z -> x += msg -> LN2 -> W1 -> GELU -> W2 -> x +=
 #include "tc_common.cuh"
 #include "tc_path.cuh"
 
@@ -23,60 +34,104 @@
 namespace oetr {
 using namespace tc;
 
-constexpr int TILE = 128;                    // tokens per CTA
-constexpr int N_ROW_THREADS = 256;           // warps 0-7
-constexpr int N_THREADS = 320;               // + producer warp + MMA warp
-constexpr int CHUNK_HALFS = 128 * 64;        // one weight chunk: [128 N rows][64 K cols] fp16 = 16 KB
-constexpr uint32_t CHUNK_BYTES = CHUNK_HALFS * 2;
+constexpr int TILE = 128;                       // tokens per CTA
+constexpr int N_ROW_THREADS = 512;              // warps 0-15
+constexpr int WARP_PRODUCER = 16, WARP_MMA = 17;
+constexpr int N_THREADS = 576;
+constexpr int STAGE_HALFS = 128 * 64;           // one ring stage: [128 N rows][64 K cols] fp16, swizzled, 16 KB
+constexpr uint32_t STAGE_BYTES = STAGE_HALFS * 2;
 constexpr int RING = 4;
-constexpr uint32_t SLAB_BYTES = TILE * 128;  // one [128 x 64] fp16 operand slab = 16 KB
-constexpr uint32_t AIMG_BYTES = 4 * SLAB_BYTES;   // a [128 x 256] fp16 operand image = 64 KB
-constexpr int CHUNKS_PER_GEMM = 8;           // a 256x256 weight block = 2 N-halves x 4 K-slabs
-constexpr int KV_STREAM_CHUNKS = 16;         // Wv | Wk
-constexpr int LAYER_STREAM_CHUNKS = 48;      // Wq | Wm | W1a | W2a | W1b | W2b
-constexpr size_t ENC_LAYER_HALFS = (size_t)(KV_STREAM_CHUNKS + LAYER_STREAM_CHUNKS) * CHUNK_HALFS;
-constexpr size_t DEC_LAYER_HALFS = (size_t)KV_STREAM_CHUNKS * CHUNK_HALFS;
+constexpr int GEMM_STAGES = 16;                 // a 256x256 weight block: 4 k-slabs x {hi n0, hi n1, lo n0, lo n1}
+constexpr size_t GEMM_HALFS = (size_t)GEMM_STAGES * STAGE_HALFS;      // 256 KB
+constexpr uint32_t SLAB_BYTES = TILE * 128;     // one [128 x 64] fp16 operand slab = 16 KB
+constexpr uint32_t IMG_BYTES = 4 * SLAB_BYTES;  // a [128 x 256] fp16 operand image = 64 KB
+// per encoder layer: Wq | W1a | W1b | W2a | W2b | Wv | Wk ; per decoder layer: Wv | Wk
+constexpr int ENC_LAYER_GEMMS = 7, DEC_LAYER_GEMMS = 2;
+constexpr size_t ENC_LAYER_HALFS = ENC_LAYER_GEMMS * GEMM_HALFS;
+constexpr size_t DEC_LAYER_HALFS = DEC_LAYER_GEMMS * GEMM_HALFS;
 
-constexpr uint32_t IDESC_N128 = umma_idesc_f16(128, 128, 0, 0);
-constexpr uint32_t IDESC_N32 = umma_idesc_f16(128, 32, 0, 0);
+constexpr uint32_t IDESC_N256 = umma_idesc_f16(128, 256, 0, 0);
 constexpr uint32_t IDESC_KV = umma_idesc_f16(128, 128, 1, 1);      // both operands MN-major (token = K)
 constexpr uint32_t IDESC_KSUM = umma_idesc_f16(128, 16, 1, 1);
 
 // shared-memory map (dynamic, 1024-byte aligned)
-constexpr uint32_t SM_A0 = 0;
-constexpr uint32_t SM_A1 = SM_A0 + AIMG_BYTES;
-constexpr uint32_t SM_RING = SM_A1 + AIMG_BYTES;
-constexpr uint32_t SM_AUX = SM_RING + RING * CHUNK_BYTES;          // 16 KB: ones slab (k_tc_kv) / KV^T image (k_tc_layer)
-constexpr uint32_t SM_VEC = SM_AUX + SLAB_BYTES;                   // 8 float[256] vectors
-constexpr uint32_t SM_RED = SM_VEC + 8 * 256 * 4;                  // float[2][2][128] LayerNorm partials
-constexpr uint32_t SM_BAR = SM_RED + 2 * 2 * 128 * 4;              // mbarriers + tmem pointer
+constexpr uint32_t SM_AHI = 0;                                     // operand image, hi part (64 KB)
+constexpr uint32_t SM_ALO = SM_AHI + IMG_BYTES;                    // operand image, lo part (64 KB)
+constexpr uint32_t SM_RING = SM_ALO + IMG_BYTES;                   // 4 x 16 KB weight stages
+constexpr uint32_t SM_ONES = SM_RING + RING * STAGE_BYTES;         // 16 KB slab of fp16 ones (Ksum product)
+constexpr uint32_t SM_KSUM = SM_ONES + SLAB_BYTES;                 // float[256]  Ksum of the source image
+constexpr uint32_t SM_RED = SM_KSUM + 256 * 4;                     // float[2][4][128] LayerNorm partials
+constexpr uint32_t SM_BAR = SM_RED + 2 * 4 * 128 * 4;              // mbarriers + tmem pointer
 constexpr uint32_t SM_TOTAL = SM_BAR + 128;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+// the kv phase re-uses the operand image space for the MN-major half images (tokens = K dimension)
+constexpr uint32_t KF_OFF = 0;                                     // Kf half image: 2 slabs (32 KB) inside hi / lo
+constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
 
 struct Bars {
     uint64_t full[RING], empty[RING];
-    uint64_t a_full;      // row warps -> MMA: operand image(s) written (count 256)
-    uint64_t s_full;      // MMA -> row warps: accumulator ready (tcgen05.commit)
-    uint64_t s_full2;     // second accumulator of k_tc_kv (two commits may be in flight back to back)
+    uint64_t a_full[2];   // row warps -> MMA: column pass p of the operand image written (count 512)
+    uint64_t s_full[2];   // MMA -> row warps: accumulator S0 / S1 complete (tcgen05.commit)
     uint32_t tmem_base;
     uint32_t pad;
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) fp16 split and the swizzled operand-image stores
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// columns [c0, c0+32) (c0 % 32 == 0) of row r into a (hi, lo) pair of operand images made of 64-column slabs
+__device__ __forceinline__ void store_row32_split(uint8_t* img_hi, uint8_t* img_lo, uint32_t r, uint32_t c0,
+                                                  const float (&v)[32]) {
+    const uint32_t slab = (c0 >> 6) * SLAB_BYTES;
+    const uint32_t j0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 h, l;
+        split8(&v[8 * j], h, l);
+        const uint32_t off = slab + slab_chunk_off(r, j0 + j);
+        *reinterpret_cast<uint4*>(img_hi + off) = h;
+        *reinterpret_cast<uint4*>(img_lo + off) = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // weight images
 // ---------------------------------------------------------------------------------------------------------
-// 8 chunks (n-half outer, k-slab inner) of the 256x256 block W[row0.., col0..] (row-major fp32, leading dim ld)
-__global__ void k_make_chunks(const float* __restrict__ W, int ld, int row0, int col0, __half* __restrict__ out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte chunk (8 halfs) per thread
-    if (idx >= CHUNKS_PER_GEMM * 128 * 8) return;
-    const int j = idx & 7, r = (idx >> 3) & 127, chunk = idx >> 10;
-    const int nh = chunk >> 2, ks = chunk & 3;
+// stage order of one 256x256 block W[n][k]: for ks (k-slab of 64): hi n<128 | hi n>=128 | lo n<128 | lo n>=128
+__host__ __device__ __forceinline__ size_t gemm_stage_off(int ks, int lo, int nh) {
+    return (size_t)((ks * 2 + lo) * 2 + nh) * STAGE_HALFS;
+}
+
+__global__ void k_make_gemm_image(const float* __restrict__ W, int ld, int row0, int col0, __half* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte chunk (8 halfs) of hi and of lo
+    if (idx >= 4 * 2 * 128 * 8) return;
+    const int j = idx & 7, r = (idx >> 3) & 127, nh = (idx >> 10) & 1, ks = idx >> 11;
     const float* src = W + (size_t)(row0 + nh * 128 + r) * ld + col0 + ks * 64 + j * 8;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = src[e];
-    uint8_t* dst = reinterpret_cast<uint8_t*>(out + (size_t)chunk * CHUNK_HALFS) + slab_chunk_off(r, j);
-    *reinterpret_cast<uint4*>(dst) = pack8_f16(v);
+    uint4 h, l;
+    split8(v, h, l);
+    const uint32_t off = slab_chunk_off(r, j);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out + gemm_stage_off(ks, 0, nh)) + off) = h;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out + gemm_stage_off(ks, 1, nh)) + off) = l;
+}
+
+static void make_gemm_image(const float* W, int ld, int row0, int col0, __half* out, cudaStream_t s = 0) {
+    k_make_gemm_image<<<(4 * 2 * 128 * 8 + 255) / 256, 256, 0, s>>>(W, ld, row0, col0, out);
 }
 
 int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char* msg, size_t msg_len) {
@@ -87,25 +142,22 @@ int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char*
         snprintf(msg, msg_len, "weight image allocation failed");
         return -1;
     }
-    const int grid = (CHUNKS_PER_GEMM * 128 * 8 + 255) / 256;
-    const size_t G = (size_t)CHUNKS_PER_GEMM * CHUNK_HALFS;
     for (int i = 0; i < N_ENC; ++i) {
         const EncW& e = L.enc[i];
         __half* o = out.enc_img + (size_t)i * ENC_LAYER_HALFS;
-        k_make_chunks<<<grid, 256>>>(d_w + e.wv, C, 0, 0, o + 0 * G);           // kv stream: Wv, Wk
-        k_make_chunks<<<grid, 256>>>(d_w + e.wk, C, 0, 0, o + 1 * G);
-        k_make_chunks<<<grid, 256>>>(d_w + e.wq, C, 0, 0, o + 2 * G);           // layer stream
-        k_make_chunks<<<grid, 256>>>(d_w + e.wm, C, 0, 0, o + 3 * G);
-        k_make_chunks<<<grid, 256>>>(d_w + e.w1, C, 0, 0, o + 4 * G);           // W1[0:256, :]
-        k_make_chunks<<<grid, 256>>>(d_w + e.w2, FF, 0, 0, o + 5 * G);          // W2[:, 0:256]
-        k_make_chunks<<<grid, 256>>>(d_w + e.w1, C, 256, 0, o + 6 * G);         // W1[256:512, :]
-        k_make_chunks<<<grid, 256>>>(d_w + e.w2, FF, 0, 256, o + 7 * G);        // W2[:, 256:512]
+        make_gemm_image(d_w + e.wq, C, 0, 0, o + 0 * GEMM_HALFS);
+        make_gemm_image(d_w + e.w1, C, 0, 0, o + 1 * GEMM_HALFS);           // W1[0:256, :]
+        make_gemm_image(d_w + e.w1, C, 256, 0, o + 2 * GEMM_HALFS);         // W1[256:512, :]
+        make_gemm_image(d_w + e.w2, FF, 0, 0, o + 3 * GEMM_HALFS);          // W2[:, 0:256]
+        make_gemm_image(d_w + e.w2, FF, 0, 256, o + 4 * GEMM_HALFS);        // W2[:, 256:512]
+        make_gemm_image(d_w + e.wv, C, 0, 0, o + 5 * GEMM_HALFS);
+        make_gemm_image(d_w + e.wk, C, 0, 0, o + 6 * GEMM_HALFS);
     }
     for (int j = 0; j < N_DEC; ++j) {
         const DecW& d = L.dec[j];
         __half* o = out.dec_img + (size_t)j * DEC_LAYER_HALFS;
-        k_make_chunks<<<grid, 256>>>(d_w + d.ca.wv, C, 0, 0, o + 0 * G);
-        k_make_chunks<<<grid, 256>>>(d_w + d.ca.wk, C, 0, 0, o + 1 * G);
+        make_gemm_image(d_w + d.ca.wv, C, 0, 0, o + 0 * GEMM_HALFS);
+        make_gemm_image(d_w + d.ca.wk, C, 0, 0, o + 1 * GEMM_HALFS);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -122,93 +174,6 @@ void tc_free_weights(TcWeights& w) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// device building blocks shared by the kernels and the self-test
-// ---------------------------------------------------------------------------------------------------------
-struct RingState { uint32_t g = 0; };       // running chunk counter (producer and consumer each keep one)
-
-__device__ __forceinline__ void produce_chunks(const __half* wimg, int nchunks, uint8_t* smem, Bars* bars, int* flag) {
-    for (int g = 0; g < nchunks; ++g) {
-        const int st = g % RING;
-        mbar_wait(&bars->empty[st], ((g / RING) & 1) ^ 1, flag);
-        mbar_arrive_expect_tx(&bars->full[st], CHUNK_BYTES);
-        bulk_g2s(smem + SM_RING + st * CHUNK_BYTES, wimg + (size_t)g * CHUNK_HALFS, CHUNK_BYTES, &bars->full[st]);
-    }
-}
-
-// D[128 x 256] (tmem columns d_col..d_col+255) (+)= A[128 x 256](image at a_off) . W^T, consuming 8 ring chunks
-__device__ __forceinline__ void mma_gemm256(uint32_t smem_base, uint32_t a_off, uint32_t d_tmem, bool accumulate,
-                                            RingState& rs, Bars* bars, int* flag) {
-    for (int nh = 0; nh < 2; ++nh)
-        for (int ks = 0; ks < 4; ++ks) {
-            const int st = rs.g % RING;
-            mbar_wait(&bars->full[st], (rs.g / RING) & 1, flag);
-            tc_fence_after();
-            const uint32_t a_slab = smem_base + a_off + ks * SLAB_BYTES;
-            const uint32_t b_slab = smem_base + SM_RING + st * CHUNK_BYTES;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem + nh * 128, umma_desc(a_slab + k * 32, 16, ATOM_BYTES),
-                         umma_desc(b_slab + k * 32, 16, ATOM_BYTES), IDESC_N128, (accumulate || ks > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&bars->empty[st]);
-            rs.g++;
-        }
-}
-
-// per-head O_h[128 x 32] = Qf[:, 32h:32h+32] . KVt_h^T ; Qf image at a_off, KV^T image (4 slabs of 32 rows) at SM_AUX
-__device__ __forceinline__ void mma_attn_apply(uint32_t smem_base, uint32_t a_off, uint32_t d_tmem) {
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-        const uint32_t a_addr = smem_base + a_off + (h >> 1) * SLAB_BYTES + (h & 1) * 64;
-        const uint32_t b_addr = smem_base + SM_AUX + (h >> 1) * (32 * 128) + (h & 1) * 64;
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            umma_f16(d_tmem + h * 32, umma_desc(a_addr + k * 32, 16, ATOM_BYTES), umma_desc(b_addr + k * 32, 16, ATOM_BYTES),
-                     IDESC_N32, k);
-    }
-}
-
-// KV halves: D[0:128) = Kf[:,0:128]^T V[:,0:128], D[128:256) = Kf[:,128:256]^T V[:,128:256];
-// Ksum: D[256:272) / D[272:288) = Kf-half^T . ones.   Kf image at SM_A0, V image at SM_A1, ones slab at SM_AUX.
-// lbo/sbo are parameters only so that the self-test can probe the MN-major descriptor convention.
-__device__ __forceinline__ void mma_kv(uint32_t smem_base, uint32_t d_tmem, uint32_t lbo, uint32_t sbo) {
-    for (int half = 0; half < 2; ++half) {
-        const uint32_t a0 = smem_base + SM_A0 + half * 2 * SLAB_BYTES;
-        const uint32_t b0 = smem_base + SM_A1 + half * 2 * SLAB_BYTES;
-#pragma unroll
-        for (int k = 0; k < TILE / 16; ++k) {
-            const uint64_t ad = umma_desc(a0 + k * 16 * 128, lbo, sbo);
-            umma_f16(d_tmem + half * 128, ad, umma_desc(b0 + k * 16 * 128, lbo, sbo), IDESC_KV, k);
-            umma_f16(d_tmem + 256 + half * 16, ad, umma_desc(smem_base + SM_AUX + k * 16 * 128, lbo, sbo), IDESC_KSUM, k);
-        }
-    }
-}
-
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __expf(x); }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
-
-// common prologue: barriers, TMEM allocation.  Returns the TMEM base address.
-__device__ __forceinline__ uint32_t cta_setup(uint8_t* smem, Bars* bars) {
-    const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < RING; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-        mbar_init(&bars->a_full, N_ROW_THREADS);
-        mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->s_full2, 1);
-        fence_mbar_init();
-    }
-    if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    return bars->tmem_base;
-}
-__device__ __forceinline__ void cta_teardown(uint32_t tmem_base) {
-    tc_fence_before();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 8) tmem_dealloc(tmem_base, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // tile bookkeeping
 // ---------------------------------------------------------------------------------------------------------
 struct TileGeom {
@@ -216,381 +181,468 @@ struct TileGeom {
     __host__ __device__ int tiles() const { return B * (T1 + T2); }
 };
 struct TileInfo { int set, b, ti, L, T, img, valid, first_tile_of_img; };
-__device__ __forceinline__ TileInfo tile_info(const TileGeom& g, int t) {
+__host__ __device__ __forceinline__ TileInfo tile_info(const TileGeom& g, int t) {
     TileInfo ti;
     if (t < g.B * g.T1) { ti.set = 0; ti.b = t / g.T1; ti.ti = t % g.T1; ti.L = g.L1; ti.T = g.T1; ti.first_tile_of_img = ti.b * g.T1; }
     else { const int u = t - g.B * g.T1; ti.set = 1; ti.b = u / g.T2; ti.ti = u % g.T2; ti.L = g.L2; ti.T = g.T2;
            ti.first_tile_of_img = g.B * g.T1 + ti.b * g.T2; }
     ti.img = ti.set * g.B + ti.b;
-    ti.valid = min(TILE, ti.L - ti.ti * TILE);
+    ti.valid = ti.L - ti.ti * TILE < TILE ? ti.L - ti.ti * TILE : TILE;
     return ti;
 }
 // tile-blocked fp32 layout [tile][64 col-quads][128 rows][4]: a warp's rows read/write one col-quad coalesced
-__device__ __forceinline__ size_t xt_off(int tile, int quad, int r) { return (((size_t)tile * 64 + quad) * TILE + r) * 4; }
+__host__ __device__ __forceinline__ size_t xt_off(int tile, int quad, int r) { return (((size_t)tile * 64 + quad) * TILE + r) * 4; }
 
-// LayerNorm statistics of a row split over two threads (column halves): shifted one-pass sums, combined via smem
-__device__ __forceinline__ void ln_combine(float s, float q, float* red, int r, int ch, float& mean_shifted, float& rstd) {
-    red[(0 * 2 + ch) * TILE + r] = s;
-    red[(1 * 2 + ch) * TILE + r] = q;
-    named_bar_sync(1, N_ROW_THREADS);
-    const float S = red[(0 * 2 + 0) * TILE + r] + red[(0 * 2 + 1) * TILE + r];
-    const float Q = red[(1 * 2 + 0) * TILE + r] + red[(1 * 2 + 1) * TILE + r];
-    mean_shifted = S * (1.f / C);
-    rstd = rsqrtf(fmaxf(Q * (1.f / C) - mean_shifted * mean_shifted, 0.f) + LN_EPS);
-    named_bar_sync(1, N_ROW_THREADS);          // red[] may be reused afterwards
-}
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_tc_kv : source-side kernel
+// k_enc
 // ---------------------------------------------------------------------------------------------------------
-struct KvParams {
+struct EncParams {
     TileGeom g;
-    const float* feat1;      // NCHW inputs (first encoder layer only) or nullptr
+    const float* feat1;         // NCHW inputs, read when load_feat
     const float* feat2;
-    float* xt;               // tile-blocked residual stream (read when feat == nullptr, written when feat != nullptr)
-    const float* post1;      // tile-blocked positional rows of set 0 / set 1
-    const float* post2;
-    const float *ln_g, *ln_b;   // LayerNorm affine or nullptr (decoder: memory is used un-normalised)
-    const float *bk, *bv;       // projection biases or nullptr
-    int pos_on_v;               // encoder: k and v share LN(x)+pos; decoder: k = x+pos, v = x
-    const __half* wimg;         // 16 chunks: Wv | Wk
-    float* kv_part;             // [tiles][KVS]
+    float* xt;                  // tile-blocked residual stream (read unless load_feat; written when store_x)
+    const float *post1, *post2; // tile-blocked positional rows of set 0 / set 1
+    int load_feat, store_x, do_q, do_kv;
+    // query phase (encoder layer i)
+    const float *lnq_g, *lnq_b, *ln2_g, *ln2_b;
+    const __half* w_q;          // Wq                         (16 stages)
+    const __half* w_mlp;        // W1a | W1b | W2a | W2b      (64 stages)
+    const __half* mimg;         // [2B images][GEMM_HALFS] folded merge weights of the source image
+    const float* ksum;          // [2B images][256]
+    int cross;                  // 1: the source is the partner image (transformer.py:354-358)
+    // kv phase (encoder layer i+1, or a decoder layer's cross-attention when lnkv_g == nullptr)
+    const float *lnkv_g, *lnkv_b;   // nullptr: decoder mode: k = (x+pos) Wk^T + bk, v = x Wv^T + bv
+    const float *bk, *bv;
+    const __half* w_kv;         // Wv | Wk                    (32 stages)
+    float* kv_part;             // [tiles][KVS] per-tile partial summaries
     int* flag;
-    uint32_t mn_lbo, mn_sbo;
 };
 
-__global__ void __launch_bounds__(N_THREADS, 1) k_tc_kv(const KvParams p) {
+__global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
-    float* vec = reinterpret_cast<float*>(smem + SM_VEC);        // [0]=gamma [1]=beta [2]=bk [3]=bv
-    float* red = reinterpret_cast<float*>(smem + SM_RED);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const TileInfo ti = tile_info(p.g, blockIdx.x);
-    const uint32_t tmem = cta_setup(smem, bars);
     const uint32_t smem_base = smem_u32(smem);
+    const bool dec_mode = p.lnkv_g == nullptr;
 
-    if (warp == 8) {
-        if (lane == 0) produce_chunks(p.wimg, KV_STREAM_CHUNKS, smem, bars, p.flag);
-        __syncwarp();
-    } else if (warp == 9) {
+    if (tid == 0) {
+        for (int i = 0; i < RING; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->a_full[0], N_ROW_THREADS);
+        mbar_init(&bars->a_full[1], N_ROW_THREADS);
+        mbar_init(&bars->s_full[0], 1);
+        mbar_init(&bars->s_full[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == WARP_PRODUCER) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t S0 = tmem, S1 = tmem + 256;
+
+    int src_img = ti.img, src_len = ti.L;
+    if (p.cross) { src_img = ti.set == 0 ? p.g.B + ti.b : ti.b; src_len = ti.set == 0 ? p.g.L2 : p.g.L1; }
+
+    if (warp == WARP_PRODUCER) {
+        // ------------------------------------------------------------------ weight stream
         if (lane == 0) {
-            RingState rs;
-            mbar_wait(&bars->a_full, 0, p.flag);
-            tc_fence_after();
-            mma_gemm256(smem_base, p.pos_on_v ? SM_A0 : SM_A1, tmem + 0, false, rs, bars, p.flag);     // v
-            umma_commit(&bars->s_full);
-            mma_gemm256(smem_base, SM_A0, tmem + 256, false, rs, bars, p.flag);                         // k
-            umma_commit(&bars->s_full2);
-            mbar_wait(&bars->a_full, 1, p.flag);
-            tc_fence_after();
-            mma_kv(smem_base, tmem, p.mn_lbo, p.mn_sbo);
-            umma_commit(&bars->s_full);
+            uint32_t g = 0;
+            auto stream = [&](const __half* src, int nstages) {
+                for (int i = 0; i < nstages; ++i, ++g) {
+                    const int st = g % RING;
+                    mbar_wait(&bars->empty[st], ((g / RING) & 1) ^ 1, p.flag);
+                    mbar_arrive_expect_tx(&bars->full[st], STAGE_BYTES);
+                    bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, STAGE_BYTES, &bars->full[st]);
+                }
+            };
+            if (p.do_q) {
+                stream(p.w_q, GEMM_STAGES);
+                stream(p.mimg + (size_t)src_img * GEMM_HALFS, GEMM_STAGES);
+                stream(p.w_mlp, 4 * GEMM_STAGES);
+            }
+            if (p.do_kv) stream(p.w_kv, 2 * GEMM_STAGES);
         }
         __syncwarp();
-    } else {
-        const int q = warp & 3, ch = warp >> 2;
-        const int r = q * 32 + lane;
+    } else if (warp == WARP_MMA) {
+        // ------------------------------------------------------------------ MMA issue
+        if (lane == 0) {
+            uint32_t g = 0, na0 = 0, na1 = 0;
+            auto wait_a = [&](int pass) {
+                mbar_wait(&bars->a_full[pass], (pass ? na1++ : na0++) & 1, p.flag);
+                tc_fence_after();
+            };
+            // D[128 x 256] (tmem columns d..d+255) (+)= A[128 x 256] . W^T with the 3-term split; 16 ring stages
+            auto gemm = [&](uint32_t d, bool accumulate, bool wait) {
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (wait && ks == 0) wait_a(0);
+                    if (wait && ks == 2) wait_a(1);
+                    const uint32_t a_hi = smem_base + SM_AHI + ks * SLAB_BYTES;
+                    const uint32_t a_lo = smem_base + SM_ALO + ks * SLAB_BYTES;
+                    {   // w_hi: two adjacent stages form the [256 x 64] B tile
+                        const int st = g % RING;
+                        mbar_wait(&bars->full[st], (g / RING) & 1, p.flag);
+                        mbar_wait(&bars->full[st + 1], (g / RING) & 1, p.flag);
+                        tc_fence_after();
+                        const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                                     IDESC_N256, (accumulate || ks > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(d, umma_desc(a_lo + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                                     IDESC_N256, 1u);
+                        umma_commit(&bars->empty[st]);
+                        umma_commit(&bars->empty[st + 1]);
+                        g += 2;
+                    }
+                    {   // w_lo
+                        const int st = g % RING;
+                        mbar_wait(&bars->full[st], (g / RING) & 1, p.flag);
+                        mbar_wait(&bars->full[st + 1], (g / RING) & 1, p.flag);
+                        tc_fence_after();
+                        const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                                     IDESC_N256, 1u);
+                        umma_commit(&bars->empty[st]);
+                        umma_commit(&bars->empty[st + 1]);
+                        g += 2;
+                    }
+                }
+            };
+            if (p.do_q) {
+                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
+                gemm(S1, false, true);  umma_commit(&bars->s_full[1]);     // msg = (phi(q)/Z) M_img^T
+                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // h_a = LN2(x) W1a^T
+                gemm(S1, false, false); umma_commit(&bars->s_full[1]);     // h_b = LN2(x) W1b^T
+                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // y   = gelu(h_a) W2a^T
+                gemm(S0, true, true);   umma_commit(&bars->s_full[0]);     // y  += gelu(h_b) W2b^T
+            }
+            if (p.do_kv) {
+                gemm(S0, false, true);      umma_commit(&bars->s_full[0]); // v
+                gemm(S1, false, dec_mode);  umma_commit(&bars->s_full[1]); // k (decoder: from a second image)
+                // per 128-channel half: KV = Kf^T V (diagonal 32x32 blocks are the heads), Ksum = Kf^T 1
+                for (int half = 0; half < 2; ++half) {
+                    wait_a(half);
+                    const uint32_t kf_hi = smem_base + SM_AHI + KF_OFF, kf_lo = smem_base + SM_ALO + KF_OFF;
+                    const uint32_t v_hi = smem_base + SM_AHI + V_OFF, v_lo = smem_base + SM_ALO + V_OFF;
+                    const uint32_t ones = smem_base + SM_ONES;
+                    const uint32_t dkv = S0 + half * 128, dks = S1 + half * 16;
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; ++k)
+                        umma_f16(dkv, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
+                                 umma_desc(v_hi + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, k);
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; ++k)
+                        umma_f16(dkv, umma_desc(kf_lo + k * 2048, SLAB_BYTES, ATOM_BYTES),
+                                 umma_desc(v_hi + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, 1u);
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; ++k)
+                        umma_f16(dkv, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
+                                 umma_desc(v_lo + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, 1u);
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; ++k)
+                        umma_f16(dks, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
+                                 umma_desc(ones + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KSUM, k);
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; ++k)
+                        umma_f16(dks, umma_desc(kf_lo + k * 2048, SLAB_BYTES, ATOM_BYTES),
+                                 umma_desc(ones + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KSUM, 1u);
+                    umma_commit(&bars->s_full[half]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < WARP_PRODUCER) {
+        // ------------------------------------------------------------------ row warps
+        const int q = warp & 3, cq = warp >> 2;            // TMEM lane quarter, column quarter
+        const int r = q * 32 + lane;                       // token row of the tile
         const bool valid = r < ti.valid;
-        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        // stage per-channel vectors and the ones slab
-        vec[0 * 256 + tid] = p.ln_g ? p.ln_g[tid] : 1.f;
-        vec[1 * 256 + tid] = p.ln_b ? p.ln_b[tid] : 0.f;
-        vec[2 * 256 + tid] = p.bk ? p.bk[tid] : 0.f;
-        vec[3 * 256 + tid] = p.bv ? p.bv[tid] : 0.f;
-        {
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float* red = reinterpret_cast<float*>(smem + SM_RED);
+        float* ksum_s = reinterpret_cast<float*>(smem + SM_KSUM);
+        uint8_t* img_hi = smem + SM_AHI;
+        uint8_t* img_lo = smem + SM_ALO;
+        const float* post = (ti.set == 0 ? p.post1 : p.post2);
+        uint32_t ns0 = 0, ns1 = 0;
+        auto wait_s = [&](int b) {
+            mbar_wait(&bars->s_full[b], (b ? ns1++ : ns0++) & 1, p.flag);
+            tc_fence_after();
+        };
+        auto publish = [&](int pass) {                     // operand image pass written; accumulator reads done
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(&bars->a_full[pass]);
+        };
+        // one-time staging: Ksum of the source image, the ones slab
+        if (p.do_q && tid < 256) ksum_s[tid] = p.ksum[(size_t)src_img * C + tid];
+        if (p.do_kv) {
             const __half2 one2 = __floats2half2_rn(1.f, 1.f);
             uint4 ones;
             ones.x = ones.y = ones.z = ones.w = *reinterpret_cast<const uint32_t*>(&one2);
-            for (uint32_t i = tid; i < SLAB_BYTES / 16; i += N_ROW_THREADS) reinterpret_cast<uint4*>(smem + SM_AUX)[i] = ones;
+            for (uint32_t i = tid; i < SLAB_BYTES / 16; i += N_ROW_THREADS) reinterpret_cast<uint4*>(smem + SM_ONES)[i] = ones;
+            fence_async_smem();
         }
-        const float* feat = ti.set == 0 ? p.feat1 : p.feat2;
-        const float* post = (ti.set == 0 ? p.post1 : p.post2);
-        const size_t tok0 = (size_t)ti.ti * TILE;
-        auto load_quad = [&](int quad) -> float4 {                 // 4 channels [4*quad, 4*quad+4) of row r
-            if (!valid) return make_float4(0.f, 0.f, 0.f, 0.f);
-            if (feat) {
-                const float* f = feat + ((size_t)ti.b * C + quad * 4) * ti.L + tok0 + r;
-                return make_float4(f[0], f[(size_t)ti.L], f[(size_t)2 * ti.L], f[(size_t)3 * ti.L]);
-            }
-            return *reinterpret_cast<const float4*>(p.xt + xt_off(blockIdx.x, quad, r));
-        };
-        // pass 1: LayerNorm statistics (shifted by the row's first channel)
-        float mean_s = 0.f, rstd = 1.f, shift = 0.f;
-        if (p.ln_g) {
-            shift = load_quad(0).x;
-            float s = 0.f, sq = 0.f;
-#pragma unroll 4
-            for (int jq = 0; jq < 32; ++jq) {
-                const float4 v = load_quad(ch * 32 + jq);
-                const float a = v.x - shift, b = v.y - shift, c = v.z - shift, d = v.w - shift;
-                s += (a + b) + (c + d);
-                sq += (a * a + b * b) + (c * c + d * d);
-            }
-            ln_combine(s, sq, red, r, ch, mean_s, rstd);
-        }
-        __syncwarp();
-        // pass 2: operand images.  A0 = LN(x)+pos (encoder) or x+pos (decoder); A1 = x (decoder only)
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c0 = ch * 128 + cc * 32;
-            float a0[32], a1[32];
+        // ---- the residual stream of this thread: columns [32*cq, +32) and [128 + 32*cq, +32) of row r
+        float x[2][32];
 #pragma unroll
-            for (int jq = 0; jq < 8; ++jq) {
-                const int quad = (c0 >> 2) + jq;
-                const float4 v = load_quad(quad);
-                if (feat) *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, quad, r)) = v;
-                const float4 ps = *reinterpret_cast<const float4*>(post + xt_off(ti.ti, quad, r));
-                const float x[4] = {v.x, v.y, v.z, v.w}, pp[4] = {ps.x, ps.y, ps.z, ps.w};
+        for (int pass = 0; pass < 2; ++pass) {
+            const int c0 = pass * 128 + cq * 32;
+            if (p.load_feat) {
+                const float* feat = ti.set == 0 ? p.feat1 : p.feat2;
+                const float* f = feat + ((size_t)ti.b * C + c0) * ti.L + (size_t)ti.ti * TILE + r;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = c0 + jq * 4 + e;
-                    const float n = p.ln_g ? ((x[e] - shift) - mean_s) * rstd * vec[c] + vec[256 + c] : x[e];
-                    a0[jq * 4 + e] = n + pp[e];
-                    a1[jq * 4 + e] = x[e];
+                for (int e = 0; e < 32; ++e) x[pass][e] = valid ? f[(size_t)e * ti.L] : 0.f;
+            } else {
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq) {
+                    const float4 v = *reinterpret_cast<const float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r));
+                    x[pass][jq * 4 + 0] = v.x; x[pass][jq * 4 + 1] = v.y; x[pass][jq * 4 + 2] = v.z; x[pass][jq * 4 + 3] = v.w;
                 }
             }
-            store_row32_f16(smem + SM_A0, SLAB_BYTES, r, c0, a0);
-            if (!p.pos_on_v) store_row32_f16(smem + SM_A1, SLAB_BYTES, r, c0, a1);
         }
-        fence_async_smem();
-        mbar_arrive(&bars->a_full);
-        // v = S0 + bv  -> V image (A1); padded rows are zero so they add nothing to KV
-        mbar_wait(&bars->s_full, 0, p.flag);
-        tc_fence_after();
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c0 = ch * 128 + cc * 32;
-            float v[32];
-            tmem_ld32(lane_addr + c0, v);
+        auto store_x = [&]() {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = valid ? v[e] + vec[3 * 256 + c0 + e] : 0.f;
-            store_row32_f16(smem + SM_A1, SLAB_BYTES, r, c0, v);
-        }
-        // k = elu(S1 + bk) + 1 -> Kf image (A0)
-        mbar_wait(&bars->s_full2, 0, p.flag);
-        tc_fence_after();
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c0 = ch * 128 + cc * 32;
-            float v[32];
-            tmem_ld32(lane_addr + 256 + c0, v);
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e] + vec[2 * 256 + c0 + e]) : 0.f;
-            store_row32_f16(smem + SM_A0, SLAB_BYTES, r, c0, v);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        mbar_arrive(&bars->a_full);
-        // KV diagonal blocks: this warp's TMEM lanes are the d-channels of head (4*ch + q)
-        mbar_wait(&bars->s_full, 1, p.flag);
-        tc_fence_after();
-        {
-            const int h = ch * 4 + q;
-            float v[32];
-            tmem_ld32(lane_addr + ch * 128 + q * 32, v);
-            float* o = p.kv_part + (size_t)blockIdx.x * KVS + h * HD * HD + lane * HD;
+                for (int jq = 0; jq < 8; ++jq)
+                    *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r)) =
+                        make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
+            }
+        };
+        named_bar_sync(1, N_ROW_THREADS);                  // ksum_s / ones visible to all row warps
+
+        // two-pass LayerNorm statistics of the row (4 threads per row, combined through shared memory)
+        auto ln_stats = [&](float& mean, float& rstd) {
+            float s = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            if (ch == 0) {       // Ksum: column 0 of the two ones-products
-                tmem_ld32(lane_addr + 256, v);
-                float* ks = p.kv_part + (size_t)blockIdx.x * KVS + NH * HD * HD;
-                ks[q * 32 + lane] = v[0];
-                ks[128 + q * 32 + lane] = v[16];
+            for (int e = 0; e < 32; ++e) s += x[0][e] + x[1][e];
+            red[(0 * 4 + cq) * TILE + r] = s;
+            named_bar_sync(1, N_ROW_THREADS);
+            mean = (red[(0 * 4 + 0) * TILE + r] + red[(0 * 4 + 1) * TILE + r] + red[(0 * 4 + 2) * TILE + r] +
+                    red[(0 * 4 + 3) * TILE + r]) * (1.f / C);
+            float sq = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float d0 = x[0][e] - mean, d1 = x[1][e] - mean;
+                sq = fmaf(d0, d0, sq);
+                sq = fmaf(d1, d1, sq);
             }
-        }
-    }
-    cta_teardown(tmem);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_tc_layer : query-side kernel (one full encoder layer update of the tile's residual stream)
-// ---------------------------------------------------------------------------------------------------------
-struct LayerParams {
-    TileGeom g;
-    float* xt;
-    const float *post1, *post2;
-    const float *lnq_g, *lnq_b, *ln2_g, *ln2_b;
-    const __half* wimg;         // 48 chunks: Wq | Wm | W1a | W2a | W1b | W2b
-    const float* kv_part;       // per-tile partial summaries written by k_tc_kv
-    int cross;                  // 1: read the partner image's summary (transformer.py:354-358)
-    int* flag;
-};
-
-__global__ void __launch_bounds__(N_THREADS, 1) k_tc_layer(const LayerParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
-    float* vec = reinterpret_cast<float*>(smem + SM_VEC);   // [0]=lnq_g [1]=lnq_b [2]=ln2_g [3]=ln2_b [4]=Ksum
-    float* red = reinterpret_cast<float*>(smem + SM_RED);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const TileInfo ti = tile_info(p.g, blockIdx.x);
-    const uint32_t tmem = cta_setup(smem, bars);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t X = tmem, S = tmem + 256;
-
-    if (warp == 8) {
-        if (lane == 0) produce_chunks(p.wimg, LAYER_STREAM_CHUNKS, smem, bars, p.flag);
-        __syncwarp();
-    } else if (warp == 9) {
-        if (lane == 0) {
-            RingState rs;
-            mbar_wait(&bars->a_full, 0, p.flag); tc_fence_after();
-            mma_gemm256(smem_base, SM_A0, S, false, rs, bars, p.flag);         // q = (LNq(x)+pos) Wq^T
-            umma_commit(&bars->s_full);
-            mbar_wait(&bars->a_full, 1, p.flag); tc_fence_after();
-            mma_attn_apply(smem_base, SM_A1, S);                               // O_h = Qf_h KV_h
-            umma_commit(&bars->s_full);
-            mbar_wait(&bars->a_full, 0, p.flag); tc_fence_after();
-            mma_gemm256(smem_base, SM_A0, X, true, rs, bars, p.flag);          // x += (O/Z) Wm^T
-            umma_commit(&bars->s_full);
-            mbar_wait(&bars->a_full, 1, p.flag); tc_fence_after();
-            mma_gemm256(smem_base, SM_A1, S, false, rs, bars, p.flag);         // h_a = LN2(x) W1a^T
-            umma_commit(&bars->s_full);
-            mbar_wait(&bars->a_full, 0, p.flag); tc_fence_after();
-            mma_gemm256(smem_base, SM_A0, X, true, rs, bars, p.flag);          // x += gelu(h_a) W2a^T
-            mma_gemm256(smem_base, SM_A1, S, false, rs, bars, p.flag);         // h_b = LN2(x) W1b^T
-            umma_commit(&bars->s_full);
-            mbar_wait(&bars->a_full, 1, p.flag); tc_fence_after();
-            mma_gemm256(smem_base, SM_A0, X, true, rs, bars, p.flag);          // x += gelu(h_b) W2b^T
-            umma_commit(&bars->s_full);
-        }
-        __syncwarp();
-    } else {
-        const int q = warp & 3, ch = warp >> 2;
-        const int r = q * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        vec[0 * 256 + tid] = p.lnq_g[tid]; vec[1 * 256 + tid] = p.lnq_b[tid];
-        vec[2 * 256 + tid] = p.ln2_g[tid]; vec[3 * 256 + tid] = p.ln2_b[tid];
-        // ---- linear-attention summary of the source image: sum the per-tile partials in tile order
-        {
-            int src_first = ti.first_tile_of_img, src_T = ti.T;
-            if (p.cross) {
-                if (ti.set == 0) { src_first = p.g.B * p.g.T1 + ti.b * p.g.T2; src_T = p.g.T2; }
-                else { src_first = ti.b * p.g.T1; src_T = p.g.T1; }
-            }
-            const float* part = p.kv_part + (size_t)src_first * KVS;
-            // KV[h][d][e] -> B operand rows e, K = d:  image slab h/2, row e, column (h&1)*32 + d
-            for (int idx = tid; idx < NH * HD * HD; idx += N_ROW_THREADS) {
-                float acc = 0.f;
-                for (int t = 0; t < src_T; ++t) acc += part[(size_t)t * KVS + idx];
-                const int h = idx >> 10, d = (idx >> 5) & 31, e = idx & 31;
-                const uint32_t col = (h & 1) * 32 + d;
-                uint8_t* dst = smem + SM_AUX + (h >> 1) * (32 * 128) + slab_chunk_off(e, col >> 3) + (col & 7) * 2;
-                *reinterpret_cast<__half*>(dst) = __float2half_rn(acc);
-            }
-            float acc = 0.f;
-            for (int t = 0; t < src_T; ++t) acc += part[(size_t)t * KVS + NH * HD * HD + tid];
-            vec[4 * 256 + tid] = acc;
-        }
-        const float* post = (ti.set == 0 ? p.post1 : p.post2);
-        // ---- (1) x -> TMEM, LNq statistics
-        float mean_s, rstd, shift;
-        {
-            shift = p.xt[xt_off(blockIdx.x, 0, r)];
-            float s = 0.f, sq = 0.f;
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c0 = ch * 128 + cc * 32;
+            red[(1 * 4 + cq) * TILE + r] = sq;
+            named_bar_sync(1, N_ROW_THREADS);
+            const float var = (red[(1 * 4 + 0) * TILE + r] + red[(1 * 4 + 1) * TILE + r] + red[(1 * 4 + 2) * TILE + r] +
+                               red[(1 * 4 + 3) * TILE + r]) * (1.f / C);
+            rstd = rsqrtf(var + LN_EPS);
+        };
+        // operand image <- [LN](x) [+ pos], both column passes
+        auto image_from_x = [&](const float* gamma, const float* beta, bool with_pos) {
+            float mean = 0.f, rstd = 1.f;
+            if (gamma) ln_stats(mean, rstd);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
                 float v[32];
 #pragma unroll
                 for (int jq = 0; jq < 8; ++jq) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r));
-                    v[jq * 4 + 0] = x4.x; v[jq * 4 + 1] = x4.y; v[jq * 4 + 2] = x4.z; v[jq * 4 + 3] = x4.w;
+                    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(ti.ti, (c0 >> 2) + jq, r));
+                    const float pp[4] = {ps.x, ps.y, ps.z, ps.w};
+                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gamma) {
+                        g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + jq);
+                        b4 = __ldg(reinterpret_cast<const float4*>(beta + c0) + jq);
+                    }
+                    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float xv = x[pass][jq * 4 + e];
+                        v[jq * 4 + e] = (gamma ? (xv - mean) * rstd * gg[e] + bb[e] : xv) + pp[e];
+                    }
                 }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) { const float d = v[e] - shift; s += d; sq = fmaf(d, d, sq); }
-                tmem_st32(X + lane_addr + c0, v);
+                store_row32_split(img_hi, img_lo, r, c0, v);
+                publish(pass);
             }
-            tmem_st_wait();
-            ln_combine(s, sq, red, r, ch, mean_s, rstd);
-        }
-        // ---- (2) A0 = LNq(x) + pos
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c0 = ch * 128 + cc * 32;
-            float v[32];
-            tmem_ld32(X + lane_addr + c0, v);
+        };
+
+        if (p.do_q) {
+            // (E0) A = LNq(x) + pos
+            image_from_x(p.lnq_g, p.lnq_b, true);
+            // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
+            wait_s(0);
+            const float eps_s = ATTN_EPS / (float)src_len;    // summaries arrive scaled by 1/S (k_fold)
 #pragma unroll
-            for (int jq = 0; jq < 8; ++jq) {
-                const float4 ps = *reinterpret_cast<const float4*>(post + xt_off(ti.ti, (c0 >> 2) + jq, r));
-                const float pp[4] = {ps.x, ps.y, ps.z, ps.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = c0 + jq * 4 + e;
-                    v[jq * 4 + e] = ((v[jq * 4 + e] - shift) - mean_s) * rstd * vec[c] + vec[256 + c] + pp[e];
-                }
-            }
-            store_row32_f16(smem + SM_A0, SLAB_BYTES, r, c0, v);
-        }
-        tc_fence_before(); fence_async_smem(); mbar_arrive(&bars->a_full);
-        // ---- (3) Qf = elu(q)+1 -> A1 ; 1/Z per head (linear_attention.py:46)
-        float inv_den[4];
-        mbar_wait(&bars->s_full, 0, p.flag); tc_fence_after();
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c0 = ch * 128 + cc * 32;            // one head per 32-column chunk
-            float v[32];
-            tmem_ld32(S + lane_addr + c0, v);
-            float den = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) { v[e] = elu1(v[e]); den = fmaf(v[e], vec[4 * 256 + c0 + e], den); }
-            inv_den[cc] = 1.f / (den + ATTN_EPS);
-            store_row32_f16(smem + SM_A1, SLAB_BYTES, r, c0, v);
-        }
-        tc_fence_before(); fence_async_smem(); mbar_arrive(&bars->a_full);
-        // ---- (4) message = (Qf KV) / Z -> A0
-        mbar_wait(&bars->s_full, 1, p.flag); tc_fence_after();
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c0 = ch * 128 + cc * 32;
-            float v[32];
-            tmem_ld32(S + lane_addr + c0, v);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] *= inv_den[cc];
-            store_row32_f16(smem + SM_A0, SLAB_BYTES, r, c0, v);
-        }
-        tc_fence_before(); fence_async_smem(); mbar_arrive(&bars->a_full);
-        // ---- (5) after x += merge(message): A1 = LN2(x)
-        mbar_wait(&bars->s_full, 0, p.flag); tc_fence_after();
-        {
-            float v[32];
-            tmem_ld32(X + lane_addr, v);              // column 0 of the row = shift (both halves use the same)
-            shift = v[0];
-            float s = 0.f, sq = 0.f;
-            for (int cc = 0; cc < 4; ++cc) {
-                tmem_ld32(X + lane_addr + ch * 128 + cc * 32, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) { const float d = v[e] - shift; s += d; sq = fmaf(d, d, sq); }
-            }
-            ln_combine(s, sq, red, r, ch, mean_s, rstd);
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c0 = ch * 128 + cc * 32;
-                tmem_ld32(X + lane_addr + c0, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    v[e] = ((v[e] - shift) - mean_s) * rstd * vec[2 * 256 + c0 + e] + vec[3 * 256 + c0 + e];
-                store_row32_f16(smem + SM_A1, SLAB_BYTES, r, c0, v);
-            }
-        }
-        tc_fence_before(); fence_async_smem(); mbar_arrive(&bars->a_full);
-        // ---- (6),(7) gelu(h) -> A0, twice (hidden halves)
-        for (int half = 0; half < 2; ++half) {
-            mbar_wait(&bars->s_full, half ? 0 : 1, p.flag); tc_fence_after();
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c0 = ch * 128 + cc * 32;
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;      // one head per 32-column chunk
                 float v[32];
-                tmem_ld32(S + lane_addr + c0, v);
+                tmem_ld32(S0 + lane_addr + c0, v);
+                float den = 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) { v[e] = elu1(v[e]); den = fmaf(v[e], ksum_s[c0 + e], den); }
+                const float inv = 1.f / (den + eps_s);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] *= inv;
+                store_row32_split(img_hi, img_lo, r, c0, v);
+                publish(pass);
+            }
+            // (E2) x += msg ; A = LN2(x)
+            wait_s(1);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                float v[32];
+                tmem_ld32(S1 + lane_addr + pass * 128 + cq * 32, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
+            }
+            image_from_x(p.ln2_g, p.ln2_b, false);
+            // (E3) A = gelu(h_a)   (needs h_a in S0, and h_b complete: the LN2 image is then free)
+            wait_s(0);
+            wait_s(1);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+                float v[32];
+                tmem_ld32(S0 + lane_addr + c0, v);
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
-                store_row32_f16(smem + SM_A0, SLAB_BYTES, r, c0, v);
+                store_row32_split(img_hi, img_lo, r, c0, v);
+                publish(pass);
             }
-            tc_fence_before(); fence_async_smem(); mbar_arrive(&bars->a_full);
-        }
-        // ---- (8) write the updated residual stream back
-        mbar_wait(&bars->s_full, 1, p.flag); tc_fence_after();
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c0 = ch * 128 + cc * 32;
-            float v[32];
-            tmem_ld32(X + lane_addr + c0, v);
+            // (E4) A = gelu(h_b)   (the image is free once y = gelu(h_a) W2a^T has completed)
 #pragma unroll
-            for (int jq = 0; jq < 8; ++jq)
-                *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r)) =
-                    make_float4(v[jq * 4], v[jq * 4 + 1], v[jq * 4 + 2], v[jq * 4 + 3]);
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+                float v[32];
+                tmem_ld32(S1 + lane_addr + c0, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
+                if (pass == 0) wait_s(0);
+                store_row32_split(img_hi, img_lo, r, c0, v);
+                publish(pass);
+            }
+            // (E5) x += y
+            wait_s(0);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                float v[32];
+                tmem_ld32(S0 + lane_addr + pass * 128 + cq * 32, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
+            }
+            tc_fence_before();
+        }
+        if (p.store_x) store_x();
+        if (p.do_kv) {
+            if (!dec_mode) {
+                image_from_x(p.lnkv_g, p.lnkv_b, true);        // k and v share LN_kv(x)+pos (transformer.py:119-126)
+                wait_s(0);
+                wait_s(1);
+            } else {
+                image_from_x(nullptr, nullptr, false);         // v = x Wv^T + bv      (transformer.py:243-249)
+                wait_s(0);
+                image_from_x(nullptr, nullptr, true);          // k = (x+pos) Wk^T + bk
+                wait_s(1);
+            }
+            // half images (tokens = K dimension): V and Kf = elu(k)+1; padded rows are zero
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32, ch = cq * 32;      // ch: column inside the 128-channel half
+                float v[32];
+                tmem_ld32(S0 + lane_addr + c0, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = valid ? v[e] + (p.bv ? __ldg(p.bv + c0 + e) : 0.f) : 0.f;
+                if (pass == 1) wait_s(0);                               // KV of half 0 has consumed the images
+                store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
+                tmem_ld32(S1 + lane_addr + c0, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e] + (p.bk ? __ldg(p.bk + c0 + e) : 0.f)) : 0.f;
+                store_row32_split(img_hi + KF_OFF, img_lo + KF_OFF, r, ch, v);
+                publish(pass);
+            }
+            // results: KV diagonal blocks (this warp's TMEM lanes are the d-channels of head 4*half + q) and Ksum
+            wait_s(1);
+            float* part = p.kv_part + (size_t)blockIdx.x * KVS;
+            if (cq < 2) {
+                const int half = cq, h = half * 4 + q;
+                float v[32];
+                tmem_ld32(S0 + lane_addr + half * 128 + q * 32, v);
+                float* o = part + h * HD * HD + lane * HD;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            } else if (cq == 2) {
+                float v[32];
+                tmem_ld32(S1 + lane_addr, v);               // columns 0 / 16: the two ones-products
+                float* ks = part + NH * HD * HD;
+                ks[q * 32 + lane] = v[0];
+                ks[128 + q * 32 + lane] = v[16];
+            }
+            tc_fence_before();
         }
     }
-    cta_teardown(tmem);
+    // teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_PRODUCER) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_fold: per (image, head): KV_h = sum of tile partials; M_img[n][h*32+d] = sum_e Wm[n][h*32+e] KV_h[d][e];
+// written as the (hi, lo) stage images k_enc streams; also Ksum[img][256].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, TileGeom g, const float* __restrict__ Wm,
+                                              __half* __restrict__ mimg, float* __restrict__ ksum) {
+    __shared__ float kv[HD][HD + 1];
+    const int img = blockIdx.x >> 3, h = blockIdx.x & 7;
+    const int set = img / g.B, b = img % g.B;
+    const int T = set == 0 ? g.T1 : g.T2;
+    const int first = set == 0 ? b * g.T1 : g.B * g.T1 + b * g.T2;
+    const float* src = part + (size_t)first * KVS;
+    // both summaries are scaled by 1/S (S = source length) like the reference's v / v_length
+    // (linear_attention.py:43-48): keeps phi(q)/Z and M_img inside fp16 range for any S; k_enc scales eps alike
+    const float inv_s = 1.f / (float)(set == 0 ? g.L1 : g.L2);
+    for (int i = threadIdx.x; i < HD * HD; i += 256) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc += src[(size_t)t * KVS + h * HD * HD + i];
+        kv[i >> 5][i & 31] = acc * inv_s;
+    }
+    if (threadIdx.x < HD) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc += src[(size_t)t * KVS + NH * HD * HD + h * HD + threadIdx.x];
+        ksum[(size_t)img * C + h * HD + threadIdx.x] = acc * inv_s;
+    }
+    __syncthreads();
+    const int n = threadIdx.x;                         // output channel of merge
+    float w[HD], out[HD];
+    const float4* wr = reinterpret_cast<const float4*>(Wm + (size_t)n * C + h * HD);
+#pragma unroll
+    for (int e4 = 0; e4 < HD / 4; ++e4) {
+        const float4 t = __ldg(wr + e4);
+        w[e4 * 4] = t.x; w[e4 * 4 + 1] = t.y; w[e4 * 4 + 2] = t.z; w[e4 * 4 + 3] = t.w;
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < HD; ++e) acc = fmaf(w[e], kv[d][e], acc);
+        out[d] = acc;
+    }
+    // K index = h*32 + d: k-slab h/2, columns (h&1)*32 .. +32 of row n
+    __half* dst = mimg + (size_t)img * GEMM_HALFS;
+    const int ks = h >> 1, nh = n >> 7, r = n & 127, j0 = (h & 1) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 hi, lo;
+        split8(&out[8 * j], hi, lo);
+        const uint32_t off = slab_chunk_off(r, j0 + j);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 0, nh)) + off) = hi;
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 1, nh)) + off) = lo;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -617,7 +669,7 @@ __global__ void k_untile(const float* __restrict__ xt, TileGeom g, float* __rest
             *reinterpret_cast<const float4*>(xt + xt_off(blockIdx.x, quad, r));
     }
 }
-// per-image sum of per-tile partial summaries
+// per-image sum of per-tile partial summaries (decoder cross-attention consumes the raw summaries)
 __global__ void k_sum_partials(const float* __restrict__ part, TileGeom g, float* __restrict__ out) {
     const int img = blockIdx.x;                      // 0..2B-1
     const int set = img / g.B, b = img % g.B;
@@ -642,26 +694,26 @@ static TileGeom make_geom(int B, int L1, int L2) {
 void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
     const TileGeom g = make_geom(B, L1, L2);
     char* b = static_cast<char*>(base);
-    auto take = [&](size_t nfloats) {
-        off = (off + 255) & ~size_t(255);
-        float* p = b ? reinterpret_cast<float*>(b + off) : nullptr;
-        off += nfloats * sizeof(float);
+    auto take = [&](size_t nbytes) {
+        off = (off + 1023) & ~size_t(1023);
+        void* p = b ? static_cast<void*>(b + off) : nullptr;
+        off += nbytes;
         return p;
     };
-    w.xt = take((size_t)g.tiles() * TILE * C);
-    w.post = take((size_t)(g.T1 + g.T2) * TILE * C);
-    w.kv_part = take((size_t)g.tiles() * KVS);
-    w.dec_kvs = take((size_t)N_DEC * 2 * B * KVS);
+    w.xt = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));
+    w.post = static_cast<float*>(take((size_t)(g.T1 + g.T2) * TILE * C * sizeof(float)));
+    w.kv_part = static_cast<float*>(take((size_t)g.tiles() * KVS * sizeof(float)));
+    w.dec_kvs = static_cast<float*>(take((size_t)N_DEC * 2 * B * KVS * sizeof(float)));
+    w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
+    w.ksum = static_cast<float*>(take((size_t)2 * B * C * sizeof(float)));
 }
 
 static bool g_attr_set = false;
 static int set_attrs(char* msg, size_t msg_len) {
     if (g_attr_set) return 0;
-    cudaError_t e1 = cudaFuncSetAttribute(k_tc_kv, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    cudaError_t e2 = cudaFuncSetAttribute(k_tc_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        snprintf(msg, msg_len, "cudaFuncSetAttribute(max dynamic smem %u): %s", SM_TOTAL,
-                 cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    cudaError_t e1 = cudaFuncSetAttribute(k_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e1 != cudaSuccess) {
+        snprintf(msg, msg_len, "cudaFuncSetAttribute(max dynamic smem %u): %s", SM_TOTAL, cudaGetErrorString(e1));
         return -1;
     }
     g_attr_set = true;
@@ -679,33 +731,47 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
     k_pos_tiles<<<g.T1, 256, 0, s>>>(d_pe, max_w, wf1, L1, post1); lc.n++;
     k_pos_tiles<<<g.T2, 256, 0, s>>>(d_pe, max_w, wf2, L2, post2); lc.n++;
     const int tiles = g.tiles();
+    EncParams base{};
+    base.g = g; base.feat1 = feat1; base.feat2 = feat2; base.xt = ws.xt; base.post1 = post1; base.post2 = post2;
+    base.mimg = ws.mimg; base.ksum = ws.ksum; base.kv_part = ws.kv_part; base.flag = flag;
+    auto set_kv_enc = [&](EncParams& p, int layer) {
+        const EncW& e = L.enc[layer];
+        p.do_kv = 1; p.lnkv_g = d_w + e.lnkv_g; p.lnkv_b = d_w + e.lnkv_b; p.bk = nullptr; p.bv = nullptr;
+        p.w_kv = tw.enc_img + (size_t)layer * ENC_LAYER_HALFS + 5 * GEMM_HALFS;
+    };
+    auto set_kv_dec = [&](EncParams& p, int layer) {
+        const DecW& d = L.dec[layer];
+        p.do_kv = 1; p.lnkv_g = nullptr; p.lnkv_b = nullptr; p.bk = d_w + d.ca.bk; p.bv = d_w + d.ca.bv;
+        p.w_kv = tw.dec_img + (size_t)layer * DEC_LAYER_HALFS;
+    };
+    // source phase of layer 0 straight from the NCHW features
+    {
+        EncParams p = base;
+        p.load_feat = 1; p.store_x = 1;
+        set_kv_enc(p, 0);
+        k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
+        k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, d_w + L.enc[0].wm, ws.mimg, ws.ksum); lc.n++;
+    }
     for (int i = 0; i < N_ENC; ++i) {
         const EncW& e = L.enc[i];
         const __half* img = tw.enc_img + (size_t)i * ENC_LAYER_HALFS;
-        KvParams kp{};
-        kp.g = g; kp.feat1 = i == 0 ? feat1 : nullptr; kp.feat2 = i == 0 ? feat2 : nullptr; kp.xt = ws.xt;
-        kp.post1 = post1; kp.post2 = post2; kp.ln_g = d_w + e.lnkv_g; kp.ln_b = d_w + e.lnkv_b;
-        kp.bk = nullptr; kp.bv = nullptr; kp.pos_on_v = 1; kp.wimg = img; kp.kv_part = ws.kv_part; kp.flag = flag;
-        kp.mn_lbo = SLAB_BYTES; kp.mn_sbo = ATOM_BYTES;
-        k_tc_kv<<<tiles, N_THREADS, SM_TOTAL, s>>>(kp); lc.n++;
-        LayerParams lp{};
-        lp.g = g; lp.xt = ws.xt; lp.post1 = post1; lp.post2 = post2;
-        lp.lnq_g = d_w + e.lnq_g; lp.lnq_b = d_w + e.lnq_b; lp.ln2_g = d_w + e.ln2_g; lp.ln2_b = d_w + e.ln2_b;
-        lp.wimg = img + (size_t)KV_STREAM_CHUNKS * CHUNK_HALFS; lp.kv_part = ws.kv_part; lp.cross = i & 1; lp.flag = flag;
+        EncParams p = base;
+        p.store_x = 1; p.do_q = 1; p.cross = i & 1;
+        p.lnq_g = d_w + e.lnq_g; p.lnq_b = d_w + e.lnq_b; p.ln2_g = d_w + e.ln2_g; p.ln2_b = d_w + e.ln2_b;
+        p.w_q = img; p.w_mlp = img + GEMM_HALFS;
+        if (i + 1 < N_ENC) set_kv_enc(p, i + 1); else set_kv_dec(p, 0);
         if (prof) prof->mark(s);
-        k_tc_layer<<<tiles, N_THREADS, SM_TOTAL, s>>>(lp); lc.n++;
+        k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
         if (prof) prof->mark(s);
+        if (i + 1 < N_ENC) { k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, d_w + L.enc[i + 1].wm, ws.mimg, ws.ksum); lc.n++; }
+        else { k_sum_partials<<<2 * B, 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs); lc.n++; }
     }
-    // decoder cross-attention summaries: k = (memory+pos) Wk^T + bk, v = memory Wv^T + bv (transformer.py:243-249)
-    for (int j = 0; j < N_DEC; ++j) {
-        const DecW& d = L.dec[j];
-        KvParams kp{};
-        kp.g = g; kp.feat1 = nullptr; kp.feat2 = nullptr; kp.xt = ws.xt; kp.post1 = post1; kp.post2 = post2;
-        kp.ln_g = nullptr; kp.ln_b = nullptr; kp.bk = d_w + d.ca.bk; kp.bv = d_w + d.ca.bv; kp.pos_on_v = 0;
-        kp.wimg = tw.dec_img + (size_t)j * DEC_LAYER_HALFS; kp.kv_part = ws.kv_part; kp.flag = flag;
-        kp.mn_lbo = SLAB_BYTES; kp.mn_sbo = ATOM_BYTES;
-        k_tc_kv<<<tiles, N_THREADS, SM_TOTAL, s>>>(kp); lc.n++;
-        k_sum_partials<<<2 * B, 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs + (size_t)j * 2 * B * KVS); lc.n++;
+    // decoder layer 1 cross-attention summaries: k = (memory+pos) Wk^T + bk, v = memory Wv^T + bv
+    {
+        EncParams p = base;
+        set_kv_dec(p, 1);
+        k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
+        k_sum_partials<<<2 * B, 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs + (size_t)2 * B * KVS); lc.n++;
     }
     k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++;
     cudaError_t e = cudaGetLastError();
@@ -717,161 +783,210 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// self-test of the building blocks on one tile
+// self-test of the kernels on one synthetic pair of 100-token images (one partial tile each) against an fp64
+// host computation of the same encoder layer (no rounding model: the split products are expected to be
+// fp32-accurate):
+//   errs[0] KV summary of the source phase            errs[1] Ksum
+//   errs[2] folded merge weights M_img (hi+lo) vs host
+//   errs[3] residual stream after a self layer        errs[4] timeout flag raised by any mbarrier wait (0 = none)
+//   errs[5] KV summary of the fused follow-up source phase (next layer's weights = same weights)
+//   errs[6] residual stream after a cross layer
 // ---------------------------------------------------------------------------------------------------------
-// Runs k_tc_kv and k_tc_layer on ONE synthetic 128-token image with LayerNorm disabled / identity so that the
-// expected outputs are plain matrix products computed on the host:
-//   errs[0] v-projection path + KV summary (K-major GEMM, MN-major KV MMA)   [with LBO = slab stride]
-//   errs[1] Ksum (N=16 ones-product)
-//   errs[2] unused (0)
-//   errs[3] full layer kernel vs host fp32 emulation of the same tile
-//   errs[4] timeout flag raised by any mbarrier wait (0 = none)
 int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
-    for (int i = 0; i < n_errs; ++i) errs[i] = -1.f;
+    for (int i = 0; i < n_errs; ++i) errs[i] = i < 7 ? -1.f : 0.f;
     if (set_attrs(msg, msg_len)) return -1;
-    const int L = 100;                              // one partial tile: rows 100..127 are padding
+    const int L = 100;
     const TileGeom g = make_geom(1, L, L);
     auto frand = [](uint32_t& s) { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.f - 0.5f; };
     uint32_t seed = 12345u;
     std::vector<float> feat((size_t)2 * C * L), wk(C * C), wv(C * C), wq(C * C), wm(C * C), w1(FF * C), w2(C * FF);
+    std::vector<float> lng(3 * C), lnb(3 * C), pos((size_t)TILE * C, 0.f);
     for (auto& v : feat) v = 2.f * frand(seed);
     for (auto* w : {&wk, &wv, &wq, &wm, &w1, &w2}) for (auto& v : *w) v = 0.25f * frand(seed);
-    std::vector<float> ones(C, 1.f), zeros(C, 0.f), pos((size_t)2 * TILE * C, 0.f);
-    auto h16 = [](float x) { return __half2float(__float2half_rn(x)); };
+    for (auto& v : lng) v = 1.f + 0.5f * frand(seed);
+    for (auto& v : lnb) v = 0.4f * frand(seed);
+    std::vector<float> posrow((size_t)L * C);
+    for (auto& v : posrow) v = 2.f * frand(seed);
+    for (int l = 0; l < L; ++l) for (int c = 0; c < C; ++c) pos[xt_off(0, c / 4, l) + c % 4] = posrow[(size_t)l * C + c];
 
-    float *d_feat, *d_wk, *d_wv, *d_wq, *d_wm, *d_w1, *d_w2, *d_ones, *d_zeros, *d_xt, *d_post, *d_part;
-    __half* d_img;
+    float *d_feat, *d_wm, *d_tmp, *d_ln, *d_xt, *d_post, *d_part, *d_ksum;
+    __half *d_img, *d_mimg;
     int* d_flag;
-    const size_t img_halfs = ENC_LAYER_HALFS;
 #define ST(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(msg, msg_len, "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
-    ST(cudaMalloc(&d_feat, feat.size() * 4)); ST(cudaMalloc(&d_wk, wk.size() * 4)); ST(cudaMalloc(&d_wv, wv.size() * 4));
-    ST(cudaMalloc(&d_wq, wq.size() * 4)); ST(cudaMalloc(&d_wm, wm.size() * 4)); ST(cudaMalloc(&d_w1, w1.size() * 4));
-    ST(cudaMalloc(&d_w2, w2.size() * 4)); ST(cudaMalloc(&d_ones, C * 4)); ST(cudaMalloc(&d_zeros, C * 4));
-    ST(cudaMalloc(&d_xt, (size_t)2 * TILE * C * 4)); ST(cudaMalloc(&d_post, pos.size() * 4));
-    ST(cudaMalloc(&d_part, (size_t)2 * KVS * 4)); ST(cudaMalloc(&d_img, img_halfs * 2)); ST(cudaMalloc(&d_flag, 4));
+    ST(cudaMalloc(&d_feat, feat.size() * 4)); ST(cudaMalloc(&d_wm, wm.size() * 4)); ST(cudaMalloc(&d_tmp, (size_t)FF * C * 4));
+    ST(cudaMalloc(&d_ln, 6 * C * 4)); ST(cudaMalloc(&d_xt, (size_t)2 * TILE * C * 4)); ST(cudaMalloc(&d_post, pos.size() * 4));
+    ST(cudaMalloc(&d_part, (size_t)2 * KVS * 4)); ST(cudaMalloc(&d_ksum, 2 * C * 4));
+    ST(cudaMalloc(&d_img, ENC_LAYER_HALFS * 2)); ST(cudaMalloc(&d_mimg, 2 * GEMM_HALFS * 2)); ST(cudaMalloc(&d_flag, 4));
     ST(cudaMemcpy(d_feat, feat.data(), feat.size() * 4, cudaMemcpyHostToDevice));
-    ST(cudaMemcpy(d_wk, wk.data(), wk.size() * 4, cudaMemcpyHostToDevice));
-    ST(cudaMemcpy(d_wv, wv.data(), wv.size() * 4, cudaMemcpyHostToDevice));
-    ST(cudaMemcpy(d_wq, wq.data(), wq.size() * 4, cudaMemcpyHostToDevice));
     ST(cudaMemcpy(d_wm, wm.data(), wm.size() * 4, cudaMemcpyHostToDevice));
-    ST(cudaMemcpy(d_w1, w1.data(), w1.size() * 4, cudaMemcpyHostToDevice));
-    ST(cudaMemcpy(d_w2, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice));
-    ST(cudaMemcpy(d_ones, ones.data(), C * 4, cudaMemcpyHostToDevice));
-    ST(cudaMemset(d_zeros, 0, C * 4)); ST(cudaMemset(d_post, 0, pos.size() * 4)); ST(cudaMemset(d_flag, 0, 4));
-    const int grid = (CHUNKS_PER_GEMM * 128 * 8 + 255) / 256;
-    const size_t G = (size_t)CHUNKS_PER_GEMM * CHUNK_HALFS;
-    k_make_chunks<<<grid, 256>>>(d_wv, C, 0, 0, d_img + 0 * G);
-    k_make_chunks<<<grid, 256>>>(d_wk, C, 0, 0, d_img + 1 * G);
-    k_make_chunks<<<grid, 256>>>(d_wq, C, 0, 0, d_img + 2 * G);
-    k_make_chunks<<<grid, 256>>>(d_wm, C, 0, 0, d_img + 3 * G);
-    k_make_chunks<<<grid, 256>>>(d_w1, C, 0, 0, d_img + 4 * G);
-    k_make_chunks<<<grid, 256>>>(d_w2, FF, 0, 0, d_img + 5 * G);
-    k_make_chunks<<<grid, 256>>>(d_w1, C, 256, 0, d_img + 6 * G);
-    k_make_chunks<<<grid, 256>>>(d_w2, FF, 0, 256, d_img + 7 * G);
+    ST(cudaMemcpy(d_ln, lng.data(), 3 * C * 4, cudaMemcpyHostToDevice));
+    ST(cudaMemcpy(d_ln + 3 * C, lnb.data(), 3 * C * 4, cudaMemcpyHostToDevice));
+    ST(cudaMemcpy(d_post, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice));
+    ST(cudaMemset(d_flag, 0, 4));
+    auto upload_image = [&](const std::vector<float>& w, int ld, int row0, int col0, int slot) -> int {
+        ST(cudaMemcpy(d_tmp, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+        make_gemm_image(d_tmp, ld, row0, col0, d_img + (size_t)slot * GEMM_HALFS);
+        ST(cudaDeviceSynchronize());
+        return 0;
+    };
+    if (upload_image(wq, C, 0, 0, 0) || upload_image(w1, C, 0, 0, 1) || upload_image(w1, C, 256, 0, 2) ||
+        upload_image(w2, FF, 0, 0, 3) || upload_image(w2, FF, 0, 256, 4) || upload_image(wv, C, 0, 0, 5) ||
+        upload_image(wk, C, 0, 0, 6)) return -1;
 
-    // host reference for the kv kernel with LN disabled and no pos: a = fp16(x); v = a Wv^T ; k = elu1(a Wk^T)
-    std::vector<float> xa((size_t)2 * L * C);                      // [img][l][c]
-    for (int im = 0; im < 2; ++im) for (int c = 0; c < C; ++c) for (int l = 0; l < L; ++l)
-        xa[((size_t)im * L + l) * C + c] = feat[((size_t)im * C + c) * L + l];
-    auto gemm_nt_h = [&](const std::vector<float>& A, int rows, int K, const std::vector<float>& W, int N, std::vector<double>& out) {
+    // ---- host fp64 reference -------------------------------------------------------------------------
+    auto ln = [&](const std::vector<double>& x, int which, std::vector<double>& out) {   // rows x C
+        const int rows = (int)(x.size() / C);
+        out.resize(x.size());
+        for (int i = 0; i < rows; ++i) {
+            double mu = 0, var = 0;
+            for (int c = 0; c < C; ++c) mu += x[(size_t)i * C + c];
+            mu /= C;
+            for (int c = 0; c < C; ++c) var += (x[(size_t)i * C + c] - mu) * (x[(size_t)i * C + c] - mu);
+            const double rs = 1.0 / std::sqrt(var / C + 1e-5);
+            for (int c = 0; c < C; ++c) out[(size_t)i * C + c] = (x[(size_t)i * C + c] - mu) * rs * lng[which * C + c] + lnb[which * C + c];
+        }
+    };
+    auto gemm_nt_h = [&](const std::vector<double>& A, int K, const std::vector<float>& W, int ldw, int N, std::vector<double>& out) {
+        const int rows = (int)(A.size() / K);
         out.assign((size_t)rows * N, 0.0);
         for (int i = 0; i < rows; ++i) for (int n = 0; n < N; ++n) {
             double acc = 0;
-            for (int k = 0; k < K; ++k) acc += (double)h16(A[(size_t)i * K + k]) * (double)h16(W[(size_t)n * K + k]);
+            for (int k = 0; k < K; ++k) acc += A[(size_t)i * K + k] * (double)W[(size_t)n * ldw + k];
             out[(size_t)i * N + n] = acc;
         }
     };
-    std::vector<double> vh, kh;
-    gemm_nt_h(xa, 2 * L, C, wv, C, vh);
-    gemm_nt_h(xa, 2 * L, C, wk, C, kh);
-    std::vector<double> kv_ref((size_t)2 * KVS, 0.0);
-    for (int im = 0; im < 2; ++im) for (int l = 0; l < L; ++l) for (int h = 0; h < NH; ++h) for (int d = 0; d < HD; ++d) {
-        const double kf = h16((float)(kh[((size_t)im * L + l) * C + h * HD + d] > 0 ? kh[((size_t)im * L + l) * C + h * HD + d] + 1.0
-                                                                               : std::exp(kh[((size_t)im * L + l) * C + h * HD + d])));
-        kv_ref[(size_t)im * KVS + NH * HD * HD + h * HD + d] += kf;
-        for (int e = 0; e < HD; ++e)
-            kv_ref[(size_t)im * KVS + h * HD * HD + d * HD + e] += kf * (double)h16((float)vh[((size_t)im * L + l) * C + h * HD + e]);
+    auto phi = [](double x) { return x > 0 ? x + 1.0 : std::exp(x); };
+    // summaries of one image: KV[h][d][e], Ksum[h][d]  (LN index 1 = pre_norm_kv)
+    auto summary = [&](const std::vector<double>& x, std::vector<double>& kvs) {
+        std::vector<double> a, kh, vh;
+        ln(x, 1, a);
+        for (int l = 0; l < L; ++l) for (int c = 0; c < C; ++c) a[(size_t)l * C + c] += posrow[(size_t)l * C + c];
+        gemm_nt_h(a, C, wk, C, C, kh);
+        gemm_nt_h(a, C, wv, C, C, vh);
+        kvs.assign(KVS, 0.0);
+        for (int l = 0; l < L; ++l) for (int h = 0; h < NH; ++h) for (int d = 0; d < HD; ++d) {
+            const double kf = phi(kh[(size_t)l * C + h * HD + d]);
+            kvs[NH * HD * HD + h * HD + d] += kf;
+            for (int e = 0; e < HD; ++e) kvs[h * HD * HD + d * HD + e] += kf * vh[(size_t)l * C + h * HD + e];
+        }
+    };
+    auto layer = [&](std::vector<double>& x, const std::vector<double>& kvs) {       // LN index 0 = pre_norm_q, 2 = norm2
+        std::vector<double> a, qh, msgv((size_t)L * C), m, h1, y;
+        ln(x, 0, a);
+        for (int l = 0; l < L; ++l) for (int c = 0; c < C; ++c) a[(size_t)l * C + c] += posrow[(size_t)l * C + c];
+        gemm_nt_h(a, C, wq, C, C, qh);
+        for (int l = 0; l < L; ++l) for (int h = 0; h < NH; ++h) {
+            double den = 1e-6;
+            for (int d = 0; d < HD; ++d) den += phi(qh[(size_t)l * C + h * HD + d]) * kvs[NH * HD * HD + h * HD + d];
+            for (int e = 0; e < HD; ++e) {
+                double acc = 0;
+                for (int d = 0; d < HD; ++d) acc += phi(qh[(size_t)l * C + h * HD + d]) * kvs[h * HD * HD + d * HD + e];
+                msgv[(size_t)l * C + h * HD + e] = acc / den;
+            }
+        }
+        gemm_nt_h(msgv, C, wm, C, C, m);
+        for (size_t i = 0; i < x.size(); ++i) x[i] += m[i];
+        ln(x, 2, a);
+        gemm_nt_h(a, C, w1, C, FF, h1);
+        for (auto& v : h1) v = 0.5 * v * (1.0 + std::erf(v / std::sqrt(2.0)));
+        gemm_nt_h(h1, FF, w2, FF, C, y);
+        for (size_t i = 0; i < x.size(); ++i) x[i] += y[i];
+    };
+    std::vector<double> x0((size_t)L * C), x1((size_t)L * C);
+    for (int c = 0; c < C; ++c) for (int l = 0; l < L; ++l) {
+        x0[(size_t)l * C + c] = feat[((size_t)0 * C + c) * L + l];
+        x1[(size_t)l * C + c] = feat[((size_t)1 * C + c) * L + l];
     }
-    std::vector<float> part((size_t)2 * KVS);
-    for (int variant = 0; variant < 1; ++variant) {   // (the swapped LBO/SBO probe addressed out of range on B200: convention settled)
-        KvParams kp{};
-        kp.g = g; kp.feat1 = d_feat; kp.feat2 = d_feat + (size_t)C * L; kp.xt = d_xt; kp.post1 = d_post; kp.post2 = d_post;
-        kp.ln_g = nullptr; kp.ln_b = nullptr; kp.bk = nullptr; kp.bv = nullptr; kp.pos_on_v = 1; kp.wimg = d_img;
-        kp.kv_part = d_part; kp.flag = d_flag;
-        kp.mn_lbo = variant == 0 ? SLAB_BYTES : ATOM_BYTES; kp.mn_sbo = variant == 0 ? ATOM_BYTES : SLAB_BYTES;
-        ST(cudaMemset(d_part, 0, part.size() * 4));
-        k_tc_kv<<<2, N_THREADS, SM_TOTAL>>>(kp);
+    std::vector<double> kvs0, kvs1;
+    summary(x0, kvs0);
+    summary(x1, kvs1);
+
+    auto max_rel = [](const float* got, const double* want, size_t n) {
+        double e = 0, s = 0;
+        for (size_t i = 0; i < n; ++i) { e = std::max(e, std::abs((double)got[i] - want[i])); s = std::max(s, std::abs(want[i])); }
+        return (float)(e / std::max(s, 1e-30));
+    };
+    EncParams base{};
+    base.g = g; base.feat1 = d_feat; base.feat2 = d_feat + (size_t)C * L; base.xt = d_xt; base.post1 = d_post; base.post2 = d_post;
+    base.mimg = d_mimg; base.ksum = d_ksum; base.kv_part = d_part; base.flag = d_flag;
+    base.lnq_g = d_ln + 0 * C; base.lnq_b = d_ln + 3 * C; base.lnkv_g = d_ln + 1 * C; base.lnkv_b = d_ln + 4 * C;
+    base.ln2_g = d_ln + 2 * C; base.ln2_b = d_ln + 5 * C;
+    base.w_q = d_img; base.w_mlp = d_img + GEMM_HALFS; base.w_kv = d_img + 5 * GEMM_HALFS;
+    std::vector<float> part((size_t)2 * KVS), xt((size_t)2 * TILE * C);
+    // (1) source phase from the NCHW features
+    {
+        EncParams p = base;
+        p.load_feat = 1; p.store_x = 1; p.do_kv = 1;
+        k_enc<<<2, N_THREADS, SM_TOTAL>>>(p);
         ST(cudaDeviceSynchronize());
         ST(cudaMemcpy(part.data(), d_part, part.size() * 4, cudaMemcpyDeviceToHost));
-        double e_kv = 0, e_ks = 0;
-        for (int im = 0; im < 2; ++im) {
-            for (int i = 0; i < NH * HD * HD; ++i) e_kv = std::max(e_kv, std::abs(part[(size_t)im * KVS + i] - kv_ref[(size_t)im * KVS + i]));
-            for (int i = 0; i < NH * HD; ++i) e_ks = std::max(e_ks, std::abs(part[(size_t)im * KVS + NH * HD * HD + i] - kv_ref[(size_t)im * KVS + NH * HD * HD + i]));
-        }
-        double scale = 0;
-        for (int i = 0; i < NH * HD * HD; ++i) scale = std::max(scale, std::abs(kv_ref[i]));
-        if (variant == 0) { errs[0] = (float)(e_kv / scale); if (n_errs > 1) errs[1] = (float)(e_ks / L); }
+        errs[0] = std::max(max_rel(part.data(), kvs0.data(), NH * HD * HD), max_rel(part.data() + KVS, kvs1.data(), NH * HD * HD));
+        if (n_errs > 1) errs[1] = std::max(max_rel(part.data() + NH * HD * HD, kvs0.data() + NH * HD * HD, NH * HD),
+                                           max_rel(part.data() + KVS + NH * HD * HD, kvs1.data() + NH * HD * HD, NH * HD));
     }
-    if (n_errs > 2) errs[2] = 0.f;
-    // layer kernel (self layer) with the variant-0 summaries: host emulation with the same rounding points
+    // (2) fold
+    k_fold<<<2 * NH, 256>>>(d_part, g, d_wm, d_mimg, d_ksum);
+    ST(cudaDeviceSynchronize());
+    if (n_errs > 2) {
+        std::vector<__half> mi(GEMM_HALFS);
+        ST(cudaMemcpy(mi.data(), d_mimg, GEMM_HALFS * 2, cudaMemcpyDeviceToHost));
+        double e = 0, sc = 0;
+        for (int n = 0; n < C; n += 5) for (int k = 0; k < C; k += 3) {
+            const int h = k / HD, d = k % HD;
+            double want = 0;
+            for (int ee = 0; ee < HD; ++ee) want += (double)wm[(size_t)n * C + h * HD + ee] * kvs0[h * HD * HD + d * HD + ee];
+            want /= L;                                   // k_fold scales the summaries by 1/S
+            const int ks = k / 64, col = k % 64, nh = n / 128, r = n % 128;
+            const size_t boff = slab_chunk_off(r, col >> 3) + (col & 7) * 2;
+            const __half hi = *reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(mi.data() + gemm_stage_off(ks, 0, nh)) + boff);
+            const __half lo = *reinterpret_cast<const __half*>(reinterpret_cast<const uint8_t*>(mi.data() + gemm_stage_off(ks, 1, nh)) + boff);
+            e = std::max(e, std::abs((double)__half2float(hi) + (double)__half2float(lo) - want));
+            sc = std::max(sc, std::abs(want));
+        }
+        errs[2] = (float)(e / sc);
+    }
+    auto compare_x = [&](const std::vector<double>& want0, const std::vector<double>& want1) {
+        double e = 0, sc = 0;
+        for (int im = 0; im < 2; ++im) for (int l = 0; l < L; ++l) for (int c = 0; c < C; ++c) {
+            const double w = (im ? want1 : want0)[(size_t)l * C + c];
+            e = std::max(e, std::abs((double)xt[xt_off(im, c / 4, l) + c % 4] - w));
+            sc = std::max(sc, std::abs(w));
+        }
+        return (float)(e / sc);
+    };
+    // (3) self layer + fused source phase of the "next" layer (same weights)
     if (n_errs > 3) {
-        KvParams kp{};
-        kp.g = g; kp.feat1 = d_feat; kp.feat2 = d_feat + (size_t)C * L; kp.xt = d_xt; kp.post1 = d_post; kp.post2 = d_post;
-        kp.pos_on_v = 1; kp.wimg = d_img; kp.kv_part = d_part; kp.flag = d_flag; kp.mn_lbo = SLAB_BYTES; kp.mn_sbo = ATOM_BYTES;
-        k_tc_kv<<<2, N_THREADS, SM_TOTAL>>>(kp);
-        LayerParams lp{};
-        lp.g = g; lp.xt = d_xt; lp.post1 = d_post; lp.post2 = d_post; lp.lnq_g = d_ones; lp.lnq_b = d_zeros;
-        lp.ln2_g = d_ones; lp.ln2_b = d_zeros; lp.wimg = d_img + (size_t)KV_STREAM_CHUNKS * CHUNK_HALFS; lp.kv_part = d_part;
-        lp.cross = 0; lp.flag = d_flag;
-        k_tc_layer<<<2, N_THREADS, SM_TOTAL>>>(lp);
+        EncParams p = base;
+        p.store_x = 1; p.do_q = 1; p.do_kv = 1; p.cross = 0;
+        k_enc<<<2, N_THREADS, SM_TOTAL>>>(p);
         ST(cudaDeviceSynchronize());
-        std::vector<float> xt((size_t)2 * TILE * C);
         ST(cudaMemcpy(xt.data(), d_xt, xt.size() * 4, cudaMemcpyDeviceToHost));
         ST(cudaMemcpy(part.data(), d_part, part.size() * 4, cudaMemcpyDeviceToHost));
-        double err = 0, scale = 0;
-        const int im = 0;
-        for (int l = 0; l < L; l += 7) {                 // a sample of rows of image 0
-            std::vector<double> x(C), a(C), qv(C), msg_(C), hid(FF);
-            double mu = 0, var = 0;
-            for (int c = 0; c < C; ++c) { x[c] = xa[((size_t)im * L + l) * C + c]; mu += x[c]; }
-            mu /= C;
-            for (int c = 0; c < C; ++c) var += (x[c] - mu) * (x[c] - mu);
-            double rs = 1.0 / std::sqrt(var / C + 1e-5);
-            for (int c = 0; c < C; ++c) a[c] = h16((float)((x[c] - mu) * rs));
-            for (int n = 0; n < C; ++n) { double acc = 0; for (int k = 0; k < C; ++k) acc += a[k] * h16(wq[(size_t)n * C + k]); qv[n] = acc > 0 ? acc + 1.0 : std::exp(acc); }
-            for (int h = 0; h < NH; ++h) {
-                double den = 1e-6;
-                for (int d = 0; d < HD; ++d) den += qv[h * HD + d] * part[(size_t)im * KVS + NH * HD * HD + h * HD + d];
-                for (int e = 0; e < HD; ++e) {
-                    double acc = 0;
-                    for (int d = 0; d < HD; ++d) acc += (double)h16((float)qv[h * HD + d]) * (double)h16(part[(size_t)im * KVS + h * HD * HD + d * HD + e]);
-                    msg_[h * HD + e] = h16((float)(acc / den));
-                }
-            }
-            for (int n = 0; n < C; ++n) { double acc = 0; for (int k = 0; k < C; ++k) acc += msg_[k] * h16(wm[(size_t)n * C + k]); x[n] += acc; }
-            mu = 0; var = 0;
-            for (int c = 0; c < C; ++c) mu += x[c];
-            mu /= C;
-            for (int c = 0; c < C; ++c) var += (x[c] - mu) * (x[c] - mu);
-            rs = 1.0 / std::sqrt(var / C + 1e-5);
-            for (int c = 0; c < C; ++c) a[c] = h16((float)((x[c] - mu) * rs));
-            for (int n = 0; n < FF; ++n) { double acc = 0; for (int k = 0; k < C; ++k) acc += a[k] * h16(w1[(size_t)n * C + k]); hid[n] = h16((float)(0.5 * acc * (1.0 + std::erf(acc / std::sqrt(2.0))))); }
-            for (int n = 0; n < C; ++n) { double acc = 0; for (int k = 0; k < FF; ++k) acc += hid[k] * h16(w2[(size_t)n * FF + k]); x[n] += acc; }
-            for (int c = 0; c < C; ++c) {
-                const float got = xt[(((size_t)0 * 64 + c / 4) * TILE + l) * 4 + c % 4];
-                err = std::max(err, std::abs(got - x[c]));
-                scale = std::max(scale, std::abs(x[c]));
-            }
-        }
-        errs[3] = (float)(err / scale);
+        layer(x0, kvs0);
+        layer(x1, kvs1);
+        errs[3] = compare_x(x0, x1);
+        summary(x0, kvs0);
+        summary(x1, kvs1);
+        if (n_errs > 5) errs[5] = std::max(max_rel(part.data(), kvs0.data(), NH * HD * HD), max_rel(part.data() + KVS, kvs1.data(), NH * HD * HD));
+    }
+    // (4) cross layer (each image reads the partner's summary), query phase only
+    if (n_errs > 6) {
+        k_fold<<<2 * NH, 256>>>(d_part, g, d_wm, d_mimg, d_ksum);
+        EncParams p = base;
+        p.store_x = 1; p.do_q = 1; p.do_kv = 0; p.cross = 1;
+        k_enc<<<2, N_THREADS, SM_TOTAL>>>(p);
+        ST(cudaDeviceSynchronize());
+        ST(cudaMemcpy(xt.data(), d_xt, xt.size() * 4, cudaMemcpyDeviceToHost));
+        layer(x0, kvs1);
+        layer(x1, kvs0);
+        errs[6] = compare_x(x0, x1);
     }
     int flag = 0;
     ST(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
     if (n_errs > 4) errs[4] = (float)flag;
-    for (int i = 5; i < n_errs; ++i) errs[i] = 0.f;
 #undef ST
-    cudaFree(d_feat); cudaFree(d_wk); cudaFree(d_wv); cudaFree(d_wq); cudaFree(d_wm); cudaFree(d_w1); cudaFree(d_w2);
-    cudaFree(d_ones); cudaFree(d_zeros); cudaFree(d_xt); cudaFree(d_post); cudaFree(d_part); cudaFree(d_img); cudaFree(d_flag);
+    cudaFree(d_feat); cudaFree(d_wm); cudaFree(d_tmp); cudaFree(d_ln); cudaFree(d_xt); cudaFree(d_post); cudaFree(d_part);
+    cudaFree(d_ksum); cudaFree(d_img); cudaFree(d_mimg); cudaFree(d_flag);
     return 0;
 }
 

@@ -18,9 +18,11 @@ struct TcWorkspace {
     float* post = nullptr;         // tile-blocked positional rows per geometry
     float* kv_part = nullptr;      // per-tile linear-attention partial summaries [tiles][KVS]
     float* dec_kvs = nullptr;      // [2 decoder layers][2B][KVS] cross-attention summaries
+    __half* mimg = nullptr;        // [2B images] folded merge weights (hi/lo stage images, 256 KB each)
+    float* ksum = nullptr;         // [2B][256] Ksum of every image for the current layer
 };
 
-// CUDA-event bracket around every launch of the dominant kernel (k_tc_layer); read back by bench.py through
+// CUDA-event bracket around every launch of the dominant kernel (k_enc with a query phase); read back by bench.py through
 // oetr_profile_read.  Events are recorded on the launching stream, consecutive pairs = (begin, end).
 struct KernelProfiler {
     bool on = false;
