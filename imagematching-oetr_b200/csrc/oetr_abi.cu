@@ -287,7 +287,7 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
     CUH(cudaMemset(h->d_flag, 0, sizeof(int)));
     if (operand_precision == OETR_PREC_FP16) {
         char msg[256] = "";
-        if (tc_prepare_weights(h->d_w, L, h->tc, msg, sizeof(msg)) != 0)
+        if (tc_prepare_weights(h->d_w, h->d_w9, L, h->tc, msg, sizeof(msg)) != 0)
             return bail(fail(OETR_E_CUDA, "oetr_create: %s", msg));
     }
     CUH(cudaDeviceSynchronize());
@@ -395,15 +395,15 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
         encoder_fp32(h, w, B, L1, L2, s, lc);
         decoder_fp32(h, w, B, s, lc, [&](int j) { decoder_kv_fp32(h, w, j, B, L1, L2, s, lc); });
     } else {
-        // tcgen05 encoder + decoder K/V summaries; leaves token-major memory in w.X
+        // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
+        // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
         char msg[256] = "";
-        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_pe, h->max_w, w.X,
-                       h->d_flag, &h->prof, s, lc, msg, sizeof(msg)) != 0)
+        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_pe, h->max_w,
+                       dbg_memory ? w.X : nullptr, h->d_flag, &h->prof, s, lc, msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
-        decoder_fp32(h, w, B, s, lc, [&](int j) {
-            cudaMemcpyAsync(w.dkvs, w.tc.dec_kvs + (size_t)j * 2 * B * KVS, (size_t)2 * B * KVS * sizeof(float),
-                            cudaMemcpyDeviceToDevice, s);
-        });
+        if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, B, hf1, wf1, hf2, wf2, w.dt, w.O, h->d_flag, s, lc, msg,
+                            sizeof(msg)) != 0)
+            return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
     }
     // memory = encoder output (w.X), hs = decoder output (w.dt)
     if (dbg_memory) cudaMemcpyAsync(dbg_memory, w.X, (size_t)(R1 + R2) * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -411,9 +411,11 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
 
     // head: heat = memory * <memory, hs>; conv3x3 (+bias) -> Y ; then the row-wise tail per image
     float *G = w.T, *Gs = w.Q, *Y = w.O;
-    heat_scale(w.X, w.dt, G, R1, L1, s, lc);
-    heat_scale(w.X + (size_t)R1 * C, w.dt + (size_t)B * C, G + (size_t)R1 * C, R2, L2, s, lc);
-    head_conv_fp32(h, w, B, hf1, wf1, hf2, wf2, G, Gs, Y, s, lc);
+    if (h->prec == OETR_PREC_FP32) {
+        heat_scale(w.X, w.dt, G, R1, L1, s, lc);
+        heat_scale(w.X + (size_t)R1 * C, w.dt + (size_t)B * C, G + (size_t)R1 * C, R2, L2, s, lc);
+        head_conv_fp32(h, w, B, hf1, wf1, hf2, wf2, G, Gs, Y, s, lc);
+    }
     HeadParams p{};
     p.gn_g = W + h->L.hm_gn_g; p.gn_b = W + h->L.hm_gn_b; p.w3 = W + h->L.hm_w3; p.b3 = W + h->L.hm_b3;
     p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;

@@ -49,6 +49,7 @@ constexpr uint32_t IMG_BYTES = 4 * SLAB_BYTES;  // a [128 x 256] fp16 operand im
 constexpr int ENC_LAYER_GEMMS = 7, DEC_LAYER_GEMMS = 2;
 constexpr size_t ENC_LAYER_HALFS = ENC_LAYER_GEMMS * GEMM_HALFS;
 constexpr size_t DEC_LAYER_HALFS = DEC_LAYER_GEMMS * GEMM_HALFS;
+constexpr size_t DEC_T_FLOATS = (size_t)6 * C * C + (size_t)2 * FF * C;   // transposed fp32 decoder weights per layer
 
 constexpr uint32_t IDESC_N256 = umma_idesc_f16(128, 256, 0, 0);
 constexpr uint32_t IDESC_KV = umma_idesc_f16(128, 128, 1, 1);      // both operands MN-major (token = K)
@@ -72,6 +73,7 @@ struct Bars {
     uint64_t full[RING], empty[RING];
     uint64_t a_full[2];   // row warps -> MMA: column pass p of the operand image written (count 512)
     uint64_t s_full[2];   // MMA -> row warps: accumulator S0 / S1 complete (tcgen05.commit)
+    uint64_t a_free[2];   // MMA -> row warps (k_conv): the MMAs reading column pass p of the image have completed
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -130,15 +132,19 @@ __global__ void k_make_gemm_image(const float* __restrict__ W, int ld, int row0,
     *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out + gemm_stage_off(ks, 1, nh)) + off) = l;
 }
 
+__global__ void k_transpose(const float* __restrict__ W, int N, int K, float* __restrict__ WT);
+
 static void make_gemm_image(const float* W, int ld, int row0, int col0, __half* out, cudaStream_t s = 0) {
     k_make_gemm_image<<<(4 * 2 * 128 * 8 + 255) / 256, 256, 0, s>>>(W, ld, row0, col0, out);
 }
 
-int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char* msg, size_t msg_len) {
+int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, TcWeights& out, char* msg, size_t msg_len) {
     out.enc_layer_halfs = ENC_LAYER_HALFS;
     out.dec_layer_halfs = DEC_LAYER_HALFS;
     if (cudaMalloc(&out.enc_img, N_ENC * ENC_LAYER_HALFS * sizeof(__half)) != cudaSuccess ||
-        cudaMalloc(&out.dec_img, N_DEC * DEC_LAYER_HALFS * sizeof(__half)) != cudaSuccess) {
+        cudaMalloc(&out.dec_img, N_DEC * DEC_LAYER_HALFS * sizeof(__half)) != cudaSuccess ||
+        cudaMalloc(&out.head_img, 9 * GEMM_HALFS * sizeof(__half)) != cudaSuccess ||
+        cudaMalloc(&out.dec_t, N_DEC * DEC_T_FLOATS * sizeof(float)) != cudaSuccess) {
         snprintf(msg, msg_len, "weight image allocation failed");
         return -1;
     }
@@ -158,7 +164,14 @@ int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char*
         __half* o = out.dec_img + (size_t)j * DEC_LAYER_HALFS;
         make_gemm_image(d_w + d.ca.wv, C, 0, 0, o + 0 * GEMM_HALFS);
         make_gemm_image(d_w + d.ca.wk, C, 0, 0, o + 1 * GEMM_HALFS);
+        // transposed fp32 copies for k_decoder: sa.wq | sa.wk | sa.wv | sa.wm | ca.wq | ca.wm | w1 | w2
+        float* t = out.dec_t + (size_t)j * DEC_T_FLOATS;
+        const size_t srcs[6] = {d.sa.wq, d.sa.wk, d.sa.wv, d.sa.wm, d.ca.wq, d.ca.wm};
+        for (int i = 0; i < 6; ++i) k_transpose<<<dim3(C / 32, C / 32), dim3(32, 8)>>>(d_w + srcs[i], C, C, t + (size_t)i * C * C);
+        k_transpose<<<dim3(FF / 32, C / 32), dim3(32, 8)>>>(d_w + d.w1, FF, C, t + (size_t)6 * C * C);
+        k_transpose<<<dim3(C / 32, FF / 32), dim3(32, 8)>>>(d_w + d.w2, C, FF, t + (size_t)6 * C * C + (size_t)FF * C);
     }
+    for (int tap = 0; tap < 9; ++tap) make_gemm_image(d_w9 + (size_t)tap * C * C, C, 0, 0, out.head_img + (size_t)tap * GEMM_HALFS);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(msg, msg_len, "weight image kernels: %s", cudaGetErrorString(e));
@@ -170,7 +183,10 @@ int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char*
 void tc_free_weights(TcWeights& w) {
     cudaFree(w.enc_img);
     cudaFree(w.dec_img);
-    w.enc_img = w.dec_img = nullptr;
+    cudaFree(w.head_img);
+    cudaFree(w.dec_t);
+    w.enc_img = w.dec_img = w.head_img = nullptr;
+    w.dec_t = nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -195,6 +211,87 @@ __host__ __device__ __forceinline__ size_t xt_off(int tile, int quad, int r) { r
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __expf(x); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// device building blocks shared by k_enc and k_conv
+// ---------------------------------------------------------------------------------------------------------
+// barriers + TMEM allocation (whole CTA); returns the TMEM base address
+__device__ __forceinline__ uint32_t cta_setup(Bars* bars, int alloc_warp) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RING; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->a_full[i], N_ROW_THREADS);
+            mbar_init(&bars->s_full[i], 1);
+            mbar_init(&bars->a_free[i], 1);
+        }
+        fence_mbar_init();
+    }
+    if ((int)(threadIdx.x >> 5) == alloc_warp) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return bars->tmem_base;
+}
+// producer: nstages consecutive 16 KB stages global -> ring
+__device__ __forceinline__ void ring_stream(uint8_t* smem, Bars* bars, int* flag, uint32_t& g, const __half* src, int nstages) {
+    for (int i = 0; i < nstages; ++i, ++g) {
+        const int st = g % RING;
+        mbar_wait(&bars->empty[st], ((g / RING) & 1) ^ 1, flag);
+        mbar_arrive_expect_tx(&bars->full[st], STAGE_BYTES);
+        bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, STAGE_BYTES, &bars->full[st]);
+    }
+}
+struct MmaState { uint32_t g = 0, na0 = 0, na1 = 0; };
+__device__ __forceinline__ void mma_wait_a(Bars* bars, int* flag, MmaState& ms, int pass) {
+    mbar_wait(&bars->a_full[pass], (pass ? ms.na1++ : ms.na0++) & 1, flag);
+    tc_fence_after();
+}
+// D[128 x 256] (tmem columns d..d+255) (+)= A[128 x 256] . W^T with the 3-term split; consumes 16 ring stages.
+// wait: the operand image is (re)written for this GEMM -> wait for column pass 0 before k-slab 0 and pass 1
+// before k-slab 2.  signal_free: commit a_free[p] once the MMAs reading pass p have been issued (k_conv).
+__device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* flag, MmaState& ms, uint32_t d,
+                                           bool accumulate, bool wait, bool signal_free) {
+    for (int ks = 0; ks < 4; ++ks) {
+        if (wait && ks == 0) mma_wait_a(bars, flag, ms, 0);
+        if (wait && ks == 2) mma_wait_a(bars, flag, ms, 1);
+        const uint32_t a_hi = smem_base + SM_AHI + ks * SLAB_BYTES;
+        const uint32_t a_lo = smem_base + SM_ALO + ks * SLAB_BYTES;
+        {   // w_hi: two adjacent stages form the [256 x 64] B tile
+            const int st = ms.g % RING;
+            mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
+            mbar_wait(&bars->full[st + 1], (ms.g / RING) & 1, flag);
+            tc_fence_after();
+            const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                         IDESC_N256, (accumulate || ks > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16(d, umma_desc(a_lo + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                         IDESC_N256, 1u);
+            umma_commit(&bars->empty[st]);
+            umma_commit(&bars->empty[st + 1]);
+            ms.g += 2;
+        }
+        {   // w_lo
+            const int st = ms.g % RING;
+            mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
+            mbar_wait(&bars->full[st + 1], (ms.g / RING) & 1, flag);
+            tc_fence_after();
+            const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                         IDESC_N256, 1u);
+            umma_commit(&bars->empty[st]);
+            umma_commit(&bars->empty[st + 1]);
+            ms.g += 2;
+        }
+        if (signal_free && (ks & 1)) umma_commit(&bars->a_free[ks >> 1]);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // k_enc
@@ -229,19 +326,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
     const uint32_t smem_base = smem_u32(smem);
     const bool dec_mode = p.lnkv_g == nullptr;
 
-    if (tid == 0) {
-        for (int i = 0; i < RING; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-        mbar_init(&bars->a_full[0], N_ROW_THREADS);
-        mbar_init(&bars->a_full[1], N_ROW_THREADS);
-        mbar_init(&bars->s_full[0], 1);
-        mbar_init(&bars->s_full[1], 1);
-        fence_mbar_init();
-    }
-    if (warp == WARP_PRODUCER) tmem_alloc(&bars->tmem_base, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
     const uint32_t S0 = tmem, S1 = tmem + 256;
 
     int src_img = ti.img, src_len = ti.L;
@@ -251,14 +336,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         // ------------------------------------------------------------------ weight stream
         if (lane == 0) {
             uint32_t g = 0;
-            auto stream = [&](const __half* src, int nstages) {
-                for (int i = 0; i < nstages; ++i, ++g) {
-                    const int st = g % RING;
-                    mbar_wait(&bars->empty[st], ((g / RING) & 1) ^ 1, p.flag);
-                    mbar_arrive_expect_tx(&bars->full[st], STAGE_BYTES);
-                    bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, STAGE_BYTES, &bars->full[st]);
-                }
-            };
+            auto stream = [&](const __half* src, int nstages) { ring_stream(smem, bars, p.flag, g, src, nstages); };
             if (p.do_q) {
                 stream(p.w_q, GEMM_STAGES);
                 stream(p.mimg + (size_t)src_img * GEMM_HALFS, GEMM_STAGES);
@@ -270,52 +348,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
     } else if (warp == WARP_MMA) {
         // ------------------------------------------------------------------ MMA issue
         if (lane == 0) {
-            uint32_t g = 0, na0 = 0, na1 = 0;
-            auto wait_a = [&](int pass) {
-                mbar_wait(&bars->a_full[pass], (pass ? na1++ : na0++) & 1, p.flag);
-                tc_fence_after();
-            };
-            // D[128 x 256] (tmem columns d..d+255) (+)= A[128 x 256] . W^T with the 3-term split; 16 ring stages
-            auto gemm = [&](uint32_t d, bool accumulate, bool wait) {
-                for (int ks = 0; ks < 4; ++ks) {
-                    if (wait && ks == 0) wait_a(0);
-                    if (wait && ks == 2) wait_a(1);
-                    const uint32_t a_hi = smem_base + SM_AHI + ks * SLAB_BYTES;
-                    const uint32_t a_lo = smem_base + SM_ALO + ks * SLAB_BYTES;
-                    {   // w_hi: two adjacent stages form the [256 x 64] B tile
-                        const int st = g % RING;
-                        mbar_wait(&bars->full[st], (g / RING) & 1, p.flag);
-                        mbar_wait(&bars->full[st + 1], (g / RING) & 1, p.flag);
-                        tc_fence_after();
-                        const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                     IDESC_N256, (accumulate || ks > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(d, umma_desc(a_lo + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                     IDESC_N256, 1u);
-                        umma_commit(&bars->empty[st]);
-                        umma_commit(&bars->empty[st + 1]);
-                        g += 2;
-                    }
-                    {   // w_lo
-                        const int st = g % RING;
-                        mbar_wait(&bars->full[st], (g / RING) & 1, p.flag);
-                        mbar_wait(&bars->full[st + 1], (g / RING) & 1, p.flag);
-                        tc_fence_after();
-                        const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                     IDESC_N256, 1u);
-                        umma_commit(&bars->empty[st]);
-                        umma_commit(&bars->empty[st + 1]);
-                        g += 2;
-                    }
-                }
-            };
+            MmaState ms;
+            auto wait_a = [&](int pass) { mma_wait_a(bars, p.flag, ms, pass); };
+            auto gemm = [&](uint32_t d, bool accumulate, bool wait) { gemm_issue(smem_base, bars, p.flag, ms, d, accumulate, wait, false); };
             if (p.do_q) {
                 gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
                 gemm(S1, false, true);  umma_commit(&bars->s_full[1]);     // msg = (phi(q)/Z) M_img^T
@@ -645,6 +680,269 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// k_att: att[l] = <memory[l,:], hs[img,:]> per token (src/model.py:147-149), tile-blocked like xt; 0 on padding
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_att(const float* __restrict__ xt, TileGeom g, const float* __restrict__ hs,
+                                             float* __restrict__ att) {
+    __shared__ float part[TILE];
+    __shared__ __align__(16) float hsv[C];
+    const TileInfo ti = tile_info(g, blockIdx.x);
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    hsv[threadIdx.x] = hs[(size_t)ti.img * C + threadIdx.x];
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll 8
+    for (int jq = 0; jq < 32; ++jq) {
+        const int quad = half * 32 + jq;
+        const float4 v = *reinterpret_cast<const float4*>(xt + xt_off(blockIdx.x, quad, r));
+        const float4 h = *reinterpret_cast<const float4*>(hsv + quad * 4);
+        acc += v.x * h.x + v.y * h.y + v.z * h.z + v.w * h.w;
+    }
+    if (half == 1) part[r] = acc;
+    __syncthreads();
+    if (half == 0) att[(size_t)blockIdx.x * TILE + r] = r < ti.valid ? acc + part[r] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_conv: heatmap_conv.0 (3x3, 256->256, pad 1, src/model.py:65-77,152-161) as an implicit GEMM on the tensor
+// cores.  heat[l,:] = memory[l,:] * att[l] is formed on the fly; for each of the 9 taps the row warps gather the
+// shifted rows (zero outside the map) into the operand image and the MMA warp accumulates
+// Y += G_tap . W_tap^T into S0 (3-term split).  The image of tap t+1 is written per column pass as soon as the
+// MMAs of tap t that read that pass have completed (a_free), so the gather overlaps the tensor work.
+// ---------------------------------------------------------------------------------------------------------
+struct ConvParams {
+    TileGeom g;
+    int hf1, wf1, hf2, wf2;
+    const float* xt;            // tile-blocked encoder output (memory)
+    const float* att;           // tile-blocked per-token scale
+    const __half* w;            // 9 tap GEMM images
+    const float* bias;          // heatmap_conv.0.bias
+    float* Y;                   // token-major [B*L1 + B*L2][256]
+    int* flag;
+};
+
+__global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const TileInfo ti = tile_info(p.g, blockIdx.x);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
+    const uint32_t S0 = tmem;
+
+    if (warp == WARP_PRODUCER) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            ring_stream(smem, bars, p.flag, g, p.w, 9 * GEMM_STAGES);
+        }
+        __syncwarp();
+    } else if (warp == WARP_MMA) {
+        if (lane == 0) {
+            MmaState ms;
+            for (int tap = 0; tap < 9; ++tap) gemm_issue(smem_base, bars, p.flag, ms, S0, tap > 0, true, true);
+            umma_commit(&bars->s_full[0]);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3, cq = warp >> 2;
+        const int r = q * 32 + lane;
+        const bool valid = r < ti.valid;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int wf = ti.set == 0 ? p.wf1 : p.wf2, hf = ti.set == 0 ? p.hf1 : p.hf2;
+        const int l = ti.ti * TILE + r;
+        const int y0 = l / wf, x0 = l - y0 * wf;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const bool ok = valid && (unsigned)(y0 + dy) < (unsigned)hf && (unsigned)(x0 + dx) < (unsigned)wf;
+            const int n = ok ? l + dy * wf + dx : 0;
+            const int tile_n = ti.first_tile_of_img + (n >> 7), rn = n & 127;
+            const float a = ok ? p.att[(size_t)tile_n * TILE + rn] : 0.f;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+                float v[32];
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) t = *reinterpret_cast<const float4*>(p.xt + xt_off(tile_n, (c0 >> 2) + jq, rn));
+                    v[jq * 4 + 0] = t.x * a; v[jq * 4 + 1] = t.y * a; v[jq * 4 + 2] = t.z * a; v[jq * 4 + 3] = t.w * a;
+                }
+                if (tap > 0) mbar_wait(&bars->a_free[pass], (tap - 1) & 1, p.flag);
+                store_row32_split(smem + SM_AHI, smem + SM_ALO, r, c0, v);
+                fence_async_smem();
+                mbar_arrive(&bars->a_full[pass]);
+            }
+        }
+        mbar_wait(&bars->s_full[0], 0, p.flag);
+        tc_fence_after();
+        const size_t row = (ti.set == 0 ? (size_t)ti.b * p.g.L1 : (size_t)p.g.B * p.g.L1 + (size_t)ti.b * p.g.L2) + l;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int c0 = pass * 128 + cq * 32;
+            float v[32];
+            tmem_ld32(S0 + lane_addr + c0, v);
+            if (valid) {
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + jq);
+                    *reinterpret_cast<float4*>(p.Y + row * C + c0 + jq * 4) =
+                        make_float4(v[jq * 4] + b4.x, v[jq * 4 + 1] + b4.y, v[jq * 4 + 2] + b4.z, v[jq * 4 + 3] + b4.w);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_PRODUCER) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_decoder: the whole 2-layer query decoder (transformer.py:224-284,361-381) for DEC_R query tokens per CTA.
+// fp32 on the CUDA cores: thread n owns output channel n of every projection; the transposed weights
+// WT[k][n] make the loads coalesced; each weight is read once per CTA and used for DEC_R rows.
+// Rows: [0,B) = image set 1 with query_embed1, [B,2B) = set 2 with query_embed2.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DEC_R = 4;
+struct DecLayerT {
+    const float *sa_wq, *sa_wk, *sa_wv, *sa_wm, *ca_wq, *ca_wm, *w1, *w2;      // transposed [K][N]
+    const float *sa_bq, *sa_bk, *sa_bv, *ca_bq;
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+};
+struct DecParams {
+    DecLayerT layer[N_DEC];
+    const float* qe;            // query_embed1 | query_embed2 (adjacent, [2][256])
+    const float* kvs;           // [N_DEC][2B][KVS] cross-attention summaries of the memory
+    float* hs;                  // out [2B][256]
+    int B;
+};
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// acc[r] = sum_k WT[k][n] * xin[r][k]   (xin in shared memory, row stride K)
+template <int K>
+__device__ __forceinline__ void dec_matvec(const float* __restrict__ WT, int N, int n, const float* xin, float (&acc)[DEC_R]) {
+#pragma unroll
+    for (int r = 0; r < DEC_R; ++r) acc[r] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+        const float w = __ldg(WT + (size_t)k * N + n);
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) acc[r] = fmaf(w, xin[r * K + k], acc[r]);
+    }
+}
+// out[r][:] = LN(in[r][:]) (two-pass variance); warps 0..DEC_R-1, one row each
+__device__ __forceinline__ void dec_ln(const float* in, const float* __restrict__ g, const float* __restrict__ b, float* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < DEC_R) {
+        float v[8], s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = in[warp * C + lane + 32 * i]; s += v[i]; }
+        const float mu = warp_sum_f(s) * (1.f / C);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; sq = fmaf(d, d, sq); }
+        const float rstd = rsqrtf(warp_sum_f(sq) * (1.f / C) + LN_EPS);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[warp * C + lane + 32 * i] = (v[i] - mu) * rstd * g[lane + 32 * i] + b[lane + 32 * i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
+    __shared__ float t[DEC_R * C], u[DEC_R * C], a[DEC_R * C], qv[DEC_R * C], hid[DEC_R * FF];
+    const int n = threadIdx.x, lane = n & 31;
+    const int row0 = blockIdx.x * DEC_R, rows = 2 * p.B;
+    float qe[DEC_R];
+#pragma unroll
+    for (int r = 0; r < DEC_R; ++r) {
+        const int row = min(row0 + r, rows - 1);
+        qe[r] = p.qe[(row >= p.B ? C : 0) + n];
+        t[r * C + n] = 0.f;                                                    // tgt = zeros (transformer.py:361)
+    }
+    __syncthreads();
+    for (int j = 0; j < N_DEC; ++j) {
+        const DecLayerT& w = p.layer[j];
+        float acc[DEC_R], kk[DEC_R], vv[DEC_R];
+        // ---- self-attention over the single query token (transformer.py:236-241, linear_attention.py:22-50)
+        dec_ln(t, w.ln1_g, w.ln1_b, u);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
+        __syncthreads();
+        dec_matvec<C>(w.sa_wq, C, n, a, acc);
+        dec_matvec<C>(w.sa_wk, C, n, a, kk);
+        dec_matvec<C>(w.sa_wv, C, n, u, vv);
+        __syncthreads();                                                       // all reads of a[] done
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) {
+            const float qf = elu1(acc[r] + w.sa_bq[n]), kf = elu1(kk[r] + w.sa_bk[n]);
+            const float sden = warp_sum_f(qf * kf);                           // warp = head
+            a[r * C + n] = (vv[r] + w.sa_bv[n]) * sden / (sden + ATTN_EPS);   // KV = kf v^T, Z = 1/(qf.kf + eps)
+        }
+        __syncthreads();
+        dec_matvec<C>(w.sa_wm, C, n, a, acc);
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
+        __syncthreads();
+        // ---- cross-attention into the memory summaries (transformer.py:243-250)
+        dec_ln(t, w.ln2_g, w.ln2_b, u);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
+        __syncthreads();
+        dec_matvec<C>(w.ca_wq, C, n, a, acc);
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) qv[r * C + n] = elu1(acc[r] + w.ca_bq[n]);
+        __syncthreads();
+        {
+            const int h = n >> 5;
+#pragma unroll
+            for (int r = 0; r < DEC_R; ++r) {
+                const int row = min(row0 + r, rows - 1);
+                const float* kv = p.kvs + ((size_t)j * rows + row) * KVS;
+                const float den = warp_sum_f(qv[r * C + n] * kv[NH * HD * HD + n]);
+                float o = 0.f;
+#pragma unroll 8
+                for (int d = 0; d < HD; ++d) o = fmaf(qv[r * C + h * HD + d], kv[(h * HD + d) * HD + lane], o);
+                a[r * C + n] = o / (den + ATTN_EPS);
+            }
+        }
+        __syncthreads();
+        dec_matvec<C>(w.ca_wm, C, n, a, acc);
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
+        __syncthreads();
+        // ---- feed-forward (transformer.py:252-254)
+        dec_ln(t, w.ln3_g, w.ln3_b, u);
+        __syncthreads();
+        dec_matvec<C>(w.w1, FF, n, u, acc);
+        dec_matvec<C>(w.w1, FF, n + C, u, kk);
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) { hid[r * FF + n] = fmaxf(acc[r], 0.f); hid[r * FF + C + n] = fmaxf(kk[r], 0.f); }
+        __syncthreads();
+        dec_matvec<FF>(w.w2, C, n, hid, acc);
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < DEC_R; ++r)
+        if (row0 + r < rows) p.hs[(size_t)(row0 + r) * C + n] = t[r * C + n];
+}
+
+__global__ void k_transpose(const float* __restrict__ W, int N, int K, float* __restrict__ WT) {   // W[N][K] -> WT[K][N]
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = W[(size_t)(n0 + i) * K + k0 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) WT[(size_t)(k0 + i) * N + n0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // small layout kernels
 // ---------------------------------------------------------------------------------------------------------
@@ -706,12 +1004,14 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
     w.dec_kvs = static_cast<float*>(take((size_t)N_DEC * 2 * B * KVS * sizeof(float)));
     w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
     w.ksum = static_cast<float*>(take((size_t)2 * B * C * sizeof(float)));
+    w.att = static_cast<float*>(take((size_t)g.tiles() * TILE * sizeof(float)));
 }
 
 static bool g_attr_set = false;
 static int set_attrs(char* msg, size_t msg_len) {
     if (g_attr_set) return 0;
     cudaError_t e1 = cudaFuncSetAttribute(k_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (e1 != cudaSuccess) {
         snprintf(msg, msg_len, "cudaFuncSetAttribute(max dynamic smem %u): %s", SM_TOTAL, cudaGetErrorString(e1));
         return -1;
@@ -773,10 +1073,44 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
         k_sum_partials<<<2 * B, 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs + (size_t)2 * B * KVS); lc.n++;
     }
-    k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++;
+    if (X_out) { k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++; }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(msg, msg_len, "tcgen05 encoder launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+
+// query decoder (fp32, one fused kernel) + heat-map 3x3 convolution (tcgen05): hs_out [2B][256], Y [rows][256]
+int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, int B, int hf1,
+                    int wf1, int hf2, int wf2, float* hs_out, float* Y, int* flag, cudaStream_t s, LaunchCounter& lc,
+                    char* msg, size_t msg_len) {
+    if (set_attrs(msg, msg_len)) return -1;
+    const TileGeom g = make_geom(B, hf1 * wf1, hf2 * wf2);
+    DecParams dp{};
+    for (int j = 0; j < N_DEC; ++j) {
+        const DecW& d = L.dec[j];
+        const float* t = tw.dec_t + (size_t)j * DEC_T_FLOATS;
+        DecLayerT& w = dp.layer[j];
+        w.sa_wq = t; w.sa_wk = t + (size_t)1 * C * C; w.sa_wv = t + (size_t)2 * C * C; w.sa_wm = t + (size_t)3 * C * C;
+        w.ca_wq = t + (size_t)4 * C * C; w.ca_wm = t + (size_t)5 * C * C;
+        w.w1 = t + (size_t)6 * C * C; w.w2 = t + (size_t)6 * C * C + (size_t)FF * C;
+        w.sa_bq = d_w + d.sa.bq; w.sa_bk = d_w + d.sa.bk; w.sa_bv = d_w + d.sa.bv; w.ca_bq = d_w + d.ca.bq;
+        w.ln1_g = d_w + d.ln1_g; w.ln1_b = d_w + d.ln1_b; w.ln2_g = d_w + d.ln2_g; w.ln2_b = d_w + d.ln2_b;
+        w.ln3_g = d_w + d.ln3_g; w.ln3_b = d_w + d.ln3_b;
+    }
+    dp.qe = d_w + L.qe1; dp.kvs = ws.dec_kvs; dp.hs = hs_out; dp.B = B;
+    k_decoder<<<(2 * B + DEC_R - 1) / DEC_R, 256, 0, s>>>(dp); lc.n++;
+    k_att<<<g.tiles(), 256, 0, s>>>(ws.xt, g, hs_out, ws.att); lc.n++;
+    ConvParams cp{};
+    cp.g = g; cp.hf1 = hf1; cp.wf1 = wf1; cp.hf2 = hf2; cp.wf2 = wf2; cp.xt = ws.xt; cp.att = ws.att; cp.w = tw.head_img;
+    cp.bias = d_w + L.hm_b0; cp.Y = Y; cp.flag = flag;
+    k_conv<<<g.tiles(), N_THREADS, SM_TOTAL, s>>>(cp); lc.n++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(msg, msg_len, "decoder/head launch: %s", cudaGetErrorString(e));
         return -1;
     }
     return 0;

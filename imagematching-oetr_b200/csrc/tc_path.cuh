@@ -10,6 +10,8 @@ namespace oetr {
 struct TcWeights {
     __half* enc_img = nullptr;     // per encoder layer: the chunk stream the layer kernels consume (see tc_kernels.cu)
     __half* dec_img = nullptr;     // decoder cross-attention k/v projection chunk streams (2 layers)
+    __half* head_img = nullptr;    // heatmap_conv.0: 9 tap GEMM images
+    float* dec_t = nullptr;        // transposed fp32 decoder weights (k_decoder)
     size_t enc_layer_halfs = 0, dec_layer_halfs = 0;
 };
 
@@ -20,6 +22,7 @@ struct TcWorkspace {
     float* dec_kvs = nullptr;      // [2 decoder layers][2B][KVS] cross-attention summaries
     __half* mimg = nullptr;        // [2B images] folded merge weights (hi/lo stage images, 256 KB each)
     float* ksum = nullptr;         // [2B][256] Ksum of every image for the current layer
+    float* att = nullptr;          // [tiles][128] per-token <memory, hs> (head)
 };
 
 // CUDA-event bracket around every launch of the dominant kernel (k_enc with a query phase); read back by bench.py through
@@ -40,12 +43,16 @@ struct KernelProfiler {
 };
 
 void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w);
-int tc_prepare_weights(const float* d_w, const WLayout& L, TcWeights& out, char* msg, size_t msg_len);
+int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, TcWeights& out, char* msg, size_t msg_len);
 void tc_free_weights(TcWeights& w);
 // runs the 8 encoder layers and the decoder's cross-attention K/V summaries; writes token-major memory to X_out
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* d_pe, int max_w,
                float* X_out, int* timeout_flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
+// fused fp32 query decoder -> hs_out [2B][256]; tcgen05 3x3 heat-map convolution (+bias) -> Y [B*L1+B*L2][256]
+int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, int B, int hf1,
+                    int wf1, int hf2, int wf2, float* hs_out, float* Y, int* timeout_flag, cudaStream_t s,
+                    LaunchCounter& lc, char* msg, size_t msg_len);
 int tc_selftest(float* errs_host, int n_errs, char* msg, size_t msg_len);
 
 }  // namespace oetr
