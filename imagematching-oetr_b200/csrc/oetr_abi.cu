@@ -39,6 +39,10 @@ struct oetr_handle {
     TcWeights tc;              // fp16 UMMA operand images (FP16 path only)
     KernelProfiler prof;       // optional CUDA-event brackets around the dominant kernel
     int* d_flag = nullptr;     // raised by a device-side mbarrier wait that timed out (protocol bug guard)
+    // FP16 path: tile-blocked positional rows of the two most recent geometries (regenerated only on change)
+    float* d_post[2] = {nullptr, nullptr};
+    size_t post_cap[2] = {0, 0};
+    int post_hw[2][2] = {{0, 0}, {0, 0}};
     int last_launches = 0;
     // staging owned by the handle for oetr_forward_host only
     float *st_feat1 = nullptr, *st_feat2 = nullptr, *st_boxes = nullptr;
@@ -299,6 +303,7 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
 int oetr_destroy(oetr_handle* h) {
     if (!h) return OETR_OK;
     cudaFree(h->d_w); cudaFree(h->d_w9); cudaFree(h->d_pe); cudaFree(h->d_flag);
+    cudaFree(h->d_post[0]); cudaFree(h->d_post[1]);
     tc_free_weights(h->tc);
     for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
     cudaFree(h->st_feat1); cudaFree(h->st_feat2); cudaFree(h->st_boxes); cudaFree(h->st_ws);
@@ -385,11 +390,10 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
     const int R1 = B * L1, R2 = B * L2;
     const float* W = h->d_w;
 
-    // positional rows for both geometries (PositionEncodingSine.forward slice, models/utils.py:200-205)
-    k_gather_pos<<<(L1 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf1, L1, w.pos); lc.n++;
-    k_gather_pos<<<(L2 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf2, L2, w.pos + (size_t)L1 * C); lc.n++;
-
     if (h->prec == OETR_PREC_FP32) {
+        // positional rows for both geometries (PositionEncodingSine.forward slice, models/utils.py:200-205)
+        k_gather_pos<<<(L1 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf1, L1, w.pos); lc.n++;
+        k_gather_pos<<<(L2 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf2, L2, w.pos + (size_t)L1 * C); lc.n++;
         nchw_to_tokens(feat1, w.X, B, L1, s, lc);
         nchw_to_tokens(feat2, w.X + (size_t)R1 * C, B, L2, s, lc);
         encoder_fp32(h, w, B, L1, L2, s, lc);
@@ -398,7 +402,22 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
         // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
         // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
         char msg[256] = "";
-        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_pe, h->max_w,
+        // positional rows, tile-blocked, cached per geometry (the only state oetr_forward keeps between calls; a
+        // geometry change regenerates it on `s`, growing the buffer with cudaMalloc if needed)
+        const int geo[2][2] = {{hf1, wf1}, {hf2, wf2}};
+        for (int k = 0; k < 2; ++k) {
+            if (h->post_hw[k][0] == geo[k][0] && h->post_hw[k][1] == geo[k][1]) continue;
+            const int Lk = geo[k][0] * geo[k][1];
+            const size_t need = tc_pos_tile_floats(Lk);
+            if (h->post_cap[k] < need) {
+                cudaFree(h->d_post[k]); h->d_post[k] = nullptr; h->post_cap[k] = 0; h->post_hw[k][0] = h->post_hw[k][1] = 0;
+                CU(cudaMalloc(&h->d_post[k], need * sizeof(float)));
+                h->post_cap[k] = need;
+            }
+            tc_pos_tiles(h->d_pe, h->max_w, geo[k][1], Lk, h->d_post[k], s, lc);
+            h->post_hw[k][0] = geo[k][0]; h->post_hw[k][1] = geo[k][1];
+        }
+        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
                        dbg_memory ? w.X : nullptr, h->d_flag, &h->prof, s, lc, msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
         if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, B, hf1, wf1, hf2, wf2, w.dt, w.O, h->d_flag, s, lc, msg,

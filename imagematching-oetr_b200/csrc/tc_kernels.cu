@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
 // WT[k][n] make the loads coalesced; each weight is read once per CTA and used for DEC_R rows.
 // Rows: [0,B) = image set 1 with query_embed1, [B,2B) = set 2 with query_embed2.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int DEC_R = 4;
+constexpr int DEC_R = 2;
 struct DecLayerT {
     const float *sa_wq, *sa_wk, *sa_wv, *sa_wm, *ca_wq, *ca_wm, *w1, *w2;      // transposed [K][N]
     const float *sa_bq, *sa_bk, *sa_bv, *ca_bq;
@@ -824,16 +824,47 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// acc[r] = sum_k WT[k][n] * xin[r][k]   (xin in shared memory, row stride K)
+// acc[r] = sum_k WT[k][col0 + n] * xin[r][k] for this thread's column n = threadIdx.x (256 columns per call).
+// Warp w streams the k-slice [w*K/8, (w+1)*K/8) of all 256 columns with 16-byte loads (two per k and lane, deep
+// unroll: the kernel is bound by how many weight bytes one SM keeps in flight); the 8 partial sums meet in red[].
 template <int K>
-__device__ __forceinline__ void dec_matvec(const float* __restrict__ WT, int N, int n, const float* xin, float (&acc)[DEC_R]) {
+__device__ __forceinline__ void dec_matvec(const float* __restrict__ WT, int N, int col0, const float* xin, float* red,
+                                           float (&acc)[DEC_R]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float part[DEC_R][8];
 #pragma unroll
-    for (int r = 0; r < DEC_R; ++r) acc[r] = 0.f;
+    for (int r = 0; r < DEC_R; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[r][j] = 0.f;
+    const int k0 = warp * (K / 8);
+    const float4* w4 = reinterpret_cast<const float4*>(WT + (size_t)k0 * N + col0) + lane;
 #pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float w = __ldg(WT + (size_t)k * N + n);
+    for (int k = 0; k < K / 8; ++k) {
+        const float4 a = __ldg(w4 + (size_t)k * (N / 4));
+        const float4 b = __ldg(w4 + (size_t)k * (N / 4) + 32);
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) acc[r] = fmaf(w, xin[r * K + k], acc[r]);
+        for (int r = 0; r < DEC_R; ++r) {
+            const float xv = xin[r * K + k0 + k];
+            part[r][0] = fmaf(a.x, xv, part[r][0]); part[r][1] = fmaf(a.y, xv, part[r][1]);
+            part[r][2] = fmaf(a.z, xv, part[r][2]); part[r][3] = fmaf(a.w, xv, part[r][3]);
+            part[r][4] = fmaf(b.x, xv, part[r][4]); part[r][5] = fmaf(b.y, xv, part[r][5]);
+            part[r][6] = fmaf(b.z, xv, part[r][6]); part[r][7] = fmaf(b.w, xv, part[r][7]);
+        }
+    }
+    __syncthreads();                                   // previous users of red[] are done
+#pragma unroll
+    for (int r = 0; r < DEC_R; ++r) {
+        float* o = red + (size_t)(warp * DEC_R + r) * C;
+        *reinterpret_cast<float4*>(o + lane * 4) = make_float4(part[r][0], part[r][1], part[r][2], part[r][3]);
+        *reinterpret_cast<float4*>(o + 128 + lane * 4) = make_float4(part[r][4], part[r][5], part[r][6], part[r][7]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < DEC_R; ++r) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[(size_t)(w * DEC_R + r) * C + threadIdx.x];
+        acc[r] = sum;
     }
 }
 // out[r][:] = LN(in[r][:]) (two-pass variance); warps 0..DEC_R-1, one row each
@@ -854,7 +885,8 @@ __device__ __forceinline__ void dec_ln(const float* in, const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
-    __shared__ float t[DEC_R * C], u[DEC_R * C], a[DEC_R * C], qv[DEC_R * C], hid[DEC_R * FF];
+    __shared__ __align__(16) float t[DEC_R * C], u[DEC_R * C], a[DEC_R * C], qv[DEC_R * C], hid[DEC_R * FF];
+    __shared__ __align__(16) float red[8 * DEC_R * C];
     const int n = threadIdx.x, lane = n & 31;
     const int row0 = blockIdx.x * DEC_R, rows = 2 * p.B;
     float qe[DEC_R];
@@ -874,9 +906,9 @@ __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
         __syncthreads();
-        dec_matvec<C>(w.sa_wq, C, n, a, acc);
-        dec_matvec<C>(w.sa_wk, C, n, a, kk);
-        dec_matvec<C>(w.sa_wv, C, n, u, vv);
+        dec_matvec<C>(w.sa_wq, C, 0, a, red, acc);
+        dec_matvec<C>(w.sa_wk, C, 0, a, red, kk);
+        dec_matvec<C>(w.sa_wv, C, 0, u, red, vv);
         __syncthreads();                                                       // all reads of a[] done
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) {
@@ -885,7 +917,7 @@ __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
             a[r * C + n] = (vv[r] + w.sa_bv[n]) * sden / (sden + ATTN_EPS);   // KV = kf v^T, Z = 1/(qf.kf + eps)
         }
         __syncthreads();
-        dec_matvec<C>(w.sa_wm, C, n, a, acc);
+        dec_matvec<C>(w.sa_wm, C, 0, a, red, acc);
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
         __syncthreads();
@@ -895,7 +927,7 @@ __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
         __syncthreads();
-        dec_matvec<C>(w.ca_wq, C, n, a, acc);
+        dec_matvec<C>(w.ca_wq, C, 0, a, red, acc);
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) qv[r * C + n] = elu1(acc[r] + w.ca_bq[n]);
         __syncthreads();
@@ -913,19 +945,19 @@ __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
             }
         }
         __syncthreads();
-        dec_matvec<C>(w.ca_wm, C, n, a, acc);
+        dec_matvec<C>(w.ca_wm, C, 0, a, red, acc);
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
         __syncthreads();
         // ---- feed-forward (transformer.py:252-254)
         dec_ln(t, w.ln3_g, w.ln3_b, u);
         __syncthreads();
-        dec_matvec<C>(w.w1, FF, n, u, acc);
-        dec_matvec<C>(w.w1, FF, n + C, u, kk);
+        dec_matvec<C>(w.w1, FF, 0, u, red, acc);
+        dec_matvec<C>(w.w1, FF, C, u, red, kk);
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) { hid[r * FF + n] = fmaxf(acc[r], 0.f); hid[r * FF + C + n] = fmaxf(kk[r], 0.f); }
         __syncthreads();
-        dec_matvec<FF>(w.w2, C, n, hid, acc);
+        dec_matvec<FF>(w.w2, C, 0, hid, red, acc);
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
         __syncthreads();
@@ -999,7 +1031,6 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
         return p;
     };
     w.xt = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));
-    w.post = static_cast<float*>(take((size_t)(g.T1 + g.T2) * TILE * C * sizeof(float)));
     w.kv_part = static_cast<float*>(take((size_t)g.tiles() * KVS * sizeof(float)));
     w.dec_kvs = static_cast<float*>(take((size_t)N_DEC * 2 * B * KVS * sizeof(float)));
     w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
@@ -1020,16 +1051,18 @@ static int set_attrs(char* msg, size_t msg_len) {
     return 0;
 }
 
+size_t tc_pos_tile_floats(int L) { return (size_t)((L + TILE - 1) / TILE) * TILE * C; }
+void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cudaStream_t s, LaunchCounter& lc) {
+    k_pos_tiles<<<(L + TILE - 1) / TILE, 256, 0, s>>>(d_pe, max_w, wf, L, post);
+    lc.n++;
+}
+
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
-               const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* d_pe, int max_w,
+               const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
                float* X_out, int* flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len) {
     if (set_attrs(msg, msg_len)) return -1;
     const int L1 = hf1 * wf1, L2 = hf2 * wf2;
     const TileGeom g = make_geom(B, L1, L2);
-    float* post1 = ws.post;
-    float* post2 = ws.post + (size_t)g.T1 * TILE * C;
-    k_pos_tiles<<<g.T1, 256, 0, s>>>(d_pe, max_w, wf1, L1, post1); lc.n++;
-    k_pos_tiles<<<g.T2, 256, 0, s>>>(d_pe, max_w, wf2, L2, post2); lc.n++;
     const int tiles = g.tiles();
     EncParams base{};
     base.g = g; base.feat1 = feat1; base.feat2 = feat2; base.xt = ws.xt; base.post1 = post1; base.post2 = post2;

@@ -17,7 +17,6 @@ struct TcWeights {
 
 struct TcWorkspace {
     float* xt = nullptr;           // tile-blocked fp32 residual stream [tiles][64][128][4]
-    float* post = nullptr;         // tile-blocked positional rows per geometry
     float* kv_part = nullptr;      // per-tile linear-attention partial summaries [tiles][KVS]
     float* dec_kvs = nullptr;      // [2 decoder layers][2B][KVS] cross-attention summaries
     __half* mimg = nullptr;        // [2B images] folded merge weights (hi/lo stage images, 256 KB each)
@@ -46,8 +45,11 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w);
 int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, TcWeights& out, char* msg, size_t msg_len);
 void tc_free_weights(TcWeights& w);
 // runs the 8 encoder layers and the decoder's cross-attention K/V summaries; writes token-major memory to X_out
+// tile-blocked positional rows of one (hf,wf) geometry (cached by the handle, see oetr_abi.cu)
+size_t tc_pos_tile_floats(int L);
+void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cudaStream_t s, LaunchCounter& lc);
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
-               const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* d_pe, int max_w,
+               const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
                float* X_out, int* timeout_flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
 // fused fp32 query decoder -> hs_out [2B][256]; tcgen05 3x3 heat-map convolution (+bias) -> Y [B*L1+B*L2][256]
 int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, int B, int hf1,
