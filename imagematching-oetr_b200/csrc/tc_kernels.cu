@@ -61,7 +61,8 @@ constexpr uint32_t SM_ALO = SM_AHI + IMG_BYTES;                    // operand im
 constexpr uint32_t SM_RING = SM_ALO + IMG_BYTES;                   // 4 x 16 KB weight stages
 constexpr uint32_t SM_ONES = SM_RING + RING * STAGE_BYTES;         // 16 KB slab of fp16 ones (Ksum product)
 constexpr uint32_t SM_KSUM = SM_ONES + SLAB_BYTES;                 // float[256]  Ksum of the source image
-constexpr uint32_t SM_RED = SM_KSUM + 256 * 4;                     // float[2][4][128] LayerNorm partials
+constexpr uint32_t SM_VEC = SM_KSUM + 256 * 4;                     // float[8][256] LN gammas/betas, decoder biases
+constexpr uint32_t SM_RED = SM_VEC + 8 * 256 * 4;                  // float[2][4][128] LayerNorm partials
 constexpr uint32_t SM_BAR = SM_RED + 2 * 4 * 128 * 4;              // mbarriers + tmem pointer
 constexpr uint32_t SM_TOTAL = SM_BAR + 128;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -101,6 +102,21 @@ __device__ __forceinline__ void store_row32_split(uint8_t* img_hi, uint8_t* img_
     const uint32_t j0 = (c0 & 63) >> 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+        uint4 h, l;
+        split8(&v[8 * j], h, l);
+        const uint32_t off = slab + slab_chunk_off(r, j0 + j);
+        *reinterpret_cast<uint4*>(img_hi + off) = h;
+        *reinterpret_cast<uint4*>(img_lo + off) = l;
+    }
+}
+
+// columns [c0, c0+16) (c0 % 16 == 0)
+__device__ __forceinline__ void store_row16_split(uint8_t* img_hi, uint8_t* img_lo, uint32_t r, uint32_t c0,
+                                                  const float (&v)[16]) {
+    const uint32_t slab = (c0 >> 6) * SLAB_BYTES;
+    const uint32_t j0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
         uint4 h, l;
         split8(&v[8 * j], h, l);
         const uint32_t off = slab + slab_chunk_off(r, j0 + j);
@@ -210,7 +226,20 @@ __host__ __device__ __forceinline__ TileInfo tile_info(const TileGeom& g, int t)
 __host__ __device__ __forceinline__ size_t xt_off(int tile, int quad, int r) { return (((size_t)tile * 64 + quad) * TILE + r) * 4; }
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __expf(x); }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// nn.GELU (erf form, transformer.py:93).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), branch-free:
+// ~15 instructions instead of erff's divergent ~35; the result error (<= 2e-7 |x|) is far inside the parity budget.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float erf_abs = fmaf(-poly, __expf(-z * z), 1.f);
+    const float hx = 0.5f * x;
+    return fmaf(hx, copysignf(erf_abs, x), hx);
+}
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -402,6 +431,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float* red = reinterpret_cast<float*>(smem + SM_RED);
         float* ksum_s = reinterpret_cast<float*>(smem + SM_KSUM);
+        float* vec = reinterpret_cast<float*>(smem + SM_VEC);   // [0]lnq_g [1]lnq_b [2]ln2_g [3]ln2_b [4]lnkv_g [5]lnkv_b [6]bk [7]bv
         uint8_t* img_hi = smem + SM_AHI;
         uint8_t* img_lo = smem + SM_ALO;
         const float* post = (ti.set == 0 ? p.post1 : p.post2);
@@ -415,8 +445,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             fence_async_smem();
             mbar_arrive(&bars->a_full[pass]);
         };
-        // one-time staging: Ksum of the source image, the ones slab
-        if (p.do_q && tid < 256) ksum_s[tid] = p.ksum[(size_t)src_img * C + tid];
+        // one-time staging: per-channel vectors, Ksum of the source image, the ones slab
+        if (tid < 256) {
+            if (p.do_q) {
+                ksum_s[tid] = p.ksum[(size_t)src_img * C + tid];
+                vec[0 * 256 + tid] = p.lnq_g[tid]; vec[1 * 256 + tid] = p.lnq_b[tid];
+                vec[2 * 256 + tid] = p.ln2_g[tid]; vec[3 * 256 + tid] = p.ln2_b[tid];
+            }
+            if (p.do_kv) {
+                vec[4 * 256 + tid] = dec_mode ? 1.f : p.lnkv_g[tid];
+                vec[5 * 256 + tid] = dec_mode ? 0.f : p.lnkv_b[tid];
+                vec[6 * 256 + tid] = p.bk ? p.bk[tid] : 0.f;
+                vec[7 * 256 + tid] = p.bv ? p.bv[tid] : 0.f;
+            }
+        }
         if (p.do_kv) {
             const __half2 one2 = __floats2half2_rn(1.f, 1.f);
             uint4 ones;
@@ -442,17 +484,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 }
             }
         }
-        auto store_x = [&]() {
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq)
-                    *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r)) =
-                        make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
-            }
-        };
-        named_bar_sync(1, N_ROW_THREADS);                  // ksum_s / ones visible to all row warps
+        named_bar_sync(1, N_ROW_THREADS);                  // staged vectors / ones visible to all row warps
 
         // two-pass LayerNorm statistics of the row (4 threads per row, combined through shared memory)
         auto ln_stats = [&](float& mean, float& rstd) {
@@ -476,10 +508,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                                red[(1 * 4 + 3) * TILE + r]) * (1.f / C);
             rstd = rsqrtf(var + LN_EPS);
         };
-        // operand image <- [LN](x) [+ pos], both column passes
-        auto image_from_x = [&](const float* gamma, const float* beta, bool with_pos) {
+        // operand image <- [LN](x) [+ pos], both column passes.  gb: index of (gamma, beta) in vec, < 0: no LN
+        auto image_from_x = [&](int gb, bool with_pos) {
             float mean = 0.f, rstd = 1.f;
-            if (gamma) ln_stats(mean, rstd);
+            if (gb >= 0) ln_stats(mean, rstd);
+            const float* gam = vec + (gb >= 0 ? gb : 4) * 256;     // dec mode stages gamma = 1, beta = 0 in slot 4/5
+            const float shift = gb >= 0 ? -mean * rstd : 0.f;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32;
@@ -488,18 +522,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 for (int jq = 0; jq < 8; ++jq) {
                     float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(ti.ti, (c0 >> 2) + jq, r));
-                    const float pp[4] = {ps.x, ps.y, ps.z, ps.w};
-                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gamma) {
-                        g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + jq);
-                        b4 = __ldg(reinterpret_cast<const float4*>(beta + c0) + jq);
-                    }
-                    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float xv = x[pass][jq * 4 + e];
-                        v[jq * 4 + e] = (gamma ? (xv - mean) * rstd * gg[e] + bb[e] : xv) + pp[e];
-                    }
+                    const float4 g4 = *reinterpret_cast<const float4*>(gam + c0 + jq * 4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(gam + 256 + c0 + jq * 4);
+                    // (x - mean) * rstd * g + b + pos  ==  fma(fma(x, rstd, shift), g, b + pos)
+                    v[jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), g4.x, b4.x + ps.x);
+                    v[jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), g4.y, b4.y + ps.y);
+                    v[jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), g4.z, b4.z + ps.z);
+                    v[jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), g4.w, b4.w + ps.w);
                 }
                 store_row32_split(img_hi, img_lo, r, c0, v);
                 publish(pass);
@@ -508,18 +537,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 
         if (p.do_q) {
             // (E0) A = LNq(x) + pos
-            image_from_x(p.lnq_g, p.lnq_b, true);
+            image_from_x(0, true);
             // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
             wait_s(0);
             const float eps_s = ATTN_EPS / (float)src_len;    // summaries arrive scaled by 1/S (k_fold)
-#pragma unroll
+#pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32;      // one head per 32-column chunk
                 float v[32];
                 tmem_ld32(S0 + lane_addr + c0, v);
                 float den = 0.f;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) { v[e] = elu1(v[e]); den = fmaf(v[e], ksum_s[c0 + e], den); }
+                for (int e4 = 0; e4 < 8; ++e4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(ksum_s + c0 + e4 * 4);
+                    v[e4 * 4 + 0] = elu1(v[e4 * 4 + 0]); den = fmaf(v[e4 * 4 + 0], k4.x, den);
+                    v[e4 * 4 + 1] = elu1(v[e4 * 4 + 1]); den = fmaf(v[e4 * 4 + 1], k4.y, den);
+                    v[e4 * 4 + 2] = elu1(v[e4 * 4 + 2]); den = fmaf(v[e4 * 4 + 2], k4.z, den);
+                    v[e4 * 4 + 3] = elu1(v[e4 * 4 + 3]); den = fmaf(v[e4 * 4 + 3], k4.w, den);
+                }
                 const float inv = 1.f / (den + eps_s);
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] *= inv;
@@ -535,31 +570,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
             }
-            image_from_x(p.ln2_g, p.ln2_b, false);
-            // (E3) A = gelu(h_a)   (needs h_a in S0, and h_b complete: the LN2 image is then free)
-            wait_s(0);
-            wait_s(1);
+            image_from_x(2, false);
+            // (E3) A = gelu(h_a): needs h_a (S0) and, for the image to be free, h_b complete (S1)
+            // (E4) A = gelu(h_b): the image is free once y = gelu(h_a) W2a^T has completed (S0 commit)
+#pragma unroll 1
+            for (int which = 0; which < 2; ++which) {
+                if (which == 0) { wait_s(0); wait_s(1); }
+                const uint32_t S = which ? S1 : S0;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int c0 = pass * 128 + cq * 32;
+                    float v[32];
+                    tmem_ld32(S + lane_addr + c0, v);
+                    // the GEMM that consumes pass 0 overwrites ALL of S0 (h_a): release pass 0 only once this
+                    // thread has also read its pass-1 columns
+                    if (pass == 1) publish(0);
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-                float v[32];
-                tmem_ld32(S0 + lane_addr + c0, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
-                store_row32_split(img_hi, img_lo, r, c0, v);
-                publish(pass);
-            }
-            // (E4) A = gelu(h_b)   (the image is free once y = gelu(h_a) W2a^T has completed)
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-                float v[32];
-                tmem_ld32(S1 + lane_addr + c0, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
-                if (pass == 0) wait_s(0);
-                store_row32_split(img_hi, img_lo, r, c0, v);
-                publish(pass);
+                    for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
+                    if (which == 1 && pass == 0) wait_s(0);
+                    store_row32_split(img_hi, img_lo, r, c0, v);
+                }
+                publish(1);
             }
             // (E5) x += y
             wait_s(0);
@@ -572,31 +603,40 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             }
             tc_fence_before();
         }
-        if (p.store_x) store_x();
+        if (p.store_x) {
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq)
+                    *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r)) =
+                        make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
+            }
+        }
         if (p.do_kv) {
             if (!dec_mode) {
-                image_from_x(p.lnkv_g, p.lnkv_b, true);        // k and v share LN_kv(x)+pos (transformer.py:119-126)
+                image_from_x(4, true);                         // k and v share LN_kv(x)+pos (transformer.py:119-126)
                 wait_s(0);
                 wait_s(1);
             } else {
-                image_from_x(nullptr, nullptr, false);         // v = x Wv^T + bv      (transformer.py:243-249)
+                image_from_x(-1, false);                       // v = x Wv^T + bv      (transformer.py:243-249)
                 wait_s(0);
-                image_from_x(nullptr, nullptr, true);          // k = (x+pos) Wk^T + bk
+                image_from_x(-1, true);                        // k = (x+pos) Wk^T + bk
                 wait_s(1);
             }
             // half images (tokens = K dimension): V and Kf = elu(k)+1; padded rows are zero
-#pragma unroll
+#pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32, ch = cq * 32;      // ch: column inside the 128-channel half
                 float v[32];
                 tmem_ld32(S0 + lane_addr + c0, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = valid ? v[e] + (p.bv ? __ldg(p.bv + c0 + e) : 0.f) : 0.f;
+                for (int e = 0; e < 32; ++e) v[e] = valid ? v[e] + vec[7 * 256 + c0 + e] : 0.f;
                 if (pass == 1) wait_s(0);                               // KV of half 0 has consumed the images
                 store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
                 tmem_ld32(S1 + lane_addr + c0, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e] + (p.bk ? __ldg(p.bk + c0 + e) : 0.f)) : 0.f;
+                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e] + vec[6 * 256 + c0 + e]) : 0.f;
                 store_row32_split(img_hi + KF_OFF, img_lo + KF_OFF, r, ch, v);
                 publish(pass);
             }
