@@ -29,6 +29,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace oetr {
@@ -66,6 +67,7 @@ constexpr uint32_t SM_RED = SM_VEC + 8 * 256 * 4;                  // float[2][4
 constexpr uint32_t SM_BAR = SM_RED + 2 * 4 * 128 * 4;              // mbarriers + tmem pointer
 constexpr uint32_t SM_TOTAL = SM_BAR + 128;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(uint64_t) * (2 * RING + 6) + 8 <= 128, "Bars must fit its reservation");
 // the kv phase re-uses the operand image space for the MN-major half images (tokens = K dimension)
 constexpr uint32_t KF_OFF = 0;                                     // Kf half image: 2 slabs (32 KB) inside hi / lo
 constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
@@ -271,9 +273,11 @@ __device__ __forceinline__ void ring_stream(uint8_t* smem, Bars* bars, int* flag
         bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, STAGE_BYTES, &bars->full[st]);
     }
 }
-struct MmaState { uint32_t g = 0, na0 = 0, na1 = 0; };
+struct MmaState { uint32_t g = 0, na0 = 0, na1 = 0; long long t_a = 0, t_ring = 0; };   // t_*: cycles spent waiting (profiling aid)
 __device__ __forceinline__ void mma_wait_a(Bars* bars, int* flag, MmaState& ms, int pass) {
+    const long long t0 = clock64();
     mbar_wait(&bars->a_full[pass], (pass ? ms.na1++ : ms.na0++) & 1, flag);
+    ms.t_a += clock64() - t0;
     tc_fence_after();
 }
 // D[128 x 256] (tmem columns d..d+255) (+)= A[128 x 256] . W^T with the 3-term split; consumes 16 ring stages.
@@ -288,8 +292,10 @@ __device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* 
         const uint32_t a_lo = smem_base + SM_ALO + ks * SLAB_BYTES;
         {   // w_hi: two adjacent stages form the [256 x 64] B tile
             const int st = ms.g % RING;
+            const long long t0 = clock64();
             mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
             mbar_wait(&bars->full[st + 1], (ms.g / RING) & 1, flag);
+            ms.t_ring += clock64() - t0;
             tc_fence_after();
             const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
 #pragma unroll
@@ -306,8 +312,10 @@ __device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* 
         }
         {   // w_lo
             const int st = ms.g % RING;
+            const long long t0 = clock64();
             mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
             mbar_wait(&bars->full[st + 1], (ms.g / RING) & 1, flag);
+            ms.t_ring += clock64() - t0;
             tc_fence_after();
             const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
 #pragma unroll
@@ -345,6 +353,7 @@ struct EncParams {
     const __half* w_kv;         // Wv | Wk                    (32 stages)
     float* kv_part;             // [tiles][KVS] per-tile partial summaries
     int* flag;
+    long long* dbg_clock;       // nullable: per CTA {total, MMA wait on operand image, MMA wait on weights, 0} cycles
 };
 
 __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
@@ -378,6 +387,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         // ------------------------------------------------------------------ MMA issue
         if (lane == 0) {
             MmaState ms;
+            const long long t_begin = clock64();
             auto wait_a = [&](int pass) { mma_wait_a(bars, p.flag, ms, pass); };
             auto gemm = [&](uint32_t d, bool accumulate, bool wait) { gemm_issue(smem_base, bars, p.flag, ms, d, accumulate, wait, false); };
             if (p.do_q) {
@@ -420,6 +430,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                                  umma_desc(ones + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KSUM, 1u);
                     umma_commit(&bars->s_full[half]);
                 }
+            }
+            if (p.dbg_clock) {
+                long long* o = p.dbg_clock + (size_t)blockIdx.x * 4;
+                o[0] = clock64() - t_begin; o[1] = ms.t_a; o[2] = ms.t_ring; o[3] = 0;
             }
         }
         __syncwarp();
@@ -1104,6 +1118,14 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
     const int L1 = hf1 * wf1, L2 = hf2 * wf2;
     const TileGeom g = make_geom(B, L1, L2);
     const int tiles = g.tiles();
+    // OETR_TIMING=1: print where the MMA thread of encoder layer 4 waits (debugging aid; synchronises)
+    static long long* dbg_clock_buf = nullptr;
+    static int dbg_clock_tiles = 0;
+    long long* dbg_clock = nullptr;
+    if (getenv("OETR_TIMING")) {
+        if (dbg_clock_tiles < tiles) { cudaFree(dbg_clock_buf); cudaMalloc(&dbg_clock_buf, (size_t)tiles * 4 * sizeof(long long)); dbg_clock_tiles = tiles; }
+        dbg_clock = dbg_clock_buf;
+    }
     EncParams base{};
     base.g = g; base.feat1 = feat1; base.feat2 = feat2; base.xt = ws.xt; base.post1 = post1; base.post2 = post2;
     base.mimg = ws.mimg; base.ksum = ws.ksum; base.kv_part = ws.kv_part; base.flag = flag;
@@ -1133,6 +1155,7 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         p.lnq_g = d_w + e.lnq_g; p.lnq_b = d_w + e.lnq_b; p.ln2_g = d_w + e.ln2_g; p.ln2_b = d_w + e.ln2_b;
         p.w_q = img; p.w_mlp = img + GEMM_HALFS;
         if (i + 1 < N_ENC) set_kv_enc(p, i + 1); else set_kv_dec(p, 0);
+        if (i == 4 && dbg_clock) p.dbg_clock = dbg_clock;
         if (prof) prof->mark(s);
         k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
         if (prof) prof->mark(s);
@@ -1147,6 +1170,15 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         k_sum_partials<<<2 * B, 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs + (size_t)2 * B * KVS); lc.n++;
     }
     if (X_out) { k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++; }
+    if (dbg_clock) {
+        std::vector<long long> hbuf((size_t)tiles * 4);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hbuf.data(), dbg_clock, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double sum[3] = {0, 0, 0};
+        for (int t = 0; t < tiles; ++t) for (int k = 0; k < 3; ++k) sum[k] += (double)hbuf[(size_t)t * 4 + k];
+        fprintf(stderr, "[oetr timing] layer 4, %d tiles: MMA thread total %.0f cycles, waiting on operand image %.0f, on weights %.0f (means)\n",
+                tiles, sum[0] / tiles, sum[1] / tiles, sum[2] / tiles);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(msg, msg_len, "tcgen05 encoder launch: %s", cudaGetErrorString(e));
