@@ -420,31 +420,32 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
         if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
                        dbg_memory ? w.X : nullptr, h->d_flag, &h->prof, s, lc, msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
-        if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, B, hf1, wf1, hf2, wf2, w.dt, w.O, h->d_flag, s, lc, msg,
-                            sizeof(msg)) != 0)
+        const HeadGeom hg{B, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp};
+        if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, hg, w.dt, w.O, boxes1, boxes2, dbg_cxy, dbg_tlbr, h->d_flag, s, lc,
+                            msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
     }
     // memory = encoder output (w.X), hs = decoder output (w.dt)
     if (dbg_memory) cudaMemcpyAsync(dbg_memory, w.X, (size_t)(R1 + R2) * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (dbg_hs) cudaMemcpyAsync(dbg_hs, w.dt, (size_t)2 * B * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
 
-    // head: heat = memory * <memory, hs>; conv3x3 (+bias) -> Y ; then the row-wise tail per image
-    float *G = w.T, *Gs = w.Q, *Y = w.O;
     if (h->prec == OETR_PREC_FP32) {
+        // head: heat = memory * <memory, hs>; conv3x3 (+bias) -> Y ; then the row-wise tail per image
+        float *G = w.T, *Gs = w.Q, *Y = w.O;
         heat_scale(w.X, w.dt, G, R1, L1, s, lc);
         heat_scale(w.X + (size_t)R1 * C, w.dt + (size_t)B * C, G + (size_t)R1 * C, R2, L2, s, lc);
         head_conv_fp32(h, w, B, hf1, wf1, hf2, wf2, G, Gs, Y, s, lc);
+        HeadParams p{};
+        p.gn_g = W + h->L.hm_gn_g; p.gn_b = W + h->L.hm_gn_b; p.w3 = W + h->L.hm_w3; p.b3 = W + h->L.hm_b3;
+        p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;
+        p.batch = B; p.clamp = clamp;
+        p.Y = Y; p.hs = w.dt; p.hf = hf1; p.wf = wf1; p.img_h = img_h1; p.img_w = img_w1;
+        p.boxes = boxes1; p.dbg_cxy = dbg_cxy; p.dbg_tlbr = dbg_tlbr;
+        head_finalize(p, s, lc);
+        p.Y = Y + (size_t)R1 * C; p.hs = w.dt + (size_t)B * C; p.hf = hf2; p.wf = wf2; p.img_h = img_h2; p.img_w = img_w2;
+        p.boxes = boxes2; p.dbg_cxy = dbg_cxy ? dbg_cxy + 2 * B : nullptr; p.dbg_tlbr = dbg_tlbr ? dbg_tlbr + 4 * B : nullptr;
+        head_finalize(p, s, lc);
     }
-    HeadParams p{};
-    p.gn_g = W + h->L.hm_gn_g; p.gn_b = W + h->L.hm_gn_b; p.w3 = W + h->L.hm_w3; p.b3 = W + h->L.hm_b3;
-    p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;
-    p.batch = B; p.clamp = clamp;
-    p.Y = Y; p.hs = w.dt; p.hf = hf1; p.wf = wf1; p.img_h = img_h1; p.img_w = img_w1;
-    p.boxes = boxes1; p.dbg_cxy = dbg_cxy; p.dbg_tlbr = dbg_tlbr;
-    head_finalize(p, s, lc);
-    p.Y = Y + (size_t)R1 * C; p.hs = w.dt + (size_t)B * C; p.hf = hf2; p.wf = wf2; p.img_h = img_h2; p.img_w = img_w2;
-    p.boxes = boxes2; p.dbg_cxy = dbg_cxy ? dbg_cxy + 2 * B : nullptr; p.dbg_tlbr = dbg_tlbr ? dbg_tlbr + 4 * B : nullptr;
-    head_finalize(p, s, lc);
 
     h->last_launches = lc.n;
     cudaError_t e = cudaGetLastError();

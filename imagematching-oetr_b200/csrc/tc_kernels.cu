@@ -162,7 +162,7 @@ int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, Tc
     if (cudaMalloc(&out.enc_img, N_ENC * ENC_LAYER_HALFS * sizeof(__half)) != cudaSuccess ||
         cudaMalloc(&out.dec_img, N_DEC * DEC_LAYER_HALFS * sizeof(__half)) != cudaSuccess ||
         cudaMalloc(&out.head_img, 9 * GEMM_HALFS * sizeof(__half)) != cudaSuccess ||
-        cudaMalloc(&out.dec_t, N_DEC * DEC_T_FLOATS * sizeof(float)) != cudaSuccess) {
+        cudaMalloc(&out.dec_t, (N_DEC * DEC_T_FLOATS + (size_t)C * C) * sizeof(float)) != cudaSuccess) {
         snprintf(msg, msg_len, "weight image allocation failed");
         return -1;
     }
@@ -189,6 +189,7 @@ int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, Tc
         k_transpose<<<dim3(FF / 32, C / 32), dim3(32, 8)>>>(d_w + d.w1, FF, C, t + (size_t)6 * C * C);
         k_transpose<<<dim3(C / 32, FF / 32), dim3(32, 8)>>>(d_w + d.w2, C, FF, t + (size_t)6 * C * C + (size_t)FF * C);
     }
+    k_transpose<<<dim3(C / 32, C / 32), dim3(32, 8)>>>(d_w + L.tl_w0, C, C, out.dec_t + N_DEC * DEC_T_FLOATS);
     for (int tap = 0; tap < 9; ++tap) make_gemm_image(d_w9 + (size_t)tap * C * C, C, 0, 0, out.head_img + (size_t)tap * GEMM_HALFS);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, TileGeom g, const float* __restrict__ Wm,
                                               __half* __restrict__ mimg, float* __restrict__ ksum) {
-    __shared__ float kv[HD][HD + 1];
+    __shared__ __align__(16) float kv[HD][HD];
     const int img = blockIdx.x >> 3, h = blockIdx.x & 7;
     const int set = img / g.B, b = img % g.B;
     const int T = set == 0 ? g.T1 : g.T2;
@@ -695,17 +696,20 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
     // both summaries are scaled by 1/S (S = source length) like the reference's v / v_length
     // (linear_attention.py:43-48): keeps phi(q)/Z and M_img inside fp16 range for any S; k_enc scales eps alike
     const float inv_s = 1.f / (float)(set == 0 ? g.L1 : g.L2);
-    for (int i = threadIdx.x; i < HD * HD; i += 256) {
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc += src[(size_t)t * KVS + h * HD * HD + i];
-        kv[i >> 5][i & 31] = acc * inv_s;
+    {
+        const int i = threadIdx.x * 4;                      // 4 consecutive elements of KV_h per thread
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < T; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t * KVS + h * HD * HD + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(&kv[0][0] + i) = make_float4(acc.x * inv_s, acc.y * inv_s, acc.z * inv_s, acc.w * inv_s);
     }
     if (threadIdx.x < HD) {
         float acc = 0.f;
         for (int t = 0; t < T; ++t) acc += src[(size_t)t * KVS + NH * HD * HD + h * HD + threadIdx.x];
         ksum[(size_t)img * C + h * HD + threadIdx.x] = acc * inv_s;
     }
-    __syncthreads();
     const int n = threadIdx.x;                         // output channel of merge
     float w[HD], out[HD];
     const float4* wr = reinterpret_cast<const float4*>(Wm + (size_t)n * C + h * HD);
@@ -714,11 +718,16 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
         const float4 t = __ldg(wr + e4);
         w[e4 * 4] = t.x; w[e4 * 4 + 1] = t.y; w[e4 * 4 + 2] = t.z; w[e4 * 4 + 3] = t.w;
     }
+    __syncthreads();
 #pragma unroll
     for (int d = 0; d < HD; ++d) {
         float acc = 0.f;
 #pragma unroll
-        for (int e = 0; e < HD; ++e) acc = fmaf(w[e], kv[d][e], acc);
+        for (int e4 = 0; e4 < HD / 4; ++e4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(&kv[d][e4 * 4]);     // warp-wide broadcast
+            acc = fmaf(w[e4 * 4], k4.x, acc); acc = fmaf(w[e4 * 4 + 1], k4.y, acc);
+            acc = fmaf(w[e4 * 4 + 2], k4.z, acc); acc = fmaf(w[e4 * 4 + 3], k4.w, acc);
+        }
         out[d] = acc;
     }
     // K index = h*32 + d: k-slab h/2, columns (h&1)*32 .. +32 of row n
@@ -733,7 +742,6 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
         *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 1, nh)) + off) = lo;
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------
 // k_att: att[l] = <memory[l,:], hs[img,:]> per token (src/model.py:147-149), tile-blocked like xt; 0 on padding
@@ -774,6 +782,7 @@ struct ConvParams {
     const __half* w;            // 9 tap GEMM images
     const float* bias;          // heatmap_conv.0.bias
     float* Y;                   // token-major [B*L1 + B*L2][256]
+    float* gstat;               // [tiles][32 groups][2]: per-tile GroupNorm partials (mean, M2) over the valid rows
     int* flag;
 };
 
@@ -831,26 +840,182 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
         }
         mbar_wait(&bars->s_full[0], 0, p.flag);
         tc_fence_after();
+        float* red = reinterpret_cast<float*>(smem + SM_RED);         // [4 row quarters][32 groups]
         const size_t row = (ti.set == 0 ? (size_t)ti.b * p.g.L1 : (size_t)p.g.B * p.g.L1 + (size_t)ti.b * p.g.L2) + l;
+        float y[2][32];
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
             const int c0 = pass * 128 + cq * 32;
-            float v[32];
-            tmem_ld32(S0 + lane_addr + c0, v);
-            if (valid) {
+            tmem_ld32(S0 + lane_addr + c0, y[pass]);
 #pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + jq);
+            for (int jq = 0; jq < 8; ++jq) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + jq);
+                y[pass][jq * 4 + 0] += b4.x; y[pass][jq * 4 + 1] += b4.y; y[pass][jq * 4 + 2] += b4.z; y[pass][jq * 4 + 3] += b4.w;
+                if (valid)
                     *reinterpret_cast<float4*>(p.Y + row * C + c0 + jq * 4) =
-                        make_float4(v[jq * 4] + b4.x, v[jq * 4 + 1] + b4.y, v[jq * 4 + 2] + b4.z, v[jq * 4 + 3] + b4.w);
-                }
+                        make_float4(y[pass][jq * 4], y[pass][jq * 4 + 1], y[pass][jq * 4 + 2], y[pass][jq * 4 + 3]);
             }
         }
         tc_fence_before();
+        // GroupNorm partials of this tile (32 groups of 8 channels, src/model.py:71): exact two-pass (mean, M2) over the
+        // valid rows; k_logits merges the tiles of an image with Chan's update.  Thread: groups pass*16 + cq*4 + {0..3}
+        const float inv_n = 1.f / (8.f * (float)ti.valid);
+        float mean_t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int pass = i >> 2, g4 = i & 3;
+            float sgrp = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sgrp += y[pass][g4 * 8 + e];
+            sgrp = valid ? sgrp : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sgrp += __shfl_xor_sync(0xffffffffu, sgrp, o);
+            if (lane == 0) red[q * 32 + pass * 16 + cq * 4 + g4] = sgrp;
+        }
+        named_bar_sync(1, N_ROW_THREADS);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int gi = (i >> 2) * 16 + cq * 4 + (i & 3);
+            mean_t[i] = (red[gi] + red[32 + gi] + red[64 + gi] + red[96 + gi]) * inv_n;
+        }
+        named_bar_sync(1, N_ROW_THREADS);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int pass = i >> 2, g4 = i & 3;
+            float m2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = y[pass][g4 * 8 + e] - mean_t[i]; m2 = fmaf(d, d, m2); }
+            m2 = valid ? m2 : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+            if (lane == 0) red[q * 32 + pass * 16 + cq * 4 + g4] = m2;
+        }
+        named_bar_sync(1, N_ROW_THREADS);
+        if (q == 0 && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int gi = (i >> 2) * 16 + cq * 4 + (i & 3);
+                float* o = p.gstat + ((size_t)blockIdx.x * 32 + gi) * 2;
+                o[0] = mean_t[i];
+                o[1] = red[gi] + red[32 + gi] + red[64 + gi] + red[96 + gi];
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == WARP_PRODUCER) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_logits: GroupNorm (image statistics merged from the tile partials) -> ReLU -> 1x1 conv (src/model.py:71-76);
+// one CTA per tile, one warp per token.  z is tile-blocked: token l of an image sits at z[first_tile*128 + l].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_logits(const float* __restrict__ Y, const float* __restrict__ gstat, TileGeom g,
+                                                const float* __restrict__ gn_g, const float* __restrict__ gn_b,
+                                                const float* __restrict__ w3, const float* __restrict__ b3,
+                                                float* __restrict__ z) {
+    __shared__ float gm[32], gr[32];
+    __shared__ __align__(16) float sc[C], sh[C], w3s[C];
+    const TileInfo ti = tile_info(g, blockIdx.x);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < 32) {
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        for (int t = 0; t < ti.T; ++t) {                                   // Chan et al. pairwise update, fixed order
+            const float nb = 8.f * (float)min(TILE, ti.L - t * TILE);
+            const float* st = gstat + ((size_t)(ti.first_tile_of_img + t) * 32 + tid) * 2;
+            const float delta = st[0] - mean, ntot = n + nb;
+            mean += delta * nb / ntot;
+            m2 += st[1] + delta * delta * n * nb / ntot;
+            n = ntot;
+        }
+        gm[tid] = mean;
+        gr[tid] = rsqrtf(m2 / n + GN_EPS);
+    }
+    __syncthreads();
+    {
+        const float rs = gr[tid >> 3] * gn_g[tid];
+        sc[tid] = rs; sh[tid] = gn_b[tid] - gm[tid >> 3] * rs; w3s[tid] = w3[tid];
+    }
+    __syncthreads();
+    const float bias = b3[0];
+    const size_t row0 = (ti.set == 0 ? (size_t)ti.b * g.L1 : (size_t)g.B * g.L1 + (size_t)ti.b * g.L2) + (size_t)ti.ti * TILE;
+    float4 s0 = reinterpret_cast<const float4*>(sc)[lane], s1 = reinterpret_cast<const float4*>(sc)[lane + 32];
+    float4 h0 = reinterpret_cast<const float4*>(sh)[lane], h1 = reinterpret_cast<const float4*>(sh)[lane + 32];
+    float4 w0 = reinterpret_cast<const float4*>(w3s)[lane], w1 = reinterpret_cast<const float4*>(w3s)[lane + 32];
+#pragma unroll 4
+    for (int r = w; r < ti.valid; r += 8) {
+        const float4 a = reinterpret_cast<const float4*>(Y + (row0 + r) * C)[lane];
+        const float4 b = reinterpret_cast<const float4*>(Y + (row0 + r) * C)[lane + 32];
+        float acc = w0.x * fmaxf(fmaf(a.x, s0.x, h0.x), 0.f);
+        acc = fmaf(w0.y, fmaxf(fmaf(a.y, s0.y, h0.y), 0.f), acc);
+        acc = fmaf(w0.z, fmaxf(fmaf(a.z, s0.z, h0.z), 0.f), acc);
+        acc = fmaf(w0.w, fmaxf(fmaf(a.w, s0.w, h0.w), 0.f), acc);
+        acc = fmaf(w1.x, fmaxf(fmaf(b.x, s1.x, h1.x), 0.f), acc);
+        acc = fmaf(w1.y, fmaxf(fmaf(b.y, s1.y, h1.y), 0.f), acc);
+        acc = fmaf(w1.z, fmaxf(fmaf(b.z, s1.z, h1.z), 0.f), acc);
+        acc = fmaf(w1.w, fmaxf(fmaf(b.w, s1.w, h1.w), 0.f), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) z[(size_t)blockIdx.x * TILE + r] = acc + bias;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_box: softmax over the tokens + soft-argmax on the (x+0.5, y+0.5)*stride grid, stride = img_h / hf for both
+// axes (src/model.py:173-184), box assembly from (cx,cy) and tlbr (models/utils.py:16-28 / model.py:193-211)
+// ---------------------------------------------------------------------------------------------------------
+struct BoxParams {
+    TileGeom g;
+    int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
+    const float* z;             // tile-blocked logits
+    const float* tlbr;          // [2B][4] sigmoid(top,left,bottom,right) from k_decoder
+    float *boxes1, *boxes2, *dbg_cxy, *dbg_tlbr;
+};
+__global__ void __launch_bounds__(256) k_box(const BoxParams p) {
+    __shared__ float red[8];
+    const int img = blockIdx.x, set = img / p.g.B, b = img % p.g.B;
+    const int L = set == 0 ? p.g.L1 : p.g.L2, wf = set == 0 ? p.wf1 : p.wf2, hf = set == 0 ? p.hf1 : p.hf2;
+    const int img_h = set == 0 ? p.img_h1 : p.img_h2, img_w = set == 0 ? p.img_w1 : p.img_w2;
+    const int first = set == 0 ? b * p.g.T1 : p.g.B * p.g.T1 + b * p.g.T2;
+    const float* z = p.z + (size_t)first * TILE;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    auto block_reduce = [&](float v, bool is_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, t) : v + t; }
+        __syncthreads();
+        if (lane == 0) red[w] = v;
+        __syncthreads();
+        float r = red[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+        return r;
+    };
+    float mx = -INFINITY;
+    for (int l = tid; l < L; l += 256) mx = fmaxf(mx, z[l]);
+    mx = block_reduce(mx, true);
+    const float stride = (float)(img_h / hf);
+    float se = 0.f, sx = 0.f, sy = 0.f;
+    for (int l = tid; l < L; l += 256) {
+        const float e = expf(z[l] - mx);
+        se += e;
+        sx = fmaf(e, ((float)(l % wf) + 0.5f) * stride, sx);
+        sy = fmaf(e, ((float)(l / wf) + 0.5f) * stride, sy);
+    }
+    se = block_reduce(se, false); sx = block_reduce(sx, false); sy = block_reduce(sy, false);
+    if (tid == 0) {
+        const float cx = sx / se, cy = sy / se;
+        const float* tl = p.tlbr + (size_t)img * 4;
+        const float W_ = (float)img_w, H_ = (float)img_h;
+        float x1 = cx - tl[1] * W_, y1 = cy - tl[0] * H_, x2 = cx + tl[3] * W_, y2 = cy + tl[2] * H_;
+        if (p.clamp) {
+            x1 = fminf(fmaxf(x1, 0.f), W_); x2 = fminf(fmaxf(x2, 0.f), W_);
+            y1 = fminf(fmaxf(y1, 0.f), H_); y2 = fminf(fmaxf(y2, 0.f), H_);
+        }
+        float* o = (set == 0 ? p.boxes1 : p.boxes2) + (size_t)b * 4;
+        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+        if (p.dbg_cxy) { p.dbg_cxy[img * 2] = cx; p.dbg_cxy[img * 2 + 1] = cy; }
+        if (p.dbg_tlbr) { for (int i = 0; i < 4; ++i) p.dbg_tlbr[img * 4 + i] = tl[i]; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -870,6 +1035,8 @@ struct DecParams {
     const float* qe;            // query_embed1 | query_embed2 (adjacent, [2][256])
     const float* kvs;           // [N_DEC][2B][KVS] cross-attention summaries of the memory
     float* hs;                  // out [2B][256]
+    const float *tl_w0t, *tl_w2, *tl_b2;   // tlbr_reg: transposed [256][256], [4][256], [4]  (src/model.py:59-63)
+    float* tlbr;                // out [2B][4] sigmoid(top,left,bottom,right)
     int B;
 };
 
@@ -1019,6 +1186,25 @@ __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
 #pragma unroll
     for (int r = 0; r < DEC_R; ++r)
         if (row0 + r < rows) p.hs[(size_t)(row0 + r) * C + n] = t[r * C + n];
+    // ---- size regression (src/model.py:188-191): sigmoid(W_b relu(W_a hs) + b)
+    {
+        float acc[DEC_R];
+        dec_matvec<C>(p.tl_w0t, C, 0, t, red, acc);
+#pragma unroll
+        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = fmaxf(acc[r], 0.f);
+        __syncthreads();
+        const int w = n >> 5;
+        if (w < 4) {
+#pragma unroll
+            for (int r = 0; r < DEC_R; ++r) {
+                float o = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o = fmaf(p.tl_w2[(size_t)w * C + lane + 32 * i], a[r * C + lane + 32 * i], o);
+                o = warp_sum_f(o);
+                if (lane == 0 && row0 + r < rows) p.tlbr[(size_t)(row0 + r) * 4 + w] = 1.f / (1.f + expf(-(o + p.tl_b2[w])));
+            }
+        }
+    }
 }
 
 __global__ void k_transpose(const float* __restrict__ W, int N, int K, float* __restrict__ WT) {   // W[N][K] -> WT[K][N]
@@ -1053,17 +1239,20 @@ __global__ void k_untile(const float* __restrict__ xt, TileGeom g, float* __rest
             *reinterpret_cast<const float4*>(xt + xt_off(blockIdx.x, quad, r));
     }
 }
-// per-image sum of per-tile partial summaries (decoder cross-attention consumes the raw summaries)
-__global__ void k_sum_partials(const float* __restrict__ part, TileGeom g, float* __restrict__ out) {
+// per-image sum of per-tile partial summaries (decoder cross-attention consumes the raw summaries); grid (2B, 9)
+__global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ part, TileGeom g, float* __restrict__ out) {
     const int img = blockIdx.x;                      // 0..2B-1
     const int set = img / g.B, b = img % g.B;
     const int T = set == 0 ? g.T1 : g.T2;
     const int first = set == 0 ? b * g.T1 : g.B * g.T1 + b * g.T2;
-    for (int i = threadIdx.x; i < KVS; i += blockDim.x) {
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc += part[(size_t)(first + t) * KVS + i];
-        out[(size_t)img * KVS + i] = acc;
+    const int i = (blockIdx.y * 256 + threadIdx.x) * 4;
+    if (i >= KVS) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)(first + t) * KVS + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
+    *reinterpret_cast<float4*>(out + (size_t)img * KVS + i) = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1090,6 +1279,9 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
     w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
     w.ksum = static_cast<float*>(take((size_t)2 * B * C * sizeof(float)));
     w.att = static_cast<float*>(take((size_t)g.tiles() * TILE * sizeof(float)));
+    w.gstat = static_cast<float*>(take((size_t)g.tiles() * 64 * sizeof(float)));
+    w.z = static_cast<float*>(take((size_t)g.tiles() * TILE * sizeof(float)));
+    w.tlbr = static_cast<float*>(take((size_t)2 * B * 4 * sizeof(float)));
 }
 
 static bool g_attr_set = false;
@@ -1160,14 +1352,14 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
         if (prof) prof->mark(s);
         if (i + 1 < N_ENC) { k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, d_w + L.enc[i + 1].wm, ws.mimg, ws.ksum); lc.n++; }
-        else { k_sum_partials<<<2 * B, 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs); lc.n++; }
+        else { k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs); lc.n++; }
     }
     // decoder layer 1 cross-attention summaries: k = (memory+pos) Wk^T + bk, v = memory Wv^T + bv
     {
         EncParams p = base;
         set_kv_dec(p, 1);
         k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
-        k_sum_partials<<<2 * B, 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs + (size_t)2 * B * KVS); lc.n++;
+        k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, ws.dec_kvs + (size_t)2 * B * KVS); lc.n++;
     }
     if (X_out) { k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++; }
     if (dbg_clock) {
@@ -1188,12 +1380,14 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
 }
 
 
-// query decoder (fp32, one fused kernel) + heat-map 3x3 convolution (tcgen05): hs_out [2B][256], Y [rows][256]
-int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, int B, int hf1,
-                    int wf1, int hf2, int wf2, float* hs_out, float* Y, int* flag, cudaStream_t s, LaunchCounter& lc,
-                    char* msg, size_t msg_len) {
+// query decoder + size regression (fp32, one fused kernel), heat-map 3x3 convolution (tcgen05) with GroupNorm
+// partials, logits, soft-argmax + box assembly.  hs_out [2B][256], Y scratch [B*L1+B*L2][256].
+int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const HeadGeom& hg,
+                    float* hs_out, float* Y, float* boxes1, float* boxes2, float* dbg_cxy, float* dbg_tlbr, int* flag,
+                    cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len) {
     if (set_attrs(msg, msg_len)) return -1;
-    const TileGeom g = make_geom(B, hf1 * wf1, hf2 * wf2);
+    const int B = hg.B;
+    const TileGeom g = make_geom(B, hg.hf1 * hg.wf1, hg.hf2 * hg.wf2);
     DecParams dp{};
     for (int j = 0; j < N_DEC; ++j) {
         const DecW& d = L.dec[j];
@@ -1207,12 +1401,19 @@ int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, con
         w.ln3_g = d_w + d.ln3_g; w.ln3_b = d_w + d.ln3_b;
     }
     dp.qe = d_w + L.qe1; dp.kvs = ws.dec_kvs; dp.hs = hs_out; dp.B = B;
+    dp.tl_w0t = tw.dec_t + N_DEC * DEC_T_FLOATS; dp.tl_w2 = d_w + L.tl_w2; dp.tl_b2 = d_w + L.tl_b2; dp.tlbr = ws.tlbr;
     k_decoder<<<(2 * B + DEC_R - 1) / DEC_R, 256, 0, s>>>(dp); lc.n++;
     k_att<<<g.tiles(), 256, 0, s>>>(ws.xt, g, hs_out, ws.att); lc.n++;
     ConvParams cp{};
-    cp.g = g; cp.hf1 = hf1; cp.wf1 = wf1; cp.hf2 = hf2; cp.wf2 = wf2; cp.xt = ws.xt; cp.att = ws.att; cp.w = tw.head_img;
-    cp.bias = d_w + L.hm_b0; cp.Y = Y; cp.flag = flag;
+    cp.g = g; cp.hf1 = hg.hf1; cp.wf1 = hg.wf1; cp.hf2 = hg.hf2; cp.wf2 = hg.wf2; cp.xt = ws.xt; cp.att = ws.att;
+    cp.w = tw.head_img; cp.bias = d_w + L.hm_b0; cp.Y = Y; cp.gstat = ws.gstat; cp.flag = flag;
     k_conv<<<g.tiles(), N_THREADS, SM_TOTAL, s>>>(cp); lc.n++;
+    k_logits<<<g.tiles(), 256, 0, s>>>(Y, ws.gstat, g, d_w + L.hm_gn_g, d_w + L.hm_gn_b, d_w + L.hm_w3, d_w + L.hm_b3, ws.z); lc.n++;
+    BoxParams bp{};
+    bp.g = g; bp.hf1 = hg.hf1; bp.wf1 = hg.wf1; bp.hf2 = hg.hf2; bp.wf2 = hg.wf2;
+    bp.img_h1 = hg.img_h1; bp.img_w1 = hg.img_w1; bp.img_h2 = hg.img_h2; bp.img_w2 = hg.img_w2; bp.clamp = hg.clamp;
+    bp.z = ws.z; bp.tlbr = ws.tlbr; bp.boxes1 = boxes1; bp.boxes2 = boxes2; bp.dbg_cxy = dbg_cxy; bp.dbg_tlbr = dbg_tlbr;
+    k_box<<<2 * B, 256, 0, s>>>(bp); lc.n++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(msg, msg_len, "decoder/head launch: %s", cudaGetErrorString(e));

@@ -22,6 +22,9 @@ struct TcWorkspace {
     __half* mimg = nullptr;        // [2B images] folded merge weights (hi/lo stage images, 256 KB each)
     float* ksum = nullptr;         // [2B][256] Ksum of every image for the current layer
     float* att = nullptr;          // [tiles][128] per-token <memory, hs> (head)
+    float* gstat = nullptr;        // [tiles][32][2] per-tile GroupNorm partials (mean, M2)
+    float* z = nullptr;            // [tiles][128] heat-map logits
+    float* tlbr = nullptr;         // [2B][4]
 };
 
 // CUDA-event bracket around every launch of the dominant kernel (k_enc with a query phase); read back by bench.py through
@@ -51,10 +54,12 @@ void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cuda
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
                float* X_out, int* timeout_flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
-// fused fp32 query decoder -> hs_out [2B][256]; tcgen05 3x3 heat-map convolution (+bias) -> Y [B*L1+B*L2][256]
-int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, int B, int hf1,
-                    int wf1, int hf2, int wf2, float* hs_out, float* Y, int* timeout_flag, cudaStream_t s,
-                    LaunchCounter& lc, char* msg, size_t msg_len);
+struct HeadGeom { int B, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp; };
+// fused fp32 query decoder (+ tlbr regression) -> hs_out [2B][256]; tcgen05 3x3 heat-map convolution -> Y scratch
+// [B*L1+B*L2][256]; GroupNorm/ReLU/1x1 logits; softmax + soft-argmax + box assembly -> boxes1/boxes2 [B][4]
+int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const HeadGeom& hg,
+                    float* hs_out, float* Y, float* boxes1, float* boxes2, float* dbg_cxy, float* dbg_tlbr,
+                    int* timeout_flag, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
 int tc_selftest(float* errs_host, int n_errs, char* msg, size_t msg_len);
 
 }  // namespace oetr
