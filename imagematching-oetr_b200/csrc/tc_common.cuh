@@ -68,6 +68,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a contiguous global range (no destination; SASS: UBLKPF)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

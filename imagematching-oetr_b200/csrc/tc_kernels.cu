@@ -265,13 +265,17 @@ __device__ __forceinline__ uint32_t cta_setup(Bars* bars, int alloc_warp) {
     tc_fence_after();
     return bars->tmem_base;
 }
-// producer: nstages consecutive 16 KB stages global -> ring
+// producer: nstages (even) consecutive 16 KB stages global -> ring, ONE 32 KB bulk copy per pair of stages.  The
+// issuing thread pays ~480 cycles per copy whatever its size (measured, tools/bulk_bw.cu: 16 KB copies stream at
+// 34 B/cycle/SM, 32 KB copies at 68), and the 3-term MMAs consume 43 B/cycle: 16 KB copies starve the tensor core.
+// Only the even stage's full barrier is used; both empty barriers are still committed by the consumer.
 __device__ __forceinline__ void ring_stream(uint8_t* smem, Bars* bars, int* flag, uint32_t& g, const __half* src, int nstages) {
-    for (int i = 0; i < nstages; ++i, ++g) {
+    for (int i = 0; i < nstages; i += 2, g += 2) {
         const int st = g % RING;
         mbar_wait(&bars->empty[st], ((g / RING) & 1) ^ 1, flag);
-        mbar_arrive_expect_tx(&bars->full[st], STAGE_BYTES);
-        bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, STAGE_BYTES, &bars->full[st]);
+        mbar_wait(&bars->empty[st + 1], ((g / RING) & 1) ^ 1, flag);
+        mbar_arrive_expect_tx(&bars->full[st], 2 * STAGE_BYTES);
+        bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, 2 * STAGE_BYTES, &bars->full[st]);
     }
 }
 struct MmaState { uint32_t g = 0, na0 = 0, na1 = 0; long long t_a = 0, t_ring = 0; };   // t_*: cycles spent waiting (profiling aid)
@@ -295,7 +299,6 @@ __device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* 
             const int st = ms.g % RING;
             const long long t0 = clock64();
             mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
-            mbar_wait(&bars->full[st + 1], (ms.g / RING) & 1, flag);
             ms.t_ring += clock64() - t0;
             tc_fence_after();
             const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
@@ -315,7 +318,6 @@ __device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* 
             const int st = ms.g % RING;
             const long long t0 = clock64();
             mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
-            mbar_wait(&bars->full[st + 1], (ms.g / RING) & 1, flag);
             ms.t_ring += clock64() - t0;
             tc_fence_after();
             const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
@@ -355,6 +357,10 @@ struct EncParams {
     float* kv_part;             // [tiles][KVS] per-tile partial summaries
     int* flag;
     long long* dbg_clock;       // nullable: per CTA {total, MMA wait on operand image, MMA wait on weights, 0} cycles
+    // L2 prefetch: every layer's weights are read once per forward, so without it each stage is a DRAM-latency
+    // miss for the whole first wave.  The grid spreads these ranges (the NEXT launch's weights) in 16 KB pieces.
+    const void* pf_ptr[3];
+    uint32_t pf_bytes[3];
 };
 
 __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
@@ -374,6 +380,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
     if (warp == WARP_PRODUCER) {
         // ------------------------------------------------------------------ weight stream
         if (lane == 0) {
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k)
+                for (uint32_t off = blockIdx.x * STAGE_BYTES; off < p.pf_bytes[k]; off += gridDim.x * STAGE_BYTES)
+                    bulk_prefetch_l2(static_cast<const uint8_t*>(p.pf_ptr[k]) + off, min(STAGE_BYTES, p.pf_bytes[k] - off));
             uint32_t g = 0;
             auto stream = [&](const __half* src, int nstages) { ring_stream(smem, bars, p.flag, g, src, nstages); };
             if (p.do_q) {
@@ -1331,11 +1341,25 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         p.do_kv = 1; p.lnkv_g = nullptr; p.lnkv_b = nullptr; p.bk = d_w + d.ca.bk; p.bv = d_w + d.ca.bv;
         p.w_kv = tw.dec_img + (size_t)layer * DEC_LAYER_HALFS;
     };
+    const uint32_t G = (uint32_t)(GEMM_HALFS * sizeof(__half));
+    // weights the launch for encoder layer i (query phase i + source phase i+1) streams
+    auto set_prefetch_for = [&](EncParams& p, int i) {
+        if (i < N_ENC) {
+            p.pf_ptr[0] = tw.enc_img + (size_t)i * ENC_LAYER_HALFS; p.pf_bytes[0] = 5 * G;
+            if (i + 1 < N_ENC) { p.pf_ptr[1] = tw.enc_img + (size_t)(i + 1) * ENC_LAYER_HALFS + 5 * GEMM_HALFS; p.pf_bytes[1] = 2 * G; }
+            else { p.pf_ptr[1] = tw.dec_img; p.pf_bytes[1] = 2 * G; }
+        } else {   // after the last encoder layer: decoder layer 1 projections, then the head convolution
+            p.pf_ptr[0] = tw.dec_img + DEC_LAYER_HALFS; p.pf_bytes[0] = 2 * G;
+            p.pf_ptr[1] = tw.head_img; p.pf_bytes[1] = 9 * G;
+        }
+    };
     // source phase of layer 0 straight from the NCHW features
     {
         EncParams p = base;
         p.load_feat = 1; p.store_x = 1;
         set_kv_enc(p, 0);
+        set_prefetch_for(p, 0);
+        p.pf_ptr[2] = p.w_kv; p.pf_bytes[2] = 2 * G;          // its own weights: nobody ran before it
         k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
         k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, d_w + L.enc[0].wm, ws.mimg, ws.ksum); lc.n++;
     }
@@ -1347,6 +1371,7 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         p.lnq_g = d_w + e.lnq_g; p.lnq_b = d_w + e.lnq_b; p.ln2_g = d_w + e.ln2_g; p.ln2_b = d_w + e.ln2_b;
         p.w_q = img; p.w_mlp = img + GEMM_HALFS;
         if (i + 1 < N_ENC) set_kv_enc(p, i + 1); else set_kv_dec(p, 0);
+        set_prefetch_for(p, i + 1);
         if (i == 4 && dbg_clock) p.dbg_clock = dbg_clock;
         if (prof) prof->mark(s);
         k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
