@@ -41,7 +41,7 @@ constexpr int WARP_PRODUCER = 16, WARP_MMA = 17;
 constexpr int N_THREADS = 576;
 constexpr int STAGE_HALFS = 128 * 64;           // one ring stage: [128 N rows][64 K cols] fp16, swizzled, 16 KB
 constexpr uint32_t STAGE_BYTES = STAGE_HALFS * 2;
-constexpr int RING = 4;
+constexpr int RING = 6;                         // 3 units of two adjacent stages (one [256 x 64] B tile each)
 constexpr int GEMM_STAGES = 16;                 // a 256x256 weight block: 4 k-slabs x {hi n0, hi n1, lo n0, lo n1}
 constexpr size_t GEMM_HALFS = (size_t)GEMM_STAGES * STAGE_HALFS;      // 256 KB
 constexpr uint32_t SLAB_BYTES = TILE * 128;     // one [128 x 64] fp16 operand slab = 16 KB
@@ -54,20 +54,18 @@ constexpr size_t DEC_T_FLOATS = (size_t)6 * C * C + (size_t)2 * FF * C;   // tra
 
 constexpr uint32_t IDESC_N256 = umma_idesc_f16(128, 256, 0, 0);
 constexpr uint32_t IDESC_KV = umma_idesc_f16(128, 128, 1, 1);      // both operands MN-major (token = K)
-constexpr uint32_t IDESC_KSUM = umma_idesc_f16(128, 16, 1, 1);
 
 // shared-memory map (dynamic, 1024-byte aligned)
 constexpr uint32_t SM_AHI = 0;                                     // operand image, hi part (64 KB)
 constexpr uint32_t SM_ALO = SM_AHI + IMG_BYTES;                    // operand image, lo part (64 KB)
 constexpr uint32_t SM_RING = SM_ALO + IMG_BYTES;                   // 4 x 16 KB weight stages
-constexpr uint32_t SM_ONES = SM_RING + RING * STAGE_BYTES;         // 16 KB slab of fp16 ones (Ksum product)
-constexpr uint32_t SM_KSUM = SM_ONES + SLAB_BYTES;                 // float[256]  Ksum of the source image
-constexpr uint32_t SM_VEC = SM_KSUM + 256 * 4;                     // float[8][256] LN gammas/betas, decoder biases
-constexpr uint32_t SM_RED = SM_VEC + 8 * 256 * 4;                  // float[2][4][128] LayerNorm partials
-constexpr uint32_t SM_BAR = SM_RED + 2 * 4 * 128 * 4;              // mbarriers + tmem pointer
-constexpr uint32_t SM_TOTAL = SM_BAR + 128;
+constexpr uint32_t SM_X = SM_RING + RING * STAGE_BYTES;            // float[512] scratch of the row warps: LayerNorm
+                                                                   // partials -> (gamma | beta) -> Ksum of the source
+                                                                   // image -> Ksum exchange (one user at a time)
+constexpr uint32_t SM_BAR = SM_X + 512 * 4;                        // mbarriers + tmem pointer
+constexpr uint32_t SM_TOTAL = SM_BAR + 256;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(uint64_t) * (2 * RING + 6) + 8 <= 128, "Bars must fit its reservation");
+static_assert(sizeof(uint64_t) * (2 * RING + 6) + 8 <= 256, "Bars must fit its reservation");
 // the kv phase re-uses the operand image space for the MN-major half images (tokens = K dimension)
 constexpr uint32_t KF_OFF = 0;                                     // Kf half image: 2 slabs (32 KB) inside hi / lo
 constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
@@ -412,13 +410,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             if (p.do_kv) {
                 gemm(S0, false, true);      umma_commit(&bars->s_full[0]); // v
                 gemm(S1, false, dec_mode);  umma_commit(&bars->s_full[1]); // k (decoder: from a second image)
-                // per 128-channel half: KV = Kf^T V (diagonal 32x32 blocks are the heads), Ksum = Kf^T 1
+                // per 128-channel half: KV = Kf^T V (diagonal 32x32 blocks are the heads); Ksum is reduced by the row warps
                 for (int half = 0; half < 2; ++half) {
                     wait_a(half);
                     const uint32_t kf_hi = smem_base + SM_AHI + KF_OFF, kf_lo = smem_base + SM_ALO + KF_OFF;
                     const uint32_t v_hi = smem_base + SM_AHI + V_OFF, v_lo = smem_base + SM_ALO + V_OFF;
-                    const uint32_t ones = smem_base + SM_ONES;
-                    const uint32_t dkv = S0 + half * 128, dks = S1 + half * 16;
+                    const uint32_t dkv = S0 + half * 128;
 #pragma unroll
                     for (int k = 0; k < TILE / 16; ++k)
                         umma_f16(dkv, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
@@ -431,14 +428,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     for (int k = 0; k < TILE / 16; ++k)
                         umma_f16(dkv, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
                                  umma_desc(v_lo + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, 1u);
-#pragma unroll
-                    for (int k = 0; k < TILE / 16; ++k)
-                        umma_f16(dks, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
-                                 umma_desc(ones + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KSUM, k);
-#pragma unroll
-                    for (int k = 0; k < TILE / 16; ++k)
-                        umma_f16(dks, umma_desc(kf_lo + k * 2048, SLAB_BYTES, ATOM_BYTES),
-                                 umma_desc(ones + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KSUM, 1u);
                     umma_commit(&bars->s_full[half]);
                 }
             }
@@ -454,9 +443,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         const int r = q * 32 + lane;                       // token row of the tile
         const bool valid = r < ti.valid;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float* red = reinterpret_cast<float*>(smem + SM_RED);
-        float* ksum_s = reinterpret_cast<float*>(smem + SM_KSUM);
-        float* vec = reinterpret_cast<float*>(smem + SM_VEC);   // [0]lnq_g [1]lnq_b [2]ln2_g [3]ln2_b [4]lnkv_g [5]lnkv_b [6]bk [7]bv
+        float* X = reinterpret_cast<float*>(smem + SM_X);       // 512-float scratch, see the shared-memory map
         uint8_t* img_hi = smem + SM_AHI;
         uint8_t* img_lo = smem + SM_ALO;
         const float* post = (ti.set == 0 ? p.post1 : p.post2);
@@ -470,27 +457,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             fence_async_smem();
             mbar_arrive(&bars->a_full[pass]);
         };
-        // one-time staging: per-channel vectors, Ksum of the source image, the ones slab
-        if (tid < 256) {
-            if (p.do_q) {
-                ksum_s[tid] = p.ksum[(size_t)src_img * C + tid];
-                vec[0 * 256 + tid] = p.lnq_g[tid]; vec[1 * 256 + tid] = p.lnq_b[tid];
-                vec[2 * 256 + tid] = p.ln2_g[tid]; vec[3 * 256 + tid] = p.ln2_b[tid];
-            }
-            if (p.do_kv) {
-                vec[4 * 256 + tid] = dec_mode ? 1.f : p.lnkv_g[tid];
-                vec[5 * 256 + tid] = dec_mode ? 0.f : p.lnkv_b[tid];
-                vec[6 * 256 + tid] = p.bk ? p.bk[tid] : 0.f;
-                vec[7 * 256 + tid] = p.bv ? p.bv[tid] : 0.f;
-            }
-        }
-        if (p.do_kv) {
-            const __half2 one2 = __floats2half2_rn(1.f, 1.f);
-            uint4 ones;
-            ones.x = ones.y = ones.z = ones.w = *reinterpret_cast<const uint32_t*>(&one2);
-            for (uint32_t i = tid; i < SLAB_BYTES / 16; i += N_ROW_THREADS) reinterpret_cast<uint4*>(smem + SM_ONES)[i] = ones;
-            fence_async_smem();
-        }
         // ---- the residual stream of this thread: columns [32*cq, +32) and [128 + 32*cq, +32) of row r
         float x[2][32];
 #pragma unroll
@@ -509,17 +475,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 }
             }
         }
-        named_bar_sync(1, N_ROW_THREADS);                  // staged vectors / ones visible to all row warps
-
-        // two-pass LayerNorm statistics of the row (4 threads per row, combined through shared memory)
-        auto ln_stats = [&](float& mean, float& rstd) {
+        // two-pass LayerNorm statistics of the row (4 threads per row, combined through X), then (gamma | beta) are
+        // staged into X for the normalisation pass (their global loads are issued before the statistics)
+        auto ln_stats = [&](const float* __restrict__ gamma, const float* __restrict__ beta, float& mean, float& rstd) {
+            const float gb = tid < 256 ? __ldg(gamma + tid) : __ldg(beta + tid - 256);
             float s = 0.f;
 #pragma unroll
             for (int e = 0; e < 32; ++e) s += x[0][e] + x[1][e];
-            red[(0 * 4 + cq) * TILE + r] = s;
+            X[cq * TILE + r] = s;
             named_bar_sync(1, N_ROW_THREADS);
-            mean = (red[(0 * 4 + 0) * TILE + r] + red[(0 * 4 + 1) * TILE + r] + red[(0 * 4 + 2) * TILE + r] +
-                    red[(0 * 4 + 3) * TILE + r]) * (1.f / C);
+            mean = (X[0 * TILE + r] + X[1 * TILE + r] + X[2 * TILE + r] + X[3 * TILE + r]) * (1.f / C);
             float sq = 0.f;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -527,18 +492,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 sq = fmaf(d0, d0, sq);
                 sq = fmaf(d1, d1, sq);
             }
-            red[(1 * 4 + cq) * TILE + r] = sq;
+            named_bar_sync(1, N_ROW_THREADS);              // every thread has read the sums
+            X[cq * TILE + r] = sq;
             named_bar_sync(1, N_ROW_THREADS);
-            const float var = (red[(1 * 4 + 0) * TILE + r] + red[(1 * 4 + 1) * TILE + r] + red[(1 * 4 + 2) * TILE + r] +
-                               red[(1 * 4 + 3) * TILE + r]) * (1.f / C);
+            const float var = (X[0 * TILE + r] + X[1 * TILE + r] + X[2 * TILE + r] + X[3 * TILE + r]) * (1.f / C);
             rstd = rsqrtf(var + LN_EPS);
+            named_bar_sync(1, N_ROW_THREADS);
+            X[tid] = gb;                                   // X[0,256) = gamma, X[256,512) = beta
+            named_bar_sync(1, N_ROW_THREADS);
         };
-        // operand image <- [LN](x) [+ pos], both column passes.  gb: index of (gamma, beta) in vec, < 0: no LN
-        auto image_from_x = [&](int gb, bool with_pos) {
+        // operand image <- [LN](x) [+ pos], both column passes (gamma == nullptr: no LayerNorm)
+        auto image_from_x = [&](const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos) {
             float mean = 0.f, rstd = 1.f;
-            if (gb >= 0) ln_stats(mean, rstd);
-            const float* gam = vec + (gb >= 0 ? gb : 4) * 256;     // dec mode stages gamma = 1, beta = 0 in slot 4/5
-            const float shift = gb >= 0 ? -mean * rstd : 0.f;
+            if (gamma) ln_stats(gamma, beta, mean, rstd);
+            const float shift = -mean * rstd;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32;
@@ -547,8 +514,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 for (int jq = 0; jq < 8; ++jq) {
                     float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(ti.ti, (c0 >> 2) + jq, r));
-                    const float4 g4 = *reinterpret_cast<const float4*>(gam + c0 + jq * 4);
-                    const float4 b4 = *reinterpret_cast<const float4*>(gam + 256 + c0 + jq * 4);
+                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gamma) {
+                        g4 = *reinterpret_cast<const float4*>(X + c0 + jq * 4);
+                        b4 = *reinterpret_cast<const float4*>(X + 256 + c0 + jq * 4);
+                    }
                     // (x - mean) * rstd * g + b + pos  ==  fma(fma(x, rstd, shift), g, b + pos)
                     v[jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), g4.x, b4.x + ps.x);
                     v[jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), g4.y, b4.y + ps.y);
@@ -562,7 +532,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 
         if (p.do_q) {
             // (E0) A = LNq(x) + pos
-            image_from_x(0, true);
+            image_from_x(p.lnq_g, p.lnq_b, true);
+            // Ksum of the source image -> X (every thread is done with gamma/beta after the barrier)
+            named_bar_sync(1, N_ROW_THREADS);
+            if (tid < 256) X[tid] = __ldg(p.ksum + (size_t)src_img * C + tid);
+            named_bar_sync(1, N_ROW_THREADS);
             // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
             wait_s(0);
             const float eps_s = ATTN_EPS / (float)src_len;    // summaries arrive scaled by 1/S (k_fold)
@@ -574,7 +548,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 float den = 0.f;
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(ksum_s + c0 + e4 * 4);
+                    const float4 k4 = *reinterpret_cast<const float4*>(X + c0 + e4 * 4);
                     v[e4 * 4 + 0] = elu1(v[e4 * 4 + 0]); den = fmaf(v[e4 * 4 + 0], k4.x, den);
                     v[e4 * 4 + 1] = elu1(v[e4 * 4 + 1]); den = fmaf(v[e4 * 4 + 1], k4.y, den);
                     v[e4 * 4 + 2] = elu1(v[e4 * 4 + 2]); den = fmaf(v[e4 * 4 + 2], k4.z, den);
@@ -595,7 +569,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
             }
-            image_from_x(2, false);
+            image_from_x(p.ln2_g, p.ln2_b, false);
             // (E3) A = gelu(h_a): needs h_a (S0) and, for the image to be free, h_b complete (S1)
             // (E4) A = gelu(h_b): the image is free once y = gelu(h_a) W2a^T has completed (S0 commit)
 #pragma unroll 1
@@ -640,34 +614,53 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         }
         if (p.do_kv) {
             if (!dec_mode) {
-                image_from_x(4, true);                         // k and v share LN_kv(x)+pos (transformer.py:119-126)
+                image_from_x(p.lnkv_g, p.lnkv_b, true);        // k and v share LN_kv(x)+pos (transformer.py:119-126)
                 wait_s(0);
                 wait_s(1);
             } else {
-                image_from_x(-1, false);                       // v = x Wv^T + bv      (transformer.py:243-249)
+                image_from_x(nullptr, nullptr, false);         // v = x Wv^T + bv      (transformer.py:243-249)
                 wait_s(0);
-                image_from_x(-1, true);                        // k = (x+pos) Wk^T + bk
+                image_from_x(nullptr, nullptr, true);          // k = (x+pos) Wk^T + bk
                 wait_s(1);
             }
             // half images (tokens = K dimension): V and Kf = elu(k)+1; padded rows are zero
+            float* part = p.kv_part + (size_t)blockIdx.x * KVS;
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32, ch = cq * 32;      // ch: column inside the 128-channel half
                 float v[32];
                 tmem_ld32(S0 + lane_addr + c0, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = valid ? v[e] + vec[7 * 256 + c0 + e] : 0.f;
+                for (int e = 0; e < 32; ++e) v[e] = valid ? v[e] + (p.bv ? __ldg(p.bv + c0 + e) : 0.f) : 0.f;
                 if (pass == 1) wait_s(0);                               // KV of half 0 has consumed the images
                 store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
                 tmem_ld32(S1 + lane_addr + c0, v);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e] + vec[6 * 256 + c0 + e]) : 0.f;
+                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e] + (p.bk ? __ldg(p.bk + c0 + e) : 0.f)) : 0.f;
                 store_row32_split(img_hi + KF_OFF, img_lo + KF_OFF, r, ch, v);
                 publish(pass);
+                // Ksum[c0 + j] = sum over the tile's rows of Kf[:, c0 + j] (fp32, exact operands): butterfly
+                // transpose-reduce inside the warp (lane j ends with column j summed over the warp's 32 rows),
+                // then across the 4 row quarters through X
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send = up ? v[i] : v[i + off];
+                        const float keep = up ? v[i + off] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                X[(cq * 4 + q) * 32 + lane] = v[0];
+                named_bar_sync(1, N_ROW_THREADS);
+                if (q == 0)
+                    part[NH * HD * HD + c0 + lane] = X[(cq * 4 + 0) * 32 + lane] + X[(cq * 4 + 1) * 32 + lane] +
+                                                     X[(cq * 4 + 2) * 32 + lane] + X[(cq * 4 + 3) * 32 + lane];
+                named_bar_sync(1, N_ROW_THREADS);
             }
-            // results: KV diagonal blocks (this warp's TMEM lanes are the d-channels of head 4*half + q) and Ksum
+            // results: KV diagonal blocks (this warp's TMEM lanes are the d-channels of head 4*half + q)
             wait_s(1);
-            float* part = p.kv_part + (size_t)blockIdx.x * KVS;
             if (cq < 2) {
                 const int half = cq, h = half * 4 + q;
                 float v[32];
@@ -675,12 +668,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 float* o = part + h * HD * HD + lane * HD;
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            } else if (cq == 2) {
-                float v[32];
-                tmem_ld32(S1 + lane_addr, v);               // columns 0 / 16: the two ones-products
-                float* ks = part + NH * HD * HD;
-                ks[q * 32 + lane] = v[0];
-                ks[128 + q * 32 + lane] = v[16];
             }
             tc_fence_before();
         }
@@ -850,7 +837,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
         }
         mbar_wait(&bars->s_full[0], 0, p.flag);
         tc_fence_after();
-        float* red = reinterpret_cast<float*>(smem + SM_RED);         // [4 row quarters][32 groups]
+        float* red = reinterpret_cast<float*>(smem + SM_X);           // [4 row quarters][32 groups]
         const size_t row = (ti.set == 0 ? (size_t)ti.b * p.g.L1 : (size_t)p.g.B * p.g.L1 + (size_t)ti.b * p.g.L2) + l;
         float y[2][32];
 #pragma unroll
