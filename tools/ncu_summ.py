@@ -53,3 +53,31 @@ if __name__ == '__main__':
     if cmd == 'launches': launches(sys.argv[2])
     elif cmd == 'raw': raw(sys.argv[2])
     elif cmd == 'sass': sass(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40)
+
+def lines(rep, kernel, n=40):
+    """per CUDA source line: executed warp instructions and stall samples (needs -lineinfo + --import-source)"""
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--kernel-name', kernel],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    agg = {}; cur_file = ''; hdr = None
+    for r in rows:
+        if not r: continue
+        if r[0] == 'File Path': cur_file = r[1].split('/')[-1]; continue
+        if r[0] == 'Line No': hdr = r; continue
+        if hdr is None or len(r) != len(hdr): continue
+        if r[0] == '' : continue          # sass rows have empty line number; cuda rows carry aggregated metrics
+        try:
+            ln = int(r[0]); samples = int(r[hdr.index('# Samples')] or 0); inst = int(r[hdr.index('Instructions Executed')] or 0)
+        except ValueError: continue
+        a = agg.setdefault((cur_file, ln), [r[1].strip()[:90], 0, 0]); a[1] += samples; a[2] += inst
+    ts = sum(a[1] for a in agg.values()); ti = sum(a[2] for a in agg.values())
+    print('total samples %d, executed warp-instructions %d' % (ts, ti))
+    print('--- by executed instructions')
+    for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][2])[:n]:
+        print('%5.1f%% inst %5.1f%% smp  %s:%d  %s' % (100.0 * a[2] / max(ti, 1), 100.0 * a[1] / max(ts, 1), f, ln, a[0]))
+    print('--- by stall samples')
+    for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:n]:
+        print('%5.1f%% smp %5.1f%% inst  %s:%d  %s' % (100.0 * a[1] / max(ts, 1), 100.0 * a[2] / max(ti, 1), f, ln, a[0]))
+
+if __name__ == '__main__' and sys.argv[1] == 'lines':
+    lines(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40)
