@@ -10,9 +10,10 @@ scaling, replicated weights) and the boxes are all-gathered (configs[2]).  One J
   value          pairs/s, inputs resident in HBM, CUDA-event time of exactly K steps, max over ranks
   e2e            the same metric through the C-ABI host-buffer entry point (oetr_forward_host): pinned host
                  features -> H2D -> hot path -> D2H boxes, every step, wall clock
-  roofline       dominant kernel (k_tc_layer, one launch per encoder layer): algorithmic FLOPs / launch over the
+  roofline       dominant kernel (k_enc, one launch per encoder layer): algorithmic FLOPs / launch over the
                  CUDA-event launch duration measured inside the timed region, against the measured bf16/fp16
-                 tensor peak (MEASURED_PEAKS.json, sustained figure: the kernel is timed inside a long step)
+                 tensor peak (MEASURED_PEAKS.json, sustained figure: the kernel is timed inside a long step);
+                 traffic = DRAM bytes per launch from the committed ncu capture (profiles/r01_k_enc_metrics.json)
   cpu_baseline   the numpy port of the reference algorithm (oracle/) on the host cores, bounded sample
   --impl reference   times that same CPU implementation as the reference arm (the reference itself is pure
                  Python under /root/reference, which does not exist on the GPU box; the port is pinned to it by
@@ -38,11 +39,21 @@ IMG = 640
 PAIRS_PER_GPU = 32
 N_ROTATE = 8                     # input batches cycled so that a step never finds its inputs in L2
 
-# algorithmic FLOPs (multiply-add = 2), per token, of one k_tc_layer launch:
-#   q_proj 2*256^2 + merge 2*256^2 + MLP 2*(2*256*512) + Q.KV 2*8*32*32
-FLOPS_LAYER_PER_TOKEN = 2 * 256 * 256 * 2 + 2 * 2 * 256 * 512 + 2 * 8 * 32 * 32
+# algorithmic FLOPs (multiply-add = 2), per token, of one k_enc launch = query phase of layer i + source phase of
+# layer i+1: q, merge, k, v projections 4 * 2*256^2, MLP 2 * (2*256*512),
+# Q.KV and K^T V 2 * (2*8*32*32).  The 3-term split executes 3x these on the tensor cores; only 1x is counted.
+FLOPS_LAYER_PER_TOKEN = 4 * 2 * 256 * 256 + 2 * 2 * 256 * 512 + 2 * 2 * 8 * 32 * 32
 # whole hot path per pair at L=400: 8.32 GFLOP
 FLOPS_PER_PAIR = 8.32e9
+
+
+def _traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k_enc_metrics.json")) as f:
+            m = json.load(f)
+        return float(m["dram__bytes_read.sum"]) + float(m["dram__bytes_write.sum"])
+    except Exception:
+        return None
 
 
 def _peaks():
@@ -236,8 +247,10 @@ def run_b200(args):
     roof = None
     if n_layer:
         ach = FLOPS_LAYER_PER_TOKEN * tokens / (layer_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_tc_layer", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        roof = {"bound": "tensor", "kernel": "k_enc", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": _traffic(), "peak_source": peak_src,
+                "flops_per_launch": FLOPS_LAYER_PER_TOKEN * tokens,
+                "note": "algorithmic FLOPs; every product is a 3-term split-fp16 MMA (parity), so frac <= 1/3",
                 "launch_ms": layer_ms, "launches_timed": n_layer,
                 "share_of_step": layer_ms * 8 / (ms / K),
                 "whole_path_tflops": FLOPS_PER_PAIR * B * K / (ms * 1e-3) / 1e12}
