@@ -705,59 +705,71 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, TileGeom g, const float* __restrict__ Wm,
                                               __half* __restrict__ mimg, float* __restrict__ ksum) {
-    __shared__ __align__(16) float kv[HD][HD];
+    // register-tiled [256 n x 32 d] = W_h[256 x 32 e] . KV_h^T: thread = 8 n x 4 d, operands k-major in shared memory
+    __shared__ __align__(16) float wT[HD][C + 4];          // [e][n]
+    __shared__ __align__(16) float kvT[HD][HD + 4];        // [e][d]
     const int img = blockIdx.x >> 3, h = blockIdx.x & 7;
     const int set = img / g.B, b = img % g.B;
     const int T = set == 0 ? g.T1 : g.T2;
     const int first = set == 0 ? b * g.T1 : g.B * g.T1 + b * g.T2;
     const float* src = part + (size_t)first * KVS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // both summaries are scaled by 1/S (S = source length) like the reference's v / v_length
     // (linear_attention.py:43-48): keeps phi(q)/Z and M_img inside fp16 range for any S; k_enc scales eps alike
     const float inv_s = 1.f / (float)(set == 0 ? g.L1 : g.L2);
     {
-        const int i = threadIdx.x * 4;                      // 4 consecutive elements of KV_h per thread
+        const int i = tid * 4, d = i >> 5, e0 = i & 31;    // 4 consecutive e of KV_h[d][:]
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < T; ++t) {
             const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t * KVS + h * HD * HD + i);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        *reinterpret_cast<float4*>(&kv[0][0] + i) = make_float4(acc.x * inv_s, acc.y * inv_s, acc.z * inv_s, acc.w * inv_s);
+        kvT[e0][d] = acc.x * inv_s; kvT[e0 + 1][d] = acc.y * inv_s; kvT[e0 + 2][d] = acc.z * inv_s; kvT[e0 + 3][d] = acc.w * inv_s;
     }
-    if (threadIdx.x < HD) {
+    if (tid < HD) {
         float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc += src[(size_t)t * KVS + NH * HD * HD + h * HD + threadIdx.x];
-        ksum[(size_t)img * C + h * HD + threadIdx.x] = acc * inv_s;
+        for (int t = 0; t < T; ++t) acc += src[(size_t)t * KVS + NH * HD * HD + h * HD + tid];
+        ksum[(size_t)img * C + h * HD + tid] = acc * inv_s;
     }
-    const int n = threadIdx.x;                         // output channel of merge
-    float w[HD], out[HD];
-    const float4* wr = reinterpret_cast<const float4*>(Wm + (size_t)n * C + h * HD);
-#pragma unroll
-    for (int e4 = 0; e4 < HD / 4; ++e4) {
-        const float4 t = __ldg(wr + e4);
-        w[e4 * 4] = t.x; w[e4 * 4 + 1] = t.y; w[e4 * 4 + 2] = t.z; w[e4 * 4 + 3] = t.w;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+        const int n = warp * 32 + i;
+        wT[lane][n] = __ldg(Wm + (size_t)n * C + h * HD + lane);
     }
     __syncthreads();
+    const int tn = tid >> 3, td = tid & 7;
+    float acc[8][4];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
-        float acc = 0.f;
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int e4 = 0; e4 < HD / 4; ++e4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(&kv[d][e4 * 4]);     // warp-wide broadcast
-            acc = fmaf(w[e4 * 4], k4.x, acc); acc = fmaf(w[e4 * 4 + 1], k4.y, acc);
-            acc = fmaf(w[e4 * 4 + 2], k4.z, acc); acc = fmaf(w[e4 * 4 + 3], k4.w, acc);
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < HD; ++e) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&wT[e][8 * tn]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&wT[e][8 * tn + 4]);
+        const float4 k4 = *reinterpret_cast<const float4*>(&kvT[e][4 * td]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i][0] = fmaf(a[i], k4.x, acc[i][0]); acc[i][1] = fmaf(a[i], k4.y, acc[i][1]);
+            acc[i][2] = fmaf(a[i], k4.z, acc[i][2]); acc[i][3] = fmaf(a[i], k4.w, acc[i][3]);
         }
-        out[d] = acc;
     }
-    // K index = h*32 + d: k-slab h/2, columns (h&1)*32 .. +32 of row n
+    // K index = h*32 + d: k-slab h/2, columns (h&1)*32 + 4*td .. +4 of row n; 8-byte pieces of the 16-byte chunks
     __half* dst = mimg + (size_t)img * GEMM_HALFS;
-    const int ks = h >> 1, nh = n >> 7, r = n & 127, j0 = (h & 1) * 4;
+    const int ks = h >> 1, col = (h & 1) * 32 + 4 * td;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 hi, lo;
-        split8(&out[8 * j], hi, lo);
-        const uint32_t off = slab_chunk_off(r, j0 + j);
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 0, nh)) + off) = hi;
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 1, nh)) + off) = lo;
+    for (int i = 0; i < 8; ++i) {
+        const int n = 8 * tn + i, nh = n >> 7, r = n & 127;
+        const __half2 h0 = __floats2half2_rn(acc[i][0], acc[i][1]), h1 = __floats2half2_rn(acc[i][2], acc[i][3]);
+        const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(acc[i][0] - b0.x, acc[i][1] - b0.y), l1 = __floats2half2_rn(acc[i][2] - b1.x, acc[i][3] - b1.y);
+        const uint32_t off = slab_chunk_off(r, col >> 3) + (col & 7) * 2;
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 0, nh)) + off) = hv;
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 1, nh)) + off) = lv;
     }
 }
 
