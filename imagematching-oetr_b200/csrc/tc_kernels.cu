@@ -1056,7 +1056,6 @@ __global__ void __launch_bounds__(256) k_box(const BoxParams p) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int DEC_R = 2;
 struct DecLayerT {
-    const float *sa_wq, *sa_wk, *sa_wv, *sa_wm, *ca_wq, *ca_wm, *w1, *w2;      // transposed [K][N]
     const float *sa_bq, *sa_bk, *sa_bv, *ca_bq;
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
 };
@@ -1065,7 +1064,8 @@ struct DecParams {
     const float* qe;            // query_embed1 | query_embed2 (adjacent, [2][256])
     const float* kvs;           // [N_DEC][2B][KVS] cross-attention summaries of the memory
     float* hs;                  // out [2B][256]
-    const float *tl_w0t, *tl_w2, *tl_b2;   // tlbr_reg: transposed [256][256], [4][256], [4]  (src/model.py:59-63)
+    const float* wt;            // all transposed fp32 weights in consumption order (see k_decoder)
+    const float *tl_w2, *tl_b2; // tlbr_reg.2: [4][256], [4]  (src/model.py:59-63)
     float* tlbr;                // out [2B][4] sigmoid(top,left,bottom,right)
     int B;
 };
@@ -1075,47 +1075,47 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// acc[r] = sum_k WT[k][col0 + n] * xin[r][k] for this thread's column n = threadIdx.x (256 columns per call).
-// Warp w streams the k-slice [w*K/8, (w+1)*K/8) of all 256 columns with 16-byte loads (two per k and lane, deep
-// unroll: the kernel is bound by how many weight bytes one SM keeps in flight); the 8 partial sums meet in red[].
-template <int K>
-__device__ __forceinline__ void dec_matvec(const float* __restrict__ WT, int N, int col0, const float* xin, float* red,
-                                           float (&acc)[DEC_R]) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float part[DEC_R][8];
+// Weight streaming: the transposed fp32 weights of both layers and tlbr_reg.0 are ONE contiguous array in the
+// order the kernel consumes them (sa.wq | sa.wk | sa.wv | sa.wm | ca.wq | ca.wm | w1 | w2 per layer, then tl_w0),
+// so a producer lane streams it linearly in 32 KB bulk copies through a 5-stage ring, running ahead across
+// matvec boundaries; the 256 compute threads never wait on global-memory latency (the first version, with
+// register loads, was bound by the bytes one SM can keep in flight: 185 us for 5.8 MB).
+constexpr int DEC_THREADS = 256 + 32;                 // warps 0-7 compute, warp 8 = producer
+constexpr int DEC_STAGES = 5;
+constexpr uint32_t DEC_CHUNK_BYTES = 32768;
+constexpr int DEC_CHUNK_FLOATS = DEC_CHUNK_BYTES / 4;
+constexpr uint32_t DEC_SMEM = DEC_STAGES * DEC_CHUNK_BYTES + 256;
+struct DecRing { uint64_t* full; uint64_t* empty; const float* stage0; uint32_t g; };
+
+// acc[r][c] = sum_k WT[k][n + 256*c] * xin[r][k]   (c < N/256), WT consumed from the ring (K*N*4/32 KB chunks)
+template <int K, int N>
+__device__ __forceinline__ void dec_matvec(DecRing& ring, const float* xin, float (&acc)[DEC_R][N / 256]) {
+    constexpr int ROWS = DEC_CHUNK_FLOATS / N;        // k rows per chunk
+    const int n = threadIdx.x;
 #pragma unroll
     for (int r = 0; r < DEC_R; ++r)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) part[r][j] = 0.f;
-    const int k0 = warp * (K / 8);
-    const float4* w4 = reinterpret_cast<const float4*>(WT + (size_t)k0 * N + col0) + lane;
-#pragma unroll 8
-    for (int k = 0; k < K / 8; ++k) {
-        const float4 a = __ldg(w4 + (size_t)k * (N / 4));
-        const float4 b = __ldg(w4 + (size_t)k * (N / 4) + 32);
+        for (int c = 0; c < N / 256; ++c) acc[r][c] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += ROWS, ++ring.g) {
+        const int st = ring.g % DEC_STAGES;
+        mbar_wait(&ring.full[st], (ring.g / DEC_STAGES) & 1, nullptr);
+        const float* ws = ring.stage0 + (size_t)st * DEC_CHUNK_FLOATS;
+#pragma unroll 4
+        for (int kk = 0; kk < ROWS; kk += 4) {
+            float4 xv[DEC_R];
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) {
-            const float xv = xin[r * K + k0 + k];
-            part[r][0] = fmaf(a.x, xv, part[r][0]); part[r][1] = fmaf(a.y, xv, part[r][1]);
-            part[r][2] = fmaf(a.z, xv, part[r][2]); part[r][3] = fmaf(a.w, xv, part[r][3]);
-            part[r][4] = fmaf(b.x, xv, part[r][4]); part[r][5] = fmaf(b.y, xv, part[r][5]);
-            part[r][6] = fmaf(b.z, xv, part[r][6]); part[r][7] = fmaf(b.w, xv, part[r][7]);
+            for (int r = 0; r < DEC_R; ++r) xv[r] = *reinterpret_cast<const float4*>(xin + r * K + k0 + kk);
+#pragma unroll
+            for (int c = 0; c < N / 256; ++c) {
+                const float w0 = ws[(kk + 0) * N + n + 256 * c], w1 = ws[(kk + 1) * N + n + 256 * c];
+                const float w2 = ws[(kk + 2) * N + n + 256 * c], w3 = ws[(kk + 3) * N + n + 256 * c];
+#pragma unroll
+                for (int r = 0; r < DEC_R; ++r)
+                    acc[r][c] = fmaf(w3, xv[r].w, fmaf(w2, xv[r].z, fmaf(w1, xv[r].y, fmaf(w0, xv[r].x, acc[r][c]))));
+            }
         }
-    }
-    __syncthreads();                                   // previous users of red[] are done
-#pragma unroll
-    for (int r = 0; r < DEC_R; ++r) {
-        float* o = red + (size_t)(warp * DEC_R + r) * C;
-        *reinterpret_cast<float4*>(o + lane * 4) = make_float4(part[r][0], part[r][1], part[r][2], part[r][3]);
-        *reinterpret_cast<float4*>(o + 128 + lane * 4) = make_float4(part[r][4], part[r][5], part[r][6], part[r][7]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < DEC_R; ++r) {
-        float sum = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) sum += red[(size_t)(w * DEC_R + r) * C + threadIdx.x];
-        acc[r] = sum;
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&ring.empty[st]);
     }
 }
 // out[r][:] = LN(in[r][:]) (two-pass variance); warps 0..DEC_R-1, one row each
@@ -1135,10 +1135,31 @@ __device__ __forceinline__ void dec_ln(const float* in, const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
+__global__ void __launch_bounds__(DEC_THREADS) k_decoder(const DecParams p) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
     __shared__ __align__(16) float t[DEC_R * C], u[DEC_R * C], a[DEC_R * C], qv[DEC_R * C], hid[DEC_R * FF];
-    __shared__ __align__(16) float red[8 * DEC_R * C];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + DEC_STAGES * DEC_CHUNK_BYTES);
     const int n = threadIdx.x, lane = n & 31;
+    if (n == 0) {
+        for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[DEC_STAGES + i], 8); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (n >= 256) {
+        // ---- producer: the whole weight array, linearly
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)((N_DEC * DEC_T_FLOATS + (size_t)C * C) * sizeof(float) / DEC_CHUNK_BYTES);
+            for (uint32_t g = 0; g < total; ++g) {
+                const int st = g % DEC_STAGES;
+                mbar_wait(&bars[DEC_STAGES + st], ((g / DEC_STAGES) & 1) ^ 1, nullptr);
+                mbar_arrive_expect_tx(&bars[st], DEC_CHUNK_BYTES);
+                bulk_g2s(dsm + (size_t)st * DEC_CHUNK_BYTES, reinterpret_cast<const uint8_t*>(p.wt) + (size_t)g * DEC_CHUNK_BYTES,
+                         DEC_CHUNK_BYTES, &bars[st]);
+            }
+        }
+        return;
+    }
+    DecRing ring{bars, bars + DEC_STAGES, reinterpret_cast<const float*>(dsm), 0u};
     const int row0 = blockIdx.x * DEC_R, rows = 2 * p.B;
     float qe[DEC_R];
 #pragma unroll
@@ -1147,41 +1168,41 @@ __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
         qe[r] = p.qe[(row >= p.B ? C : 0) + n];
         t[r * C + n] = 0.f;                                                    // tgt = zeros (transformer.py:361)
     }
-    __syncthreads();
+    named_bar_sync(2, 256);
     for (int j = 0; j < N_DEC; ++j) {
         const DecLayerT& w = p.layer[j];
-        float acc[DEC_R], kk[DEC_R], vv[DEC_R];
+        float acc[DEC_R][1], kk[DEC_R][1], vv[DEC_R][1], h2[DEC_R][2];
         // ---- self-attention over the single query token (transformer.py:236-241, linear_attention.py:22-50)
         dec_ln(t, w.ln1_g, w.ln1_b, u);
-        __syncthreads();
+        named_bar_sync(2, 256);
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
-        __syncthreads();
-        dec_matvec<C>(w.sa_wq, C, 0, a, red, acc);
-        dec_matvec<C>(w.sa_wk, C, 0, a, red, kk);
-        dec_matvec<C>(w.sa_wv, C, 0, u, red, vv);
-        __syncthreads();                                                       // all reads of a[] done
+        named_bar_sync(2, 256);
+        dec_matvec<C, C>(ring, a, acc);
+        dec_matvec<C, C>(ring, a, kk);
+        dec_matvec<C, C>(ring, u, vv);
+        named_bar_sync(2, 256);                                                // all reads of a[] done
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) {
-            const float qf = elu1(acc[r] + w.sa_bq[n]), kf = elu1(kk[r] + w.sa_bk[n]);
+            const float qf = elu1(acc[r][0] + w.sa_bq[n]), kf = elu1(kk[r][0] + w.sa_bk[n]);
             const float sden = warp_sum_f(qf * kf);                           // warp = head
-            a[r * C + n] = (vv[r] + w.sa_bv[n]) * sden / (sden + ATTN_EPS);   // KV = kf v^T, Z = 1/(qf.kf + eps)
+            a[r * C + n] = (vv[r][0] + w.sa_bv[n]) * sden / (sden + ATTN_EPS); // KV = kf v^T, Z = 1/(qf.kf + eps)
         }
-        __syncthreads();
-        dec_matvec<C>(w.sa_wm, C, 0, a, red, acc);
+        named_bar_sync(2, 256);
+        dec_matvec<C, C>(ring, a, acc);
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
-        __syncthreads();
+        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r][0];
+        named_bar_sync(2, 256);
         // ---- cross-attention into the memory summaries (transformer.py:243-250)
         dec_ln(t, w.ln2_g, w.ln2_b, u);
-        __syncthreads();
+        named_bar_sync(2, 256);
 #pragma unroll
         for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
-        __syncthreads();
-        dec_matvec<C>(w.ca_wq, C, 0, a, red, acc);
+        named_bar_sync(2, 256);
+        dec_matvec<C, C>(ring, a, acc);
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) qv[r * C + n] = elu1(acc[r] + w.ca_bq[n]);
-        __syncthreads();
+        for (int r = 0; r < DEC_R; ++r) qv[r * C + n] = elu1(acc[r][0] + w.ca_bq[n]);
+        named_bar_sync(2, 256);
         {
             const int h = n >> 5;
 #pragma unroll
@@ -1195,34 +1216,33 @@ __global__ void __launch_bounds__(256) k_decoder(const DecParams p) {
                 a[r * C + n] = o / (den + ATTN_EPS);
             }
         }
-        __syncthreads();
-        dec_matvec<C>(w.ca_wm, C, 0, a, red, acc);
+        named_bar_sync(2, 256);
+        dec_matvec<C, C>(ring, a, acc);
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
-        __syncthreads();
+        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r][0];
+        named_bar_sync(2, 256);
         // ---- feed-forward (transformer.py:252-254)
         dec_ln(t, w.ln3_g, w.ln3_b, u);
-        __syncthreads();
-        dec_matvec<C>(w.w1, FF, 0, u, red, acc);
-        dec_matvec<C>(w.w1, FF, C, u, red, kk);
+        named_bar_sync(2, 256);
+        dec_matvec<C, FF>(ring, u, h2);
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) { hid[r * FF + n] = fmaxf(acc[r], 0.f); hid[r * FF + C + n] = fmaxf(kk[r], 0.f); }
-        __syncthreads();
-        dec_matvec<FF>(w.w2, C, 0, hid, red, acc);
+        for (int r = 0; r < DEC_R; ++r) { hid[r * FF + n] = fmaxf(h2[r][0], 0.f); hid[r * FF + C + n] = fmaxf(h2[r][1], 0.f); }
+        named_bar_sync(2, 256);
+        dec_matvec<FF, C>(ring, hid, acc);
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r];
-        __syncthreads();
+        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r][0];
+        named_bar_sync(2, 256);
     }
 #pragma unroll
     for (int r = 0; r < DEC_R; ++r)
         if (row0 + r < rows) p.hs[(size_t)(row0 + r) * C + n] = t[r * C + n];
     // ---- size regression (src/model.py:188-191): sigmoid(W_b relu(W_a hs) + b)
     {
-        float acc[DEC_R];
-        dec_matvec<C>(p.tl_w0t, C, 0, t, red, acc);
+        float acc[DEC_R][1];
+        dec_matvec<C, C>(ring, t, acc);
 #pragma unroll
-        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = fmaxf(acc[r], 0.f);
-        __syncthreads();
+        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = fmaxf(acc[r][0], 0.f);
+        named_bar_sync(2, 256);
         const int w = n >> 5;
         if (w < 4) {
 #pragma unroll
@@ -1319,6 +1339,7 @@ static int set_attrs(char* msg, size_t msg_len) {
     if (g_attr_set) return 0;
     cudaError_t e1 = cudaFuncSetAttribute(k_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_decoder, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
     if (e1 != cudaSuccess) {
         snprintf(msg, msg_len, "cudaFuncSetAttribute(max dynamic smem %u): %s", SM_TOTAL, cudaGetErrorString(e1));
         return -1;
@@ -1436,18 +1457,14 @@ int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, con
     DecParams dp{};
     for (int j = 0; j < N_DEC; ++j) {
         const DecW& d = L.dec[j];
-        const float* t = tw.dec_t + (size_t)j * DEC_T_FLOATS;
         DecLayerT& w = dp.layer[j];
-        w.sa_wq = t; w.sa_wk = t + (size_t)1 * C * C; w.sa_wv = t + (size_t)2 * C * C; w.sa_wm = t + (size_t)3 * C * C;
-        w.ca_wq = t + (size_t)4 * C * C; w.ca_wm = t + (size_t)5 * C * C;
-        w.w1 = t + (size_t)6 * C * C; w.w2 = t + (size_t)6 * C * C + (size_t)FF * C;
         w.sa_bq = d_w + d.sa.bq; w.sa_bk = d_w + d.sa.bk; w.sa_bv = d_w + d.sa.bv; w.ca_bq = d_w + d.ca.bq;
         w.ln1_g = d_w + d.ln1_g; w.ln1_b = d_w + d.ln1_b; w.ln2_g = d_w + d.ln2_g; w.ln2_b = d_w + d.ln2_b;
         w.ln3_g = d_w + d.ln3_g; w.ln3_b = d_w + d.ln3_b;
     }
     dp.qe = d_w + L.qe1; dp.kvs = ws.dec_kvs; dp.hs = hs_out; dp.B = B;
-    dp.tl_w0t = tw.dec_t + N_DEC * DEC_T_FLOATS; dp.tl_w2 = d_w + L.tl_w2; dp.tl_b2 = d_w + L.tl_b2; dp.tlbr = ws.tlbr;
-    k_decoder<<<(2 * B + DEC_R - 1) / DEC_R, 256, 0, s>>>(dp); lc.n++;
+    dp.wt = tw.dec_t; dp.tl_w2 = d_w + L.tl_w2; dp.tl_b2 = d_w + L.tl_b2; dp.tlbr = ws.tlbr;
+    k_decoder<<<(2 * B + DEC_R - 1) / DEC_R, DEC_THREADS, DEC_SMEM, s>>>(dp); lc.n++;
     k_att<<<g.tiles(), 256, 0, s>>>(ws.xt, g, hs_out, ws.att); lc.n++;
     ConvParams cp{};
     cp.g = g; cp.hf1 = hg.hf1; cp.wf1 = hg.wf1; cp.hf2 = hg.hf2; cp.wf2 = hg.wf2; cp.xt = ws.xt; cp.att = ws.att;
