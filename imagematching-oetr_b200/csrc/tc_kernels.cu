@@ -814,6 +814,7 @@ struct ConvParams {
     float* Y;                   // token-major [B*L1 + B*L2][256]
     float* gstat;               // [tiles][32 groups][2]: per-tile GroupNorm partials (mean, M2) over the valid rows
     int* flag;
+    long long* dbg_clock;       // nullable, like EncParams::dbg_clock
 };
 
 __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
@@ -834,8 +835,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
     } else if (warp == WARP_MMA) {
         if (lane == 0) {
             MmaState ms;
+            const long long t_begin = clock64();
             for (int tap = 0; tap < 9; ++tap) gemm_issue(smem_base, bars, p.flag, ms, S0, tap > 0, true, true);
             umma_commit(&bars->s_full[0]);
+            if (p.dbg_clock) {
+                long long* o = p.dbg_clock + (size_t)blockIdx.x * 4;
+                o[0] = clock64() - t_begin; o[1] = ms.t_a; o[2] = ms.t_ring; o[3] = 0;
+            }
         }
         __syncwarp();
     } else {
@@ -1469,7 +1475,22 @@ int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, con
     ConvParams cp{};
     cp.g = g; cp.hf1 = hg.hf1; cp.wf1 = hg.wf1; cp.hf2 = hg.hf2; cp.wf2 = hg.wf2; cp.xt = ws.xt; cp.att = ws.att;
     cp.w = tw.head_img; cp.bias = d_w + L.hm_b0; cp.Y = Y; cp.gstat = ws.gstat; cp.flag = flag;
+    static long long* conv_clock = nullptr;
+    static int conv_clock_tiles = 0;
+    if (getenv("OETR_TIMING")) {
+        if (conv_clock_tiles < g.tiles()) { cudaFree(conv_clock); cudaMalloc(&conv_clock, (size_t)g.tiles() * 4 * sizeof(long long)); conv_clock_tiles = g.tiles(); }
+        cp.dbg_clock = conv_clock;
+    }
     k_conv<<<g.tiles(), N_THREADS, SM_TOTAL, s>>>(cp); lc.n++;
+    if (cp.dbg_clock) {
+        std::vector<long long> hbuf((size_t)g.tiles() * 4);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hbuf.data(), conv_clock, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double sum[3] = {0, 0, 0};
+        for (int t = 0; t < g.tiles(); ++t) for (int k = 0; k < 3; ++k) sum[k] += (double)hbuf[(size_t)t * 4 + k];
+        fprintf(stderr, "[oetr timing] k_conv, %d tiles: MMA thread total %.0f cycles, waiting on operand image %.0f, on weights %.0f (means)\n",
+                g.tiles(), sum[0] / g.tiles(), sum[1] / g.tiles(), sum[2] / g.tiles());
+    }
     k_logits<<<g.tiles(), 256, 0, s>>>(Y, ws.gstat, g, d_w + L.hm_gn_g, d_w + L.hm_gn_b, d_w + L.hm_w3, d_w + L.hm_b3, ws.z); lc.n++;
     BoxParams bp{};
     bp.g = g; bp.hf1 = hg.hf1; bp.wf1 = hg.wf1; bp.hf2 = hg.hf2; bp.wf2 = hg.wf2;
