@@ -113,6 +113,11 @@ def cpu_port_pairs_per_s(n_pairs, reps):
     """Time the numpy port (fp32, all BLAS threads) on `n_pairs` pairs of the bench workload."""
     from oetr_b200 import weights
     from oracle import oetr_oracle as orc
+    try:  # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core explicitly
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     W = weights.synthetic_hot_path_weights(0)
     f1 = weights.synthetic_features(n_pairs, FEAT_HW, FEAT_HW, seed=21, tag="cpu1")
     f2 = weights.synthetic_features(n_pairs, FEAT_HW, FEAT_HW, seed=21, tag="cpu2")
