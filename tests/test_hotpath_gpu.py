@@ -156,3 +156,39 @@ def test_selftest_tcgen05_building_blocks():
     vals = list(errs)
     print("tcgen05 selftest errors:", vals)
     assert all(v == v and v < 2e-3 for v in vals[:8]), vals
+
+
+def test_geometry_changes_between_calls_and_host_entry():
+    """One handle, changing feature-map geometries call after call (the handle caches the tile-blocked position
+    rows per geometry), device and host-buffer entry points, batch 1 and an odd batch."""
+    W = weights.synthetic_hot_path_weights(0)
+    hot = oetr_b200.OverlapHotPath(W, precision="fp16")
+    for b, fm1, fm2 in ((1, (20, 20), (20, 20)), (3, (15, 20), (20, 15)), (1, (20, 20), (20, 20)), (5, (26, 26), (13, 9))):
+        hw1, hw2 = (fm1[0] * 32, fm1[1] * 32), (fm2[0] * 32, fm2[1] * 32)
+        f1 = weights.synthetic_features(b, *fm1, seed=17, tag="g1")
+        f2 = weights.synthetic_features(b, *fm2, seed=17, tag="g2")
+        want = orc.hot_path(W, f1, f2, hw1, hw2)
+        a1, a2 = hot.forward(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(), hw1, hw2, clamp=False)
+        h1, h2 = hot.forward_host(f1, f2, hw1, hw2, clamp=False)
+        hot.poll_error()
+        for got, ref, hw in ((a1.cpu().numpy(), want["box1_raw"], hw1), (a2.cpu().numpy(), want["box2_raw"], hw2),
+                             (h1, want["box1_raw"], hw1), (h2, want["box2_raw"], hw2)):
+            assert np.abs(got - ref).max() / max(hw) < TOL["fp16"]["box"], (fm1, fm2)
+    hot.close()
+
+
+def test_large_token_regime_840():
+    """BASELINE config 4: 840x840 pairs, batch 16 (26x26 maps, 676 tokens = 6 tiles per image)."""
+    W = weights.synthetic_hot_path_weights(0)
+    b = 16
+    f1 = torch.from_numpy(weights.synthetic_features(b, 26, 26, seed=4, tag="l1")).cuda()
+    f2 = torch.from_numpy(weights.synthetic_features(b, 26, 26, seed=4, tag="l2")).cuda()
+    hot = oetr_b200.OverlapHotPath(W, precision="fp16")
+    a1, a2 = hot.forward(f1, f2, (840, 840), (840, 840), clamp=False)
+    c1, c2 = hot.forward(f1, f2, (840, 840), (840, 840), clamp=False)
+    assert torch.equal(a1, c1) and torch.equal(a2, c2)
+    want = orc.hot_path(W, f1[:2].cpu().numpy(), f2[:2].cpu().numpy(), (840, 840), (840, 840))
+    assert np.abs(a1[:2].cpu().numpy() - want["box1_raw"]).max() / 840 < TOL["fp16"]["box"]
+    assert np.abs(a2[:2].cpu().numpy() - want["box2_raw"]).max() / 840 < TOL["fp16"]["box"]
+    hot.poll_error()
+    hot.close()
