@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -30,8 +31,20 @@ static int fail(int code, const char* fmt, ...) {
                         #call, cudaGetErrorString(e_), __FILE__, __LINE__);                          \
     } while (0)
 
+// Sub-batch scheduling of the FP16 path.  Pairs are independent, and one k_enc CTA owns a whole SM, so
+// a batch of 256 tiles runs as two waves on 148 SMs with the second wave 27 % empty and every small kernel (k_fold,
+// k_decoder, ...) leaving most of the GPU idle.  The batch is therefore cut into sub-batches of `chunk_pairs` pairs,
+// each with its own workspace slice and its own stream: the block scheduler back-fills free SMs with CTAs of
+// whichever sub-batch is ready (different layers interleave), and in oetr_forward_host the H2D copy of sub-batch
+// c+1 overlaps the compute of sub-batch c.  Fork/join is by events on the caller's stream: no host synchronisation.
+constexpr int MAX_CHUNKS = 8;
+
 struct oetr_handle {
     int attn_mode = 0, prec = 0, max_h = 0, max_w = 0, device = 0;
+    int chunk_pairs = 8;       // pairs per sub-batch (0: never split); oetr_set_chunk_pairs
+    cudaStream_t aux[MAX_CHUNKS] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHUNKS] = {};
+    std::mutex mu;             // fork/launch/join section (the events are shared by all callers of this handle)
     WLayout L;
     float* d_w = nullptr;      // packed fp32 weights (canonical order)
     float* d_w9 = nullptr;     // heatmap_conv.0.weight repacked per tap: [9][256 out][256 in]
@@ -46,8 +59,10 @@ struct oetr_handle {
     int last_launches = 0;
     // staging owned by the handle for oetr_forward_host only
     float *st_feat1 = nullptr, *st_feat2 = nullptr, *st_boxes = nullptr;
+    float* st_boxes_pin = nullptr;   // pinned host landing buffer of the boxes (a D2H copy into pageable memory would
+                                     // block the launching thread and serialise the sub-batches)
     void* st_ws = nullptr;
-    size_t st_feat1_n = 0, st_feat2_n = 0, st_boxes_n = 0, st_ws_n = 0;
+    size_t st_feat1_n = 0, st_feat2_n = 0, st_boxes_n = 0, st_boxes_pin_n = 0, st_ws_n = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -289,6 +304,12 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
     CUH(cudaMemcpy(h->d_pe, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUH(cudaMalloc(&h->d_flag, sizeof(int)));
     CUH(cudaMemset(h->d_flag, 0, sizeof(int)));
+    if (const char* env = getenv("OETR_CHUNK_PAIRS")) h->chunk_pairs = atoi(env) > 0 ? atoi(env) : 0;
+    CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_CHUNKS; ++i) {
+        CUH(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+        CUH(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
     if (operand_precision == OETR_PREC_FP16) {
         char msg[256] = "";
         if (tc_prepare_weights(h->d_w, h->d_w9, L, h->tc, msg, sizeof(msg)) != 0)
@@ -306,7 +327,13 @@ int oetr_destroy(oetr_handle* h) {
     cudaFree(h->d_post[0]); cudaFree(h->d_post[1]);
     tc_free_weights(h->tc);
     for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int i = 0; i < MAX_CHUNKS; ++i) {
+        if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
     cudaFree(h->st_feat1); cudaFree(h->st_feat2); cudaFree(h->st_boxes); cudaFree(h->st_ws);
+    cudaFreeHost(h->st_boxes_pin);
     delete h;
     return OETR_OK;
 }
@@ -321,11 +348,37 @@ static int check_shapes(const oetr_handle* h, int batch, int hf1, int wf1, int h
     return OETR_OK;
 }
 
+// sub-batch sizes of a batch (balanced; 1 chunk = no split)
+static int chunk_plan(const oetr_handle* h, int B, int* sizes) {
+    int n = 1;
+    if (h->prec == OETR_PREC_FP16 && h->chunk_pairs > 0 && B > h->chunk_pairs)
+        n = (B + h->chunk_pairs - 1) / h->chunk_pairs;
+    if (n > MAX_CHUNKS) n = MAX_CHUNKS;
+    for (int i = 0; i < n; ++i) sizes[i] = B / n + (i < B % n ? 1 : 0);
+    return n;
+}
+static size_t chunked_bytes(const oetr_handle* h, int B, int L1, int L2) {
+    int sizes[MAX_CHUNKS];
+    const int n = chunk_plan(h, B, sizes);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += (carve(nullptr, h, sizes[i], L1, L2).bytes + 1023) & ~size_t(1023);
+    return total;
+}
+
 int oetr_workspace_bytes(const oetr_handle* h, int batch, int hf1, int wf1, int hf2, int wf2, size_t* out) {
     if (!out) return fail(OETR_E_ARG, "oetr_workspace_bytes: null out");
     int rc = check_shapes(h, batch, hf1, wf1, hf2, wf2);
     if (rc) return rc;
-    *out = carve(nullptr, h, batch, hf1 * wf1, hf2 * wf2).bytes + 256;
+    const size_t whole = carve(nullptr, h, batch, hf1 * wf1, hf2 * wf2).bytes;
+    const size_t split = chunked_bytes(h, batch, hf1 * wf1, hf2 * wf2);
+    *out = (whole > split ? whole : split) + 256;
+    return OETR_OK;
+}
+
+int oetr_set_chunk_pairs(oetr_handle* h, int pairs_per_chunk) {
+    if (!h) return fail(OETR_E_ARG, "null handle");
+    if (pairs_per_chunk < 0) return fail(OETR_E_ARG, "oetr_set_chunk_pairs: %d < 0", pairs_per_chunk);
+    h->chunk_pairs = pairs_per_chunk;
     return OETR_OK;
 }
 
@@ -367,6 +420,137 @@ int oetr_poll_error(oetr_handle* h) {
     return OETR_OK;
 }
 
+namespace {
+// optional host endpoints of a forward (oetr_forward_host): features are copied H2D and boxes D2H on the stream
+// that runs the (sub-)batch, so that with sub-batch scheduling the copies overlap the other sub-batches' compute
+struct HostIO { const float *feat1, *feat2; float *boxes1, *boxes2; };
+
+struct FwdArgs {
+    int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
+    float *dbg_hs, *dbg_memory, *dbg_cxy, *dbg_tlbr;
+};
+
+// one (sub-)batch of B pairs on stream s with workspace slice w
+int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const float* feat2, int B, const FwdArgs& a,
+              float* boxes1, float* boxes2, const HostIO* hio, bool profile, cudaStream_t s, LaunchCounter& lc) {
+    const int hf1 = a.hf1, wf1 = a.wf1, hf2 = a.hf2, wf2 = a.wf2;
+    const int L1 = hf1 * wf1, L2 = hf2 * wf2, R1 = B * L1, R2 = B * L2;
+    const float* W = h->d_w;
+    if (hio) {
+        CU(cudaMemcpyAsync(const_cast<float*>(feat1), hio->feat1, (size_t)R1 * C * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(const_cast<float*>(feat2), hio->feat2, (size_t)R2 * C * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (h->prec == OETR_PREC_FP32) {
+        // positional rows for both geometries (PositionEncodingSine.forward slice, models/utils.py:200-205)
+        k_gather_pos<<<(L1 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf1, L1, w.pos); lc.n++;
+        k_gather_pos<<<(L2 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf2, L2, w.pos + (size_t)L1 * C); lc.n++;
+        nchw_to_tokens(feat1, w.X, B, L1, s, lc);
+        nchw_to_tokens(feat2, w.X + (size_t)R1 * C, B, L2, s, lc);
+        encoder_fp32(h, w, B, L1, L2, s, lc);
+        decoder_fp32(h, w, B, s, lc, [&](int j) { decoder_kv_fp32(h, w, j, B, L1, L2, s, lc); });
+    } else {
+        // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
+        // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
+        char msg[256] = "";
+        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
+                       a.dbg_memory ? w.X : nullptr, h->d_flag, profile ? &h->prof : nullptr, s, lc, msg, sizeof(msg)) != 0)
+            return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
+        const HeadGeom hg{B, hf1, wf1, hf2, wf2, a.img_h1, a.img_w1, a.img_h2, a.img_w2, a.clamp};
+        if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, hg, w.dt, w.O, boxes1, boxes2, a.dbg_cxy, a.dbg_tlbr, h->d_flag, s, lc,
+                            msg, sizeof(msg)) != 0)
+            return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
+    }
+    // memory = encoder output (w.X), hs = decoder output (w.dt)
+    if (a.dbg_memory) cudaMemcpyAsync(a.dbg_memory, w.X, (size_t)(R1 + R2) * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (a.dbg_hs) cudaMemcpyAsync(a.dbg_hs, w.dt, (size_t)2 * B * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
+
+    if (h->prec == OETR_PREC_FP32) {
+        // head: heat = memory * <memory, hs>; conv3x3 (+bias) -> Y ; then the row-wise tail per image
+        float *G = w.T, *Gs = w.Q, *Y = w.O;
+        heat_scale(w.X, w.dt, G, R1, L1, s, lc);
+        heat_scale(w.X + (size_t)R1 * C, w.dt + (size_t)B * C, G + (size_t)R1 * C, R2, L2, s, lc);
+        head_conv_fp32(h, w, B, hf1, wf1, hf2, wf2, G, Gs, Y, s, lc);
+        HeadParams p{};
+        p.gn_g = W + h->L.hm_gn_g; p.gn_b = W + h->L.hm_gn_b; p.w3 = W + h->L.hm_w3; p.b3 = W + h->L.hm_b3;
+        p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;
+        p.batch = B; p.clamp = a.clamp;
+        p.Y = Y; p.hs = w.dt; p.hf = hf1; p.wf = wf1; p.img_h = a.img_h1; p.img_w = a.img_w1;
+        p.boxes = boxes1; p.dbg_cxy = a.dbg_cxy; p.dbg_tlbr = a.dbg_tlbr;
+        head_finalize(p, s, lc);
+        p.Y = Y + (size_t)R1 * C; p.hs = w.dt + (size_t)B * C; p.hf = hf2; p.wf = wf2; p.img_h = a.img_h2; p.img_w = a.img_w2;
+        p.boxes = boxes2; p.dbg_cxy = a.dbg_cxy ? a.dbg_cxy + 2 * B : nullptr; p.dbg_tlbr = a.dbg_tlbr ? a.dbg_tlbr + 4 * B : nullptr;
+        head_finalize(p, s, lc);
+    }
+    if (hio) {
+        CU(cudaMemcpyAsync(hio->boxes1, boxes1, (size_t)B * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(hio->boxes2, boxes2, (size_t)B * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    return OETR_OK;
+}
+
+int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int batch, const FwdArgs& a, float* boxes1,
+                 float* boxes2, void* workspace, size_t workspace_bytes, cudaStream_t s, const HostIO* hio) {
+    const int B = batch, L1 = a.hf1 * a.wf1, L2 = a.hf2 * a.wf2;
+    LaunchCounter lc;
+    if (h->prec == OETR_PREC_FP16) {
+        // positional rows, tile-blocked, cached per geometry (the only state a forward keeps between calls; a
+        // geometry change regenerates it on `s`, growing the buffer with cudaMalloc if needed)
+        const int geo[2][2] = {{a.hf1, a.wf1}, {a.hf2, a.wf2}};
+        for (int k = 0; k < 2; ++k) {
+            if (h->post_hw[k][0] == geo[k][0] && h->post_hw[k][1] == geo[k][1]) continue;
+            const int Lk = geo[k][0] * geo[k][1];
+            const size_t need = tc_pos_tile_floats(Lk);
+            if (h->post_cap[k] < need) {
+                cudaFree(h->d_post[k]); h->d_post[k] = nullptr; h->post_cap[k] = 0; h->post_hw[k][0] = h->post_hw[k][1] = 0;
+                CU(cudaMalloc(&h->d_post[k], need * sizeof(float)));
+                h->post_cap[k] = need;
+            }
+            tc_pos_tiles(h->d_pe, h->max_w, geo[k][1], Lk, h->d_post[k], s, lc);
+            h->post_hw[k][0] = geo[k][0]; h->post_hw[k][1] = geo[k][1];
+        }
+    }
+    int sizes[MAX_CHUNKS];
+    int nc = chunk_plan(h, B, sizes);
+    // the debug taps are laid out for the whole batch and the kernel profiler brackets launches on one stream
+    if (a.dbg_hs || a.dbg_memory || a.dbg_cxy || a.dbg_tlbr || h->prof.on) nc = 1;
+    if (nc == 1) {
+        const Workspace w = carve(workspace, h, B, L1, L2);
+        if (w.bytes > workspace_bytes)
+            return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes, w.bytes);
+        int rc = run_batch(h, w, feat1, feat2, B, a, boxes1, boxes2, hio, true, s, lc);
+        if (rc) return rc;
+    } else {
+        if (chunked_bytes(h, B, L1, L2) > workspace_bytes)
+            return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes,
+                        chunked_bytes(h, B, L1, L2));
+        std::lock_guard<std::mutex> lock(h->mu);
+        CU(cudaEventRecord(h->ev_fork, s));
+        char* base = static_cast<char*>(workspace);
+        int b0 = 0;
+        for (int c = 0; c < nc; ++c) {
+            const int Bc = sizes[c];
+            cudaStream_t sc = h->aux[c];
+            CU(cudaStreamWaitEvent(sc, h->ev_fork, 0));
+            const Workspace w = carve(base, h, Bc, L1, L2);
+            base += (w.bytes + 1023) & ~size_t(1023);
+            HostIO sub{};
+            if (hio) sub = HostIO{hio->feat1 + (size_t)b0 * C * L1, hio->feat2 + (size_t)b0 * C * L2,
+                                  hio->boxes1 + (size_t)b0 * 4, hio->boxes2 + (size_t)b0 * 4};
+            int rc = run_batch(h, w, feat1 + (size_t)b0 * C * L1, feat2 + (size_t)b0 * C * L2, Bc, a,
+                               boxes1 + (size_t)b0 * 4, boxes2 + (size_t)b0 * 4, hio ? &sub : nullptr, false, sc, lc);
+            if (rc) return rc;
+            CU(cudaEventRecord(h->ev_join[c], sc));
+            CU(cudaStreamWaitEvent(s, h->ev_join[c], 0));
+            b0 += Bc;
+        }
+    }
+    h->last_launches = lc.n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(OETR_E_CUDA, "oetr_forward: launch failed: %s", cudaGetErrorString(e));
+    return OETR_OK;
+}
+}  // namespace
+
 int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int batch, int hf1, int wf1, int hf2,
                  int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp, float* boxes1, float* boxes2,
                  float* dbg_hs, float* dbg_memory, float* dbg_cxy, float* dbg_tlbr, void* workspace,
@@ -381,76 +565,9 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
                     img_w1, img_h2, img_w2);
     if (reinterpret_cast<uintptr_t>(workspace) & 255)
         return fail(OETR_E_ARG, "oetr_forward: workspace must be 256-byte aligned");
-    const int B = batch, L1 = hf1 * wf1, L2 = hf2 * wf2;
-    const Workspace w = carve(workspace, h, B, L1, L2);
-    if (w.bytes > workspace_bytes)
-        return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes, w.bytes);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    LaunchCounter lc;
-    const int R1 = B * L1, R2 = B * L2;
-    const float* W = h->d_w;
-
-    if (h->prec == OETR_PREC_FP32) {
-        // positional rows for both geometries (PositionEncodingSine.forward slice, models/utils.py:200-205)
-        k_gather_pos<<<(L1 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf1, L1, w.pos); lc.n++;
-        k_gather_pos<<<(L2 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf2, L2, w.pos + (size_t)L1 * C); lc.n++;
-        nchw_to_tokens(feat1, w.X, B, L1, s, lc);
-        nchw_to_tokens(feat2, w.X + (size_t)R1 * C, B, L2, s, lc);
-        encoder_fp32(h, w, B, L1, L2, s, lc);
-        decoder_fp32(h, w, B, s, lc, [&](int j) { decoder_kv_fp32(h, w, j, B, L1, L2, s, lc); });
-    } else {
-        // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
-        // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
-        char msg[256] = "";
-        // positional rows, tile-blocked, cached per geometry (the only state oetr_forward keeps between calls; a
-        // geometry change regenerates it on `s`, growing the buffer with cudaMalloc if needed)
-        const int geo[2][2] = {{hf1, wf1}, {hf2, wf2}};
-        for (int k = 0; k < 2; ++k) {
-            if (h->post_hw[k][0] == geo[k][0] && h->post_hw[k][1] == geo[k][1]) continue;
-            const int Lk = geo[k][0] * geo[k][1];
-            const size_t need = tc_pos_tile_floats(Lk);
-            if (h->post_cap[k] < need) {
-                cudaFree(h->d_post[k]); h->d_post[k] = nullptr; h->post_cap[k] = 0; h->post_hw[k][0] = h->post_hw[k][1] = 0;
-                CU(cudaMalloc(&h->d_post[k], need * sizeof(float)));
-                h->post_cap[k] = need;
-            }
-            tc_pos_tiles(h->d_pe, h->max_w, geo[k][1], Lk, h->d_post[k], s, lc);
-            h->post_hw[k][0] = geo[k][0]; h->post_hw[k][1] = geo[k][1];
-        }
-        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
-                       dbg_memory ? w.X : nullptr, h->d_flag, &h->prof, s, lc, msg, sizeof(msg)) != 0)
-            return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
-        const HeadGeom hg{B, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp};
-        if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, hg, w.dt, w.O, boxes1, boxes2, dbg_cxy, dbg_tlbr, h->d_flag, s, lc,
-                            msg, sizeof(msg)) != 0)
-            return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
-    }
-    // memory = encoder output (w.X), hs = decoder output (w.dt)
-    if (dbg_memory) cudaMemcpyAsync(dbg_memory, w.X, (size_t)(R1 + R2) * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    if (dbg_hs) cudaMemcpyAsync(dbg_hs, w.dt, (size_t)2 * B * C * sizeof(float), cudaMemcpyDeviceToDevice, s);
-
-    if (h->prec == OETR_PREC_FP32) {
-        // head: heat = memory * <memory, hs>; conv3x3 (+bias) -> Y ; then the row-wise tail per image
-        float *G = w.T, *Gs = w.Q, *Y = w.O;
-        heat_scale(w.X, w.dt, G, R1, L1, s, lc);
-        heat_scale(w.X + (size_t)R1 * C, w.dt + (size_t)B * C, G + (size_t)R1 * C, R2, L2, s, lc);
-        head_conv_fp32(h, w, B, hf1, wf1, hf2, wf2, G, Gs, Y, s, lc);
-        HeadParams p{};
-        p.gn_g = W + h->L.hm_gn_g; p.gn_b = W + h->L.hm_gn_b; p.w3 = W + h->L.hm_w3; p.b3 = W + h->L.hm_b3;
-        p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;
-        p.batch = B; p.clamp = clamp;
-        p.Y = Y; p.hs = w.dt; p.hf = hf1; p.wf = wf1; p.img_h = img_h1; p.img_w = img_w1;
-        p.boxes = boxes1; p.dbg_cxy = dbg_cxy; p.dbg_tlbr = dbg_tlbr;
-        head_finalize(p, s, lc);
-        p.Y = Y + (size_t)R1 * C; p.hs = w.dt + (size_t)B * C; p.hf = hf2; p.wf = wf2; p.img_h = img_h2; p.img_w = img_w2;
-        p.boxes = boxes2; p.dbg_cxy = dbg_cxy ? dbg_cxy + 2 * B : nullptr; p.dbg_tlbr = dbg_tlbr ? dbg_tlbr + 4 * B : nullptr;
-        head_finalize(p, s, lc);
-    }
-
-    h->last_launches = lc.n;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(OETR_E_CUDA, "oetr_forward: launch failed: %s", cudaGetErrorString(e));
-    return OETR_OK;
+    const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, dbg_hs, dbg_memory, dbg_cxy, dbg_tlbr};
+    return forward_core(h, feat1, feat2, batch, a, boxes1, boxes2, workspace, workspace_bytes,
+                        static_cast<cudaStream_t>(stream), nullptr);
 }
 
 static int grow(float** p, size_t* have, size_t need) {
@@ -468,6 +585,9 @@ int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat
     if (rc) return rc;
     if (batch == 0) return OETR_OK;
     if (!feat1_host || !feat2_host || !boxes1_host || !boxes2_host) return fail(OETR_E_ARG, "oetr_forward_host: null buffer");
+    if (img_h1 < hf1 || img_h2 < hf2 || img_w1 < 1 || img_w2 < 1)
+        return fail(OETR_E_SHAPE, "oetr_forward_host: image sizes (%d,%d),(%d,%d) smaller than the feature maps", img_h1,
+                    img_w1, img_h2, img_w2);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n1 = (size_t)batch * C * hf1 * wf1, n2 = (size_t)batch * C * hf2 * wf2;
     size_t ws = 0;
@@ -481,22 +601,27 @@ int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat
         if (cudaMalloc(&h->st_ws, ws) != cudaSuccess) return fail(OETR_E_NOMEM, "oetr_forward_host: workspace allocation failed");
         h->st_ws_n = ws;
     }
-    CU(cudaMemcpyAsync(h->st_feat1, feat1_host, n1 * sizeof(float), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->st_feat2, feat2_host, n2 * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = oetr_forward(h, h->st_feat1, h->st_feat2, batch, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp,
-                      h->st_boxes, h->st_boxes + (size_t)batch * 4, nullptr, nullptr, nullptr, nullptr, h->st_ws,
-                      h->st_ws_n, stream);
+    const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, nullptr, nullptr, nullptr, nullptr};
+    if (h->st_boxes_pin_n < (size_t)batch * 8) {
+        cudaFreeHost(h->st_boxes_pin); h->st_boxes_pin = nullptr; h->st_boxes_pin_n = 0;
+        if (cudaMallocHost(&h->st_boxes_pin, (size_t)batch * 8 * sizeof(float)) != cudaSuccess)
+            return fail(OETR_E_NOMEM, "oetr_forward_host: pinned staging allocation failed");
+        h->st_boxes_pin_n = (size_t)batch * 8;
+    }
+    const HostIO hio{feat1_host, feat2_host, h->st_boxes_pin, h->st_boxes_pin + (size_t)batch * 4};
+    rc = forward_core(h, h->st_feat1, h->st_feat2, batch, a, h->st_boxes, h->st_boxes + (size_t)batch * 4, h->st_ws,
+                      h->st_ws_n, s, &hio);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(boxes1_host, h->st_boxes, (size_t)batch * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(boxes2_host, h->st_boxes + (size_t)batch * 4, (size_t)batch * 4 * sizeof(float),
-                       cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    // the timeout flag rides the same stream as the boxes: one synchronisation, no second round trip
     int flag = 0;
-    CU(cudaMemcpy(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     if (flag) {
         cudaMemset(h->d_flag, 0, sizeof(int));
         return fail(OETR_E_CUDA, "a device-side mbarrier wait timed out (pipeline protocol error); results are invalid");
     }
+    memcpy(boxes1_host, h->st_boxes_pin, (size_t)batch * 4 * sizeof(float));
+    memcpy(boxes2_host, h->st_boxes_pin + (size_t)batch * 4, (size_t)batch * 4 * sizeof(float));
     return OETR_OK;
 }
 

@@ -51,6 +51,11 @@ class OverlapHotPath:
             self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def set_chunk_pairs(self, pairs):
+        """Pairs per concurrently scheduled sub-batch of the fp16 path (0 = never split; default 8)."""
+        cabi.check(self._lib.oetr_set_chunk_pairs(self._handle, int(pairs)), self._lib)
+        self._ws = None
+
     def profile(self, enable=True):
         cabi.check(self._lib.oetr_profile_enable(self._handle, int(bool(enable))), self._lib)
 

@@ -192,3 +192,37 @@ def test_large_token_regime_840():
     assert np.abs(a2[:2].cpu().numpy() - want["box2_raw"]).max() / 840 < TOL["fp16"]["box"]
     hot.poll_error()
     hot.close()
+
+
+def test_sub_batch_scheduling_is_invisible():
+    """The fp16 path cuts a batch into sub-batches on handle-owned streams (oetr_set_chunk_pairs).  Pairs are
+    independent and every kernel is deterministic, so any split gives bit-identical boxes, on the device entry
+    and on the host-buffer entry (uneven splits, more sub-batches than the cap, a stream other than the default)."""
+    W = weights.synthetic_hot_path_weights(0)
+    b = 21
+    n1 = weights.synthetic_features(b, 20, 20, seed=31, tag="c1")
+    n2 = weights.synthetic_features(b, 14, 17, seed=31, tag="c2")
+    f1, f2 = torch.from_numpy(n1).cuda(), torch.from_numpy(n2).cuda()
+    hw1, hw2 = (640, 640), (448, 544)
+    hot = oetr_b200.OverlapHotPath(W, precision="fp16")
+    hot.set_chunk_pairs(0)
+    hot.forward(f1, f2, hw1, hw2, clamp=False)             # first call of a geometry also builds its position rows
+    r1, r2 = hot.forward(f1, f2, hw1, hw2, clamp=False)
+    assert hot.last_launch_count == 25
+    want = orc.hot_path(W, n1[:2], n2[:2], hw1, hw2)
+    assert np.abs(r1[:2].cpu().numpy() - want["box1_raw"]).max() / 640 < TOL["fp16"]["box"]
+    side = torch.cuda.Stream()
+    for pairs, chunks in ((8, 3), (5, 5), (2, 8), (1, 8), (20, 2), (21, 1), (64, 1)):
+        hot.set_chunk_pairs(pairs)
+        a1, a2 = hot.forward(f1, f2, hw1, hw2, clamp=False)
+        assert hot.last_launch_count == 25 * chunks, (pairs, hot.last_launch_count)
+        assert torch.equal(a1, r1) and torch.equal(a2, r2), pairs
+        h1, h2 = hot.forward_host(n1, n2, hw1, hw2, clamp=False)
+        assert np.array_equal(h1, r1.cpu().numpy()) and np.array_equal(h2, r2.cpu().numpy()), pairs
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            s1, s2 = hot.forward(f1, f2, hw1, hw2, clamp=False)
+        side.synchronize()
+        assert torch.equal(s1, r1) and torch.equal(s2, r2), pairs
+    hot.poll_error()
+    hot.close()
