@@ -13,6 +13,7 @@ PREC_FP32, PREC_FP16 = 0, 1
 EXPORTS = (
     "oetr_abi_version", "oetr_last_error", "oetr_packed_weight_count", "oetr_create", "oetr_destroy",
     "oetr_workspace_bytes", "oetr_forward", "oetr_last_launch_count", "oetr_poll_error", "oetr_forward_host",
+    "oetr_forward_host_submit", "oetr_forward_host_wait",
     "oetr_profile_enable", "oetr_profile_read", "oetr_set_chunk_pairs",
     "oetr_selftest_tcgen05",
 )
@@ -62,6 +63,10 @@ def load_library(path=None):
     lib.oetr_poll_error.argtypes = [vp]
     lib.oetr_forward_host.restype = c.c_int
     lib.oetr_forward_host.argtypes = [vp, vp, vp] + [c.c_int] * 10 + [vp, vp, vp]
+    lib.oetr_forward_host_submit.restype = c.c_int
+    lib.oetr_forward_host_submit.argtypes = [vp, vp, vp] + [c.c_int] * 10 + [vp, c.POINTER(c.c_int)]
+    lib.oetr_forward_host_wait.restype = c.c_int
+    lib.oetr_forward_host_wait.argtypes = [vp, c.c_int, vp, vp]
     lib.oetr_selftest_tcgen05.restype = c.c_int
     lib.oetr_selftest_tcgen05.argtypes = [f32p, c.c_int]
     if path == LIB_PATH:

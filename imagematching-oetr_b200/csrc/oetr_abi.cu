@@ -38,6 +38,20 @@ static int fail(int code, const char* fmt, ...) {
 // whichever sub-batch is ready (different layers interleave), and in oetr_forward_host the H2D copy of sub-batch
 // c+1 overlaps the compute of sub-batch c.  Fork/join is by events on the caller's stream: no host synchronisation.
 constexpr int MAX_CHUNKS = 8;
+constexpr int HOST_SLOTS = 2;
+
+// one in-flight request of oetr_forward_host_submit: device staging, pinned landing buffers, completion events
+struct HostSlot {
+    float *feat1 = nullptr, *feat2 = nullptr, *boxes = nullptr;
+    float* boxes_pin = nullptr;    // pinned host landing buffer of the boxes (a D2H copy into pageable memory would
+                                   // block the launching thread and serialise the sub-batches)
+    int* flag_pin = nullptr;       // [MAX_CHUNKS] device timeout flag as seen at the end of each sub-batch
+    void* ws = nullptr;
+    size_t feat1_n = 0, feat2_n = 0, boxes_n = 0, boxes_pin_n = 0, ws_n = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHUNKS] = {};
+    int n_join = 0, batch = 0, ticket = -1;
+    bool busy = false;
+};
 
 struct oetr_handle {
     int attn_mode = 0, prec = 0, max_h = 0, max_w = 0, device = 0;
@@ -57,12 +71,9 @@ struct oetr_handle {
     size_t post_cap[2] = {0, 0};
     int post_hw[2][2] = {{0, 0}, {0, 0}};
     int last_launches = 0;
-    // staging owned by the handle for oetr_forward_host only
-    float *st_feat1 = nullptr, *st_feat2 = nullptr, *st_boxes = nullptr;
-    float* st_boxes_pin = nullptr;   // pinned host landing buffer of the boxes (a D2H copy into pageable memory would
-                                     // block the launching thread and serialise the sub-batches)
-    void* st_ws = nullptr;
-    size_t st_feat1_n = 0, st_feat2_n = 0, st_boxes_n = 0, st_boxes_pin_n = 0, st_ws_n = 0;
+    // staging owned by the handle for the host-buffer entry points only: HOST_SLOTS requests can be in flight
+    HostSlot slot[HOST_SLOTS];
+    unsigned next_ticket = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -310,6 +321,11 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
         CUH(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
         CUH(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
     }
+    for (HostSlot& sl : h->slot) {
+        CUH(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < MAX_CHUNKS; ++i) CUH(cudaEventCreateWithFlags(&sl.ev_join[i], cudaEventDisableTiming));
+        CUH(cudaMallocHost(&sl.flag_pin, MAX_CHUNKS * sizeof(int)));
+    }
     if (operand_precision == OETR_PREC_FP16) {
         char msg[256] = "";
         if (tc_prepare_weights(h->d_w, h->d_w9, L, h->tc, msg, sizeof(msg)) != 0)
@@ -332,8 +348,13 @@ int oetr_destroy(oetr_handle* h) {
         if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
         if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     }
-    cudaFree(h->st_feat1); cudaFree(h->st_feat2); cudaFree(h->st_boxes); cudaFree(h->st_ws);
-    cudaFreeHost(h->st_boxes_pin);
+    for (HostSlot& sl : h->slot) {
+        if (sl.busy) for (int c = 0; c < sl.n_join; ++c) cudaEventSynchronize(sl.ev_join[c]);
+        cudaFree(sl.feat1); cudaFree(sl.feat2); cudaFree(sl.boxes); cudaFree(sl.ws);
+        cudaFreeHost(sl.boxes_pin); cudaFreeHost(sl.flag_pin);
+        if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
+        for (int i = 0; i < MAX_CHUNKS; ++i) if (sl.ev_join[i]) cudaEventDestroy(sl.ev_join[i]);
+    }
     delete h;
     return OETR_OK;
 }
@@ -423,7 +444,11 @@ int oetr_poll_error(oetr_handle* h) {
 namespace {
 // optional host endpoints of a forward (oetr_forward_host): features are copied H2D and boxes D2H on the stream
 // that runs the (sub-)batch, so that with sub-batch scheduling the copies overlap the other sub-batches' compute
-struct HostIO { const float *feat1, *feat2; float *boxes1, *boxes2; };
+struct HostIO { const float *feat1, *feat2; float *boxes1, *boxes2; int* flags; };
+// fork/join events of one forward.  join_caller: the caller's stream waits for the sub-batches (stream-ordered
+// entry points); otherwise completion is observed through ev_join only (host submit/wait) and even an unsplit
+// batch runs on a handle-owned stream, so that two requests forked from the same stream overlap
+struct EventSet { cudaEvent_t fork; cudaEvent_t* join; bool join_caller; int* n_join; };
 
 struct FwdArgs {
     int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
@@ -484,12 +509,14 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
     if (hio) {
         CU(cudaMemcpyAsync(hio->boxes1, boxes1, (size_t)B * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(hio->boxes2, boxes2, (size_t)B * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(hio->flags, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     }
     return OETR_OK;
 }
 
 int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int batch, const FwdArgs& a, float* boxes1,
-                 float* boxes2, void* workspace, size_t workspace_bytes, cudaStream_t s, const HostIO* hio) {
+                 float* boxes2, void* workspace, size_t workspace_bytes, cudaStream_t s, const HostIO* hio,
+                 const EventSet& es) {
     const int B = batch, L1 = a.hf1 * a.wf1, L2 = a.hf2 * a.wf2;
     LaunchCounter lc;
     if (h->prec == OETR_PREC_FP16) {
@@ -500,6 +527,9 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
             if (h->post_hw[k][0] == geo[k][0] && h->post_hw[k][1] == geo[k][1]) continue;
             const int Lk = geo[k][0] * geo[k][1];
             const size_t need = tc_pos_tile_floats(Lk);
+            // requests still in flight on the handle's own streams (host submit/wait) read the rows being replaced
+            for (HostSlot& sl : h->slot)
+                if (sl.busy) for (int c = 0; c < sl.n_join; ++c) cudaEventSynchronize(sl.ev_join[c]);
             if (h->post_cap[k] < need) {
                 cudaFree(h->d_post[k]); h->d_post[k] = nullptr; h->post_cap[k] = 0; h->post_hw[k][0] = h->post_hw[k][1] = 0;
                 CU(cudaMalloc(&h->d_post[k], need * sizeof(float)));
@@ -513,36 +543,37 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
     int nc = chunk_plan(h, B, sizes);
     // the debug taps are laid out for the whole batch and the kernel profiler brackets launches on one stream
     if (a.dbg_hs || a.dbg_memory || a.dbg_cxy || a.dbg_tlbr || h->prof.on) nc = 1;
-    if (nc == 1) {
+    if (nc == 1 && es.join_caller) {
         const Workspace w = carve(workspace, h, B, L1, L2);
         if (w.bytes > workspace_bytes)
             return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes, w.bytes);
         int rc = run_batch(h, w, feat1, feat2, B, a, boxes1, boxes2, hio, true, s, lc);
         if (rc) return rc;
     } else {
-        if (chunked_bytes(h, B, L1, L2) > workspace_bytes)
-            return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes,
-                        chunked_bytes(h, B, L1, L2));
-        std::lock_guard<std::mutex> lock(h->mu);
-        CU(cudaEventRecord(h->ev_fork, s));
+        if (nc == 1) sizes[0] = B;
+        const size_t need = nc == 1 ? carve(nullptr, h, B, L1, L2).bytes : chunked_bytes(h, B, L1, L2);
+        if (need > workspace_bytes)
+            return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes, need);
+        CU(cudaEventRecord(es.fork, s));
         char* base = static_cast<char*>(workspace);
         int b0 = 0;
         for (int c = 0; c < nc; ++c) {
             const int Bc = sizes[c];
             cudaStream_t sc = h->aux[c];
-            CU(cudaStreamWaitEvent(sc, h->ev_fork, 0));
+            CU(cudaStreamWaitEvent(sc, es.fork, 0));
             const Workspace w = carve(base, h, Bc, L1, L2);
             base += (w.bytes + 1023) & ~size_t(1023);
             HostIO sub{};
             if (hio) sub = HostIO{hio->feat1 + (size_t)b0 * C * L1, hio->feat2 + (size_t)b0 * C * L2,
-                                  hio->boxes1 + (size_t)b0 * 4, hio->boxes2 + (size_t)b0 * 4};
+                                  hio->boxes1 + (size_t)b0 * 4, hio->boxes2 + (size_t)b0 * 4, hio->flags + c};
             int rc = run_batch(h, w, feat1 + (size_t)b0 * C * L1, feat2 + (size_t)b0 * C * L2, Bc, a,
                                boxes1 + (size_t)b0 * 4, boxes2 + (size_t)b0 * 4, hio ? &sub : nullptr, false, sc, lc);
             if (rc) return rc;
-            CU(cudaEventRecord(h->ev_join[c], sc));
-            CU(cudaStreamWaitEvent(s, h->ev_join[c], 0));
+            CU(cudaEventRecord(es.join[c], sc));
+            if (es.join_caller) CU(cudaStreamWaitEvent(s, es.join[c], 0));
             b0 += Bc;
         }
+        if (es.n_join) *es.n_join = nc;
     }
     h->last_launches = lc.n;
     cudaError_t e = cudaGetLastError();
@@ -566,8 +597,10 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
     if (reinterpret_cast<uintptr_t>(workspace) & 255)
         return fail(OETR_E_ARG, "oetr_forward: workspace must be 256-byte aligned");
     const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, dbg_hs, dbg_memory, dbg_cxy, dbg_tlbr};
+    std::lock_guard<std::mutex> lock(h->mu);
+    const EventSet es{h->ev_fork, h->ev_join, true, nullptr};
     return forward_core(h, feat1, feat2, batch, a, boxes1, boxes2, workspace, workspace_bytes,
-                        static_cast<cudaStream_t>(stream), nullptr);
+                        static_cast<cudaStream_t>(stream), nullptr, es);
 }
 
 static int grow(float** p, size_t* have, size_t need) {
@@ -578,51 +611,99 @@ static int grow(float** p, size_t* have, size_t need) {
     return 0;
 }
 
-int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat2_host, int batch, int hf1, int wf1,
-                      int hf2, int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp,
-                      float* boxes1_host, float* boxes2_host, void* stream) {
+int oetr_forward_host_submit(oetr_handle* h, const float* feat1_host, const float* feat2_host, int batch, int hf1,
+                             int wf1, int hf2, int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp,
+                             void* stream, int* ticket) {
     int rc = check_shapes(h, batch, hf1, wf1, hf2, wf2);
     if (rc) return rc;
-    if (batch == 0) return OETR_OK;
-    if (!feat1_host || !feat2_host || !boxes1_host || !boxes2_host) return fail(OETR_E_ARG, "oetr_forward_host: null buffer");
-    if (img_h1 < hf1 || img_h2 < hf2 || img_w1 < 1 || img_w2 < 1)
-        return fail(OETR_E_SHAPE, "oetr_forward_host: image sizes (%d,%d),(%d,%d) smaller than the feature maps", img_h1,
-                    img_w1, img_h2, img_w2);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t n1 = (size_t)batch * C * hf1 * wf1, n2 = (size_t)batch * C * hf2 * wf2;
-    size_t ws = 0;
-    rc = oetr_workspace_bytes(h, batch, hf1, wf1, hf2, wf2, &ws);
-    if (rc) return rc;
-    if (grow(&h->st_feat1, &h->st_feat1_n, n1) || grow(&h->st_feat2, &h->st_feat2_n, n2) ||
-        grow(&h->st_boxes, &h->st_boxes_n, (size_t)batch * 8))
-        return fail(OETR_E_NOMEM, "oetr_forward_host: staging allocation failed");
-    if (h->st_ws_n < ws) {
-        cudaFree(h->st_ws); h->st_ws = nullptr; h->st_ws_n = 0;
-        if (cudaMalloc(&h->st_ws, ws) != cudaSuccess) return fail(OETR_E_NOMEM, "oetr_forward_host: workspace allocation failed");
-        h->st_ws_n = ws;
+    if (!ticket) return fail(OETR_E_ARG, "oetr_forward_host_submit: null ticket");
+    if (batch > 0 && (!feat1_host || !feat2_host)) return fail(OETR_E_ARG, "oetr_forward_host_submit: null buffer");
+    if (batch > 0 && (img_h1 < hf1 || img_h2 < hf2 || img_w1 < 1 || img_w2 < 1))
+        return fail(OETR_E_SHAPE, "oetr_forward_host_submit: image sizes (%d,%d),(%d,%d) smaller than the feature maps",
+                    img_h1, img_w1, img_h2, img_w2);
+    std::lock_guard<std::mutex> lock(h->mu);
+    HostSlot& sl = h->slot[h->next_ticket % HOST_SLOTS];
+    if (sl.busy)
+        return fail(OETR_E_ARG, "oetr_forward_host_submit: %d requests already in flight (wait for ticket %d first)",
+                    HOST_SLOTS, sl.ticket);
+    sl.batch = batch; sl.n_join = 0;
+    if (batch > 0) {
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t n1 = (size_t)batch * C * hf1 * wf1, n2 = (size_t)batch * C * hf2 * wf2;
+        size_t ws = 0;
+        rc = oetr_workspace_bytes(h, batch, hf1, wf1, hf2, wf2, &ws);
+        if (rc) return rc;
+        if (grow(&sl.feat1, &sl.feat1_n, n1) || grow(&sl.feat2, &sl.feat2_n, n2) || grow(&sl.boxes, &sl.boxes_n, (size_t)batch * 8))
+            return fail(OETR_E_NOMEM, "oetr_forward_host_submit: staging allocation failed");
+        if (sl.ws_n < ws) {
+            cudaFree(sl.ws); sl.ws = nullptr; sl.ws_n = 0;
+            if (cudaMalloc(&sl.ws, ws) != cudaSuccess) return fail(OETR_E_NOMEM, "oetr_forward_host_submit: workspace allocation failed");
+            sl.ws_n = ws;
+        }
+        if (sl.boxes_pin_n < (size_t)batch * 8) {
+            cudaFreeHost(sl.boxes_pin); sl.boxes_pin = nullptr; sl.boxes_pin_n = 0;
+            if (cudaMallocHost(&sl.boxes_pin, (size_t)batch * 8 * sizeof(float)) != cudaSuccess)
+                return fail(OETR_E_NOMEM, "oetr_forward_host_submit: pinned staging allocation failed");
+            sl.boxes_pin_n = (size_t)batch * 8;
+        }
+        const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, nullptr, nullptr, nullptr, nullptr};
+        const HostIO hio{feat1_host, feat2_host, sl.boxes_pin, sl.boxes_pin + (size_t)batch * 4, sl.flag_pin};
+        const EventSet es{sl.ev_fork, sl.ev_join, false, &sl.n_join};
+        rc = forward_core(h, sl.feat1, sl.feat2, batch, a, sl.boxes, sl.boxes + (size_t)batch * 4, sl.ws, sl.ws_n, s, &hio, es);
+        if (rc) {   // some sub-batches may have been queued: drain them before the slot can be reused
+            cudaDeviceSynchronize();
+            return rc;
+        }
     }
-    const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, nullptr, nullptr, nullptr, nullptr};
-    if (h->st_boxes_pin_n < (size_t)batch * 8) {
-        cudaFreeHost(h->st_boxes_pin); h->st_boxes_pin = nullptr; h->st_boxes_pin_n = 0;
-        if (cudaMallocHost(&h->st_boxes_pin, (size_t)batch * 8 * sizeof(float)) != cudaSuccess)
-            return fail(OETR_E_NOMEM, "oetr_forward_host: pinned staging allocation failed");
-        h->st_boxes_pin_n = (size_t)batch * 8;
+    sl.busy = true;
+    sl.ticket = (int)(h->next_ticket & 0x7fffffff);
+    *ticket = sl.ticket;
+    ++h->next_ticket;
+    return OETR_OK;
+}
+
+int oetr_forward_host_wait(oetr_handle* h, int ticket, float* boxes1_host, float* boxes2_host) {
+    if (!h) return fail(OETR_E_ARG, "null handle");
+    HostSlot* sl = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        for (HostSlot& c : h->slot) if (c.busy && c.ticket == ticket) sl = &c;
     }
-    const HostIO hio{feat1_host, feat2_host, h->st_boxes_pin, h->st_boxes_pin + (size_t)batch * 4};
-    rc = forward_core(h, h->st_feat1, h->st_feat2, batch, a, h->st_boxes, h->st_boxes + (size_t)batch * 4, h->st_ws,
-                      h->st_ws_n, s, &hio);
-    if (rc) return rc;
-    // the timeout flag rides the same stream as the boxes: one synchronisation, no second round trip
+    if (!sl) return fail(OETR_E_ARG, "oetr_forward_host_wait: ticket %d is not in flight", ticket);
+    if (sl->batch > 0 && (!boxes1_host || !boxes2_host)) return fail(OETR_E_ARG, "oetr_forward_host_wait: null buffer");
     int flag = 0;
-    CU(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    cudaError_t err = cudaSuccess;
+    for (int c = 0; c < sl->n_join; ++c) {
+        const cudaError_t e = cudaEventSynchronize(sl->ev_join[c]);
+        if (e != cudaSuccess) err = e;
+        flag |= sl->flag_pin[c];
+    }
+    const int batch = sl->batch;
+    if (err == cudaSuccess && !flag && batch > 0) {
+        memcpy(boxes1_host, sl->boxes_pin, (size_t)batch * 4 * sizeof(float));
+        memcpy(boxes2_host, sl->boxes_pin + (size_t)batch * 4, (size_t)batch * 4 * sizeof(float));
+    }
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        sl->busy = false;
+    }
+    if (err != cudaSuccess) return fail(OETR_E_CUDA, "oetr_forward_host_wait: %s", cudaGetErrorString(err));
     if (flag) {
         cudaMemset(h->d_flag, 0, sizeof(int));
         return fail(OETR_E_CUDA, "a device-side mbarrier wait timed out (pipeline protocol error); results are invalid");
     }
-    memcpy(boxes1_host, h->st_boxes_pin, (size_t)batch * 4 * sizeof(float));
-    memcpy(boxes2_host, h->st_boxes_pin + (size_t)batch * 4, (size_t)batch * 4 * sizeof(float));
     return OETR_OK;
+}
+
+int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat2_host, int batch, int hf1, int wf1,
+                      int hf2, int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp,
+                      float* boxes1_host, float* boxes2_host, void* stream) {
+    if (batch > 0 && (!boxes1_host || !boxes2_host)) return fail(OETR_E_ARG, "oetr_forward_host: null buffer");
+    int ticket = -1;
+    int rc = oetr_forward_host_submit(h, feat1_host, feat2_host, batch, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2,
+                                      img_w2, clamp, stream, &ticket);
+    if (rc) return rc;
+    return oetr_forward_host_wait(h, ticket, boxes1_host, boxes2_host);
 }
 
 int oetr_selftest_tcgen05(float* errs_host, int n_errs) {

@@ -35,6 +35,7 @@ class OverlapHotPath:
                                              _ATTN[attention], _PREC[precision], int(max_shape[0]),
                                              int(max_shape[1]), ctypes.byref(self._handle)), self._lib)
         self._ws = None
+        self._inflight = {}
 
     def close(self):
         if getattr(self, "_handle", None):
@@ -114,20 +115,37 @@ class OverlapHotPath:
                    memory2=dbg["memory"][b * l1:].view(b, hf2 * wf2, 256))
         return box1, box2, out
 
-    def forward_host(self, feat1, feat2, img_hw1, img_hw2, clamp=True):
-        """Host-buffer entry (numpy fp32 arrays or CPU tensors in, numpy boxes out): H2D copy, hot path, D2H copy
-        and a stream sync all inside the C call (oetr_forward_host)."""
+    def submit_host(self, feat1, feat2, img_hw1, img_hw2, clamp=True):
+        """Queue a host-buffer request (oetr_forward_host_submit) and return a ticket for `wait_host`.  At most two
+        requests may be in flight; the copies of one overlap the compute of the other."""
         a1 = np.ascontiguousarray(feat1.numpy() if hasattr(feat1, "numpy") else feat1, dtype=np.float32)
         a2 = np.ascontiguousarray(feat2.numpy() if hasattr(feat2, "numpy") else feat2, dtype=np.float32)
+        if a1.ndim != 4 or a2.ndim != 4 or a1.shape[1] != 256 or a2.shape[1] != 256 or a1.shape[0] != a2.shape[0]:
+            raise ValueError("features must be [B,256,h,w] with equal B, got %s and %s" % (a1.shape, a2.shape))
         b, _, hf1, wf1 = a1.shape
         _, _, hf2, wf2 = a2.shape
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        ticket = ctypes.c_int(-1)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self._lib.oetr_forward_host_submit(
+                self._handle, vp(a1), vp(a2), b, hf1, wf1, hf2, wf2, int(img_hw1[0]), int(img_hw1[1]),
+                int(img_hw2[0]), int(img_hw2[1]), int(bool(clamp)), ctypes.c_void_p(stream), ctypes.byref(ticket)),
+                self._lib)
+        self._inflight[ticket.value] = (a1, a2, b)            # keeps the feature buffers alive until the wait
+        return ticket.value
+
+    def wait_host(self, ticket):
+        """Block until the request has finished; returns (box1, box2) numpy [B,4]."""
+        a1, a2, b = self._inflight.pop(ticket)
         box1 = np.empty((b, 4), dtype=np.float32)
         box2 = np.empty((b, 4), dtype=np.float32)
         vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
         with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            cabi.check(self._lib.oetr_forward_host(
-                self._handle, vp(a1), vp(a2), b, hf1, wf1, hf2, wf2, int(img_hw1[0]), int(img_hw1[1]),
-                int(img_hw2[0]), int(img_hw2[1]), int(bool(clamp)), vp(box1), vp(box2), ctypes.c_void_p(stream)),
-                self._lib)
+            cabi.check(self._lib.oetr_forward_host_wait(self._handle, ticket, vp(box1), vp(box2)), self._lib)
         return box1, box2
+
+    def forward_host(self, feat1, feat2, img_hw1, img_hw2, clamp=True):
+        """Host-buffer entry (numpy fp32 arrays or CPU tensors in, numpy boxes out): H2D copies, hot path, D2H
+        copies and the wait for completion all inside the library (oetr_forward_host = submit + wait)."""
+        return self.wait_host(self.submit_host(feat1, feat2, img_hw1, img_hw2, clamp))

@@ -139,9 +139,23 @@ OETR_API int oetr_profile_read(oetr_handle* h, float* avg_ms, int* n_launches);
  * OETR_E_CUDA instead of hanging the GPU.  Intended for tests and debugging; not needed on the hot path. */
 OETR_API int oetr_poll_error(oetr_handle* h);
 
-/* Convenience for hosts without a CUDA runtime binding of their own (used by the host-buffer e2e path):
- *   host feats (pinned or pageable) -> device, forward, boxes -> host; synchronises `stream` before return.
- *   Device staging buffers are owned by the handle and grown on demand (the only entry point that allocates). */
+/* Host-buffer entry points, for hosts without a CUDA runtime binding of their own (the e2e path of bench.py).
+ *
+ * oetr_forward_host_submit queues  host feats (pinned or pageable) -> device, forward, boxes -> pinned landing
+ * buffer  on the handle's own streams, ordered after the work already queued on `stream`, and returns a ticket
+ * without waiting.  Up to 2 requests may be in flight (a third submit fails with OETR_E_ARG until one is waited
+ * for), so that the copies of request i+1 overlap the compute of request i.  The feature buffers must stay valid
+ * and unchanged until the matching wait returns.  Device staging is owned by the handle and grown on demand
+ * (these are the only entry points that allocate).
+ * oetr_forward_host_wait blocks until that request has finished, copies its boxes to boxes1_host / boxes2_host
+ * [batch,4] and reports a device-side failure of the request, if any.
+ * oetr_forward_host = submit + wait. */
+OETR_API int oetr_forward_host_submit(oetr_handle* h,
+                      const float* feat1_host, const float* feat2_host,
+                      int batch, int hf1, int wf1, int hf2, int wf2,
+                      int img_h1, int img_w1, int img_h2, int img_w2,
+                      int clamp, void* stream, int* ticket);
+OETR_API int oetr_forward_host_wait(oetr_handle* h, int ticket, float* boxes1_host, float* boxes2_host);
 OETR_API int oetr_forward_host(oetr_handle* h,
                       const float* feat1_host, const float* feat2_host,
                       int batch, int hf1, int wf1, int hf2, int wf2,
