@@ -290,6 +290,31 @@ def run_b200(args):
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src}
     cpu_pps, cpu_dt = cpu_port_pairs_per_s(2, 4)
+    # the same path as eager PyTorch fp32 (TF32 off) on this GPU: the "GPU bar to beat" of SURVEY.md 8(d)
+    eager = None
+    try:
+        from oracle import oetr_torch_eager as ote
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        Wt = ote.prepare(Wts, dev)
+        for _ in range(3):
+            t1, t2 = ote.hot_path(Wt, feats[0][0], feats[0][1], (IMG, IMG), (IMG, IMG))
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev4.record()
+        for i in range(5):
+            t1, t2 = ote.hot_path(Wt, feats[i % N_ROTATE][0], feats[i % N_ROTATE][1], (IMG, IMG), (IMG, IMG))
+        ev5.record()
+        torch.cuda.synchronize()
+        g1, g2 = hot.forward(feats[4][0], feats[4][1], (IMG, IMG), (IMG, IMG))
+        torch.cuda.synchronize()
+        eager = {"value": B * 5 / (ev4.elapsed_time(ev5) * 1e-3), "unit": "pairs/s",
+                 "kind": "eager PyTorch fp32 (TF32 off) restatement of the same path (oracle/oetr_torch_eager.py), "
+                         "same GPU, same batch, device-resident inputs, 5 steps",
+                 "max_box_diff_px": float(max((g1 - t1).abs().max().item(), (g2 - t2).abs().max().item()))}
+        del Wt
+    except Exception as e:  # measurement aid only
+        eager = {"error": repr(e)}
     value = world * B * K / (ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -311,6 +336,7 @@ def run_b200(args):
         "roofline": roof,
         "cpu_baseline": {"value": cpu_pps, "unit": "pairs/s", "cores": _host_threads(), "kind": "port",
                          "sample": "2 pairs x 4 runs of the numpy fp32 port (%.1f s)" % cpu_dt},
+        "gpu_eager_baseline": eager,
         "parity": {"box_err_over_image_side": float(perr), "bar": 1e-3, "pairs_checked": 2},
     }
     print(json.dumps(line))

@@ -56,3 +56,18 @@ def test_fp16_rounding_model_is_close_but_not_identical():
     q = orc.hot_path(W, f1, f2, hw1, hw2, rnd=orc.round_fp16)
     d = np.abs(q["box1_raw"] - exact["box1_raw"]).max() / max(hw1)
     assert 1e-6 < d < 1e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_b3", "ragged_640x480"])
+def test_torch_eager_restatement_matches_oracle(name):
+    """oracle/oetr_torch_eager.py (bench.py's GPU eager baseline) computes the same boxes as the pinned oracle."""
+    import torch
+    from oracle import oetr_torch_eager as ote
+    W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case(name)
+    assert attention == "linear"
+    o = orc.hot_path(W, f1, f2, hw1, hw2)
+    Wt = ote.prepare(W, "cpu", dtype=torch.float64)
+    for clamp, keys in ((False, ("box1_raw", "box2_raw")), (True, ("box1", "box2"))):
+        b1, b2 = ote.hot_path(Wt, torch.from_numpy(f1).double(), torch.from_numpy(f2).double(), hw1, hw2, clamp=clamp)
+        assert np.abs(b1.numpy() - o[keys[0]]).max() / max(hw1) < 1e-9
+        assert np.abs(b2.numpy() - o[keys[1]]).max() / max(hw2) < 1e-9
