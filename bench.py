@@ -181,40 +181,60 @@ def run_b200(args):
     B, K, Wm = PAIRS_PER_GPU, args.steps, args.warmup
 
     Wts = weights.synthetic_hot_path_weights(0)
-    hot = oetr_b200.OverlapHotPath(Wts, attention="linear", precision=args.precision, device=dev)
-    hot.set_chunk_pairs(args.chunk_pairs)
+    # `in_flight` independent batches are kept in flight, each on its own CUDA stream and handle (every step is still
+    # one complete stream-ordered forward of one batch): a sub-batch is a serial chain of ~25 launches, and with one
+    # batch in flight the tail of that chain leaves SMs idle at every step boundary
+    lanes = max(1, args.in_flight)
+    hots = [oetr_b200.OverlapHotPath(Wts, attention="linear", precision=args.precision, device=dev) for _ in range(lanes)]
+    for h_ in hots:
+        h_.set_chunk_pairs(args.chunk_pairs)
+    hot = hots[0]
+    lane_streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
     # N_ROTATE different resident input batches (8 x 26 MB > 126 MB L2)
     base1 = weights.synthetic_features(B, FEAT_HW, FEAT_HW, seed=100 + rank, tag="b1")
     base2 = weights.synthetic_features(B, FEAT_HW, FEAT_HW, seed=100 + rank, tag="b2")
     feats = []
     for i in range(N_ROTATE):
         feats.append((torch.from_numpy(np.roll(base1, i, axis=0)).to(dev), torch.from_numpy(np.roll(base2, i, axis=0)).to(dev)))
-    gathered = torch.empty(world * B, 2, 4, device=dev) if world > 1 else None
+    gathered = [torch.empty(world * B, 2, 4, device=dev) if world > 1 else None for _ in range(lanes)]
 
-    def step(i):
+    def step(i, lane=None):
         f1, f2 = feats[i % N_ROTATE]
-        b1, b2 = hot.forward(f1, f2, (IMG, IMG), (IMG, IMG), clamp=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.stack([b1, b2], dim=1))
+        if lane is None:
+            b1, b2 = hot.forward(f1, f2, (IMG, IMG), (IMG, IMG), clamp=True)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered[0], torch.stack([b1, b2], dim=1))
+            return b1, b2
+        with torch.cuda.stream(lane_streams[lane]):
+            b1, b2 = hots[lane].forward(f1, f2, (IMG, IMG), (IMG, IMG), clamp=True)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered[lane], torch.stack([b1, b2], dim=1))
         return b1, b2
 
-    for i in range(Wm):
-        step(i)
+    main = torch.cuda.current_stream(dev)
+    for i in range(Wm * lanes):
+        step(i, i % lanes)
     torch.cuda.synchronize()
-    hot.poll_error()
+    for h_ in hots:
+        h_.poll_error()
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
         ev0.record()
+        for st in lane_streams:
+            st.wait_stream(main)
         for i in range(K):
-            step(Wm + i)
+            step(Wm + i, i % lanes)
+        for st in lane_streams:
+            main.wait_stream(st)
         ev1.record()
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     launches = hot.last_launch_count * K
-    hot.poll_error()
+    for h_ in hots:
+        h_.poll_error()
     # roofline leg: the same K steps with the kernel profiler on.  It brackets every k_enc launch with CUDA events on
     # the launching stream, which needs the launches serialised on ONE stream, so sub-batch scheduling is off here:
     # the kernel is timed whole-batch (256 tiles), in isolation, inside a long step.
@@ -324,6 +344,7 @@ def run_b200(args):
                                "decoder + overlap head) on two [32,256,20,20] fp32 feature maps",
                    "pairs_per_gpu": B, "precision": args.precision, "attention": "linear",
                    "sub_batches": "%d pairs each, own stream" % args.chunk_pairs if args.chunk_pairs else "off",
+                   "batches_in_flight": "%d (one CUDA stream + handle each; every step = one complete forward)" % lanes,
                    "l2": "inputs rotate over %d resident batches (%.0f MB > 126 MB L2)" % (
                        N_ROTATE, N_ROTATE * 2 * base1.nbytes / 1e6),
                    "parallelism": "batch shards, replicated weights, all-gather of boxes" if world > 1 else "1 GPU"},
@@ -352,6 +373,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunk-pairs", type=int, default=int(os.environ.get("OETR_CHUNK_PAIRS", "8")),
                     help="pairs per concurrently scheduled sub-batch (0 = off)")
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("OETR_IN_FLIGHT", "2")),
+                    help="independent batches kept in flight in the device-resident timed region")
     ap.add_argument("--precision", default=os.environ.get("OETR_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

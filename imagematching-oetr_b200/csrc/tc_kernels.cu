@@ -224,6 +224,47 @@ __host__ __device__ __forceinline__ TileInfo tile_info(const TileGeom& g, int t)
     ti.valid = ti.L - ti.ti * TILE < TILE ? ti.L - ti.ti * TILE : TILE;
     return ti;
 }
+// Row mapping of the ENCODER tiles (k_enc, k_fold, k_sum_partials).  flat == 0: the per-image tiles of TileGeom.
+// flat == 1: the images of a set are concatenated, each padded to Lp = round_up(L, 16) rows, and the B*Lp rows are cut
+// into 128-row tiles: no per-image padding to a multiple of 128 (400 tokens: 3.125 tiles instead of 4).  With
+// Lp >= 128 a tile holds rows of at most two consecutive images and the boundary is a multiple of 16 rows (one MMA
+// k-step of the K^T V product).  The head kernels keep per-image tiles (k_retile converts the encoder output).
+struct EncGeom {
+    int flat, Lp1, Lp2, F1, F2;     // F: flat tiles per set
+};
+struct EncTile { int set, L, Lp, B, b0, l0, split, two; };
+// rows [0, split) of the tile belong to image b0 (tokens l0 ..), rows [split, 128) to image b0 + 1 (tokens 0 ..)
+__host__ __device__ __forceinline__ EncTile enc_tile(const TileGeom& g, const EncGeom& eg, int t) {
+    EncTile e;
+    e.B = g.B;
+    if (!eg.flat) {
+        const TileInfo ti = tile_info(g, t);
+        e.set = ti.set; e.L = ti.L; e.Lp = ti.L; e.b0 = ti.b; e.l0 = ti.ti * 128; e.split = 128; e.two = 0;
+    } else {
+        e.set = t >= eg.F1 ? 1 : 0;
+        const int u = t - e.set * eg.F1;
+        e.L = e.set ? g.L2 : g.L1; e.Lp = e.set ? eg.Lp2 : eg.Lp1;
+        const int base = u * 128;
+        e.b0 = base / e.Lp; e.l0 = base - e.b0 * e.Lp;
+        e.split = e.Lp - e.l0 < 128 ? e.Lp - e.l0 : 128;
+        e.two = (e.split < 128 && e.b0 + 1 < g.B) ? 1 : 0;
+    }
+    return e;
+}
+// the partial summaries of image (set, b): n = enc_parts(...), then enc_part_index(..., i) for i < n, in a fixed order.
+// ppt = partial slots per tile (flat: 2 = one per image of a tile)
+__host__ __device__ __forceinline__ int enc_parts(const TileGeom& g, const EncGeom& eg, int ppt, int set, int b) {
+    if (!eg.flat) return (set == 0 ? g.T1 : g.T2) * ppt;
+    const int L = set ? g.L2 : g.L1, Lp = set ? eg.Lp2 : eg.Lp1;
+    return (b * Lp + L - 1) / 128 - (b * Lp) / 128 + 1;
+}
+__host__ __device__ __forceinline__ int enc_part_index(const TileGeom& g, const EncGeom& eg, int ppt, int set, int b, int i) {
+    if (!eg.flat) return (set == 0 ? b * g.T1 : g.B * g.T1 + b * g.T2) * ppt + i;
+    const int Lp = set ? eg.Lp2 : eg.Lp1;
+    const int u = (b * Lp) / 128 + i;                       // flat tile inside the set
+    const int slot = b - (u * 128) / Lp;                    // 0: the tile starts inside this image, 1: inside the previous one
+    return ((set ? eg.F1 : 0) + u) * 2 + slot;
+}
 // tile-blocked fp32 layout [tile][64 col-quads][128 rows][4]: a warp's rows read/write one col-quad coalesced
 __host__ __device__ __forceinline__ size_t xt_off(int tile, int quad, int r) { return (((size_t)tile * 64 + quad) * TILE + r) * 4; }
 
@@ -340,6 +381,7 @@ __device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* 
 // ---------------------------------------------------------------------------------------------------------
 struct EncParams {
     TileGeom g;
+    EncGeom eg;                 // row mapping of the tiles (k_enc only; k_enc2 always uses the per-image tiles of g)
     const float* feat1;         // NCHW inputs, read when load_feat
     const float* feat2;
     float* xt;                  // tile-blocked residual stream (read unless load_feat; written when store_x)
@@ -369,15 +411,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const TileInfo ti = tile_info(p.g, blockIdx.x);
+    const EncTile et = enc_tile(p.g, p.eg, blockIdx.x);
+    const bool two = et.two != 0;                      // the tile holds rows of two images (flat tiling only)
     const uint32_t smem_base = smem_u32(smem);
     const bool dec_mode = p.lnkv_g == nullptr;
 
     const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
     const uint32_t S0 = tmem, S1 = tmem + 256;
 
-    int src_img = ti.img, src_len = ti.L;
-    if (p.cross) { src_img = ti.set == 0 ? p.g.B + ti.b : ti.b; src_len = ti.set == 0 ? p.g.L2 : p.g.L1; }
+    // source image of the tile's first image (the second one's is src_img + 1) and its length
+    int src_img = et.set * p.g.B + et.b0, src_len = et.L;
+    if (p.cross) { src_img = et.set == 0 ? p.g.B + et.b0 : et.b0; src_len = et.set == 0 ? p.g.L2 : p.g.L1; }
 
     if (warp == WARP_PRODUCER) {
         // ------------------------------------------------------------------ weight stream
@@ -391,6 +435,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             if (p.do_q) {
                 stream(p.w_q, GEMM_STAGES);
                 stream(p.mimg + (size_t)src_img * GEMM_HALFS, GEMM_STAGES);
+                if (two) stream(p.mimg + (size_t)(src_img + 1) * GEMM_HALFS, GEMM_STAGES);
                 stream(p.w_mlp, 4 * GEMM_STAGES);
             }
             if (p.do_kv) stream(p.w_kv, 2 * GEMM_STAGES);
@@ -406,6 +451,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             if (p.do_q) {
                 gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
                 gemm(S1, false, true);  umma_commit(&bars->s_full[1]);     // msg = (phi(q)/Z) M_img^T
+                if (two) { gemm(S0, false, false); umma_commit(&bars->s_full[0]); }   // ... with the second image's M_img
                 gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // h_a = LN2(x) W1a^T
                 gemm(S1, false, false); umma_commit(&bars->s_full[1]);     // h_b = LN2(x) W1b^T
                 gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // y   = gelu(h_a) W2a^T
@@ -415,23 +461,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 gemm(S0, false, true);      umma_commit(&bars->s_full[0]); // v
                 gemm(S1, false, dec_mode);  umma_commit(&bars->s_full[1]); // k (decoder: from a second image)
                 // per 128-channel half: KV = Kf^T V (diagonal 32x32 blocks are the heads); Ksum is reduced by the row warps
+                // the token rows are the K dimension, 16 per MMA: a two-image tile splits the k-steps at the image
+                // boundary (a multiple of 16 rows) and accumulates the second image's product in S1's columns
+                const int ksplit = two ? et.split / 16 : TILE / 16;
                 for (int half = 0; half < 2; ++half) {
                     wait_a(half);
                     const uint32_t kf_hi = smem_base + SM_AHI + KF_OFF, kf_lo = smem_base + SM_ALO + KF_OFF;
                     const uint32_t v_hi = smem_base + SM_AHI + V_OFF, v_lo = smem_base + SM_ALO + V_OFF;
-                    const uint32_t dkv = S0 + half * 128;
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t a = term == 1 ? kf_lo : kf_hi, bb = term == 2 ? v_lo : v_hi;
 #pragma unroll
-                    for (int k = 0; k < TILE / 16; ++k)
-                        umma_f16(dkv, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
-                                 umma_desc(v_hi + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, k);
-#pragma unroll
-                    for (int k = 0; k < TILE / 16; ++k)
-                        umma_f16(dkv, umma_desc(kf_lo + k * 2048, SLAB_BYTES, ATOM_BYTES),
-                                 umma_desc(v_hi + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, 1u);
-#pragma unroll
-                    for (int k = 0; k < TILE / 16; ++k)
-                        umma_f16(dkv, umma_desc(kf_hi + k * 2048, SLAB_BYTES, ATOM_BYTES),
-                                 umma_desc(v_lo + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, 1u);
+                        for (int k = 0; k < TILE / 16; ++k) {
+                            const bool second = k >= ksplit;
+                            const uint32_t dkv = (second ? S1 : S0) + half * 128;
+                            const uint32_t first_of_group = (term == 0 && (k == 0 || k == ksplit)) ? 0u : 1u;
+                            umma_f16(dkv, umma_desc(a + k * 2048, SLAB_BYTES, ATOM_BYTES),
+                                     umma_desc(bb + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, first_of_group);
+                        }
+                    }
                     umma_commit(&bars->s_full[half]);
                 }
             }
@@ -445,12 +492,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         // ------------------------------------------------------------------ row warps
         const int q = warp & 3, cq = warp >> 2;            // TMEM lane quarter, column quarter
         const int r = q * 32 + lane;                       // token row of the tile
-        const bool valid = r < ti.valid;
+        // which image / token this row is (enc_tile): rows >= split belong to the tile's second image
+        const int rel = r >= et.split ? 1 : 0;
+        const int rb = et.b0 + rel;                        // image inside the set
+        const int rl = rel ? r - et.split : et.l0 + r;     // token inside the image
+        const bool valid = rb < et.B && rl < et.L;
+        const int pl = valid ? rl : 0;                     // row of the position table
+        const bool warp_has_rel1 = two && et.split < q * 32 + 32;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float* X = reinterpret_cast<float*>(smem + SM_X);       // 512-float scratch, see the shared-memory map
         uint8_t* img_hi = smem + SM_AHI;
         uint8_t* img_lo = smem + SM_ALO;
-        const float* post = (ti.set == 0 ? p.post1 : p.post2);
+        const float* post = (et.set == 0 ? p.post1 : p.post2);
         uint32_t ns0 = 0, ns1 = 0;
         auto wait_s = [&](int b) {
             mbar_wait(&bars->s_full[b], (b ? ns1++ : ns0++) & 1, p.flag);
@@ -467,10 +520,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         for (int pass = 0; pass < 2; ++pass) {
             const int c0 = pass * 128 + cq * 32;
             if (p.load_feat) {
-                const float* feat = ti.set == 0 ? p.feat1 : p.feat2;
-                const float* f = feat + ((size_t)ti.b * C + c0) * ti.L + (size_t)ti.ti * TILE + r;
+                const float* feat = et.set == 0 ? p.feat1 : p.feat2;
+                const float* f = feat + ((size_t)(valid ? rb : 0) * C + c0) * et.L + pl;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] = valid ? f[(size_t)e * ti.L] : 0.f;
+                for (int e = 0; e < 32; ++e) x[pass][e] = valid ? f[(size_t)e * et.L] : 0.f;
             } else {
 #pragma unroll
                 for (int jq = 0; jq < 8; ++jq) {
@@ -517,7 +570,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 #pragma unroll
                 for (int jq = 0; jq < 8; ++jq) {
                     float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(ti.ti, (c0 >> 2) + jq, r));
+                    if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(pl >> 7, (c0 >> 2) + jq, pl & 127));
                     float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (gamma) {
                         g4 = *reinterpret_cast<const float4*>(X + c0 + jq * 4);
@@ -539,8 +592,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             image_from_x(p.lnq_g, p.lnq_b, true);
             // Ksum of the source image -> X (every thread is done with gamma/beta after the barrier)
             named_bar_sync(1, N_ROW_THREADS);
-            if (tid < 256) X[tid] = __ldg(p.ksum + (size_t)src_img * C + tid);
+            if (tid < 256 || two) X[tid] = __ldg(p.ksum + (size_t)(src_img + (tid >> 8)) * C + (tid & 255));   // [256, 512): second image
             named_bar_sync(1, N_ROW_THREADS);
+            const float* Xk = X + rel * 256;
             // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
             wait_s(0);
             const float eps_s = ATTN_EPS / (float)src_len;    // summaries arrive scaled by 1/S (k_fold)
@@ -552,7 +606,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 float den = 0.f;
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(X + c0 + e4 * 4);
+                    const float4 k4 = *reinterpret_cast<const float4*>(Xk + c0 + e4 * 4);
                     v[e4 * 4 + 0] = elu1(v[e4 * 4 + 0]); den = fmaf(v[e4 * 4 + 0], k4.x, den);
                     v[e4 * 4 + 1] = elu1(v[e4 * 4 + 1]); den = fmaf(v[e4 * 4 + 1], k4.y, den);
                     v[e4 * 4 + 2] = elu1(v[e4 * 4 + 2]); den = fmaf(v[e4 * 4 + 2], k4.z, den);
@@ -564,12 +618,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 store_row32_split(img_hi, img_lo, r, c0, v);
                 publish(pass);
             }
-            // (E2) x += msg ; A = LN2(x)
+            // (E2) x += msg ; A = LN2(x)   (two-image tile: rows of the second image take the product with its M_img, S0)
             wait_s(1);
+            if (two) wait_s(0);
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 float v[32];
                 tmem_ld32(S1 + lane_addr + pass * 128 + cq * 32, v);
+                if (warp_has_rel1) {
+                    float v2[32];
+                    tmem_ld32(S0 + lane_addr + pass * 128 + cq * 32, v2);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = rel ? v2[e] : v[e];
+                }
 #pragma unroll
                 for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
             }
@@ -630,7 +691,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 wait_s(1);
             }
             // half images (tokens = K dimension): V and Kf = elu(k)+1; padded rows are zero
-            float* part = p.kv_part + (size_t)blockIdx.x * KVS;
+            // partial summaries of this tile: one slot per image of the tile when the tiling is flat
+            float* part = p.kv_part + (size_t)blockIdx.x * (p.eg.flat ? 2 : 1) * KVS;
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32, ch = cq * 32;      // ch: column inside the 128-channel half
@@ -663,33 +725,41 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 publish(pass);
                 // Ksum[c0 + j] = sum over the tile's rows of Kf[:, c0 + j] (fp32, exact operands): butterfly
                 // transpose-reduce inside the warp (lane j ends with column j summed over the warp's 32 rows),
-                // then across the 4 row quarters through X
+                // then across the 4 row quarters through X; per image of the tile (rows of the other image masked)
+#pragma unroll 1
+                for (int im = 0; im < (two ? 2 : 1); ++im) {
+                    float w[32];
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
+                    for (int e = 0; e < 32; ++e) w[e] = (!two || rel == im) ? v[e] : 0.f;
 #pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float send = up ? v[i] : v[i + off];
-                        const float keep = up ? v[i + off] : v[i];
-                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = up ? w[i] : w[i + off];
+                            const float keep = up ? w[i + off] : w[i];
+                            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
                     }
+                    X[(cq * 4 + q) * 32 + lane] = w[0];
+                    named_bar_sync(1, N_ROW_THREADS);
+                    if (q == 0)
+                        part[im * KVS + NH * HD * HD + c0 + lane] = X[(cq * 4 + 0) * 32 + lane] + X[(cq * 4 + 1) * 32 + lane] +
+                                                                    X[(cq * 4 + 2) * 32 + lane] + X[(cq * 4 + 3) * 32 + lane];
+                    named_bar_sync(1, N_ROW_THREADS);
                 }
-                X[(cq * 4 + q) * 32 + lane] = v[0];
-                named_bar_sync(1, N_ROW_THREADS);
-                if (q == 0)
-                    part[NH * HD * HD + c0 + lane] = X[(cq * 4 + 0) * 32 + lane] + X[(cq * 4 + 1) * 32 + lane] +
-                                                     X[(cq * 4 + 2) * 32 + lane] + X[(cq * 4 + 3) * 32 + lane];
-                named_bar_sync(1, N_ROW_THREADS);
             }
             // results: KV diagonal blocks (this warp's TMEM lanes are the d-channels of head 4*half + q)
             wait_s(1);
             if (cq < 2) {
                 const int half = cq, h = half * 4 + q;
-                float v[32];
-                tmem_ld32(S0 + lane_addr + half * 128 + q * 32, v);
-                float* o = part + h * HD * HD + lane * HD;
+                for (int im = 0; im < (two ? 2 : 1); ++im) {
+                    float v[32];
+                    tmem_ld32((im ? S1 : S0) + lane_addr + half * 128 + q * 32, v);
+                    float* o = part + im * KVS + h * HD * HD + lane * HD;
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                }
             }
             tc_fence_before();
         }
@@ -1240,17 +1310,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(E2_THREADS, 2) k_enc
 // k_fold: per (image, head): KV_h = sum of tile partials; M_img[n][h*32+d] = sum_e Wm[n][h*32+e] KV_h[d][e];
 // written as the (hi, lo) stage images k_enc streams; also Ksum[img][256].
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, TileGeom g, int ppt, const float* __restrict__ Wm,
-                                              __half* __restrict__ mimg, float* __restrict__ ksum) {
+__global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, TileGeom g, EncGeom eg, int ppt,
+                                              const float* __restrict__ Wm, __half* __restrict__ mimg, float* __restrict__ ksum) {
     // register-tiled [256 n x 32 d] = W_h[256 x 32 e] . KV_h^T: thread = 8 n x 4 d, operands k-major in shared memory
     __shared__ __align__(16) float wT[HD][C + 4];          // [e][n]
     __shared__ __align__(16) float kvT[HD][HD + 4];        // [e][d]
     const int img = blockIdx.x >> 3, h = blockIdx.x & 7;
     const int set = img / g.B, b = img % g.B;
-    // ppt partial summaries per tile (k_enc: 1, k_enc2: one per CTA of the pair), summed in a fixed order
-    const int T = (set == 0 ? g.T1 : g.T2) * ppt;
-    const int first = (set == 0 ? b * g.T1 : g.B * g.T1 + b * g.T2) * ppt;
-    const float* src = part + (size_t)first * KVS;
+    // the image's partial summaries (per tile; k_enc2: per CTA of a pair; flat tiling: per (tile, image)), fixed order
+    const int T = enc_parts(g, eg, ppt, set, b);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // both summaries are scaled by 1/S (S = source length) like the reference's v / v_length
     // (linear_attention.py:43-48): keeps phi(q)/Z and M_img inside fp16 range for any S; k_enc scales eps alike
@@ -1259,14 +1327,14 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
         const int i = tid * 4, d = i >> 5, e0 = i & 31;    // 4 consecutive e of KV_h[d][:]
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < T; ++t) {
-            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)t * KVS + h * HD * HD + i);
+            const float4 v = *reinterpret_cast<const float4*>(part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * KVS + h * HD * HD + i);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         kvT[e0][d] = acc.x * inv_s; kvT[e0 + 1][d] = acc.y * inv_s; kvT[e0 + 2][d] = acc.z * inv_s; kvT[e0 + 3][d] = acc.w * inv_s;
     }
     if (tid < HD) {
         float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc += src[(size_t)t * KVS + NH * HD * HD + h * HD + tid];
+        for (int t = 0; t < T; ++t) acc += part[(size_t)enc_part_index(g, eg, ppt, set, b, t) * KVS + NH * HD * HD + h * HD + tid];
         ksum[(size_t)img * C + h * HD + tid] = acc * inv_s;
     }
 #pragma unroll 8
@@ -1833,17 +1901,31 @@ __global__ void k_untile(const float* __restrict__ xt, TileGeom g, float* __rest
             *reinterpret_cast<const float4*>(xt + xt_off(blockIdx.x, quad, r));
     }
 }
+// flat encoder tiles -> the per-image tiles of the head kernels (one CTA per per-image tile, thread = 16-byte chunk)
+__global__ void __launch_bounds__(256) k_retile(const float* __restrict__ xt_flat, TileGeom g, EncGeom eg, float* __restrict__ xt) {
+    const TileInfo ti = tile_info(g, blockIdx.x);
+    const int Lp = ti.set ? eg.Lp2 : eg.Lp1, f0 = ti.set ? eg.F1 : 0;
+    for (int idx = threadIdx.x; idx < 64 * TILE; idx += 256) {
+        const int r = idx & 127, quad = idx >> 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < ti.valid) {
+            const int frow = ti.b * Lp + ti.ti * TILE + r;
+            v = *reinterpret_cast<const float4*>(xt_flat + xt_off(f0 + (frow >> 7), quad, frow & 127));
+        }
+        *reinterpret_cast<float4*>(xt + xt_off(blockIdx.x, quad, r)) = v;
+    }
+}
 // per-image sum of per-tile partial summaries (decoder cross-attention consumes the raw summaries); grid (2B, 9)
-__global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ part, TileGeom g, int ppt, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ part, TileGeom g, EncGeom eg, int ppt,
+                                                      float* __restrict__ out) {
     const int img = blockIdx.x;                      // 0..2B-1
     const int set = img / g.B, b = img % g.B;
-    const int T = (set == 0 ? g.T1 : g.T2) * ppt;
-    const int first = (set == 0 ? b * g.T1 : g.B * g.T1 + b * g.T2) * ppt;
+    const int T = enc_parts(g, eg, ppt, set, b);
     const int i = (blockIdx.y * 256 + threadIdx.x) * 4;
     if (i >= KVS) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = 0; t < T; ++t) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)(first + t) * KVS + i);
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * KVS + i);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     *reinterpret_cast<float4*>(out + (size_t)img * KVS + i) = acc;
@@ -1868,6 +1950,7 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
         return p;
     };
     w.xt = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));
+    w.xt_enc = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));      // flat tiles <= per-image tiles
     w.kv_part = static_cast<float*>(take((size_t)g.tiles() * 2 * KVS * sizeof(float)));   // k_enc2: one partial per CTA of a pair
     w.dec_kvs = static_cast<float*>(take((size_t)N_DEC * 2 * B * KVS * sizeof(float)));
     w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
@@ -1907,6 +1990,18 @@ static int set_attrs(char* msg, size_t msg_len) {
     return 0;
 }
 
+// flat encoder tiling (EncGeom): on unless OETR_FLAT=0; needs both maps to have >= 128 tokens (a tile then holds at
+// most two images) and the one-CTA-per-tile kernel
+static EncGeom make_enc_geom(int B, int L1, int L2, bool pairs) {
+    static const bool off = getenv("OETR_FLAT") && atoi(getenv("OETR_FLAT")) == 0;
+    EncGeom eg{};
+    if (off || pairs || L1 < 128 || L2 < 128) return eg;
+    eg.flat = 1;
+    eg.Lp1 = (L1 + 15) / 16 * 16; eg.Lp2 = (L2 + 15) / 16 * 16;
+    eg.F1 = (B * eg.Lp1 + TILE - 1) / TILE; eg.F2 = (B * eg.Lp2 + TILE - 1) / TILE;
+    return eg;
+}
+
 bool tc_pair_kernel_selected() {
     static const bool pairs = getenv("OETR_ENC") && atoi(getenv("OETR_ENC")) == 2;
     return pairs;
@@ -1936,14 +2031,16 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
     // OETR_ENC=2 selects the experimental CTA-pair kernel (k_enc2, see its header: correct, but slower than k_enc
     // as measured in round 1); default: one CTA per tile (k_enc)
     static const bool pairs = tc_pair_kernel_selected();
-    const int ppt = pairs ? 2 : 1;
+    const EncGeom eg = make_enc_geom(B, L1, L2, pairs);
+    const int ppt = (pairs || eg.flat) ? 2 : 1;
+    const int enc_tiles = eg.flat ? eg.F1 + eg.F2 : tiles;
     auto launch_enc = [&](const EncParams& p) {
         if (pairs) k_enc2<<<2 * tiles, E2_THREADS, E2_TOTAL, s>>>(p);
-        else k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p);
+        else k_enc<<<enc_tiles, N_THREADS, SM_TOTAL, s>>>(p);
         lc.n++;
     };
     EncParams base{};
-    base.g = g; base.feat1 = feat1; base.feat2 = feat2; base.xt = ws.xt; base.post1 = post1; base.post2 = post2;
+    base.g = g; base.eg = eg; base.feat1 = feat1; base.feat2 = feat2; base.xt = eg.flat ? ws.xt_enc : ws.xt; base.post1 = post1; base.post2 = post2;
     base.mimg = ws.mimg; base.ksum = ws.ksum; base.kv_part = ws.kv_part; base.flag = flag;
     auto set_kv_enc = [&](EncParams& p, int layer) {
         const EncW& e = L.enc[layer];
@@ -1975,7 +2072,7 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         set_prefetch_for(p, 0);
         p.pf_ptr[2] = p.w_kv; p.pf_bytes[2] = 2 * G;          // its own weights: nobody ran before it
         launch_enc(p);
-        k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, ppt, d_w + L.enc[0].wm, ws.mimg, ws.ksum); lc.n++;
+        k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, eg, ppt, d_w + L.enc[0].wm, ws.mimg, ws.ksum); lc.n++;
     }
     for (int i = 0; i < N_ENC; ++i) {
         const EncW& e = L.enc[i];
@@ -1990,16 +2087,17 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         if (prof) prof->mark(s);
         launch_enc(p);
         if (prof) prof->mark(s);
-        if (i + 1 < N_ENC) { k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, ppt, d_w + L.enc[i + 1].wm, ws.mimg, ws.ksum); lc.n++; }
-        else { k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, ppt, ws.dec_kvs); lc.n++; }
+        if (i + 1 < N_ENC) { k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, eg, ppt, d_w + L.enc[i + 1].wm, ws.mimg, ws.ksum); lc.n++; }
+        else { k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, eg, ppt, ws.dec_kvs); lc.n++; }
     }
     // decoder layer 1 cross-attention summaries: k = (memory+pos) Wk^T + bk, v = memory Wv^T + bv
     {
         EncParams p = base;
         set_kv_dec(p, 1);
         launch_enc(p);
-        k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, ppt, ws.dec_kvs + (size_t)2 * B * KVS); lc.n++;
+        k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, eg, ppt, ws.dec_kvs + (size_t)2 * B * KVS); lc.n++;
     }
+    if (eg.flat) { k_retile<<<tiles, 256, 0, s>>>(ws.xt_enc, g, eg, ws.xt); lc.n++; }
     if (X_out) { k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++; }
     if (dbg_clock) {
         std::vector<long long> hbuf((size_t)tiles * 4);
@@ -2215,7 +2313,7 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
                                            max_rel(part.data() + KVS + NH * HD * HD, kvs1.data() + NH * HD * HD, NH * HD));
     }
     // (2) fold
-    k_fold<<<2 * NH, 256>>>(d_part, g, 1, d_wm, d_mimg, d_ksum);
+    k_fold<<<2 * NH, 256>>>(d_part, g, EncGeom{}, 1, d_wm, d_mimg, d_ksum);
     ST(cudaDeviceSynchronize());
     if (n_errs > 2) {
         std::vector<__half> mi(GEMM_HALFS);
@@ -2261,7 +2359,7 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
     }
     // (4) cross layer (each image reads the partner's summary), query phase only
     if (n_errs > 6) {
-        k_fold<<<2 * NH, 256>>>(d_part, g, 1, d_wm, d_mimg, d_ksum);
+        k_fold<<<2 * NH, 256>>>(d_part, g, EncGeom{}, 1, d_wm, d_mimg, d_ksum);
         EncParams p = base;
         p.store_x = 1; p.do_q = 1; p.do_kv = 0; p.cross = 1;
         k_enc<<<2, N_THREADS, SM_TOTAL>>>(p);

@@ -16,7 +16,8 @@ struct TcWeights {
 };
 
 struct TcWorkspace {
-    float* xt = nullptr;           // tile-blocked fp32 residual stream [tiles][64][128][4]
+    float* xt = nullptr;           // tile-blocked fp32 residual stream [tiles][64][128][4], per-image tiles
+    float* xt_enc = nullptr;       // the same in the encoder's flat tiling (k_retile converts it into xt for the head)
     float* kv_part = nullptr;      // per-tile linear-attention partial summaries [tiles][KVS]
     float* dec_kvs = nullptr;      // [2 decoder layers][2B][KVS] cross-attention summaries
     __half* mimg = nullptr;        // [2B images] folded merge weights (hi/lo stage images, 256 KB each)

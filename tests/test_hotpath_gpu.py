@@ -118,12 +118,15 @@ def test_full_size_properties(precision):
     # determinism
     c1, c2 = hot.forward(f1, f2, (640, 640), (640, 640), clamp=False)
     assert torch.equal(a1, c1) and torch.equal(a2, c2)
-    # pairs are independent: permuting the batch permutes the boxes, and a sub-batch reproduces its rows
+    # pairs are independent: permuting the batch permutes the boxes, and a sub-batch reproduces its rows.  Not bit for
+    # bit on the fp16 path: its flat encoder tiling cuts the concatenated images of a batch into 128-token tiles, so
+    # the order in which the linear-attention partial sums of an image are added depends on its position in the batch
+    # (fp32 rounding, ~1e-6 of the image side; tolerance 5e-3 px = 8e-6)
     perm = torch.randperm(b, generator=torch.Generator().manual_seed(0)).cuda()
     p1, p2 = hot.forward(f1[perm], f2[perm], (640, 640), (640, 640), clamp=False)
-    assert torch.allclose(p1, a1[perm], rtol=0, atol=1e-3) and torch.allclose(p2, a2[perm], rtol=0, atol=1e-3)
+    assert torch.allclose(p1, a1[perm], rtol=0, atol=5e-3) and torch.allclose(p2, a2[perm], rtol=0, atol=5e-3)
     s1, s2 = hot.forward(f1[5:8], f2[5:8], (640, 640), (640, 640), clamp=False)
-    assert torch.allclose(s1, a1[5:8], rtol=0, atol=1e-3) and torch.allclose(s2, a2[5:8], rtol=0, atol=1e-3)
+    assert torch.allclose(s1, a1[5:8], rtol=0, atol=5e-3) and torch.allclose(s2, a2[5:8], rtol=0, atol=5e-3)
     # image-size linearity of the box assembly: doubling the declared image size doubles stride and extents
     d1, _ = hot.forward(f1, f2, (1280, 1280), (1280, 1280), clamp=False)
     assert torch.allclose(d1, 2 * a1, rtol=1e-5, atol=1e-3)
@@ -197,8 +200,10 @@ def test_large_token_regime_840():
 
 def test_sub_batch_scheduling_is_invisible():
     """The fp16 path cuts a batch into sub-batches on handle-owned streams (oetr_set_chunk_pairs).  Pairs are
-    independent and every kernel is deterministic, so any split gives bit-identical boxes, on the device entry
-    and on the host-buffer entry (uneven splits, more sub-batches than the cap, a stream other than the default)."""
+    independent and every kernel is deterministic, so any split gives the same boxes -- up to the fp32 summation order
+    of the flat encoder tiling, which depends on the composition of a (sub-)batch (5e-3 px = 8e-6 of the image
+    side); the same split is bit-identical on the device entry, the host-buffer entry and any stream (uneven splits,
+    more sub-batches than the cap)."""
     W = weights.synthetic_hot_path_weights(0)
     b = 21
     n1 = weights.synthetic_features(b, 20, 20, seed=31, tag="c1")
@@ -209,7 +214,8 @@ def test_sub_batch_scheduling_is_invisible():
     hot.set_chunk_pairs(0)
     hot.forward(f1, f2, hw1, hw2, clamp=False)             # first call of a geometry also builds its position rows
     r1, r2 = hot.forward(f1, f2, hw1, hw2, clamp=False)
-    assert hot.last_launch_count == 25
+    per_forward = hot.last_launch_count
+    assert per_forward in (25, 26)                         # 26: flat encoder tiling adds the re-tiling kernel
     want = orc.hot_path(W, n1[:2], n2[:2], hw1, hw2)
     assert np.abs(r1[:2].cpu().numpy() - want["box1_raw"]).max() / 640 < TOL["fp16"]["box"]
     side = torch.cuda.Stream()
@@ -217,15 +223,15 @@ def test_sub_batch_scheduling_is_invisible():
         hot.set_chunk_pairs(pairs)
         a1, a2 = hot.forward(f1, f2, hw1, hw2, clamp=False)
         if os.environ.get("OETR_ENC") != "2":      # the experimental pair kernel runs unsplit
-            assert hot.last_launch_count == 25 * chunks, (pairs, hot.last_launch_count)
-        assert torch.equal(a1, r1) and torch.equal(a2, r2), pairs
+            assert hot.last_launch_count == per_forward * chunks, (pairs, hot.last_launch_count)
+        assert torch.allclose(a1, r1, rtol=0, atol=5e-3) and torch.allclose(a2, r2, rtol=0, atol=5e-3), pairs
         h1, h2 = hot.forward_host(n1, n2, hw1, hw2, clamp=False)
-        assert np.array_equal(h1, r1.cpu().numpy()) and np.array_equal(h2, r2.cpu().numpy()), pairs
+        assert np.array_equal(h1, a1.cpu().numpy()) and np.array_equal(h2, a2.cpu().numpy()), pairs
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             s1, s2 = hot.forward(f1, f2, hw1, hw2, clamp=False)
         side.synchronize()
-        assert torch.equal(s1, r1) and torch.equal(s2, r2), pairs
+        assert torch.equal(s1, a1) and torch.equal(s2, a2), pairs
     hot.poll_error()
     hot.close()
 
@@ -253,7 +259,7 @@ def test_host_requests_in_flight():
     c = hot.wait_host(t2)
     d = hot.wait_host(t3)
     for got, req in ((a, reqs[0]), (b_, reqs[1]), (c, reqs[2]), (d, reqs[3])):
-        assert np.array_equal(got[0], req[4]) and np.array_equal(got[1], req[5])
+        assert np.array_equal(got[0], req[4]) and np.array_equal(got[1], req[5])      # same split, same arithmetic
     with pytest.raises(cabi.OetrError):
         cabi.check(hot._lib.oetr_forward_host_wait(hot._handle, 12345, None, None), hot._lib)
     hot.poll_error()
