@@ -13,7 +13,7 @@ scaling, replicated weights) and the boxes are all-gathered (configs[2]).  One J
   roofline       dominant kernel (k_enc, one launch per encoder layer): algorithmic FLOPs / launch over the
                  CUDA-event launch duration measured inside the timed region, against the measured bf16/fp16
                  tensor peak (MEASURED_PEAKS.json, sustained figure: the kernel is timed inside a long step);
-                 traffic = DRAM bytes per launch from the committed ncu capture (profiles/r01_k_enc_metrics.json)
+                 traffic = DRAM bytes per launch from the committed ncu capture (profiles/r01c_k_enc_metrics.json)
   cpu_baseline   the numpy port of the reference algorithm (oracle/) on the host cores, bounded sample
   --impl reference   times that same CPU implementation as the reference arm (the reference itself is pure
                  Python under /root/reference, which does not exist on the GPU box; the port is pinned to it by
@@ -49,7 +49,7 @@ FLOPS_PER_PAIR = 8.32e9
 
 def _traffic():
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_k_enc_metrics.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01c_k_enc_metrics.json")) as f:
             m = json.load(f)
         return float(m["dram__bytes_read.sum"]) + float(m["dram__bytes_write.sum"])
     except Exception:
@@ -253,20 +253,23 @@ def run_b200(args):
     # e2e: host buffers through the C ABI, H2D + D2H inside the timed region
     h1 = torch.from_numpy(base1).pin_memory()
     h2 = torch.from_numpy(base2).pin_memory()
-    for _ in range(2):
+    for _ in range(12):     # every one of the handle's 4 request slots: eager run, graph capture, first replay
         hot.forward_host(h1.numpy(), h2.numpy(), (IMG, IMG), (IMG, IMG))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    # K requests, two in flight (oetr_forward_host_submit / _wait): every step's features cross PCIe from pinned host
+    # K requests, `depth` in flight (oetr_forward_host_submit / _wait): every step's features cross PCIe from pinned host
     # memory and every step's boxes are read back on the host, all inside the timed region
     hn1, hn2 = h1.numpy(), h2.numpy()
+    depth = max(1, min(4, args.e2e_in_flight))
     t0 = time.perf_counter()
-    ticket = hot.submit_host(hn1, hn2, (IMG, IMG), (IMG, IMG))
+    tickets = []
     for i in range(K):
-        nxt = hot.submit_host(hn1, hn2, (IMG, IMG), (IMG, IMG)) if i + 1 < K else None
-        eb1, eb2 = hot.wait_host(ticket)
-        ticket = nxt
+        tickets.append(hot.submit_host(hn1, hn2, (IMG, IMG), (IMG, IMG)))
+        if len(tickets) == depth:
+            eb1, eb2 = hot.wait_host(tickets.pop(0))
+    while tickets:
+        eb1, eb2 = hot.wait_host(tickets.pop(0))
     e2e_s = time.perf_counter() - t0
     # the same through the blocking call (one request at a time), for reference
     t0 = time.perf_counter()
@@ -350,7 +353,7 @@ def run_b200(args):
                    "parallelism": "batch shards, replicated weights, all-gather of boxes" if world > 1 else "1 GPU"},
         "clocks": clk.summary(),
         "e2e": {"value": world * B * K / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * base1.nbytes),
-                "d2h_bytes_per_step": int(B * 8 * 4), "api": "oetr_forward_host_submit/_wait (C ABI, pinned host feature buffers, 2 requests in flight)",
+                "d2h_bytes_per_step": int(B * 8 * 4), "api": "oetr_forward_host_submit/_wait (C ABI, pinned host feature buffers, %d requests in flight)" % depth,
                 "blocking_value": world * B * K / e2e_blocking_s,
                 "blocking_api": "oetr_forward_host (one request at a time; rank-local time)"},
         "gpu_launches": launches,
@@ -375,6 +378,7 @@ def main():
                     help="pairs per concurrently scheduled sub-batch (0 = off)")
     ap.add_argument("--in-flight", type=int, default=int(os.environ.get("OETR_IN_FLIGHT", "2")),
                     help="independent batches kept in flight in the device-resident timed region")
+    ap.add_argument("--e2e-in-flight", type=int, default=4, help="host requests kept in flight in the e2e leg (1..4)")
     ap.add_argument("--precision", default=os.environ.get("OETR_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

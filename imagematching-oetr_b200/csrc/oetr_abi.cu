@@ -38,10 +38,23 @@ static int fail(int code, const char* fmt, ...) {
 // whichever sub-batch is ready (different layers interleave), and in oetr_forward_host the H2D copy of sub-batch
 // c+1 overlaps the compute of sub-batch c.  Fork/join is by events on the caller's stream: no host synchronisation.
 constexpr int MAX_CHUNKS = 8;
-constexpr int HOST_SLOTS = 2;
+constexpr int HOST_SLOTS = 4;
+
+// CUDA graph of the ~25 kernel launches of one sub-batch of a host request.  The host path owns every device buffer
+// a sub-batch touches (staging, workspace, boxes), so the launch sequence of a (slot, sub-batch) is identical from
+// request to request as long as the problem is: it is captured on its second use and replayed with one
+// cudaGraphLaunch afterwards (the host thread then issues ~8 driver calls per sub-batch instead of ~35, which keeps
+// the end-to-end rate from being bound by launch overhead).
+struct ChunkGraph {
+    cudaGraphExec_t exec = nullptr;
+    int key[11] = {};               // Bc, geometry, image sizes, clamp
+    const void* ptr[7] = {};        // feat1, feat2, boxes1, boxes2, workspace, position rows
+    int uses = 0, launches = 0;
+};
 
 // one in-flight request of oetr_forward_host_submit: device staging, pinned landing buffers, completion events
 struct HostSlot {
+    ChunkGraph cg[MAX_CHUNKS];
     float *feat1 = nullptr, *feat2 = nullptr, *boxes = nullptr;
     float* boxes_pin = nullptr;    // pinned host landing buffer of the boxes (a D2H copy into pageable memory would
                                    // block the launching thread and serialise the sub-batches)
@@ -350,6 +363,7 @@ int oetr_destroy(oetr_handle* h) {
     }
     for (HostSlot& sl : h->slot) {
         if (sl.busy) for (int c = 0; c < sl.n_join; ++c) cudaEventSynchronize(sl.ev_join[c]);
+        for (ChunkGraph& g : sl.cg) if (g.exec) cudaGraphExecDestroy(g.exec);
         cudaFree(sl.feat1); cudaFree(sl.feat2); cudaFree(sl.boxes); cudaFree(sl.ws);
         cudaFreeHost(sl.boxes_pin); cudaFreeHost(sl.flag_pin);
         if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
@@ -444,7 +458,7 @@ int oetr_poll_error(oetr_handle* h) {
 namespace {
 // optional host endpoints of a forward (oetr_forward_host): features are copied H2D and boxes D2H on the stream
 // that runs the (sub-)batch, so that with sub-batch scheduling the copies overlap the other sub-batches' compute
-struct HostIO { const float *feat1, *feat2; float *boxes1, *boxes2; int* flags; };
+struct HostIO { const float *feat1, *feat2; float *boxes1, *boxes2; int* flags; ChunkGraph* graphs; };
 // fork/join events of one forward.  join_caller: the caller's stream waits for the sub-batches (stream-ordered
 // entry points); otherwise completion is observed through ev_join only (host submit/wait) and even an unsplit
 // batch runs on a handle-owned stream, so that two requests forked from the same stream overlap
@@ -457,14 +471,10 @@ struct FwdArgs {
 
 // one (sub-)batch of B pairs on stream s with workspace slice w
 int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const float* feat2, int B, const FwdArgs& a,
-              float* boxes1, float* boxes2, const HostIO* hio, bool profile, cudaStream_t s, LaunchCounter& lc) {
+              float* boxes1, float* boxes2, bool profile, cudaStream_t s, LaunchCounter& lc) {
     const int hf1 = a.hf1, wf1 = a.wf1, hf2 = a.hf2, wf2 = a.wf2;
     const int L1 = hf1 * wf1, L2 = hf2 * wf2, R1 = B * L1, R2 = B * L2;
     const float* W = h->d_w;
-    if (hio) {
-        CU(cudaMemcpyAsync(const_cast<float*>(feat1), hio->feat1, (size_t)R1 * C * sizeof(float), cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(const_cast<float*>(feat2), hio->feat2, (size_t)R2 * C * sizeof(float), cudaMemcpyHostToDevice, s));
-    }
     if (h->prec == OETR_PREC_FP32) {
         // positional rows for both geometries (PositionEncodingSine.forward slice, models/utils.py:200-205)
         k_gather_pos<<<(L1 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf1, L1, w.pos); lc.n++;
@@ -506,11 +516,6 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
         p.boxes = boxes2; p.dbg_cxy = a.dbg_cxy ? a.dbg_cxy + 2 * B : nullptr; p.dbg_tlbr = a.dbg_tlbr ? a.dbg_tlbr + 4 * B : nullptr;
         head_finalize(p, s, lc);
     }
-    if (hio) {
-        CU(cudaMemcpyAsync(hio->boxes1, boxes1, (size_t)B * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(hio->boxes2, boxes2, (size_t)B * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(hio->flags, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    }
     return OETR_OK;
 }
 
@@ -547,7 +552,7 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
         const Workspace w = carve(workspace, h, B, L1, L2);
         if (w.bytes > workspace_bytes)
             return fail(OETR_E_NOMEM, "oetr_forward: workspace %zu B < required %zu B", workspace_bytes, w.bytes);
-        int rc = run_batch(h, w, feat1, feat2, B, a, boxes1, boxes2, hio, true, s, lc);
+        int rc = run_batch(h, w, feat1, feat2, B, a, boxes1, boxes2, true, s, lc);
         if (rc) return rc;
     } else {
         if (nc == 1) sizes[0] = B;
@@ -561,14 +566,59 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
             const int Bc = sizes[c];
             cudaStream_t sc = h->aux[c];
             CU(cudaStreamWaitEvent(sc, es.fork, 0));
+            const float* f1c = feat1 + (size_t)b0 * C * L1;
+            const float* f2c = feat2 + (size_t)b0 * C * L2;
+            float* b1c = boxes1 + (size_t)b0 * 4;
+            float* b2c = boxes2 + (size_t)b0 * 4;
+            if (hio) {
+                CU(cudaMemcpyAsync(const_cast<float*>(f1c), hio->feat1 + (size_t)b0 * C * L1, (size_t)Bc * L1 * C * sizeof(float),
+                                   cudaMemcpyHostToDevice, sc));
+                CU(cudaMemcpyAsync(const_cast<float*>(f2c), hio->feat2 + (size_t)b0 * C * L2, (size_t)Bc * L2 * C * sizeof(float),
+                                   cudaMemcpyHostToDevice, sc));
+            }
+            // host requests replay a captured graph of the sub-batch's kernels from its third use on (ChunkGraph)
+            ChunkGraph* cg = (hio && hio->graphs && h->prec == OETR_PREC_FP16 && !h->prof.on && !getenv("OETR_TIMING") &&
+                              !getenv("OETR_NO_GRAPH")) ? &hio->graphs[c] : nullptr;
+            bool replayed = false;
+            if (cg) {
+                const int key[11] = {Bc, a.hf1, a.wf1, a.hf2, a.wf2, a.img_h1, a.img_w1, a.img_h2, a.img_w2, a.clamp, nc};
+                const void* ptr[7] = {f1c, f2c, b1c, b2c, base, h->d_post[0], h->d_post[1]};
+                const bool same = memcmp(key, cg->key, sizeof(key)) == 0 && memcmp(ptr, cg->ptr, sizeof(ptr)) == 0;
+                if (!same) {
+                    if (cg->exec) { cudaGraphExecDestroy(cg->exec); cg->exec = nullptr; }
+                    memcpy(cg->key, key, sizeof(key)); memcpy(cg->ptr, ptr, sizeof(ptr));
+                    cg->uses = 0;
+                }
+                if (!cg->exec && cg->uses >= 1) {          // second use of this problem: capture (the first ran eagerly)
+                    LaunchCounter lg;
+                    cudaGraph_t graph = nullptr;
+                    CU(cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal));
+                    const Workspace wg = carve(base, h, Bc, L1, L2);
+                    const int rcg = run_batch(h, wg, f1c, f2c, Bc, a, b1c, b2c, false, sc, lg);
+                    const cudaError_t ec = cudaStreamEndCapture(sc, &graph);
+                    if (rcg == OETR_OK && ec == cudaSuccess && graph &&
+                        cudaGraphInstantiate(&cg->exec, graph, 0) == cudaSuccess) cg->launches = lg.n;
+                    else { cg->exec = nullptr; cudaGetLastError(); }
+                    if (graph) cudaGraphDestroy(graph);
+                }
+                ++cg->uses;
+                if (cg->exec) {
+                    CU(cudaGraphLaunch(cg->exec, sc));
+                    lc.n += cg->launches;
+                    replayed = true;
+                }
+            }
             const Workspace w = carve(base, h, Bc, L1, L2);
             base += (w.bytes + 1023) & ~size_t(1023);
-            HostIO sub{};
-            if (hio) sub = HostIO{hio->feat1 + (size_t)b0 * C * L1, hio->feat2 + (size_t)b0 * C * L2,
-                                  hio->boxes1 + (size_t)b0 * 4, hio->boxes2 + (size_t)b0 * 4, hio->flags + c};
-            int rc = run_batch(h, w, feat1 + (size_t)b0 * C * L1, feat2 + (size_t)b0 * C * L2, Bc, a,
-                               boxes1 + (size_t)b0 * 4, boxes2 + (size_t)b0 * 4, hio ? &sub : nullptr, false, sc, lc);
-            if (rc) return rc;
+            if (!replayed) {
+                int rc = run_batch(h, w, f1c, f2c, Bc, a, b1c, b2c, false, sc, lc);
+                if (rc) return rc;
+            }
+            if (hio) {
+                CU(cudaMemcpyAsync(hio->boxes1 + (size_t)b0 * 4, b1c, (size_t)Bc * 4 * sizeof(float), cudaMemcpyDeviceToHost, sc));
+                CU(cudaMemcpyAsync(hio->boxes2 + (size_t)b0 * 4, b2c, (size_t)Bc * 4 * sizeof(float), cudaMemcpyDeviceToHost, sc));
+                CU(cudaMemcpyAsync(hio->flags + c, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, sc));
+            }
             CU(cudaEventRecord(es.join[c], sc));
             if (es.join_caller) CU(cudaStreamWaitEvent(s, es.join[c], 0));
             b0 += Bc;
@@ -647,7 +697,7 @@ int oetr_forward_host_submit(oetr_handle* h, const float* feat1_host, const floa
             sl.boxes_pin_n = (size_t)batch * 8;
         }
         const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, nullptr, nullptr, nullptr, nullptr};
-        const HostIO hio{feat1_host, feat2_host, sl.boxes_pin, sl.boxes_pin + (size_t)batch * 4, sl.flag_pin};
+        const HostIO hio{feat1_host, feat2_host, sl.boxes_pin, sl.boxes_pin + (size_t)batch * 4, sl.flag_pin, sl.cg};
         const EventSet es{sl.ev_fork, sl.ev_join, false, &sl.n_join};
         rc = forward_core(h, sl.feat1, sl.feat2, batch, a, sl.boxes, sl.boxes + (size_t)batch * 4, sl.ws, sl.ws_n, s, &hio, es);
         if (rc) {   // some sub-batches may have been queued: drain them before the slot can be reused

@@ -116,8 +116,8 @@ class OverlapHotPath:
         return box1, box2, out
 
     def submit_host(self, feat1, feat2, img_hw1, img_hw2, clamp=True):
-        """Queue a host-buffer request (oetr_forward_host_submit) and return a ticket for `wait_host`.  At most two
-        requests may be in flight; the copies of one overlap the compute of the other."""
+        """Queue a host-buffer request (oetr_forward_host_submit) and return a ticket for `wait_host`.  At most four
+        requests may be in flight; the copies of one overlap the compute of the others."""
         a1 = np.ascontiguousarray(feat1.numpy() if hasattr(feat1, "numpy") else feat1, dtype=np.float32)
         a2 = np.ascontiguousarray(feat2.numpy() if hasattr(feat2, "numpy") else feat2, dtype=np.float32)
         if a1.ndim != 4 or a2.ndim != 4 or a1.shape[1] != 256 or a2.shape[1] != 256 or a1.shape[0] != a2.shape[0]:

@@ -143,7 +143,7 @@ OETR_API int oetr_poll_error(oetr_handle* h);
  *
  * oetr_forward_host_submit queues  host feats (pinned or pageable) -> device, forward, boxes -> pinned landing
  * buffer  on the handle's own streams, ordered after the work already queued on `stream`, and returns a ticket
- * without waiting.  Up to 2 requests may be in flight (a third submit fails with OETR_E_ARG until one is waited
+ * without waiting.  Up to 4 requests may be in flight (a fifth submit fails with OETR_E_ARG until one is waited
  * for), so that the copies of request i+1 overlap the compute of request i.  The feature buffers must stay valid
  * and unchanged until the matching wait returns.  Device staging is owned by the handle and grown on demand
  * (these are the only entry points that allocate).

@@ -237,30 +237,39 @@ def test_sub_batch_scheduling_is_invisible():
 
 
 def test_host_requests_in_flight():
-    """oetr_forward_host_submit / _wait: two requests of different geometry in flight, results equal to the
-    stream-ordered entry; a third submit is refused until a ticket has been waited for."""
+    """oetr_forward_host_submit / _wait: four requests of different geometry in flight, results equal to the
+    stream-ordered entry; a fifth submit is refused until a ticket has been waited for; a request repeated on the
+    same slot is captured into a CUDA graph and replayed with identical results."""
     W = weights.synthetic_hot_path_weights(0)
     hot = oetr_b200.OverlapHotPath(W, precision="fp16")
     reqs = []
-    for b, fm1, fm2 in ((12, (20, 20), (20, 20)), (3, (9, 11), (26, 26)), (1, (20, 20), (20, 20)), (12, (20, 20), (20, 20))):
+    for b, fm1, fm2 in ((12, (20, 20), (20, 20)), (3, (9, 11), (26, 26)), (1, (20, 20), (20, 20)), (12, (20, 20), (20, 20)),
+                        (20, (20, 20), (15, 20))):
         hw1, hw2 = (fm1[0] * 32, fm1[1] * 32), (fm2[0] * 32, fm2[1] * 32)
         f1 = weights.synthetic_features(b, *fm1, seed=23, tag="q1")
         f2 = weights.synthetic_features(b, *fm2, seed=23, tag="q2")
         r1, r2 = hot.forward(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(), hw1, hw2, clamp=False)
         reqs.append((f1, f2, hw1, hw2, r1.cpu().numpy(), r2.cpu().numpy()))
-    t0 = hot.submit_host(*reqs[0][:4], clamp=False)
-    t1 = hot.submit_host(*reqs[1][:4], clamp=False)
+    t = [hot.submit_host(*reqs[i][:4], clamp=False) for i in range(4)]
     with pytest.raises(cabi.OetrError):
-        hot.submit_host(*reqs[2][:4], clamp=False)
-    a = hot.wait_host(t0)
-    t2 = hot.submit_host(*reqs[2][:4], clamp=False)
-    b_ = hot.wait_host(t1)
-    t3 = hot.submit_host(*reqs[3][:4], clamp=False)
-    c = hot.wait_host(t2)
-    d = hot.wait_host(t3)
-    for got, req in ((a, reqs[0]), (b_, reqs[1]), (c, reqs[2]), (d, reqs[3])):
-        assert np.array_equal(got[0], req[4]) and np.array_equal(got[1], req[5])      # same split, same arithmetic
+        hot.submit_host(*reqs[4][:4], clamp=False)
+    a = hot.wait_host(t[0])
+    t4 = hot.submit_host(*reqs[4][:4], clamp=False)
+    got = [a] + [hot.wait_host(x) for x in t[1:]] + [hot.wait_host(t4)]
+    for g_, req in zip(got, reqs):
+        assert np.array_equal(g_[0], req[4]) and np.array_equal(g_[1], req[5])      # same split, same arithmetic
     with pytest.raises(cabi.OetrError):
         cabi.check(hot._lib.oetr_forward_host_wait(hot._handle, 12345, None, None), hot._lib)
+    # the same request over and over: every slot sees it three times (eager, capture + replay, replay)
+    req = reqs[4]
+    tickets = []
+    for i in range(14):
+        tickets.append(hot.submit_host(*req[:4], clamp=False))
+        if len(tickets) == 3:
+            g_ = hot.wait_host(tickets.pop(0))
+            assert np.array_equal(g_[0], req[4]) and np.array_equal(g_[1], req[5]), i
+    while tickets:
+        g_ = hot.wait_host(tickets.pop(0))
+        assert np.array_equal(g_[0], req[4]) and np.array_equal(g_[1], req[5])
     hot.poll_error()
     hot.close()
