@@ -165,6 +165,9 @@ def run_reference(args):
 
 
 def run_b200(args):
+    # libraries (NCCL's version banner, ...) write to fd 1: keep stdout for the ONE JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -363,7 +366,8 @@ def run_b200(args):
         "gpu_eager_baseline": eager,
         "parity": {"box_err_over_image_side": float(perr), "bar": 1e-3, "pairs_checked": 2},
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
