@@ -349,7 +349,7 @@ def run_b200(args):
         "config": {"workload": "batch=32 640x640 pairs per GPU: hot path (8-layer correlation transformer + "
                                "decoder + overlap head) on two [32,256,20,20] fp32 feature maps",
                    "pairs_per_gpu": B, "precision": args.precision, "attention": "linear",
-                   "sub_batches": "%d pairs each, own stream" % args.chunk_pairs if args.chunk_pairs else "off",
+                   "sub_batches": ("%d pairs each, own stream" % (args.chunk_pairs if args.chunk_pairs > 0 else 8)) if args.chunk_pairs else "off",
                    "batches_in_flight": "%d (one CUDA stream + handle each; every step = one complete forward)" % lanes,
                    "l2": "inputs rotate over %d resident batches (%.0f MB > 126 MB L2)" % (
                        N_ROTATE, N_ROTATE * 2 * base1.nbytes / 1e6),
@@ -378,8 +378,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunk-pairs", type=int, default=int(os.environ.get("OETR_CHUNK_PAIRS", "8")),
-                    help="pairs per concurrently scheduled sub-batch (0 = off)")
+    ap.add_argument("--chunk-pairs", type=int, default=int(os.environ.get("OETR_CHUNK_PAIRS", "-1")),
+                    help="pairs per concurrently scheduled sub-batch (0 = off, -1 = automatic: 8 at 640x640)")
     ap.add_argument("--in-flight", type=int, default=int(os.environ.get("OETR_IN_FLIGHT", "2")),
                     help="independent batches kept in flight in the device-resident timed region")
     ap.add_argument("--e2e-in-flight", type=int, default=4, help="host requests kept in flight in the e2e leg (1..4)")

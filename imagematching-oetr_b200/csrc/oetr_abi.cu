@@ -68,7 +68,7 @@ struct HostSlot {
 
 struct oetr_handle {
     int attn_mode = 0, prec = 0, max_h = 0, max_w = 0, device = 0;
-    int chunk_pairs = 8;       // pairs per sub-batch (0: never split); oetr_set_chunk_pairs
+    int chunk_pairs = -1;      // pairs per sub-batch (0: never split, < 0: chosen from the geometry); oetr_set_chunk_pairs
     cudaStream_t aux[MAX_CHUNKS] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHUNKS] = {};
     std::mutex mu;             // fork/launch/join section (the events are shared by all callers of this handle)
@@ -328,7 +328,7 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
     CUH(cudaMemcpy(h->d_pe, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUH(cudaMalloc(&h->d_flag, sizeof(int)));
     CUH(cudaMemset(h->d_flag, 0, sizeof(int)));
-    if (const char* env = getenv("OETR_CHUNK_PAIRS")) h->chunk_pairs = atoi(env) > 0 ? atoi(env) : 0;
+    if (const char* env = getenv("OETR_CHUNK_PAIRS")) h->chunk_pairs = atoi(env);
     CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < MAX_CHUNKS; ++i) {
         CUH(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
@@ -384,17 +384,25 @@ static int check_shapes(const oetr_handle* h, int batch, int hf1, int wf1, int h
 }
 
 // sub-batch sizes of a batch (balanced; 1 chunk = no split)
-static int chunk_plan(const oetr_handle* h, int B, int* sizes) {
+static int chunk_plan(const oetr_handle* h, int B, int L1, int L2, int* sizes) {
     int n = 1;
-    if (h->prec == OETR_PREC_FP16 && h->chunk_pairs > 0 && B > h->chunk_pairs && !tc_pair_kernel_selected())
-        n = (B + h->chunk_pairs - 1) / h->chunk_pairs;
+    int cp = h->chunk_pairs;
+    if (cp < 0) {
+        // automatic: about 56 encoder tiles (128 tokens) per sub-batch -- three sub-batches fill the 148 SMs and a
+        // fourth back-fills; 8 pairs at 640x640 (400 tokens per image), 5 at 840x840 (676)
+        const int tiles16 = ((L1 + 15) / 16 + (L2 + 15) / 16 + 7) / 8 * 2;      // 2 x tiles per pair, flat tiling
+        cp = (2 * 56 + tiles16 / 2) / (tiles16 > 0 ? tiles16 : 1);
+        if (cp < 1) cp = 1;
+    }
+    if (h->prec == OETR_PREC_FP16 && cp > 0 && B > cp && !tc_pair_kernel_selected())
+        n = (B + cp - 1) / cp;
     if (n > MAX_CHUNKS) n = MAX_CHUNKS;
     for (int i = 0; i < n; ++i) sizes[i] = B / n + (i < B % n ? 1 : 0);
     return n;
 }
 static size_t chunked_bytes(const oetr_handle* h, int B, int L1, int L2) {
     int sizes[MAX_CHUNKS];
-    const int n = chunk_plan(h, B, sizes);
+    const int n = chunk_plan(h, B, L1, L2, sizes);
     size_t total = 0;
     for (int i = 0; i < n; ++i) total += (carve(nullptr, h, sizes[i], L1, L2).bytes + 1023) & ~size_t(1023);
     return total;
@@ -412,7 +420,6 @@ int oetr_workspace_bytes(const oetr_handle* h, int batch, int hf1, int wf1, int 
 
 int oetr_set_chunk_pairs(oetr_handle* h, int pairs_per_chunk) {
     if (!h) return fail(OETR_E_ARG, "null handle");
-    if (pairs_per_chunk < 0) return fail(OETR_E_ARG, "oetr_set_chunk_pairs: %d < 0", pairs_per_chunk);
     h->chunk_pairs = pairs_per_chunk;
     return OETR_OK;
 }
@@ -545,7 +552,7 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
         }
     }
     int sizes[MAX_CHUNKS];
-    int nc = chunk_plan(h, B, sizes);
+    int nc = chunk_plan(h, B, L1, L2, sizes);
     // the debug taps are laid out for the whole batch and the kernel profiler brackets launches on one stream
     if (a.dbg_hs || a.dbg_memory || a.dbg_cxy || a.dbg_tlbr || h->prof.on) nc = 1;
     if (nc == 1 && es.join_caller) {
@@ -577,8 +584,8 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
                                    cudaMemcpyHostToDevice, sc));
             }
             // host requests replay a captured graph of the sub-batch's kernels from its third use on (ChunkGraph)
-            ChunkGraph* cg = (hio && hio->graphs && h->prec == OETR_PREC_FP16 && !h->prof.on && !getenv("OETR_TIMING") &&
-                              !getenv("OETR_NO_GRAPH")) ? &hio->graphs[c] : nullptr;
+            static const bool no_graph = getenv("OETR_TIMING") || getenv("OETR_NO_GRAPH");
+            ChunkGraph* cg = (hio && hio->graphs && h->prec == OETR_PREC_FP16 && !h->prof.on && !no_graph) ? &hio->graphs[c] : nullptr;
             bool replayed = false;
             if (cg) {
                 const int key[11] = {Bc, a.hf1, a.wf1, a.hf2, a.wf2, a.img_h1, a.img_w1, a.img_h2, a.img_w2, a.clamp, nc};

@@ -53,7 +53,8 @@ class OverlapHotPath:
         return self._ws
 
     def set_chunk_pairs(self, pairs):
-        """Pairs per concurrently scheduled sub-batch of the fp16 path (0 = never split; default 8)."""
+        """Pairs per concurrently scheduled sub-batch of the fp16 path (0 = never split; < 0 = automatic, the default:
+        about 56 encoder tiles per sub-batch, i.e. 8 pairs at 640x640)."""
         cabi.check(self._lib.oetr_set_chunk_pairs(self._handle, int(pairs)), self._lib)
         self._ws = None
 

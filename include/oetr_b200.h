@@ -118,7 +118,8 @@ OETR_API int oetr_forward(oetr_handle* h,
                  float* dbg_hs, float* dbg_memory, float* dbg_cxy, float* dbg_tlbr,
                  void* workspace, size_t workspace_bytes, void* stream);
 
-/* Sub-batch scheduling of the FP16 path (default 8 pairs; env OETR_CHUNK_PAIRS overrides at create): a batch larger
+/* Sub-batch scheduling of the FP16 path (default: automatic, about 56 encoder tiles per sub-batch = 8 pairs at
+ * 640x640; env OETR_CHUNK_PAIRS overrides at create; < 0 = automatic): a batch larger
  * than `pairs_per_chunk` is cut into up to 8 balanced sub-batches that run on handle-owned streams, forked from and
  * joined to the caller's stream by events (no host synchronisation), so that free SMs are back-filled across
  * sub-batches and, in oetr_forward_host, copies overlap compute.  Results do not depend on it (every pair is
