@@ -763,6 +763,15 @@ int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat
     return oetr_forward_host_wait(h, ticket, boxes1_host, boxes2_host);
 }
 
+int oetr_selftest_geometry(int batch, int hf1, int wf1, int hf2, int wf2, int* flat_tiles) {
+    if (batch < 1 || hf1 < 1 || wf1 < 1 || hf2 < 1 || wf2 < 1) return fail(OETR_E_ARG, "oetr_selftest_geometry: bad arguments");
+    char msg[256] = "";
+    const int rc = tc_check_geometry(batch, hf1 * wf1, hf2 * wf2, msg, sizeof(msg));
+    if (rc == -1) return fail(OETR_E_SHAPE, "oetr_selftest_geometry: %s", msg);
+    if (flat_tiles) *flat_tiles = rc > 0 ? rc : 0;
+    return OETR_OK;
+}
+
 int oetr_selftest_tcgen05(float* errs_host, int n_errs) {
     if (!errs_host || n_errs < 1) return fail(OETR_E_ARG, "oetr_selftest_tcgen05: bad arguments");
     int dev = 0;

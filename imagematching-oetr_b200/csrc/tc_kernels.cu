@@ -2002,6 +2002,47 @@ static EncGeom make_enc_geom(int B, int L1, int L2, bool pairs) {
     return eg;
 }
 
+// Host-only check of the encoder tile geometry (flat when possible): every token of every image is one row of exactly
+// one tile, and the partial-summary slots k_fold / k_sum_partials gather for an image are exactly the (tile, image)
+// pairs that hold rows of it.  Used by the CPU test suite (no GPU needed).
+int tc_check_geometry(int B, int L1, int L2, char* msg, size_t msg_len) {
+    const TileGeom g = make_geom(B, L1, L2);
+    const EncGeom eg = make_enc_geom(B, L1, L2, false);
+    const int tiles = eg.flat ? eg.F1 + eg.F2 : g.tiles();
+    const int ppt = eg.flat ? 2 : 1;
+    std::vector<int> hits((size_t)B * (L1 + L2), 0);
+    std::vector<int> slot_rows((size_t)tiles * ppt, 0), slot_img((size_t)tiles * ppt, -1);
+    for (int t = 0; t < tiles; ++t) {
+        const EncTile et = enc_tile(g, eg, t);
+        if (et.split < 16 || et.split > 128 || (eg.flat && et.split % 16)) { snprintf(msg, msg_len, "tile %d: split %d", t, et.split); return -1; }
+        for (int r = 0; r < TILE; ++r) {
+            const int rel = r >= et.split ? 1 : 0, rb = et.b0 + rel, rl = rel ? r - et.split : et.l0 + r;
+            if (!(rb < B && rl < et.L)) continue;
+            if (rel && !et.two) { snprintf(msg, msg_len, "tile %d row %d: second image without the two-image flag", t, r); return -1; }
+            hits[(size_t)(et.set ? B * L1 : 0) + (size_t)rb * et.L + rl]++;
+            const int sl = t * ppt + (eg.flat ? rel : 0);
+            slot_rows[sl]++;
+            if (slot_img[sl] >= 0 && slot_img[sl] != et.set * B + rb) { snprintf(msg, msg_len, "tile %d: two images in one slot", t); return -1; }
+            slot_img[sl] = et.set * B + rb;
+        }
+    }
+    for (size_t i = 0; i < hits.size(); ++i)
+        if (hits[i] != 1) { snprintf(msg, msg_len, "token %zu is covered %d times", i, hits[i]); return -1; }
+    std::vector<int> seen((size_t)tiles * ppt, 0);
+    for (int img = 0; img < 2 * B; ++img) {
+        const int set = img / B, b = img % B, n = enc_parts(g, eg, ppt, set, b);
+        for (int i = 0; i < n; ++i) {
+            const int idx = enc_part_index(g, eg, ppt, set, b, i);
+            if (idx < 0 || idx >= tiles * ppt) { snprintf(msg, msg_len, "image %d: partial index %d out of range", img, idx); return -1; }
+            if (slot_img[idx] != img) { snprintf(msg, msg_len, "image %d: slot %d belongs to image %d", img, idx, slot_img[idx]); return -1; }
+            seen[idx]++;
+        }
+    }
+    for (int i = 0; i < tiles * ppt; ++i)
+        if ((slot_rows[i] > 0) != (seen[i] == 1)) { snprintf(msg, msg_len, "slot %d: %d rows, gathered %d times", i, slot_rows[i], seen[i]); return -1; }
+    return eg.flat ? tiles : -2 - tiles;     // > 0: flat tiles; <= -2: per-image tiling with (-ret - 2) tiles
+}
+
 bool tc_pair_kernel_selected() {
     static const bool pairs = getenv("OETR_ENC") && atoi(getenv("OETR_ENC")) == 2;
     return pairs;

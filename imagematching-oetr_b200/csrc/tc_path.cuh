@@ -52,6 +52,9 @@ void tc_free_weights(TcWeights& w);
 // tile-blocked positional rows of one (hf,wf) geometry (cached by the handle, see oetr_abi.cu)
 // OETR_ENC=2: the experimental CTA-pair encoder kernel is in use (sub-batch scheduling is then switched off)
 bool tc_pair_kernel_selected();
+// host-only consistency check of the encoder tiling; returns the number of flat tiles (> 0), -2 - tiles for the
+// per-image tiling, or -1 with a message
+int tc_check_geometry(int B, int L1, int L2, char* msg, size_t msg_len);
 size_t tc_pos_tile_floats(int L);
 void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cudaStream_t s, LaunchCounter& lc);
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,

@@ -168,6 +168,12 @@ OETR_API int oetr_forward_host(oetr_handle* h,
  * Returns OETR_OK when the kernels ran (inspect errs for the numeric outcome). */
 OETR_API int oetr_selftest_tcgen05(float* errs_host, int n_errs);
 
+/* Host-only (no GPU needed) consistency check of the encoder's tile geometry for a problem size: every token is one
+ * row of exactly one 128-token tile and the partial attention summaries gathered per image are exactly those of the
+ * tiles holding its rows.  *flat_tiles = number of tiles of the flat tiling, 0 when per-image tiles are used (maps
+ * under 128 tokens). */
+OETR_API int oetr_selftest_geometry(int batch, int hf1, int wf1, int hf2, int wf2, int* flat_tiles);
+
 OETR_API const char* oetr_last_error(void);
 OETR_API int oetr_abi_version(void);
 
