@@ -62,6 +62,7 @@ struct HostSlot {
     void* ws = nullptr;
     size_t feat1_n = 0, feat2_n = 0, boxes_n = 0, boxes_pin_n = 0, ws_n = 0;
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHUNKS] = {};
+    cudaStream_t aux[MAX_CHUNKS] = {};     // the slot's own sub-batch streams: requests in flight run side by side
     int n_join = 0, batch = 0, ticket = -1;
     bool busy = false;
 };
@@ -336,7 +337,10 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
     }
     for (HostSlot& sl : h->slot) {
         CUH(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
-        for (int i = 0; i < MAX_CHUNKS; ++i) CUH(cudaEventCreateWithFlags(&sl.ev_join[i], cudaEventDisableTiming));
+        for (int i = 0; i < MAX_CHUNKS; ++i) {
+            CUH(cudaEventCreateWithFlags(&sl.ev_join[i], cudaEventDisableTiming));
+            CUH(cudaStreamCreateWithFlags(&sl.aux[i], cudaStreamNonBlocking));
+        }
         CUH(cudaMallocHost(&sl.flag_pin, MAX_CHUNKS * sizeof(int)));
     }
     if (operand_precision == OETR_PREC_FP16) {
@@ -367,7 +371,10 @@ int oetr_destroy(oetr_handle* h) {
         cudaFree(sl.feat1); cudaFree(sl.feat2); cudaFree(sl.boxes); cudaFree(sl.ws);
         cudaFreeHost(sl.boxes_pin); cudaFreeHost(sl.flag_pin);
         if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
-        for (int i = 0; i < MAX_CHUNKS; ++i) if (sl.ev_join[i]) cudaEventDestroy(sl.ev_join[i]);
+        for (int i = 0; i < MAX_CHUNKS; ++i) {
+            if (sl.ev_join[i]) cudaEventDestroy(sl.ev_join[i]);
+            if (sl.aux[i]) cudaStreamDestroy(sl.aux[i]);
+        }
     }
     delete h;
     return OETR_OK;
@@ -469,7 +476,7 @@ struct HostIO { const float *feat1, *feat2; float *boxes1, *boxes2; int* flags; 
 // fork/join events of one forward.  join_caller: the caller's stream waits for the sub-batches (stream-ordered
 // entry points); otherwise completion is observed through ev_join only (host submit/wait) and even an unsplit
 // batch runs on a handle-owned stream, so that two requests forked from the same stream overlap
-struct EventSet { cudaEvent_t fork; cudaEvent_t* join; bool join_caller; int* n_join; };
+struct EventSet { cudaEvent_t fork; cudaEvent_t* join; bool join_caller; int* n_join; cudaStream_t* streams; };
 
 struct FwdArgs {
     int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
@@ -571,7 +578,7 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
         int b0 = 0;
         for (int c = 0; c < nc; ++c) {
             const int Bc = sizes[c];
-            cudaStream_t sc = h->aux[c];
+            cudaStream_t sc = es.streams[c];
             CU(cudaStreamWaitEvent(sc, es.fork, 0));
             const float* f1c = feat1 + (size_t)b0 * C * L1;
             const float* f2c = feat2 + (size_t)b0 * C * L2;
@@ -655,7 +662,7 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
         return fail(OETR_E_ARG, "oetr_forward: workspace must be 256-byte aligned");
     const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, dbg_hs, dbg_memory, dbg_cxy, dbg_tlbr};
     std::lock_guard<std::mutex> lock(h->mu);
-    const EventSet es{h->ev_fork, h->ev_join, true, nullptr};
+    const EventSet es{h->ev_fork, h->ev_join, true, nullptr, h->aux};
     return forward_core(h, feat1, feat2, batch, a, boxes1, boxes2, workspace, workspace_bytes,
                         static_cast<cudaStream_t>(stream), nullptr, es);
 }
@@ -705,7 +712,7 @@ int oetr_forward_host_submit(oetr_handle* h, const float* feat1_host, const floa
         }
         const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, nullptr, nullptr, nullptr, nullptr};
         const HostIO hio{feat1_host, feat2_host, sl.boxes_pin, sl.boxes_pin + (size_t)batch * 4, sl.flag_pin, sl.cg};
-        const EventSet es{sl.ev_fork, sl.ev_join, false, &sl.n_join};
+        const EventSet es{sl.ev_fork, sl.ev_join, false, &sl.n_join, sl.aux};
         rc = forward_core(h, sl.feat1, sl.feat2, batch, a, sl.boxes, sl.boxes + (size_t)batch * 4, sl.ws, sl.ws_n, s, &hio, es);
         if (rc) {   // some sub-batches may have been queued: drain them before the slot can be reused
             cudaDeviceSynchronize();
