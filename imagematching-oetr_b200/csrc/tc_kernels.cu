@@ -24,8 +24,17 @@
 //              merge projection:  M_img = blockdiag_h(KV_h) . Wm^T.  Linear attention followed by `merge` is
 //              then ONE GEMM per tile with per-image weights:  msg = (phi(q)/Z) . M_img^T
 //   q phase  : LN_q(x)+pos -> q -> phi(q)/Z -> x += msg -> LN2 -> W1 -> GELU -> W2 -> x +=
-#include "tc_common.cuh"
-#include "tc_path.cuh"
+//
+// Files (one translation unit -- the kernels are launched from the host code at the end of this file):
+//   tc_common.cuh     sm_100a primitives (mbarrier, bulk TMA, TMEM, UMMA descriptors, swizzled slabs)
+//   tc_tiles.cuh      tile constants, shared-memory map, operand-image stores, tile geometry, producer / MMA issue
+//   tc_enc.cuh        k_enc            tc_enc_pairs.cuh  k_enc2 (experimental CTA pairs)
+//   tc_head.cuh       k_att, k_conv, k_logits, k_box, k_decoder
+//   tc_kernels.cu     weight images, k_fold, layout kernels, workspace, launch sequences, self-tests
+#include "tc_tiles.cuh"
+#include "tc_enc.cuh"
+#include "tc_enc_pairs.cuh"
+#include "tc_head.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -35,104 +44,9 @@
 namespace oetr {
 using namespace tc;
 
-constexpr int TILE = 128;                       // tokens per CTA
-constexpr int N_ROW_THREADS = 512;              // warps 0-15
-constexpr int WARP_PRODUCER = 16, WARP_MMA = 17;
-constexpr int N_THREADS = 576;
-constexpr int STAGE_HALFS = 128 * 64;           // one ring stage: [128 N rows][64 K cols] fp16, swizzled, 16 KB
-constexpr uint32_t STAGE_BYTES = STAGE_HALFS * 2;
-constexpr int RING = 6;                         // 3 units of two adjacent stages (one [256 x 64] B tile each)
-constexpr int GEMM_STAGES = 16;                 // a 256x256 weight block: 4 k-slabs x {hi n0, hi n1, lo n0, lo n1}
-constexpr size_t GEMM_HALFS = (size_t)GEMM_STAGES * STAGE_HALFS;      // 256 KB
-constexpr uint32_t SLAB_BYTES = TILE * 128;     // one [128 x 64] fp16 operand slab = 16 KB
-constexpr uint32_t IMG_BYTES = 4 * SLAB_BYTES;  // a [128 x 256] fp16 operand image = 64 KB
-// per encoder layer: Wq | W1a | W1b | W2a | W2b | Wv | Wk ; per decoder layer: Wv | Wk
-constexpr int ENC_LAYER_GEMMS = 7, DEC_LAYER_GEMMS = 2;
-constexpr size_t ENC_LAYER_HALFS = ENC_LAYER_GEMMS * GEMM_HALFS;
-constexpr size_t DEC_LAYER_HALFS = DEC_LAYER_GEMMS * GEMM_HALFS;
-constexpr size_t DEC_T_FLOATS = (size_t)6 * C * C + (size_t)2 * FF * C;   // transposed fp32 decoder weights per layer
-
-constexpr uint32_t IDESC_N256 = umma_idesc_f16(128, 256, 0, 0);
-constexpr uint32_t IDESC_KV = umma_idesc_f16(128, 128, 1, 1);      // both operands MN-major (token = K)
-
-// shared-memory map (dynamic, 1024-byte aligned)
-constexpr uint32_t SM_AHI = 0;                                     // operand image, hi part (64 KB)
-constexpr uint32_t SM_ALO = SM_AHI + IMG_BYTES;                    // operand image, lo part (64 KB)
-constexpr uint32_t SM_RING = SM_ALO + IMG_BYTES;                   // 4 x 16 KB weight stages
-constexpr uint32_t SM_X = SM_RING + RING * STAGE_BYTES;            // float[512] scratch of the row warps: LayerNorm
-                                                                   // partials -> (gamma | beta) -> Ksum of the source
-                                                                   // image -> Ksum exchange (one user at a time)
-constexpr uint32_t SM_BAR = SM_X + 512 * 4;                        // mbarriers + tmem pointer
-constexpr uint32_t SM_TOTAL = SM_BAR + 256;
-static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(uint64_t) * (2 * RING + 6) + 8 <= 256, "Bars must fit its reservation");
-// the kv phase re-uses the operand image space for the MN-major half images (tokens = K dimension)
-constexpr uint32_t KF_OFF = 0;                                     // Kf half image: 2 slabs (32 KB) inside hi / lo
-constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
-
-struct Bars {
-    uint64_t full[RING], empty[RING];
-    uint64_t a_full[2];   // row warps -> MMA: column pass p of the operand image written (count 512)
-    uint64_t s_full[2];   // MMA -> row warps: accumulator S0 / S1 complete (tcgen05.commit)
-    uint64_t a_free[2];   // MMA -> row warps (k_conv): the MMAs reading column pass p of the image have completed
-    uint32_t tmem_base;
-    uint32_t pad;
-};
-
-// ---------------------------------------------------------------------------------------------------------
-// fp32 -> (hi, lo) fp16 split and the swizzled operand-image stores
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        const float2 back = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-// columns [c0, c0+32) (c0 % 32 == 0) of row r into a (hi, lo) pair of operand images made of 64-column slabs
-template <uint32_t SLABB = SLAB_BYTES>
-__device__ __forceinline__ void store_row32_split(uint8_t* img_hi, uint8_t* img_lo, uint32_t r, uint32_t c0,
-                                                  const float (&v)[32]) {
-    const uint32_t slab = (c0 >> 6) * SLABB;
-    const uint32_t j0 = (c0 & 63) >> 3;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 h, l;
-        split8(&v[8 * j], h, l);
-        const uint32_t off = slab + slab_chunk_off(r, j0 + j);
-        *reinterpret_cast<uint4*>(img_hi + off) = h;
-        *reinterpret_cast<uint4*>(img_lo + off) = l;
-    }
-}
-
-// columns [c0, c0+16) (c0 % 16 == 0)
-__device__ __forceinline__ void store_row16_split(uint8_t* img_hi, uint8_t* img_lo, uint32_t r, uint32_t c0,
-                                                  const float (&v)[16]) {
-    const uint32_t slab = (c0 >> 6) * SLAB_BYTES;
-    const uint32_t j0 = (c0 & 63) >> 3;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        uint4 h, l;
-        split8(&v[8 * j], h, l);
-        const uint32_t off = slab + slab_chunk_off(r, j0 + j);
-        *reinterpret_cast<uint4*>(img_hi + off) = h;
-        *reinterpret_cast<uint4*>(img_lo + off) = l;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // weight images
 // ---------------------------------------------------------------------------------------------------------
-// stage order of one 256x256 block W[n][k]: for ks (k-slab of 64): hi n<128 | hi n>=128 | lo n<128 | lo n>=128
-__host__ __device__ __forceinline__ size_t gemm_stage_off(int ks, int lo, int nh) {
-    return (size_t)((ks * 2 + lo) * 2 + nh) * STAGE_HALFS;
-}
 
 __global__ void k_make_gemm_image(const float* __restrict__ W, int ld, int row0, int col0, __half* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte chunk (8 halfs) of hi and of lo
@@ -208,1105 +122,6 @@ void tc_free_weights(TcWeights& w) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// tile bookkeeping
-// ---------------------------------------------------------------------------------------------------------
-struct TileGeom {
-    int B, L1, L2, T1, T2;          // tiles per image: T = ceil(L/128)
-    __host__ __device__ int tiles() const { return B * (T1 + T2); }
-};
-struct TileInfo { int set, b, ti, L, T, img, valid, first_tile_of_img; };
-__host__ __device__ __forceinline__ TileInfo tile_info(const TileGeom& g, int t) {
-    TileInfo ti;
-    if (t < g.B * g.T1) { ti.set = 0; ti.b = t / g.T1; ti.ti = t % g.T1; ti.L = g.L1; ti.T = g.T1; ti.first_tile_of_img = ti.b * g.T1; }
-    else { const int u = t - g.B * g.T1; ti.set = 1; ti.b = u / g.T2; ti.ti = u % g.T2; ti.L = g.L2; ti.T = g.T2;
-           ti.first_tile_of_img = g.B * g.T1 + ti.b * g.T2; }
-    ti.img = ti.set * g.B + ti.b;
-    ti.valid = ti.L - ti.ti * TILE < TILE ? ti.L - ti.ti * TILE : TILE;
-    return ti;
-}
-// Row mapping of the ENCODER tiles (k_enc, k_fold, k_sum_partials).  flat == 0: the per-image tiles of TileGeom.
-// flat == 1: the images of a set are concatenated, each padded to Lp = round_up(L, 16) rows, and the B*Lp rows are cut
-// into 128-row tiles: no per-image padding to a multiple of 128 (400 tokens: 3.125 tiles instead of 4).  With
-// Lp >= 128 a tile holds rows of at most two consecutive images and the boundary is a multiple of 16 rows (one MMA
-// k-step of the K^T V product).  The head kernels keep per-image tiles (k_retile converts the encoder output).
-struct EncGeom {
-    int flat, Lp1, Lp2, F1, F2;     // F: flat tiles per set
-};
-struct EncTile { int set, L, Lp, B, b0, l0, split, two; };
-// rows [0, split) of the tile belong to image b0 (tokens l0 ..), rows [split, 128) to image b0 + 1 (tokens 0 ..)
-__host__ __device__ __forceinline__ EncTile enc_tile(const TileGeom& g, const EncGeom& eg, int t) {
-    EncTile e;
-    e.B = g.B;
-    if (!eg.flat) {
-        const TileInfo ti = tile_info(g, t);
-        e.set = ti.set; e.L = ti.L; e.Lp = ti.L; e.b0 = ti.b; e.l0 = ti.ti * 128; e.split = 128; e.two = 0;
-    } else {
-        e.set = t >= eg.F1 ? 1 : 0;
-        const int u = t - e.set * eg.F1;
-        e.L = e.set ? g.L2 : g.L1; e.Lp = e.set ? eg.Lp2 : eg.Lp1;
-        const int base = u * 128;
-        e.b0 = base / e.Lp; e.l0 = base - e.b0 * e.Lp;
-        e.split = e.Lp - e.l0 < 128 ? e.Lp - e.l0 : 128;
-        e.two = (e.split < 128 && e.b0 + 1 < g.B) ? 1 : 0;
-    }
-    return e;
-}
-// the partial summaries of image (set, b): n = enc_parts(...), then enc_part_index(..., i) for i < n, in a fixed order.
-// ppt = partial slots per tile (flat: 2 = one per image of a tile)
-__host__ __device__ __forceinline__ int enc_parts(const TileGeom& g, const EncGeom& eg, int ppt, int set, int b) {
-    if (!eg.flat) return (set == 0 ? g.T1 : g.T2) * ppt;
-    const int L = set ? g.L2 : g.L1, Lp = set ? eg.Lp2 : eg.Lp1;
-    return (b * Lp + L - 1) / 128 - (b * Lp) / 128 + 1;
-}
-__host__ __device__ __forceinline__ int enc_part_index(const TileGeom& g, const EncGeom& eg, int ppt, int set, int b, int i) {
-    if (!eg.flat) return (set == 0 ? b * g.T1 : g.B * g.T1 + b * g.T2) * ppt + i;
-    const int Lp = set ? eg.Lp2 : eg.Lp1;
-    const int u = (b * Lp) / 128 + i;                       // flat tile inside the set
-    const int slot = b - (u * 128) / Lp;                    // 0: the tile starts inside this image, 1: inside the previous one
-    return ((set ? eg.F1 : 0) + u) * 2 + slot;
-}
-// tile-blocked fp32 layout [tile][64 col-quads][128 rows][4]: a warp's rows read/write one col-quad coalesced
-__host__ __device__ __forceinline__ size_t xt_off(int tile, int quad, int r) { return (((size_t)tile * 64 + quad) * TILE + r) * 4; }
-
-// single-instruction special functions (flush-to-zero forms: no denormal fix-up code around the MUFU)
-__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// elu(x) + 1 (linear_attention.py:12-13)
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : ex2_ftz(x * 1.4426950408889634f); }
-// nn.GELU (erf form, transformer.py:93).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), branch-free:
-// ~13 instructions instead of erff's divergent ~35; the result error (<= 3e-7 |x|) is far inside the parity budget.
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = rcp_ftz(fmaf(0.3275911f, z, 1.f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
-    const float erf_abs = fmaf(-poly, ex2_ftz(z * z * -1.4426950408889634f), 1.f);
-    const float hx = 0.5f * x;
-    return fmaf(hx, copysignf(erf_abs, x), hx);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// device building blocks shared by k_enc and k_conv
-// ---------------------------------------------------------------------------------------------------------
-// barriers + TMEM allocation (whole CTA); returns the TMEM base address
-__device__ __forceinline__ uint32_t cta_setup(Bars* bars, int alloc_warp) {
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < RING; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->a_full[i], N_ROW_THREADS);
-            mbar_init(&bars->s_full[i], 1);
-            mbar_init(&bars->a_free[i], 1);
-        }
-        fence_mbar_init();
-    }
-    if ((int)(threadIdx.x >> 5) == alloc_warp) tmem_alloc(&bars->tmem_base, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    return bars->tmem_base;
-}
-// producer: nstages (even) consecutive 16 KB stages global -> ring, ONE 32 KB bulk copy per pair of stages.  The
-// issuing thread pays ~480 cycles per copy whatever its size (measured, tools/bulk_bw.cu: 16 KB copies stream at
-// 34 B/cycle/SM, 32 KB copies at 68), and the 3-term MMAs consume 43 B/cycle: 16 KB copies starve the tensor core.
-// Only the even stage's full barrier is used; both empty barriers are still committed by the consumer.
-__device__ __forceinline__ void ring_stream(uint8_t* smem, Bars* bars, int* flag, uint32_t& g, const __half* src, int nstages) {
-    for (int i = 0; i < nstages; i += 2, g += 2) {
-        const int st = g % RING;
-        mbar_wait(&bars->empty[st], ((g / RING) & 1) ^ 1, flag);
-        mbar_wait(&bars->empty[st + 1], ((g / RING) & 1) ^ 1, flag);
-        mbar_arrive_expect_tx(&bars->full[st], 2 * STAGE_BYTES);
-        bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, 2 * STAGE_BYTES, &bars->full[st]);
-    }
-}
-struct MmaState { uint32_t g = 0, na0 = 0, na1 = 0; long long t_a = 0, t_ring = 0; };   // t_*: cycles spent waiting (profiling aid)
-__device__ __forceinline__ void mma_wait_a(Bars* bars, int* flag, MmaState& ms, int pass) {
-    const long long t0 = clock64();
-    mbar_wait(&bars->a_full[pass], (pass ? ms.na1++ : ms.na0++) & 1, flag);
-    ms.t_a += clock64() - t0;
-    tc_fence_after();
-}
-// D[128 x 256] (tmem columns d..d+255) (+)= A[128 x 256] . W^T with the 3-term split; consumes 16 ring stages.
-// wait: the operand image is (re)written for this GEMM -> wait for column pass 0 before k-slab 0 and pass 1
-// before k-slab 2.  signal_free: commit a_free[p] once the MMAs reading pass p have been issued (k_conv).
-__device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* flag, MmaState& ms, uint32_t d,
-                                           bool accumulate, bool wait, bool signal_free) {
-    for (int ks = 0; ks < 4; ++ks) {
-        if (wait && ks == 0) mma_wait_a(bars, flag, ms, 0);
-        if (wait && ks == 2) mma_wait_a(bars, flag, ms, 1);
-        const uint32_t a_hi = smem_base + SM_AHI + ks * SLAB_BYTES;
-        const uint32_t a_lo = smem_base + SM_ALO + ks * SLAB_BYTES;
-        {   // w_hi: two adjacent stages form the [256 x 64] B tile
-            const int st = ms.g % RING;
-            const long long t0 = clock64();
-            mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
-            ms.t_ring += clock64() - t0;
-            tc_fence_after();
-            const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                         IDESC_N256, (accumulate || ks > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma_f16(d, umma_desc(a_lo + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                         IDESC_N256, 1u);
-            umma_commit(&bars->empty[st]);
-            umma_commit(&bars->empty[st + 1]);
-            ms.g += 2;
-        }
-        {   // w_lo
-            const int st = ms.g % RING;
-            const long long t0 = clock64();
-            mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);
-            ms.t_ring += clock64() - t0;
-            tc_fence_after();
-            const uint32_t b = smem_base + SM_RING + st * STAGE_BYTES;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                         IDESC_N256, 1u);
-            umma_commit(&bars->empty[st]);
-            umma_commit(&bars->empty[st + 1]);
-            ms.g += 2;
-        }
-        if (signal_free && (ks & 1)) umma_commit(&bars->a_free[ks >> 1]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_enc
-// ---------------------------------------------------------------------------------------------------------
-struct EncParams {
-    TileGeom g;
-    EncGeom eg;                 // row mapping of the tiles (k_enc only; k_enc2 always uses the per-image tiles of g)
-    const float* feat1;         // NCHW inputs, read when load_feat
-    const float* feat2;
-    float* xt;                  // tile-blocked residual stream (read unless load_feat; written when store_x)
-    const float *post1, *post2; // tile-blocked positional rows of set 0 / set 1
-    int load_feat, store_x, do_q, do_kv;
-    // query phase (encoder layer i)
-    const float *lnq_g, *lnq_b, *ln2_g, *ln2_b;
-    const __half* w_q;          // Wq                         (16 stages)
-    const __half* w_mlp;        // W1a | W1b | W2a | W2b      (64 stages)
-    const __half* mimg;         // [2B images][GEMM_HALFS] folded merge weights of the source image
-    const float* ksum;          // [2B images][256]
-    int cross;                  // 1: the source is the partner image (transformer.py:354-358)
-    // kv phase (encoder layer i+1, or a decoder layer's cross-attention when lnkv_g == nullptr)
-    const float *lnkv_g, *lnkv_b;   // nullptr: decoder mode: k = (x+pos) Wk^T + bk, v = x Wv^T + bv
-    const float *bk, *bv;
-    const __half* w_kv;         // Wv | Wk                    (32 stages)
-    float* kv_part;             // [tiles][KVS] per-tile partial summaries
-    int* flag;
-    long long* dbg_clock;       // nullable: per CTA {total, MMA wait on operand image, MMA wait on weights, 0} cycles
-    // L2 prefetch: every layer's weights are read once per forward, so without it each stage is a DRAM-latency
-    // miss for the whole first wave.  The grid spreads these ranges (the NEXT launch's weights) in 16 KB pieces.
-    const void* pf_ptr[3];
-    uint32_t pf_bytes[3];
-};
-
-__global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const EncTile et = enc_tile(p.g, p.eg, blockIdx.x);
-    const bool two = et.two != 0;                      // the tile holds rows of two images (flat tiling only)
-    const uint32_t smem_base = smem_u32(smem);
-    const bool dec_mode = p.lnkv_g == nullptr;
-
-    const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
-    const uint32_t S0 = tmem, S1 = tmem + 256;
-
-    // source image of the tile's first image (the second one's is src_img + 1) and its length
-    int src_img = et.set * p.g.B + et.b0, src_len = et.L;
-    if (p.cross) { src_img = et.set == 0 ? p.g.B + et.b0 : et.b0; src_len = et.set == 0 ? p.g.L2 : p.g.L1; }
-
-    if (warp == WARP_PRODUCER) {
-        // ------------------------------------------------------------------ weight stream
-        if (lane == 0) {
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k)
-                for (uint32_t off = blockIdx.x * STAGE_BYTES; off < p.pf_bytes[k]; off += gridDim.x * STAGE_BYTES)
-                    bulk_prefetch_l2(static_cast<const uint8_t*>(p.pf_ptr[k]) + off, min(STAGE_BYTES, p.pf_bytes[k] - off));
-            uint32_t g = 0;
-            auto stream = [&](const __half* src, int nstages) { ring_stream(smem, bars, p.flag, g, src, nstages); };
-            if (p.do_q) {
-                stream(p.w_q, GEMM_STAGES);
-                stream(p.mimg + (size_t)src_img * GEMM_HALFS, GEMM_STAGES);
-                if (two) stream(p.mimg + (size_t)(src_img + 1) * GEMM_HALFS, GEMM_STAGES);
-                stream(p.w_mlp, 4 * GEMM_STAGES);
-            }
-            if (p.do_kv) stream(p.w_kv, 2 * GEMM_STAGES);
-        }
-        __syncwarp();
-    } else if (warp == WARP_MMA) {
-        // ------------------------------------------------------------------ MMA issue
-        if (lane == 0) {
-            MmaState ms;
-            const long long t_begin = clock64();
-            auto wait_a = [&](int pass) { mma_wait_a(bars, p.flag, ms, pass); };
-            auto gemm = [&](uint32_t d, bool accumulate, bool wait) { gemm_issue(smem_base, bars, p.flag, ms, d, accumulate, wait, false); };
-            if (p.do_q) {
-                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
-                gemm(S1, false, true);  umma_commit(&bars->s_full[1]);     // msg = (phi(q)/Z) M_img^T
-                if (two) { gemm(S0, false, false); umma_commit(&bars->s_full[0]); }   // ... with the second image's M_img
-                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // h_a = LN2(x) W1a^T
-                gemm(S1, false, false); umma_commit(&bars->s_full[1]);     // h_b = LN2(x) W1b^T
-                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // y   = gelu(h_a) W2a^T
-                gemm(S0, true, true);   umma_commit(&bars->s_full[0]);     // y  += gelu(h_b) W2b^T
-            }
-            if (p.do_kv) {
-                gemm(S0, false, true);      umma_commit(&bars->s_full[0]); // v
-                gemm(S1, false, dec_mode);  umma_commit(&bars->s_full[1]); // k (decoder: from a second image)
-                // per 128-channel half: KV = Kf^T V (diagonal 32x32 blocks are the heads); Ksum is reduced by the row warps
-                // the token rows are the K dimension, 16 per MMA: a two-image tile splits the k-steps at the image
-                // boundary (a multiple of 16 rows) and accumulates the second image's product in S1's columns
-                const int ksplit = two ? et.split / 16 : TILE / 16;
-                for (int half = 0; half < 2; ++half) {
-                    wait_a(half);
-                    const uint32_t kf_hi = smem_base + SM_AHI + KF_OFF, kf_lo = smem_base + SM_ALO + KF_OFF;
-                    const uint32_t v_hi = smem_base + SM_AHI + V_OFF, v_lo = smem_base + SM_ALO + V_OFF;
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t a = term == 1 ? kf_lo : kf_hi, bb = term == 2 ? v_lo : v_hi;
-#pragma unroll
-                        for (int k = 0; k < TILE / 16; ++k) {
-                            const bool second = k >= ksplit;
-                            const uint32_t dkv = (second ? S1 : S0) + half * 128;
-                            const uint32_t first_of_group = (term == 0 && (k == 0 || k == ksplit)) ? 0u : 1u;
-                            umma_f16(dkv, umma_desc(a + k * 2048, SLAB_BYTES, ATOM_BYTES),
-                                     umma_desc(bb + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, first_of_group);
-                        }
-                    }
-                    umma_commit(&bars->s_full[half]);
-                }
-            }
-            if (p.dbg_clock) {
-                long long* o = p.dbg_clock + (size_t)blockIdx.x * 4;
-                o[0] = clock64() - t_begin; o[1] = ms.t_a; o[2] = ms.t_ring; o[3] = 0;
-            }
-        }
-        __syncwarp();
-    } else if (warp < WARP_PRODUCER) {
-        // ------------------------------------------------------------------ row warps
-        const int q = warp & 3, cq = warp >> 2;            // TMEM lane quarter, column quarter
-        const int r = q * 32 + lane;                       // token row of the tile
-        // which image / token this row is (enc_tile): rows >= split belong to the tile's second image
-        const int rel = r >= et.split ? 1 : 0;
-        const int rb = et.b0 + rel;                        // image inside the set
-        const int rl = rel ? r - et.split : et.l0 + r;     // token inside the image
-        const bool valid = rb < et.B && rl < et.L;
-        const int pl = valid ? rl : 0;                     // row of the position table
-        const bool warp_has_rel1 = two && et.split < q * 32 + 32;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float* X = reinterpret_cast<float*>(smem + SM_X);       // 512-float scratch, see the shared-memory map
-        uint8_t* img_hi = smem + SM_AHI;
-        uint8_t* img_lo = smem + SM_ALO;
-        const float* post = (et.set == 0 ? p.post1 : p.post2);
-        uint32_t ns0 = 0, ns1 = 0;
-        auto wait_s = [&](int b) {
-            mbar_wait(&bars->s_full[b], (b ? ns1++ : ns0++) & 1, p.flag);
-            tc_fence_after();
-        };
-        auto publish = [&](int pass) {                     // operand image pass written; accumulator reads done
-            tc_fence_before();
-            fence_async_smem();
-            mbar_arrive(&bars->a_full[pass]);
-        };
-        // ---- the residual stream of this thread: columns [32*cq, +32) and [128 + 32*cq, +32) of row r
-        float x[2][32];
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int c0 = pass * 128 + cq * 32;
-            if (p.load_feat) {
-                const float* feat = et.set == 0 ? p.feat1 : p.feat2;
-                const float* f = feat + ((size_t)(valid ? rb : 0) * C + c0) * et.L + pl;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] = valid ? f[(size_t)e * et.L] : 0.f;
-            } else {
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    const float4 v = *reinterpret_cast<const float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r));
-                    x[pass][jq * 4 + 0] = v.x; x[pass][jq * 4 + 1] = v.y; x[pass][jq * 4 + 2] = v.z; x[pass][jq * 4 + 3] = v.w;
-                }
-            }
-        }
-        // two-pass LayerNorm statistics of the row (4 threads per row, combined through X), then (gamma | beta) are
-        // staged into X for the normalisation pass (their global loads are issued before the statistics)
-        auto ln_stats = [&](const float* __restrict__ gamma, const float* __restrict__ beta, float& mean, float& rstd) {
-            const float gb = tid < 256 ? __ldg(gamma + tid) : __ldg(beta + tid - 256);
-            float s = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) s += x[0][e] + x[1][e];
-            X[cq * TILE + r] = s;
-            named_bar_sync(1, N_ROW_THREADS);
-            mean = (X[0 * TILE + r] + X[1 * TILE + r] + X[2 * TILE + r] + X[3 * TILE + r]) * (1.f / C);
-            float sq = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float d0 = x[0][e] - mean, d1 = x[1][e] - mean;
-                sq = fmaf(d0, d0, sq);
-                sq = fmaf(d1, d1, sq);
-            }
-            named_bar_sync(1, N_ROW_THREADS);              // every thread has read the sums
-            X[cq * TILE + r] = sq;
-            named_bar_sync(1, N_ROW_THREADS);
-            const float var = (X[0 * TILE + r] + X[1 * TILE + r] + X[2 * TILE + r] + X[3 * TILE + r]) * (1.f / C);
-            rstd = rsqrtf(var + LN_EPS);
-            named_bar_sync(1, N_ROW_THREADS);
-            X[tid] = gb;                                   // X[0,256) = gamma, X[256,512) = beta
-            named_bar_sync(1, N_ROW_THREADS);
-        };
-        // operand image <- [LN](x) [+ pos], both column passes (gamma == nullptr: no LayerNorm)
-        auto image_from_x = [&](const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos) {
-            float mean = 0.f, rstd = 1.f;
-            if (gamma) ln_stats(gamma, beta, mean, rstd);
-            const float shift = -mean * rstd;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-                float v[32];
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(pl >> 7, (c0 >> 2) + jq, pl & 127));
-                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gamma) {
-                        g4 = *reinterpret_cast<const float4*>(X + c0 + jq * 4);
-                        b4 = *reinterpret_cast<const float4*>(X + 256 + c0 + jq * 4);
-                    }
-                    // (x - mean) * rstd * g + b + pos  ==  fma(fma(x, rstd, shift), g, b + pos)
-                    v[jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), g4.x, b4.x + ps.x);
-                    v[jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), g4.y, b4.y + ps.y);
-                    v[jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), g4.z, b4.z + ps.z);
-                    v[jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), g4.w, b4.w + ps.w);
-                }
-                store_row32_split(img_hi, img_lo, r, c0, v);
-                publish(pass);
-            }
-        };
-
-        if (p.do_q) {
-            // (E0) A = LNq(x) + pos
-            image_from_x(p.lnq_g, p.lnq_b, true);
-            // Ksum of the source image -> X (every thread is done with gamma/beta after the barrier)
-            named_bar_sync(1, N_ROW_THREADS);
-            if (tid < 256 || two) X[tid] = __ldg(p.ksum + (size_t)(src_img + (tid >> 8)) * C + (tid & 255));   // [256, 512): second image
-            named_bar_sync(1, N_ROW_THREADS);
-            const float* Xk = X + rel * 256;
-            // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
-            wait_s(0);
-            const float eps_s = ATTN_EPS / (float)src_len;    // summaries arrive scaled by 1/S (k_fold)
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;      // one head per 32-column chunk
-                float v[32];
-                tmem_ld32(S0 + lane_addr + c0, v);
-                float den = 0.f;
-#pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(Xk + c0 + e4 * 4);
-                    v[e4 * 4 + 0] = elu1(v[e4 * 4 + 0]); den = fmaf(v[e4 * 4 + 0], k4.x, den);
-                    v[e4 * 4 + 1] = elu1(v[e4 * 4 + 1]); den = fmaf(v[e4 * 4 + 1], k4.y, den);
-                    v[e4 * 4 + 2] = elu1(v[e4 * 4 + 2]); den = fmaf(v[e4 * 4 + 2], k4.z, den);
-                    v[e4 * 4 + 3] = elu1(v[e4 * 4 + 3]); den = fmaf(v[e4 * 4 + 3], k4.w, den);
-                }
-                const float inv = 1.f / (den + eps_s);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] *= inv;
-                store_row32_split(img_hi, img_lo, r, c0, v);
-                publish(pass);
-            }
-            // (E2) x += msg ; A = LN2(x)   (two-image tile: rows of the second image take the product with its M_img, S0)
-            wait_s(1);
-            if (two) wait_s(0);
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                tmem_ld32(S1 + lane_addr + pass * 128 + cq * 32, v);
-                if (warp_has_rel1) {
-                    float v2[32];
-                    tmem_ld32(S0 + lane_addr + pass * 128 + cq * 32, v2);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = rel ? v2[e] : v[e];
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
-            }
-            image_from_x(p.ln2_g, p.ln2_b, false);
-            // (E3) A = gelu(h_a): needs h_a (S0) and, for the image to be free, h_b complete (S1)
-            // (E4) A = gelu(h_b): the image is free once y = gelu(h_a) W2a^T has completed (S0 commit)
-#pragma unroll 1
-            for (int which = 0; which < 2; ++which) {
-                if (which == 0) wait_s(0);
-                const uint32_t S = which ? S1 : S0;
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int c0 = pass * 128 + cq * 32;
-                    float v[32];
-                    tmem_ld32(S + lane_addr + c0, v);
-                    // the GEMM that consumes pass 0 overwrites ALL of S0 (h_a): release pass 0 only once this
-                    // thread has also read its pass-1 columns
-                    if (pass == 1) publish(0);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
-                    // the image is free once the GEMM still reading it has completed: h_b (S1 commit) before
-                    // gelu(h_a) is stored, y = gelu(h_a) W2a^T (S0 commit) before gelu(h_b) is stored
-                    if (pass == 0) wait_s(which == 0 ? 1 : 0);
-                    store_row32_split(img_hi, img_lo, r, c0, v);
-                }
-                publish(1);
-            }
-            // (E5) x += y
-            wait_s(0);
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                tmem_ld32(S0 + lane_addr + pass * 128 + cq * 32, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
-            }
-            tc_fence_before();
-        }
-        if (p.store_x) {
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq)
-                    *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r)) =
-                        make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
-            }
-        }
-        if (p.do_kv) {
-            if (!dec_mode) {
-                image_from_x(p.lnkv_g, p.lnkv_b, true);        // k and v share LN_kv(x)+pos (transformer.py:119-126)
-                wait_s(0);
-                wait_s(1);
-            } else {
-                image_from_x(nullptr, nullptr, false);         // v = x Wv^T + bv      (transformer.py:243-249)
-                wait_s(0);
-                image_from_x(nullptr, nullptr, true);          // k = (x+pos) Wk^T + bk
-                wait_s(1);
-            }
-            // half images (tokens = K dimension): V and Kf = elu(k)+1; padded rows are zero
-            // partial summaries of this tile: one slot per image of the tile when the tiling is flat
-            float* part = p.kv_part + (size_t)blockIdx.x * (p.eg.flat ? 2 : 1) * KVS;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32, ch = cq * 32;      // ch: column inside the 128-channel half
-                float v[32];
-                tmem_ld32(S0 + lane_addr + c0, v);
-                if (p.bv) {
-#pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bv + c0) + e4);
-                        v[e4 * 4] += b4.x; v[e4 * 4 + 1] += b4.y; v[e4 * 4 + 2] += b4.z; v[e4 * 4 + 3] += b4.w;
-                    }
-                }
-                if (!valid) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = 0.f;
-                }
-                if (pass == 1) wait_s(0);                               // KV of half 0 has consumed the images
-                store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
-                tmem_ld32(S1 + lane_addr + c0, v);
-                if (p.bk) {
-#pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bk + c0) + e4);
-                        v[e4 * 4] += b4.x; v[e4 * 4 + 1] += b4.y; v[e4 * 4 + 2] += b4.z; v[e4 * 4 + 3] += b4.w;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e]) : 0.f;
-                store_row32_split(img_hi + KF_OFF, img_lo + KF_OFF, r, ch, v);
-                publish(pass);
-                // Ksum[c0 + j] = sum over the tile's rows of Kf[:, c0 + j] (fp32, exact operands): butterfly
-                // transpose-reduce inside the warp (lane j ends with column j summed over the warp's 32 rows),
-                // then across the 4 row quarters through X; per image of the tile (rows of the other image masked)
-#pragma unroll 1
-                for (int im = 0; im < (two ? 2 : 1); ++im) {
-                    float w[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) w[e] = (!two || rel == im) ? v[e] : 0.f;
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float send = up ? w[i] : w[i + off];
-                            const float keep = up ? w[i + off] : w[i];
-                            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
-                    }
-                    X[(cq * 4 + q) * 32 + lane] = w[0];
-                    named_bar_sync(1, N_ROW_THREADS);
-                    if (q == 0)
-                        part[im * KVS + NH * HD * HD + c0 + lane] = X[(cq * 4 + 0) * 32 + lane] + X[(cq * 4 + 1) * 32 + lane] +
-                                                                    X[(cq * 4 + 2) * 32 + lane] + X[(cq * 4 + 3) * 32 + lane];
-                    named_bar_sync(1, N_ROW_THREADS);
-                }
-            }
-            // results: KV diagonal blocks (this warp's TMEM lanes are the d-channels of head 4*half + q)
-            wait_s(1);
-            if (cq < 2) {
-                const int half = cq, h = half * 4 + q;
-                for (int im = 0; im < (two ? 2 : 1); ++im) {
-                    float v[32];
-                    tmem_ld32((im ? S1 : S0) + lane_addr + half * 128 + q * 32, v);
-                    float* o = part + im * KVS + h * HD * HD + lane * HD;
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                }
-            }
-            tc_fence_before();
-        }
-    }
-    // teardown
-    tc_fence_before();
-    __syncthreads();
-    if (warp == WARP_PRODUCER) tmem_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_enc2: the same layer kernel on CTA PAIRS (tcgen05 cta_group::2), two CTAs resident per SM.
-//
-// k_enc is a serial chain per tile (GEMM -> row-wise epilogue -> GEMM ...): the tensor core idles while the row
-// warps work and vice versa (tensor pipe 36 % busy), and one CTA owns the whole SM (226 KB of shared memory, all
-// of TMEM).  Here a 128-token tile belongs to a cluster of two CTAs on the two SMs of a TPC: each CTA holds 64
-// token rows (operand image 64 KB instead of 128) and streams only ITS half of every weight tile (the N rows
-// [128*rank, +128); ring 3 x 16 KB instead of 96 KB), and the leader's MMA lane issues M=128 N=256
-// tcgen05.mma.cta_group::2 instructions for the pair (64 cycles each: both tensor cores at full rate).  The
-// accumulators use the "2x2" TMEM layout (lanes 0-63: columns n < 128, lanes 64-127: n >= 128 of the CTA's 64 rows),
-// 128 TMEM columns each, so S0 | S1 need 256 of the 512 columns.  A CTA then needs 113 KB / 256 columns / 320
-// threads, TWO CTAs (of different pairs) fit one SM, and while one waits for its epilogue the other one's MMAs run.
-//   warps 0-7   row warps: thread <-> (token row 32*(w&1)+lane, columns [128*((w>>1)&1) + 64*(w>>2), +64)), i.e. TMEM
-//               lane quarter w%4; the fp32 residual stream stays in registers (64 per thread) as in k_enc
-//   warp 8      weight producer (both CTAs, own half), TMEM allocation
-//   warp 9      leader: MMA issue for the pair;  peer: relays "my half of the stage has landed" to the leader
-// Cross-CTA signalling: row warps of both CTAs arrive (one lane per warp, release.cluster) on the leader's a_full;
-// tcgen05.commit multicasts the ring `empty` and accumulator `s_full` arrivals to both CTAs.
-// KV = Kf^T V needs tokens as the K dimension, and the pair's tokens are split across CTAs, so the pair MMA is
-// used with N split as (own V | peer's V): CTA r keeps the half of the result built from its own V (n-half r)
-// and ignores the cross term; the per-CTA partial summaries are added by k_fold / k_sum_partials.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int HT = 64;                                  // token rows per CTA
-constexpr int E2_ROW_THREADS = 256, E2_WARP_PRODUCER = 8, E2_WARP_MMA = 9, E2_THREADS = 320;
-constexpr int E2_RING = 3;                              // ring units of ONE 16 KB stage (this CTA's half of a B tile)
-constexpr uint32_t E2_SLAB = HT * 128;                  // [64 rows x 64 K] fp16 = 8 KB
-constexpr uint32_t E2_IMG = 4 * E2_SLAB;                // 32 KB
-constexpr uint32_t E2_AHI = 0, E2_ALO = E2_IMG, E2_RINGOFF = 2 * E2_IMG;
-constexpr uint32_t E2_X = E2_RINGOFF + E2_RING * STAGE_BYTES;       // 192-float scratch (LayerNorm / Ksum exchange)
-constexpr uint32_t E2_BAR = E2_X + 192 * 4;
-constexpr uint32_t E2_TOTAL = E2_BAR + 128;
-static_assert(2 * (E2_TOTAL + 1024) <= 228 * 1024, "two CTAs per SM");
-constexpr uint32_t IDESC2_N256 = umma_idesc_f16(128, 256, 0, 0);    // pair MMA: M = 128 (64 rows per CTA)
-constexpr uint32_t IDESC2_KV = umma_idesc_f16(128, 128, 1, 1);
-
-struct Bars2 {
-    uint64_t full[E2_RING], empty[E2_RING];
-    uint64_t pfull[E2_RING];   // leader: the peer's half of the stage has landed (relayed by the peer's warp 9)
-    uint64_t a_full;           // leader: operand image written by the 16 row warps of the pair
-    uint64_t kv_a, kv_b;       // leader: KV round 0 (all 16 warps) / round 1 (the 8 warps of N half 1)
-    uint64_t s_full[2];
-    uint32_t tmem_base;
-    uint32_t pad;
-};
-static_assert(sizeof(Bars2) <= 128, "Bars2 must fit its reservation");
-
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on a barrier of any CTA of the cluster (address from mapa), release at cluster scope
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// bounded wait, acquire at cluster scope, with a suspend-time hint: a waiting warp sleeps instead of polling, so it
-// does not take issue slots from the other CTA resident on the SM
-__device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity, int* timeout_flag) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 16); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity), "r"(20000u)
-            : "memory");
-        if (done) return;
-        if ((spin & 255) == 255 && timeout_flag && *reinterpret_cast<volatile int*>(timeout_flag)) return;
-    }
-    if (timeout_flag) atomicExch(timeout_flag, 1);
-}
-// the same without the hint, for the single producer / relay / MMA lanes (their wake-up latency is on the critical
-// path of the weight ring and one polling lane costs nothing)
-__device__ __forceinline__ void mbar_wait2_poll(uint64_t* bar, uint32_t parity, int* timeout_flag) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (done) return;
-        if ((spin & 1023) == 1023 && timeout_flag && *reinterpret_cast<volatile int*>(timeout_flag)) return;
-    }
-    if (timeout_flag) atomicExch(timeout_flag, 1);
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {     // one warp in EACH CTA of the pair
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// completion of all MMAs issued so far by this thread -> one arrival on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)), "h"((uint16_t)3)
-                 : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(E2_THREADS, 2) k_enc2(const EncParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    Bars2* bars = reinterpret_cast<Bars2*>(smem + E2_BAR);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int tile = blockIdx.x >> 1;
-    const TileInfo ti = tile_info(p.g, tile);
-    const uint32_t smem_base = smem_u32(smem);
-    const bool dec_mode = p.lnkv_g == nullptr;
-
-    if (tid == 0) {
-        for (int i = 0; i < E2_RING; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); mbar_init(&bars->pfull[i], 1); }
-        mbar_init(&bars->a_full, 16);
-        mbar_init(&bars->kv_a, 16);
-        mbar_init(&bars->kv_b, 8);
-        mbar_init(&bars->s_full[0], 1);
-        mbar_init(&bars->s_full[1], 1);
-        fence_mbar_init();
-    }
-    if (warp == E2_WARP_PRODUCER) tmem_alloc2(&bars->tmem_base, 256);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();                                  // the peer's barriers are initialised before anyone signals them
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    const uint32_t S0 = tmem, S1 = tmem + 128;
-
-    int src_img = ti.img, src_len = ti.L;
-    if (p.cross) { src_img = ti.set == 0 ? p.g.B + ti.b : ti.b; src_len = ti.set == 0 ? p.g.L2 : p.g.L1; }
-    // units (16 KB stages) this launch streams per CTA: 8 per GEMM
-    const int n_units = (p.do_q ? 6 * 8 : 0) + (p.do_kv ? 2 * 8 : 0);
-
-    if (warp == E2_WARP_PRODUCER) {
-        // ------------------------------------------------------------------ weight stream (own N half)
-        if (lane == 0) {
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k)
-                for (uint32_t off = blockIdx.x * STAGE_BYTES; off < p.pf_bytes[k]; off += gridDim.x * STAGE_BYTES)
-                    bulk_prefetch_l2(static_cast<const uint8_t*>(p.pf_ptr[k]) + off, min(STAGE_BYTES, p.pf_bytes[k] - off));
-            uint32_t g = 0;
-            auto stream = [&](const __half* src, int ngemms) {
-                for (int gm = 0; gm < ngemms; ++gm)
-                    for (int ks = 0; ks < 4; ++ks)
-                        for (int lo = 0; lo < 2; ++lo, ++g) {
-                            const int st = g % E2_RING;
-                            mbar_wait2_poll(&bars->empty[st], ((g / E2_RING) & 1) ^ 1, p.flag);
-                            mbar_arrive_expect_tx(&bars->full[st], STAGE_BYTES);
-                            bulk_g2s(smem + E2_RINGOFF + st * STAGE_BYTES,
-                                     src + (size_t)gm * GEMM_HALFS + gemm_stage_off(ks, lo, (int)rank), STAGE_BYTES, &bars->full[st]);
-                        }
-            };
-            if (p.do_q) {
-                stream(p.w_q, 1);
-                stream(p.mimg + (size_t)src_img * GEMM_HALFS, 1);
-                stream(p.w_mlp, 4);
-            }
-            if (p.do_kv) stream(p.w_kv, 2);
-        }
-        __syncwarp();
-    } else if (warp == E2_WARP_MMA) {
-        if (lane == 0 && rank == 1) {
-            // ------------------------------------------------------------------ peer: relay "stage landed"
-            for (int g = 0; g < n_units; ++g) {
-                const int st = g % E2_RING;
-                mbar_wait2_poll(&bars->full[st], (g / E2_RING) & 1, p.flag);
-                mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pfull[st]), 0));
-            }
-        } else if (lane == 0) {
-            // ------------------------------------------------------------------ leader: MMA issue for the pair
-            uint32_t g = 0, na = 0;
-            const long long t_begin = clock64();
-            long long t_a = 0, t_ring = 0;
-            auto wait_unit = [&]() -> uint32_t {
-                const int st = g % E2_RING;
-                const long long t0 = clock64();
-                mbar_wait2_poll(&bars->full[st], (g / E2_RING) & 1, p.flag);
-                mbar_wait2_poll(&bars->pfull[st], (g / E2_RING) & 1, p.flag);
-                t_ring += clock64() - t0;
-                tc_fence_after();
-                return smem_base + E2_RINGOFF + st * STAGE_BYTES;
-            };
-            auto gemm = [&](uint32_t d, bool accumulate, bool wait) {
-                if (wait) {
-                    const long long t0 = clock64();
-                    mbar_wait2_poll(&bars->a_full, (na++) & 1, p.flag);
-                    t_a += clock64() - t0;
-                    tc_fence_after();
-                }
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t a_hi = smem_base + E2_AHI + ks * E2_SLAB, a_lo = smem_base + E2_ALO + ks * E2_SLAB;
-                    {
-                        const uint32_t b = wait_unit();
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma2_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                      IDESC2_N256, (accumulate || ks > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma2_f16(d, umma_desc(a_lo + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                      IDESC2_N256, 1u);
-                        umma2_commit(&bars->empty[g % E2_RING]);
-                        ++g;
-                    }
-                    {
-                        const uint32_t b = wait_unit();
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma2_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                      IDESC2_N256, 1u);
-                        umma2_commit(&bars->empty[g % E2_RING]);
-                        ++g;
-                    }
-                }
-            };
-            if (p.do_q) {
-                gemm(S0, false, true);  umma2_commit(&bars->s_full[0]);     // q
-                gemm(S1, false, true);  umma2_commit(&bars->s_full[1]);     // msg
-                gemm(S0, false, true);  umma2_commit(&bars->s_full[0]);     // h_a
-                gemm(S1, false, false); umma2_commit(&bars->s_full[1]);     // h_b
-                gemm(S0, false, true);  umma2_commit(&bars->s_full[0]);     // y  = gelu(h_a) W2a^T
-                gemm(S0, true, true);   umma2_commit(&bars->s_full[0]);     // y += gelu(h_b) W2b^T
-            }
-            if (p.do_kv) {
-                gemm(S0, false, true);      umma2_commit(&bars->s_full[0]); // v
-                gemm(S1, false, dec_mode);  umma2_commit(&bars->s_full[1]); // k
-                // KV rounds: round 0 = 64-channel groups 0,1 (N half 0), round 1 = groups 2,3.  V slabs live in the
-                // operand image (group g: slab g of hi / lo), the round's Kf slabs in the (drained) weight ring.
-                for (int round = 0; round < 2; ++round) {
-                    mbar_wait2_poll(round == 0 ? &bars->kv_a : &bars->kv_b, 0, p.flag);
-                    tc_fence_after();
-                    for (int j = 0; j < 2; ++j) {
-                        const int grp = round * 2 + j;
-                        const uint32_t kf_hi = smem_base + E2_RINGOFF + j * E2_SLAB, kf_lo = kf_hi + 2 * E2_SLAB;
-                        const uint32_t v_hi = smem_base + E2_AHI + grp * E2_SLAB, v_lo = smem_base + E2_ALO + grp * E2_SLAB;
-                        const uint32_t dkv = (round == 0 ? S0 : S1) + j * 64;
-#pragma unroll
-                        for (int k = 0; k < HT / 16; ++k)
-                            umma2_f16(dkv, umma_desc(kf_hi + k * 2048, E2_SLAB, ATOM_BYTES),
-                                      umma_desc(v_hi + k * 2048, E2_SLAB, ATOM_BYTES), IDESC2_KV, k);
-#pragma unroll
-                        for (int k = 0; k < HT / 16; ++k)
-                            umma2_f16(dkv, umma_desc(kf_lo + k * 2048, E2_SLAB, ATOM_BYTES),
-                                      umma_desc(v_hi + k * 2048, E2_SLAB, ATOM_BYTES), IDESC2_KV, 1u);
-#pragma unroll
-                        for (int k = 0; k < HT / 16; ++k)
-                            umma2_f16(dkv, umma_desc(kf_hi + k * 2048, E2_SLAB, ATOM_BYTES),
-                                      umma_desc(v_lo + k * 2048, E2_SLAB, ATOM_BYTES), IDESC2_KV, 1u);
-                    }
-                    umma2_commit(&bars->s_full[round]);
-                }
-            }
-            if (p.dbg_clock) {
-                long long* o = p.dbg_clock + (size_t)tile * 4;
-                o[0] = clock64() - t_begin; o[1] = t_a; o[2] = t_ring; o[3] = 0;
-            }
-        }
-        __syncwarp();
-    } else {
-        // ------------------------------------------------------------------ row warps
-        const int q = warp & 3, cq = warp >> 2;            // TMEM lane quarter; 64-column chunk inside the N half
-        const int rh = q & 1, nh = q >> 1;                 // row half (rows 32*rh ..), N half (columns 128*nh ..)
-        const int r = rh * 32 + lane;                      // token row inside this CTA
-        const int rt = (int)rank * HT + r;                 // token row inside the 128-row tile
-        const bool valid = rt < ti.valid;
-        const int cbase = nh * 128 + cq * 64;              // this thread's 64 columns: [cbase, cbase + 64)
-        const int idx = nh * 2 + cq;                       // 0..3: which quarter of the row
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint32_t tcol = cq * 64;                     // TMEM column of cbase inside an accumulator
-        float* X = reinterpret_cast<float*>(smem + E2_X);
-        uint8_t* img_hi = smem + E2_AHI;
-        uint8_t* img_lo = smem + E2_ALO;
-        const float* post = (ti.set == 0 ? p.post1 : p.post2);
-        const uint32_t a_full_addr = mapa_u32(smem_u32(&bars->a_full), 0);
-        uint32_t ns0 = 0, ns1 = 0;
-        auto wait_s = [&](int b) {
-            mbar_wait2(&bars->s_full[b], (b ? ns1++ : ns0++) & 1, p.flag);
-            tc_fence_after();
-        };
-        auto publish_to = [&](uint32_t cluster_addr) {     // this warp's part of the operand image is written
-            tc_fence_before();
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(cluster_addr);
-        };
-        auto publish = [&]() { publish_to(a_full_addr); };
-        // sum of one value per thread over the 4 threads that share a token row (3 slots of 64 floats)
-        auto row_sum4 = [&](float part) -> float {
-            if (idx != 0) X[(idx - 1) * HT + r] = part;
-            named_bar_sync(1, E2_ROW_THREADS);
-            float tot = part;
-            if (idx == 0) { tot = (part + X[r]) + (X[HT + r] + X[2 * HT + r]); X[r] = tot; }
-            named_bar_sync(1, E2_ROW_THREADS);
-            if (idx != 0) tot = X[r];
-            named_bar_sync(1, E2_ROW_THREADS);
-            return tot;
-        };
-        // ---- residual stream of this thread: columns [cbase, cbase+64) of row rt, as two 32-column passes
-        float x[2][32];
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int c0 = cbase + pass * 32;
-            if (p.load_feat) {
-                const float* feat = ti.set == 0 ? p.feat1 : p.feat2;
-                const float* f = feat + ((size_t)ti.b * C + c0) * ti.L + (size_t)ti.ti * TILE + rt;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] = valid ? f[(size_t)e * ti.L] : 0.f;
-            } else {
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    const float4 v = *reinterpret_cast<const float4*>(p.xt + xt_off(tile, (c0 >> 2) + jq, rt));
-                    x[pass][jq * 4 + 0] = v.x; x[pass][jq * 4 + 1] = v.y; x[pass][jq * 4 + 2] = v.z; x[pass][jq * 4 + 3] = v.w;
-                }
-            }
-        }
-        // operand image <- [LN](x) [+ pos] (two-pass statistics; gamma == nullptr: no LayerNorm), then publish
-        auto image_from_x = [&](const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos) {
-            float mean = 0.f, rstd = 1.f;
-            if (gamma) {
-                float s = 0.f;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) s += x[0][e] + x[1][e];
-                mean = row_sum4(s) * (1.f / C);
-                float sq = 0.f;
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float d0 = x[0][e] - mean, d1 = x[1][e] - mean;
-                    sq = fmaf(d0, d0, sq);
-                    sq = fmaf(d1, d1, sq);
-                }
-                rstd = rsqrtf(row_sum4(sq) * (1.f / C) + LN_EPS);
-            }
-            const float shift = -mean * rstd;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = cbase + pass * 32;
-                float v[32];
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(ti.ti, (c0 >> 2) + jq, rt));
-                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gamma) {
-                        g4 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + jq);
-                        b4 = __ldg(reinterpret_cast<const float4*>(beta + c0) + jq);
-                    }
-                    v[jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), g4.x, b4.x + ps.x);
-                    v[jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), g4.y, b4.y + ps.y);
-                    v[jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), g4.z, b4.z + ps.z);
-                    v[jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), g4.w, b4.w + ps.w);
-                }
-                store_row32_split<E2_SLAB>(img_hi, img_lo, r, c0, v);
-            }
-            publish();
-        };
-
-        if (p.do_q) {
-            // (E0) A = LNq(x) + pos
-            image_from_x(p.lnq_g, p.lnq_b, true);
-            // (E1) A = phi(q) / Z   (one head per 32-column pass)
-            const float* ks = p.ksum + (size_t)src_img * C;
-            wait_s(0);
-            const float eps_s = ATTN_EPS / (float)src_len;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = cbase + pass * 32;
-                float v[32];
-                tmem_ld32(S0 + lane_addr + tcol + pass * 32, v);
-                float den = 0.f;
-#pragma unroll
-                for (int e4 = 0; e4 < 8; ++e4) {
-                    const float4 k4 = __ldg(reinterpret_cast<const float4*>(ks + c0) + e4);
-                    v[e4 * 4 + 0] = elu1(v[e4 * 4 + 0]); den = fmaf(v[e4 * 4 + 0], k4.x, den);
-                    v[e4 * 4 + 1] = elu1(v[e4 * 4 + 1]); den = fmaf(v[e4 * 4 + 1], k4.y, den);
-                    v[e4 * 4 + 2] = elu1(v[e4 * 4 + 2]); den = fmaf(v[e4 * 4 + 2], k4.z, den);
-                    v[e4 * 4 + 3] = elu1(v[e4 * 4 + 3]); den = fmaf(v[e4 * 4 + 3], k4.w, den);
-                }
-                const float inv = 1.f / (den + eps_s);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] *= inv;
-                store_row32_split<E2_SLAB>(img_hi, img_lo, r, c0, v);
-            }
-            publish();
-            // (E2) x += msg ; A = LN2(x)
-            wait_s(1);
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                tmem_ld32(S1 + lane_addr + tcol + pass * 32, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
-            }
-            image_from_x(p.ln2_g, p.ln2_b, false);
-            // (E3) A = gelu(h_a): the image is free once h_b (the second GEMM reading LN2(x)) has completed
-            // (E4) A = gelu(h_b): the image is free once y = gelu(h_a) W2a^T has completed
-#pragma unroll 1
-            for (int which = 0; which < 2; ++which) {
-                if (which == 0) wait_s(0);
-                const uint32_t S = which ? S1 : S0;
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int c0 = cbase + pass * 32;
-                    float v[32];
-                    tmem_ld32(S + lane_addr + tcol + pass * 32, v);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
-                    if (pass == 0) wait_s(which == 0 ? 1 : 0);
-                    store_row32_split<E2_SLAB>(img_hi, img_lo, r, c0, v);
-                }
-                publish();      // the consuming GEMM starts (and may overwrite S0) only after all 16 warps got here
-            }
-            // (E5) x += y
-            wait_s(0);
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                tmem_ld32(S0 + lane_addr + tcol + pass * 32, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
-            }
-            tc_fence_before();
-        }
-        if (p.store_x) {
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = cbase + pass * 32;
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq)
-                    *reinterpret_cast<float4*>(p.xt + xt_off(tile, (c0 >> 2) + jq, rt)) =
-                        make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
-            }
-        }
-        if (p.do_kv) {
-            if (!dec_mode) {
-                image_from_x(p.lnkv_g, p.lnkv_b, true);
-                wait_s(0);
-                wait_s(1);
-            } else {
-                image_from_x(nullptr, nullptr, false);
-                wait_s(0);
-                image_from_x(nullptr, nullptr, true);
-                wait_s(1);
-            }
-            // Both projections are complete: the operand image and the weight ring are free.
-            float* part = p.kv_part + ((size_t)tile * 2 + rank) * KVS;
-            // V slab of this thread's 64-channel group idx (MN-major: the 64 columns of a slab row are the channels)
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = cbase + pass * 32;
-                float v[32];
-                tmem_ld32(S0 + lane_addr + tcol + pass * 32, v);
-                if (p.bv) {
-#pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bv + c0) + e4);
-                        v[e4 * 4] += b4.x; v[e4 * 4 + 1] += b4.y; v[e4 * 4 + 2] += b4.z; v[e4 * 4 + 3] += b4.w;
-                    }
-                }
-                if (!valid) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = 0.f;
-                }
-                store_row32_split<E2_SLAB>(img_hi + idx * E2_SLAB, img_lo + idx * E2_SLAB, r, pass * 32, v);
-            }
-            const uint32_t kv_a_addr = mapa_u32(smem_u32(&bars->kv_a), 0), kv_b_addr = mapa_u32(smem_u32(&bars->kv_b), 0);
-            uint8_t* kf_hi = smem + E2_RINGOFF + cq * E2_SLAB;
-            uint8_t* kf_lo = kf_hi + 2 * E2_SLAB;
-            if (nh == 1) publish_to(kv_a_addr);            // V written and S0 read; Kf of N half 1 follows in round 1
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = cbase + pass * 32;
-                float v[32];
-                tmem_ld32(S1 + lane_addr + tcol + pass * 32, v);
-                if (p.bk) {
-#pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bk + c0) + e4);
-                        v[e4 * 4] += b4.x; v[e4 * 4 + 1] += b4.y; v[e4 * 4 + 2] += b4.z; v[e4 * 4 + 3] += b4.w;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e]) : 0.f;
-                // round 1 re-uses the Kf slabs of round 0: wait until the round-0 MMAs have completed
-                if (nh == 1 && pass == 0) wait_s(0);
-                store_row32_split<E2_SLAB>(kf_hi, kf_lo, r, pass * 32, v);
-                // Ksum[c0 + j]: butterfly transpose-reduce over the warp's 32 rows, then across the two row halves
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float send = up ? v[i] : v[i + off];
-                        const float keep = up ? v[i + off] : v[i];
-                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-                if (rh == 1) X[idx * 32 + lane] = v[0];
-                if (nh == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
-                if (rh == 0) part[NH * HD * HD + c0 + lane] = v[0] + X[idx * 32 + lane];
-                if (nh == 0) named_bar_sync(2, 128); else named_bar_sync(3, 128);
-            }
-            publish_to(nh == 0 ? kv_a_addr : kv_b_addr);
-            // results: CTA `rank` keeps n-half `rank` of the pair product = TMEM lanes 64*rank ..: the warps with
-            // nh == rank; warp (cq, rh) reads head 2*(2*round + cq) + rh
-#pragma unroll 1
-            for (int round = 0; round < 2; ++round) {
-                if (!(nh == 1 && round == 0)) wait_s(round);        // N-half-1 warps consumed s_full[0] above
-                if (nh == (int)rank) {
-                    const int h = 2 * (2 * round + cq) + rh;
-                    float v[32];
-                    tmem_ld32((round == 0 ? S0 : S1) + lane_addr + cq * 64 + rh * 32, v);
-                    float* o = part + h * HD * HD + lane * HD;
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                }
-            }
-            tc_fence_before();
-        }
-    }
-    // teardown: nobody leaves while the peer may still signal its barriers or the pair's MMAs read its memory
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == E2_WARP_PRODUCER) tmem_dealloc2(tmem, 256);
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // k_fold: per (image, head): KV_h = sum of tile partials; M_img[n][h*32+d] = sum_e Wm[n][h*32+e] KV_h[d][e];
 // written as the (hi, lo) stage images k_enc streams; also Ksum[img][256].
 // ---------------------------------------------------------------------------------------------------------
@@ -1377,504 +192,6 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
         *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 0, nh)) + off) = hv;
         *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 1, nh)) + off) = lv;
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_att: att[l] = <memory[l,:], hs[img,:]> per token (src/model.py:147-149), tile-blocked like xt; 0 on padding
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_att(const float* __restrict__ xt, TileGeom g, const float* __restrict__ hs,
-                                             float* __restrict__ att) {
-    __shared__ float part[TILE];
-    __shared__ __align__(16) float hsv[C];
-    const TileInfo ti = tile_info(g, blockIdx.x);
-    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
-    hsv[threadIdx.x] = hs[(size_t)ti.img * C + threadIdx.x];
-    __syncthreads();
-    float acc = 0.f;
-#pragma unroll 8
-    for (int jq = 0; jq < 32; ++jq) {
-        const int quad = half * 32 + jq;
-        const float4 v = *reinterpret_cast<const float4*>(xt + xt_off(blockIdx.x, quad, r));
-        const float4 h = *reinterpret_cast<const float4*>(hsv + quad * 4);
-        acc += v.x * h.x + v.y * h.y + v.z * h.z + v.w * h.w;
-    }
-    if (half == 1) part[r] = acc;
-    __syncthreads();
-    if (half == 0) att[(size_t)blockIdx.x * TILE + r] = r < ti.valid ? acc + part[r] : 0.f;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_conv: heatmap_conv.0 (3x3, 256->256, pad 1, src/model.py:65-77,152-161) as an implicit GEMM on the tensor
-// cores.  heat[l,:] = memory[l,:] * att[l] is formed on the fly; for each of the 9 taps the row warps gather the
-// shifted rows (zero outside the map) into the operand image and the MMA warp accumulates
-// Y += G_tap . W_tap^T into S0 (3-term split).  The image of tap t+1 is written per column pass as soon as the
-// MMAs of tap t that read that pass have completed (a_free), so the gather overlaps the tensor work.
-// ---------------------------------------------------------------------------------------------------------
-struct ConvParams {
-    TileGeom g;
-    int hf1, wf1, hf2, wf2;
-    const float* xt;            // tile-blocked encoder output (memory)
-    const float* att;           // tile-blocked per-token scale
-    const __half* w;            // 9 tap GEMM images
-    const float* bias;          // heatmap_conv.0.bias
-    float* Y;                   // token-major [B*L1 + B*L2][256]
-    float* gstat;               // [tiles][32 groups][2]: per-tile GroupNorm partials (mean, M2) over the valid rows
-    int* flag;
-    long long* dbg_clock;       // nullable, like EncParams::dbg_clock
-};
-
-__global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const TileInfo ti = tile_info(p.g, blockIdx.x);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
-    const uint32_t S0 = tmem;
-
-    if (warp == WARP_PRODUCER) {
-        if (lane == 0) {
-            uint32_t g = 0;
-            ring_stream(smem, bars, p.flag, g, p.w, 9 * GEMM_STAGES);
-        }
-        __syncwarp();
-    } else if (warp == WARP_MMA) {
-        if (lane == 0) {
-            MmaState ms;
-            const long long t_begin = clock64();
-            for (int tap = 0; tap < 9; ++tap) gemm_issue(smem_base, bars, p.flag, ms, S0, tap > 0, true, true);
-            umma_commit(&bars->s_full[0]);
-            if (p.dbg_clock) {
-                long long* o = p.dbg_clock + (size_t)blockIdx.x * 4;
-                o[0] = clock64() - t_begin; o[1] = ms.t_a; o[2] = ms.t_ring; o[3] = 0;
-            }
-        }
-        __syncwarp();
-    } else {
-        const int q = warp & 3, cq = warp >> 2;
-        const int r = q * 32 + lane;
-        const bool valid = r < ti.valid;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const int wf = ti.set == 0 ? p.wf1 : p.wf2, hf = ti.set == 0 ? p.hf1 : p.hf2;
-        const int l = ti.ti * TILE + r;
-        const int y0 = l / wf, x0 = l - y0 * wf;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const bool ok = valid && (unsigned)(y0 + dy) < (unsigned)hf && (unsigned)(x0 + dx) < (unsigned)wf;
-            const int n = ok ? l + dy * wf + dx : 0;
-            const int tile_n = ti.first_tile_of_img + (n >> 7), rn = n & 127;
-            const float a = ok ? p.att[(size_t)tile_n * TILE + rn] : 0.f;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-                float v[32];
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) t = *reinterpret_cast<const float4*>(p.xt + xt_off(tile_n, (c0 >> 2) + jq, rn));
-                    v[jq * 4 + 0] = t.x * a; v[jq * 4 + 1] = t.y * a; v[jq * 4 + 2] = t.z * a; v[jq * 4 + 3] = t.w * a;
-                }
-                if (tap > 0) mbar_wait(&bars->a_free[pass], (tap - 1) & 1, p.flag);
-                store_row32_split(smem + SM_AHI, smem + SM_ALO, r, c0, v);
-                fence_async_smem();
-                mbar_arrive(&bars->a_full[pass]);
-            }
-        }
-        mbar_wait(&bars->s_full[0], 0, p.flag);
-        tc_fence_after();
-        float* red = reinterpret_cast<float*>(smem + SM_X);           // [4 row quarters][32 groups]
-        const size_t row = (ti.set == 0 ? (size_t)ti.b * p.g.L1 : (size_t)p.g.B * p.g.L1 + (size_t)ti.b * p.g.L2) + l;
-        float y[2][32];
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int c0 = pass * 128 + cq * 32;
-            tmem_ld32(S0 + lane_addr + c0, y[pass]);
-#pragma unroll
-            for (int jq = 0; jq < 8; ++jq) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + jq);
-                y[pass][jq * 4 + 0] += b4.x; y[pass][jq * 4 + 1] += b4.y; y[pass][jq * 4 + 2] += b4.z; y[pass][jq * 4 + 3] += b4.w;
-                if (valid)
-                    *reinterpret_cast<float4*>(p.Y + row * C + c0 + jq * 4) =
-                        make_float4(y[pass][jq * 4], y[pass][jq * 4 + 1], y[pass][jq * 4 + 2], y[pass][jq * 4 + 3]);
-            }
-        }
-        tc_fence_before();
-        // GroupNorm partials of this tile (32 groups of 8 channels, src/model.py:71): exact two-pass (mean, M2) over the
-        // valid rows; k_logits merges the tiles of an image with Chan's update.  Thread: groups pass*16 + cq*4 + {0..3}
-        const float inv_n = 1.f / (8.f * (float)ti.valid);
-        float mean_t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int pass = i >> 2, g4 = i & 3;
-            float sgrp = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sgrp += y[pass][g4 * 8 + e];
-            sgrp = valid ? sgrp : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sgrp += __shfl_xor_sync(0xffffffffu, sgrp, o);
-            if (lane == 0) red[q * 32 + pass * 16 + cq * 4 + g4] = sgrp;
-        }
-        named_bar_sync(1, N_ROW_THREADS);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int gi = (i >> 2) * 16 + cq * 4 + (i & 3);
-            mean_t[i] = (red[gi] + red[32 + gi] + red[64 + gi] + red[96 + gi]) * inv_n;
-        }
-        named_bar_sync(1, N_ROW_THREADS);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int pass = i >> 2, g4 = i & 3;
-            float m2 = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { const float d = y[pass][g4 * 8 + e] - mean_t[i]; m2 = fmaf(d, d, m2); }
-            m2 = valid ? m2 : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-            if (lane == 0) red[q * 32 + pass * 16 + cq * 4 + g4] = m2;
-        }
-        named_bar_sync(1, N_ROW_THREADS);
-        if (q == 0 && lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int gi = (i >> 2) * 16 + cq * 4 + (i & 3);
-                float* o = p.gstat + ((size_t)blockIdx.x * 32 + gi) * 2;
-                o[0] = mean_t[i];
-                o[1] = red[gi] + red[32 + gi] + red[64 + gi] + red[96 + gi];
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == WARP_PRODUCER) tmem_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_logits: GroupNorm (image statistics merged from the tile partials) -> ReLU -> 1x1 conv (src/model.py:71-76);
-// one CTA per tile, one warp per token.  z is tile-blocked: token l of an image sits at z[first_tile*128 + l].
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_logits(const float* __restrict__ Y, const float* __restrict__ gstat, TileGeom g,
-                                                const float* __restrict__ gn_g, const float* __restrict__ gn_b,
-                                                const float* __restrict__ w3, const float* __restrict__ b3,
-                                                float* __restrict__ z) {
-    __shared__ float gm[32], gr[32];
-    __shared__ __align__(16) float sc[C], sh[C], w3s[C];
-    const TileInfo ti = tile_info(g, blockIdx.x);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid < 32) {
-        float n = 0.f, mean = 0.f, m2 = 0.f;
-        for (int t = 0; t < ti.T; ++t) {                                   // Chan et al. pairwise update, fixed order
-            const float nb = 8.f * (float)min(TILE, ti.L - t * TILE);
-            const float* st = gstat + ((size_t)(ti.first_tile_of_img + t) * 32 + tid) * 2;
-            const float delta = st[0] - mean, ntot = n + nb;
-            mean += delta * nb / ntot;
-            m2 += st[1] + delta * delta * n * nb / ntot;
-            n = ntot;
-        }
-        gm[tid] = mean;
-        gr[tid] = rsqrtf(m2 / n + GN_EPS);
-    }
-    __syncthreads();
-    {
-        const float rs = gr[tid >> 3] * gn_g[tid];
-        sc[tid] = rs; sh[tid] = gn_b[tid] - gm[tid >> 3] * rs; w3s[tid] = w3[tid];
-    }
-    __syncthreads();
-    const float bias = b3[0];
-    const size_t row0 = (ti.set == 0 ? (size_t)ti.b * g.L1 : (size_t)g.B * g.L1 + (size_t)ti.b * g.L2) + (size_t)ti.ti * TILE;
-    float4 s0 = reinterpret_cast<const float4*>(sc)[lane], s1 = reinterpret_cast<const float4*>(sc)[lane + 32];
-    float4 h0 = reinterpret_cast<const float4*>(sh)[lane], h1 = reinterpret_cast<const float4*>(sh)[lane + 32];
-    float4 w0 = reinterpret_cast<const float4*>(w3s)[lane], w1 = reinterpret_cast<const float4*>(w3s)[lane + 32];
-#pragma unroll 4
-    for (int r = w; r < ti.valid; r += 8) {
-        const float4 a = reinterpret_cast<const float4*>(Y + (row0 + r) * C)[lane];
-        const float4 b = reinterpret_cast<const float4*>(Y + (row0 + r) * C)[lane + 32];
-        float acc = w0.x * fmaxf(fmaf(a.x, s0.x, h0.x), 0.f);
-        acc = fmaf(w0.y, fmaxf(fmaf(a.y, s0.y, h0.y), 0.f), acc);
-        acc = fmaf(w0.z, fmaxf(fmaf(a.z, s0.z, h0.z), 0.f), acc);
-        acc = fmaf(w0.w, fmaxf(fmaf(a.w, s0.w, h0.w), 0.f), acc);
-        acc = fmaf(w1.x, fmaxf(fmaf(b.x, s1.x, h1.x), 0.f), acc);
-        acc = fmaf(w1.y, fmaxf(fmaf(b.y, s1.y, h1.y), 0.f), acc);
-        acc = fmaf(w1.z, fmaxf(fmaf(b.z, s1.z, h1.z), 0.f), acc);
-        acc = fmaf(w1.w, fmaxf(fmaf(b.w, s1.w, h1.w), 0.f), acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) z[(size_t)blockIdx.x * TILE + r] = acc + bias;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_box: softmax over the tokens + soft-argmax on the (x+0.5, y+0.5)*stride grid, stride = img_h / hf for both
-// axes (src/model.py:173-184), box assembly from (cx,cy) and tlbr (models/utils.py:16-28 / model.py:193-211)
-// ---------------------------------------------------------------------------------------------------------
-struct BoxParams {
-    TileGeom g;
-    int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
-    const float* z;             // tile-blocked logits
-    const float* tlbr;          // [2B][4] sigmoid(top,left,bottom,right) from k_decoder
-    float *boxes1, *boxes2, *dbg_cxy, *dbg_tlbr;
-};
-__global__ void __launch_bounds__(256) k_box(const BoxParams p) {
-    __shared__ float red[8];
-    const int img = blockIdx.x, set = img / p.g.B, b = img % p.g.B;
-    const int L = set == 0 ? p.g.L1 : p.g.L2, wf = set == 0 ? p.wf1 : p.wf2, hf = set == 0 ? p.hf1 : p.hf2;
-    const int img_h = set == 0 ? p.img_h1 : p.img_h2, img_w = set == 0 ? p.img_w1 : p.img_w2;
-    const int first = set == 0 ? b * p.g.T1 : p.g.B * p.g.T1 + b * p.g.T2;
-    const float* z = p.z + (size_t)first * TILE;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    auto block_reduce = [&](float v, bool is_max) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, t) : v + t; }
-        __syncthreads();
-        if (lane == 0) red[w] = v;
-        __syncthreads();
-        float r = red[0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
-        return r;
-    };
-    float mx = -INFINITY;
-    for (int l = tid; l < L; l += 256) mx = fmaxf(mx, z[l]);
-    mx = block_reduce(mx, true);
-    const float stride = (float)(img_h / hf);
-    float se = 0.f, sx = 0.f, sy = 0.f;
-    for (int l = tid; l < L; l += 256) {
-        const float e = expf(z[l] - mx);
-        se += e;
-        sx = fmaf(e, ((float)(l % wf) + 0.5f) * stride, sx);
-        sy = fmaf(e, ((float)(l / wf) + 0.5f) * stride, sy);
-    }
-    se = block_reduce(se, false); sx = block_reduce(sx, false); sy = block_reduce(sy, false);
-    if (tid == 0) {
-        const float cx = sx / se, cy = sy / se;
-        const float* tl = p.tlbr + (size_t)img * 4;
-        const float W_ = (float)img_w, H_ = (float)img_h;
-        float x1 = cx - tl[1] * W_, y1 = cy - tl[0] * H_, x2 = cx + tl[3] * W_, y2 = cy + tl[2] * H_;
-        if (p.clamp) {
-            x1 = fminf(fmaxf(x1, 0.f), W_); x2 = fminf(fmaxf(x2, 0.f), W_);
-            y1 = fminf(fmaxf(y1, 0.f), H_); y2 = fminf(fmaxf(y2, 0.f), H_);
-        }
-        float* o = (set == 0 ? p.boxes1 : p.boxes2) + (size_t)b * 4;
-        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
-        if (p.dbg_cxy) { p.dbg_cxy[img * 2] = cx; p.dbg_cxy[img * 2 + 1] = cy; }
-        if (p.dbg_tlbr) { for (int i = 0; i < 4; ++i) p.dbg_tlbr[img * 4 + i] = tl[i]; }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_decoder: the whole 2-layer query decoder (transformer.py:224-284,361-381) for DEC_R query tokens per CTA.
-// fp32 on the CUDA cores: thread n owns output channel n of every projection; the transposed weights
-// WT[k][n] make the loads coalesced; each weight is read once per CTA and used for DEC_R rows.
-// Rows: [0,B) = image set 1 with query_embed1, [B,2B) = set 2 with query_embed2.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int DEC_R = 2;
-struct DecLayerT {
-    const float *sa_bq, *sa_bk, *sa_bv, *ca_bq;
-    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
-};
-struct DecParams {
-    DecLayerT layer[N_DEC];
-    const float* qe;            // query_embed1 | query_embed2 (adjacent, [2][256])
-    const float* kvs;           // [N_DEC][2B][KVS] cross-attention summaries of the memory
-    float* hs;                  // out [2B][256]
-    const float* wt;            // all transposed fp32 weights in consumption order (see k_decoder)
-    const float *tl_w2, *tl_b2; // tlbr_reg.2: [4][256], [4]  (src/model.py:59-63)
-    float* tlbr;                // out [2B][4] sigmoid(top,left,bottom,right)
-    int B;
-};
-
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-// Weight streaming: the transposed fp32 weights of both layers and tlbr_reg.0 are ONE contiguous array in the
-// order the kernel consumes them (sa.wq | sa.wk | sa.wv | sa.wm | ca.wq | ca.wm | w1 | w2 per layer, then tl_w0),
-// so a producer lane streams it linearly in 32 KB bulk copies through a 5-stage ring, running ahead across
-// matvec boundaries; the 256 compute threads never wait on global-memory latency (the first version, with
-// register loads, was bound by the bytes one SM can keep in flight: 185 us for 5.8 MB).
-constexpr int DEC_THREADS = 256 + 32;                 // warps 0-7 compute, warp 8 = producer
-constexpr int DEC_STAGES = 5;
-constexpr uint32_t DEC_CHUNK_BYTES = 32768;
-constexpr int DEC_CHUNK_FLOATS = DEC_CHUNK_BYTES / 4;
-constexpr uint32_t DEC_SMEM = DEC_STAGES * DEC_CHUNK_BYTES + 256;
-struct DecRing { uint64_t* full; uint64_t* empty; const float* stage0; uint32_t g; };
-
-// acc[r][c] = sum_k WT[k][n + 256*c] * xin[r][k]   (c < N/256), WT consumed from the ring (K*N*4/32 KB chunks)
-template <int K, int N>
-__device__ __forceinline__ void dec_matvec(DecRing& ring, const float* xin, float (&acc)[DEC_R][N / 256]) {
-    constexpr int ROWS = DEC_CHUNK_FLOATS / N;        // k rows per chunk
-    const int n = threadIdx.x;
-#pragma unroll
-    for (int r = 0; r < DEC_R; ++r)
-#pragma unroll
-        for (int c = 0; c < N / 256; ++c) acc[r][c] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += ROWS, ++ring.g) {
-        const int st = ring.g % DEC_STAGES;
-        mbar_wait(&ring.full[st], (ring.g / DEC_STAGES) & 1, nullptr);
-        const float* ws = ring.stage0 + (size_t)st * DEC_CHUNK_FLOATS;
-#pragma unroll 4
-        for (int kk = 0; kk < ROWS; kk += 4) {
-            float4 xv[DEC_R];
-#pragma unroll
-            for (int r = 0; r < DEC_R; ++r) xv[r] = *reinterpret_cast<const float4*>(xin + r * K + k0 + kk);
-#pragma unroll
-            for (int c = 0; c < N / 256; ++c) {
-                const float w0 = ws[(kk + 0) * N + n + 256 * c], w1 = ws[(kk + 1) * N + n + 256 * c];
-                const float w2 = ws[(kk + 2) * N + n + 256 * c], w3 = ws[(kk + 3) * N + n + 256 * c];
-#pragma unroll
-                for (int r = 0; r < DEC_R; ++r)
-                    acc[r][c] = fmaf(w3, xv[r].w, fmaf(w2, xv[r].z, fmaf(w1, xv[r].y, fmaf(w0, xv[r].x, acc[r][c]))));
-            }
-        }
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&ring.empty[st]);
-    }
-}
-// out[r][:] = LN(in[r][:]) (two-pass variance); warps 0..DEC_R-1, one row each
-__device__ __forceinline__ void dec_ln(const float* in, const float* __restrict__ g, const float* __restrict__ b, float* out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < DEC_R) {
-        float v[8], s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { v[i] = in[warp * C + lane + 32 * i]; s += v[i]; }
-        const float mu = warp_sum_f(s) * (1.f / C);
-        float sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; sq = fmaf(d, d, sq); }
-        const float rstd = rsqrtf(warp_sum_f(sq) * (1.f / C) + LN_EPS);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) out[warp * C + lane + 32 * i] = (v[i] - mu) * rstd * g[lane + 32 * i] + b[lane + 32 * i];
-    }
-}
-
-__global__ void __launch_bounds__(DEC_THREADS) k_decoder(const DecParams p) {
-    extern __shared__ __align__(1024) uint8_t dsm[];
-    __shared__ __align__(16) float t[DEC_R * C], u[DEC_R * C], a[DEC_R * C], qv[DEC_R * C], hid[DEC_R * FF];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + DEC_STAGES * DEC_CHUNK_BYTES);
-    const int n = threadIdx.x, lane = n & 31;
-    if (n == 0) {
-        for (int i = 0; i < DEC_STAGES; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[DEC_STAGES + i], 8); }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (n >= 256) {
-        // ---- producer: the whole weight array, linearly
-        if (lane == 0) {
-            const uint32_t total = (uint32_t)((N_DEC * DEC_T_FLOATS + (size_t)C * C) * sizeof(float) / DEC_CHUNK_BYTES);
-            for (uint32_t g = 0; g < total; ++g) {
-                const int st = g % DEC_STAGES;
-                mbar_wait(&bars[DEC_STAGES + st], ((g / DEC_STAGES) & 1) ^ 1, nullptr);
-                mbar_arrive_expect_tx(&bars[st], DEC_CHUNK_BYTES);
-                bulk_g2s(dsm + (size_t)st * DEC_CHUNK_BYTES, reinterpret_cast<const uint8_t*>(p.wt) + (size_t)g * DEC_CHUNK_BYTES,
-                         DEC_CHUNK_BYTES, &bars[st]);
-            }
-        }
-        return;
-    }
-    DecRing ring{bars, bars + DEC_STAGES, reinterpret_cast<const float*>(dsm), 0u};
-    const int row0 = blockIdx.x * DEC_R, rows = 2 * p.B;
-    float qe[DEC_R];
-#pragma unroll
-    for (int r = 0; r < DEC_R; ++r) {
-        const int row = min(row0 + r, rows - 1);
-        qe[r] = p.qe[(row >= p.B ? C : 0) + n];
-        t[r * C + n] = 0.f;                                                    // tgt = zeros (transformer.py:361)
-    }
-    named_bar_sync(2, 256);
-    for (int j = 0; j < N_DEC; ++j) {
-        const DecLayerT& w = p.layer[j];
-        float acc[DEC_R][1], kk[DEC_R][1], vv[DEC_R][1], h2[DEC_R][2];
-        // ---- self-attention over the single query token (transformer.py:236-241, linear_attention.py:22-50)
-        dec_ln(t, w.ln1_g, w.ln1_b, u);
-        named_bar_sync(2, 256);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
-        named_bar_sync(2, 256);
-        dec_matvec<C, C>(ring, a, acc);
-        dec_matvec<C, C>(ring, a, kk);
-        dec_matvec<C, C>(ring, u, vv);
-        named_bar_sync(2, 256);                                                // all reads of a[] done
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) {
-            const float qf = elu1(acc[r][0] + w.sa_bq[n]), kf = elu1(kk[r][0] + w.sa_bk[n]);
-            const float sden = warp_sum_f(qf * kf);                           // warp = head
-            a[r * C + n] = (vv[r][0] + w.sa_bv[n]) * sden / (sden + ATTN_EPS); // KV = kf v^T, Z = 1/(qf.kf + eps)
-        }
-        named_bar_sync(2, 256);
-        dec_matvec<C, C>(ring, a, acc);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r][0];
-        named_bar_sync(2, 256);
-        // ---- cross-attention into the memory summaries (transformer.py:243-250)
-        dec_ln(t, w.ln2_g, w.ln2_b, u);
-        named_bar_sync(2, 256);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = u[r * C + n] + qe[r];
-        named_bar_sync(2, 256);
-        dec_matvec<C, C>(ring, a, acc);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) qv[r * C + n] = elu1(acc[r][0] + w.ca_bq[n]);
-        named_bar_sync(2, 256);
-        {
-            const int h = n >> 5;
-#pragma unroll
-            for (int r = 0; r < DEC_R; ++r) {
-                const int row = min(row0 + r, rows - 1);
-                const float* kv = p.kvs + ((size_t)j * rows + row) * KVS;
-                const float den = warp_sum_f(qv[r * C + n] * kv[NH * HD * HD + n]);
-                float o = 0.f;
-#pragma unroll 8
-                for (int d = 0; d < HD; ++d) o = fmaf(qv[r * C + h * HD + d], kv[(h * HD + d) * HD + lane], o);
-                a[r * C + n] = o / (den + ATTN_EPS);
-            }
-        }
-        named_bar_sync(2, 256);
-        dec_matvec<C, C>(ring, a, acc);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r][0];
-        named_bar_sync(2, 256);
-        // ---- feed-forward (transformer.py:252-254)
-        dec_ln(t, w.ln3_g, w.ln3_b, u);
-        named_bar_sync(2, 256);
-        dec_matvec<C, FF>(ring, u, h2);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) { hid[r * FF + n] = fmaxf(h2[r][0], 0.f); hid[r * FF + C + n] = fmaxf(h2[r][1], 0.f); }
-        named_bar_sync(2, 256);
-        dec_matvec<FF, C>(ring, hid, acc);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) t[r * C + n] += acc[r][0];
-        named_bar_sync(2, 256);
-    }
-#pragma unroll
-    for (int r = 0; r < DEC_R; ++r)
-        if (row0 + r < rows) p.hs[(size_t)(row0 + r) * C + n] = t[r * C + n];
-    // ---- size regression (src/model.py:188-191): sigmoid(W_b relu(W_a hs) + b)
-    {
-        float acc[DEC_R][1];
-        dec_matvec<C, C>(ring, t, acc);
-#pragma unroll
-        for (int r = 0; r < DEC_R; ++r) a[r * C + n] = fmaxf(acc[r][0], 0.f);
-        named_bar_sync(2, 256);
-        const int w = n >> 5;
-        if (w < 4) {
-#pragma unroll
-            for (int r = 0; r < DEC_R; ++r) {
-                float o = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o = fmaf(p.tl_w2[(size_t)w * C + lane + 32 * i], a[r * C + lane + 32 * i], o);
-                o = warp_sum_f(o);
-                if (lane == 0 && row0 + r < rows) p.tlbr[(size_t)(row0 + r) * 4 + w] = 1.f / (1.f + expf(-(o + p.tl_b2[w])));
-            }
-        }
-    }
-}
-
-__global__ void k_transpose(const float* __restrict__ W, int N, int K, float* __restrict__ WT) {   // W[N][K] -> WT[K][N]
-    __shared__ float tile[32][33];
-    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = W[(size_t)(n0 + i) * K + k0 + threadIdx.x];
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) WT[(size_t)(k0 + i) * N + n0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
 // ---------------------------------------------------------------------------------------------------------
