@@ -115,3 +115,15 @@ def synthetic_features(batch, hf, wf, seed=1, tag="feat"):
     # sum of 4 uniforms: bell-shaped, exactly reproducible
     acc = sum(_uniform(rng, shape, 1.0).astype(np.float64) for _ in range(4))
     return (acc * (0.3 / np.sqrt(4.0 / 3.0))).astype(np.float32)
+
+
+def synthetic_mask(batch, hf, wf, tag="mask"):
+    """Deterministic padding-style masks [batch, hf, wf] (float32 0/1): image b keeps the top-left
+    (hf - r_b) x (wf - c_b) positions, with r_b, c_b small and depending on b and the tag."""
+    off = sum(ord(ch) for ch in tag) % 3
+    m = np.zeros((batch, hf, wf), dtype=np.float32)
+    for b in range(batch):
+        r = min(hf - 1, (b + 1 + off) % 4)
+        c = min(wf - 1, (2 * b + 1 + off) % 5)
+        m[b, : hf - r, : wf - c] = 1.0
+    return m

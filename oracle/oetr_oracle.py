@@ -68,11 +68,16 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + _erf(x / math.sqrt(2.0)))
 
 
-def linear_attention(q, k, v, eps=ATTN_EPS):
-    """LinearAttention.forward, src/models/linear_attention.py:22-50 (masks None).
-    q [N,L,H,D]; k,v [N,S,H,D] -> [N,L,H,D]."""
+def linear_attention(q, k, v, eps=ATTN_EPS, q_mask=None, kv_mask=None):
+    """LinearAttention.forward, src/models/linear_attention.py:22-50.
+    q [N,L,H,D]; k,v [N,S,H,D] -> [N,L,H,D]; q_mask [N,L], kv_mask [N,S] (float, optional: :36-41)."""
     Q = elu_feature_map(q)
     K = elu_feature_map(k)
+    if q_mask is not None:
+        Q = Q * q_mask[:, :, None, None]
+    if kv_mask is not None:
+        K = K * kv_mask[:, :, None, None]
+        v = v * kv_mask[:, :, None, None]
     s_len = v.shape[1]
     v = v / s_len                                                        # :43-44
     KV = np.einsum("nshd,nshv->nhdv", K, v)                              # :45
@@ -106,17 +111,23 @@ def round_fp16(a):
     return np.asarray(a).astype(np.float16).astype(np.asarray(a).dtype)
 
 
-def linear_attention_quant(q, k, v, rnd, eps=ATTN_EPS):
+def linear_attention_quant(q, k, v, rnd, eps=ATTN_EPS, q_mask=None, kv_mask=None):
     """linear_attention with the operand rounding points of the tensor-core path: elu(k)+1, v and elu(q)+1 are
     rounded before the K^T V and Q.KV contractions; KV is rounded as the B operand; Ksum / Z stay wide."""
     Q = elu_feature_map(q)
-    K = rnd(elu_feature_map(k))
+    K = elu_feature_map(k)
+    if q_mask is not None:
+        Q = Q * q_mask[:, :, None, None]
+    if kv_mask is not None:
+        K = K * kv_mask[:, :, None, None]
+        v = v * kv_mask[:, :, None, None]
+    K = rnd(K)
     KV = rnd(np.einsum("nshd,nshv->nhdv", K, rnd(v)))
     Z = 1.0 / (np.einsum("nlhd,nhd->nlh", Q, K.sum(axis=1)) + eps)
     return np.einsum("nlhd,nhdv,nlh->nlhv", rnd(Q), KV, Z)
 
 
-def encoder_layer(W, prefix, x, source, x_pos, s_pos, attention="linear", rnd=_identity):
+def encoder_layer(W, prefix, x, source, x_pos, s_pos, attention="linear", rnd=_identity, x_mask=None, s_mask=None):
     """EncoderLayer.forward, src/models/transformer.py:104-142.  x [N,L,C], source [N,S,C], pos [L,C]/[S,C].
     rnd: operand rounding model (identity = the reference's arithmetic)."""
     g = lambda name: W[prefix + name]
@@ -126,41 +137,43 @@ def encoder_layer(W, prefix, x, source, x_pos, s_pos, attention="linear", rnd=_i
     k = _heads(rnd(kv) @ rnd(g("k_proj.weight")).T)
     v = _heads(rnd(kv) @ rnd(g("v_proj.weight")).T)
     if attention != "linear":
+        if x_mask is not None or s_mask is not None:
+            raise NotImplementedError("masks are restated for linear attention only")
         att = full_attention(q, k, v)
     elif rnd is _identity:
-        att = linear_attention(q, k, v)
+        att = linear_attention(q, k, v, q_mask=x_mask, kv_mask=s_mask)
     else:
-        att = linear_attention_quant(q, k, v, rnd)
+        att = linear_attention_quant(q, k, v, rnd, q_mask=x_mask, kv_mask=s_mask)
     msg = rnd(att.reshape(x.shape)) @ rnd(g("merge.weight")).T                             # :137
     x = x + msg                                                                            # :140
     h = gelu_erf(rnd(layer_norm(x, g("norm2.weight"), g("norm2.bias"))) @ rnd(g("mlp.0.weight")).T)
     return x + rnd(h) @ rnd(g("mlp.2.weight")).T                                           # :141-142
 
 
-def _mha(W, prefix, q_in, k_in, v_in):
+def _mha(W, prefix, q_in, k_in, v_in, kv_mask=None):
     """MultiHeadAttention.forward (always linear attention, biased projections), transformer.py:55-72."""
     q = _heads(q_in @ W[prefix + "q_proj.weight"].T + W[prefix + "q_proj.bias"])
     k = _heads(k_in @ W[prefix + "k_proj.weight"].T + W[prefix + "k_proj.bias"])
     v = _heads(v_in @ W[prefix + "v_proj.weight"].T + W[prefix + "v_proj.bias"])
-    out = linear_attention(q, k, v)
+    out = linear_attention(q, k, v, kv_mask=kv_mask)
     return out.reshape(q_in.shape[0], q_in.shape[1], D_MODEL) @ W[prefix + "merge.weight"].T
 
 
-def decoder_layer(W, prefix, tgt, memory, tgt_pos, m_pos):
+def decoder_layer(W, prefix, tgt, memory, tgt_pos, m_pos, memory_mask=None):
     """DecoderLayer.forward, src/models/transformer.py:224-255 (dropout = identity in eval)."""
     g = lambda name: W[prefix + name]
     t2 = layer_norm(tgt, g("norm1.weight"), g("norm1.bias"))
     qk = t2 + tgt_pos
     tgt = tgt + _mha(W, prefix + "self_attn.", qk, qk, t2)
     t2 = layer_norm(tgt, g("norm2.weight"), g("norm2.bias"))
-    tgt = tgt + _mha(W, prefix + "multihead_attn.", t2 + tgt_pos, memory + m_pos, memory)  # no LN, no pos on v
+    tgt = tgt + _mha(W, prefix + "multihead_attn.", t2 + tgt_pos, memory + m_pos, memory, memory_mask)  # no LN, no pos on v
     t2 = layer_norm(tgt, g("norm3.weight"), g("norm3.bias"))
     t2 = np.maximum(t2 @ g("mlp.0.weight").T, 0.0) @ g("mlp.2.weight").T
     return tgt + t2
 
 
 def query_transformer(W, feat0, feat1, pos0, pos1, attention="linear", prefix="transformer.",
-                      return_layers=False, rnd=_identity):
+                      return_layers=False, rnd=_identity, mask0=None, mask1=None):
     """QueryTransformer.forward, src/models/transformer.py:313-383.
     feat* [N,C,h,w] NCHW; pos* [C,h,w].  Returns hs0,hs1 [N,1,C], memory0,memory1 [N,L,C]."""
     n = feat0.shape[0]
@@ -168,25 +181,27 @@ def query_transformer(W, feat0, feat1, pos0, pos1, attention="linear", prefix="t
     x1 = feat1.reshape(n, D_MODEL, -1).transpose(0, 2, 1)
     p0 = pos0.reshape(D_MODEL, -1).T
     p1 = pos1.reshape(D_MODEL, -1).T
+    m0 = None if mask0 is None else np.asarray(mask0, dtype=x0.dtype).reshape(n, -1)          # transformer.py:341-344
+    m1 = None if mask1 is None else np.asarray(mask1, dtype=x1.dtype).reshape(n, -1)
     layers = []
     for i in range(N_ENCODER):
         pre = "%sencoder.%d." % (prefix, i)
         if i % 2 == 0:                                                     # 'self'
-            x0 = encoder_layer(W, pre, x0, x0, p0, p0, attention, rnd)
-            x1 = encoder_layer(W, pre, x1, x1, p1, p1, attention, rnd)
+            x0 = encoder_layer(W, pre, x0, x0, p0, p0, attention, rnd, m0, m0)
+            x1 = encoder_layer(W, pre, x1, x1, p1, p1, attention, rnd, m1, m1)
         else:                                                              # 'cross': both read OLD partner
             s0, s1 = x1, x0
-            x0 = encoder_layer(W, pre, x0, s0, p0, p1, attention, rnd)
-            x1 = encoder_layer(W, pre, x1, s1, p1, p0, attention, rnd)
+            x0 = encoder_layer(W, pre, x0, s0, p0, p1, attention, rnd, m0, m1)
+            x1 = encoder_layer(W, pre, x1, s1, p1, p0, attention, rnd, m1, m0)
         if return_layers:
             layers.append((x0.copy(), x1.copy()))
     qe0 = np.broadcast_to(W["query_embed1.weight"][None], (n, 1, D_MODEL))
     qe1 = np.broadcast_to(W["query_embed2.weight"][None], (n, 1, D_MODEL))
     hs = []
-    for mem, qe, pos in ((x0, qe0, p0), (x1, qe1, p1)):
+    for mem, qe, pos, mm in ((x0, qe0, p0, m0), (x1, qe1, p1, m1)):
         t = np.zeros((n, 1, D_MODEL), dtype=mem.dtype)
         for j in range(N_DECODER):
-            t = decoder_layer(W, "%sdecoder.layers.%d." % (prefix, j), t, mem, qe, pos)
+            t = decoder_layer(W, "%sdecoder.layers.%d." % (prefix, j), t, mem, qe, pos, mm)
         hs.append(t)
     if return_layers:
         return hs[0], hs[1], x0, x1, layers
@@ -215,8 +230,9 @@ def conv3x3_same(x, weight, bias):
     return out + bias[None, :, None, None]
 
 
-def center_estimation(W, hs, memory, hf, wf, img_h):
-    """OETR.center_estimation for one image, src/model.py:145-186 (mask None, softmax_temperature 1)."""
+def center_estimation(W, hs, memory, hf, wf, img_h, mask=None):
+    """OETR.center_estimation for one image, src/model.py:145-186 (softmax_temperature 1; mask [N,hf,wf]: logits of
+    positions where mask.bool() is False are filled with -1e9, :167-171)."""
     n = memory.shape[0]
     att = np.einsum("blc,bnc->bln", memory, hs)                                             # :147
     heat = (memory * att).transpose(0, 2, 1).reshape(n, D_MODEL, hf, wf)                    # :152-155
@@ -224,6 +240,8 @@ def center_estimation(W, hs, memory, hf, wf, img_h):
     y = np.maximum(group_norm(y, W["heatmap_conv.1.weight"], W["heatmap_conv.1.bias"]), 0.0)
     z = np.einsum("nchw,c->nhw", y, W["heatmap_conv.3.weight"].reshape(-1)) + W["heatmap_conv.3.bias"][0]
     z = z.reshape(n, hf * wf)
+    if mask is not None:
+        z = np.where(np.asarray(mask).reshape(n, hf * wf) != 0, z, -1e9)
     p = np.exp(z - z.max(axis=1, keepdims=True))
     p = p / p.sum(axis=1, keepdims=True)                                                    # :173
     stride = img_h // hf                                                                    # :177 (h for both axes)
@@ -255,7 +273,7 @@ def box_tlbr_to_xyxy(cxy, tlbr, max_h, max_w, clamp=True):
 # the whole hot path
 # --------------------------------------------------------------------------------------------------------
 def hot_path(weights, feat1, feat2, img_hw1, img_hw2, attention="linear", clamp=True, dtype=np.float64,
-             max_shape=(100, 100), return_layers=False, rnd=_identity):
+             max_shape=(100, 100), return_layers=False, rnd=_identity, mask1=None, mask2=None):
     """feature_correlation + center_estimation + size_regression + box_tlbr_to_xyxy
     (src/model.py:240-250).  feat1 [N,256,hf1,wf1], feat2 [N,256,hf2,wf2] (outputs of input_proj2).
     Returns a dict of every stage boundary."""
@@ -267,10 +285,11 @@ def hot_path(weights, feat1, feat2, img_hw1, img_hw2, attention="linear", clamp=
     pe = pe_table(max_shape, dtype=dtype)
     pos1 = pe[:, :hf1, :wf1]
     pos2 = pe[:, :hf2, :wf2]
-    res = query_transformer(W, f1, f2, pos1, pos2, attention, return_layers=return_layers, rnd=rnd)
+    res = query_transformer(W, f1, f2, pos1, pos2, attention, return_layers=return_layers, rnd=rnd,
+                            mask0=mask1, mask1=mask2)
     hs1, hs2, mem1, mem2 = res[:4]
-    cxy1, z1 = center_estimation(W, hs1, mem1, hf1, wf1, img_hw1[0])
-    cxy2, z2 = center_estimation(W, hs2, mem2, hf2, wf2, img_hw2[0])
+    cxy1, z1 = center_estimation(W, hs1, mem1, hf1, wf1, img_hw1[0], mask1)
+    cxy2, z2 = center_estimation(W, hs2, mem2, hf2, wf2, img_hw2[0], mask2)
     tlbr1 = size_regression(W, hs1)
     tlbr2 = size_regression(W, hs2)
     out = dict(hs1=hs1[:, 0], hs2=hs2[:, 0], memory1=mem1, memory2=mem2, cxy1=cxy1, cxy2=cxy2,

@@ -25,15 +25,23 @@ def _built_library():
 
 
 def load_case(name):
-    """(weights dict, feat1, feat2, case tuple, golden npz) for a tests/golden case."""
-    from cases import CASES
+    """(weights dict, feat1, feat2, case tuple, golden npz) for a tests/golden case (CASES or MASK_CASES)."""
+    from cases import CASES, MASK_CASES
     from oetr_b200 import weights
-    b, fm1, fm2, hw1, hw2, attention, wseed, fseed = CASES[name]
+    b, fm1, fm2, hw1, hw2, attention, wseed, fseed = {**CASES, **MASK_CASES}[name]
     W = weights.synthetic_hot_path_weights(wseed)
     f1 = weights.synthetic_features(b, *fm1, seed=fseed, tag="feat1")
     f2 = weights.synthetic_features(b, *fm2, seed=fseed, tag="feat2")
     golden = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
-    return W, f1, f2, CASES[name], golden
+    return W, f1, f2, {**CASES, **MASK_CASES}[name], golden
+
+
+def load_masks(name):
+    """The synthetic masks of a MASK_CASES case (the generator used them for the committed reference outputs)."""
+    from cases import MASK_CASES
+    from oetr_b200 import weights
+    b, fm1, fm2 = MASK_CASES[name][:3]
+    return weights.synthetic_mask(b, *fm1, tag="mask1"), weights.synthetic_mask(b, *fm2, tag="mask2")
 
 
 def rel_err(a, b):

@@ -11,3 +11,10 @@ CASES = {
     "full_ragged": (1, (20, 20), (15, 20), (640, 640), (480, 640), "full", 0, 7),
 }
 MEMORY_STRIDE = 7      # golden files keep every 7th memory token (all channels) plus whole-tensor sums
+
+# the same tuple; both images carry a padding-style float mask from weights.synthetic_mask (masks are
+# reachable only by direct callers of forward_dummy / feature_correlation)
+MASK_CASES = {
+    "masked_640x480": (2, (20, 20), (15, 20), (640, 640), (480, 640), "linear", 0, 8),
+    "masked_tiny": (3, (5, 7), (4, 6), (160, 224), (128, 192), "linear", 3, 9),
+}

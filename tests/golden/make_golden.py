@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 import ref_loader  # noqa: E402
-from cases import CASES, MEMORY_STRIDE  # noqa: E402
+from cases import CASES, MASK_CASES, MEMORY_STRIDE  # noqa: E402
 
 from oetr_b200 import weights  # noqa: E402
 
@@ -33,8 +33,10 @@ def load_synthetic(net, seed):
     return sd
 
 
-def run_reference(net, full_tf, feat1, feat2, hw1, hw2, attention, dtype):
+def run_reference(net, full_tf, feat1, feat2, hw1, hw2, attention, dtype, mask1=None, mask2=None):
     """reference src/model.py:240-250 on precomputed features"""
+    if mask1 is not None:
+        mask1, mask2 = torch.from_numpy(mask1).to(dtype), torch.from_numpy(mask2).to(dtype)
     from src.models.utils import box_tlbr_to_xyxy
     f1 = torch.from_numpy(feat1).to(dtype)
     f2 = torch.from_numpy(feat2).to(dtype)
@@ -45,11 +47,11 @@ def run_reference(net, full_tf, feat1, feat2, hw1, hw2, attention, dtype):
     with torch.no_grad():
         pos1, pos2 = net.pos_encoding(f1), net.pos_encoding(f2)
         if attention == "linear":
-            hs1, hs2, m1, m2 = net.feature_correlation(f1, f2, pos1, pos2, None, None)
+            hs1, hs2, m1, m2 = net.feature_correlation(f1, f2, pos1, pos2, mask1, mask2)
         else:
             hs1, hs2, m1, m2 = full_tf(f1, f2, net.query_embed1.weight, net.query_embed2.weight, pos1, pos2,
                                        None, None)
-        cxy1, cxy2 = net.center_estimation(hs1, hs2, m1, m2, hf1, wf1, hf2, wf2, None, None)
+        cxy1, cxy2 = net.center_estimation(hs1, hs2, m1, m2, hf1, wf1, hf2, wf2, mask1, mask2)
         tlbr1, tlbr2 = net.size_regression(hs1, hs2)
         box1 = box_tlbr_to_xyxy(cxy1, tlbr1, max_h=hw1[0], max_w=hw1[1])
         box2 = box_tlbr_to_xyxy(cxy2, tlbr2, max_h=hw2[0], max_w=hw2[1])
@@ -64,9 +66,29 @@ def run_reference(net, full_tf, feat1, feat2, hw1, hw2, attention, dtype):
 
 def main():
     net = ref_loader.build_reference_oetr(seed=0)
-    np.savez_compressed(os.path.join(HERE, "pe_table.npz"),
-                        pe_sub=net.pos_encoding.pe[0, :, ::9, ::7].numpy(),
-                        pe_corner=net.pos_encoding.pe[0, :, :3, :3].numpy())
+    only_masked = "--masked-only" in sys.argv          # leaves the other committed files untouched
+    if not only_masked:
+        np.savez_compressed(os.path.join(HERE, "pe_table.npz"),
+                            pe_sub=net.pos_encoding.pe[0, :, ::9, ::7].numpy(),
+                            pe_corner=net.pos_encoding.pe[0, :, :3, :3].numpy())
+    for name, (b, fm1, fm2, hw1, hw2, attention, wseed, fseed) in MASK_CASES.items():
+        load_synthetic(net, wseed)
+        feat1 = weights.synthetic_features(b, *fm1, seed=fseed, tag="feat1")
+        feat2 = weights.synthetic_features(b, *fm2, seed=fseed, tag="feat2")
+        mk1, mk2 = weights.synthetic_mask(b, *fm1, tag="mask1"), weights.synthetic_mask(b, *fm2, tag="mask2")
+        net.float()
+        o32 = run_reference(net, None, feat1, feat2, hw1, hw2, attention, torch.float32, mk1, mk2)
+        net.double()
+        o64 = run_reference(net, None, feat1, feat2, hw1, hw2, attention, torch.float64, mk1, mk2)
+        net.float()
+        blob = {k: v for k, v in o32.items()}
+        blob.update({k + "_f64": v for k, v in o64.items() if not k.startswith("memory")})
+        blob["memory1_sub_f64"] = o64["memory1_sub"]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        print("%-16s box1_raw=%s  |fp32-fp64|=%.2e" % (name, o64["box1_raw"][0].round(3),
+                                                       np.abs(o32["box1_raw"] - o64["box1_raw"]).max()))
+    if only_masked:
+        return
     for name, (b, fm1, fm2, hw1, hw2, attention, wseed, fseed) in CASES.items():
         load_synthetic(net, wseed)
         full_tf = ref_loader.build_reference_full_transformer(net) if attention == "full" else None

@@ -5,8 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, MEMORY_STRIDE
-from conftest import ROOT, load_case, rel_err
+from cases import CASES, MASK_CASES, MEMORY_STRIDE
+from conftest import ROOT, load_case, load_masks, rel_err
 from oracle import oetr_oracle as orc
 
 
@@ -71,3 +71,21 @@ def test_torch_eager_restatement_matches_oracle(name):
         b1, b2 = ote.hot_path(Wt, torch.from_numpy(f1).double(), torch.from_numpy(f2).double(), hw1, hw2, clamp=clamp)
         assert np.abs(b1.numpy() - o[keys[0]]).max() / max(hw1) < 1e-9
         assert np.abs(b2.numpy() - o[keys[1]]).max() / max(hw2) < 1e-9
+
+
+@pytest.mark.parametrize("name", sorted(MASK_CASES))
+def test_oracle_matches_reference_with_masks(name):
+    """Float padding masks on both images (reference linear_attention.py:36-41, transformer.py:341-381,
+    model.py:167-171), against the reference's own outputs."""
+    W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case(name)
+    m1, m2 = load_masks(name)
+    assert 0 < m1.mean() < 1 and 0 < m2.mean() < 1
+    o = orc.hot_path(W, f1, f2, hw1, hw2, mask1=m1, mask2=m2)
+    for k in ("hs1", "hs2", "cxy1", "cxy2", "tlbr1", "tlbr2", "box1_raw", "box2_raw"):
+        assert rel_err(o[k], g[k + "_f64"]) < 1e-7, k
+    assert rel_err(o["memory1"][:, ::MEMORY_STRIDE], g["memory1_sub_f64"]) < 1e-7
+    for k, side in (("box1", max(hw1)), ("box2", max(hw2)), ("box1_raw", max(hw1)), ("box2_raw", max(hw2))):
+        assert np.abs(o[k] - g[k]).max() / side < 2e-5, k
+    # the masks matter: the unmasked result is a different box
+    u = orc.hot_path(W, f1, f2, hw1, hw2)
+    assert np.abs(u["box1_raw"] - o["box1_raw"]).max() > 1.0
