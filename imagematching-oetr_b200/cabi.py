@@ -12,7 +12,7 @@ PREC_FP32, PREC_FP16 = 0, 1
 
 EXPORTS = (
     "oetr_abi_version", "oetr_last_error", "oetr_packed_weight_count", "oetr_create", "oetr_destroy",
-    "oetr_workspace_bytes", "oetr_forward", "oetr_last_launch_count", "oetr_poll_error", "oetr_forward_host",
+    "oetr_workspace_bytes", "oetr_forward", "oetr_forward_masked", "oetr_last_launch_count", "oetr_poll_error", "oetr_forward_host",
     "oetr_forward_host_submit", "oetr_forward_host_wait",
     "oetr_profile_enable", "oetr_profile_read", "oetr_set_chunk_pairs",
     "oetr_selftest_tcgen05", "oetr_selftest_geometry",
@@ -51,6 +51,8 @@ def load_library(path=None):
     lib.oetr_workspace_bytes.argtypes = [vp, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_size_t)]
     lib.oetr_forward.restype = c.c_int
     lib.oetr_forward.argtypes = [vp, vp, vp] + [c.c_int] * 10 + [vp] * 6 + [vp, c.c_size_t, vp]
+    lib.oetr_forward_masked.restype = c.c_int
+    lib.oetr_forward_masked.argtypes = [vp, vp, vp, vp, vp] + [c.c_int] * 10 + [vp] * 6 + [vp, c.c_size_t, vp]
     lib.oetr_last_launch_count.restype = c.c_int
     lib.oetr_last_launch_count.argtypes = [vp]
     lib.oetr_set_chunk_pairs.restype = c.c_int

@@ -169,8 +169,8 @@ Workspace carve(void* base, const oetr_handle* h, int B, int L1, int L2) {
 // ---------------------------------------------------------------------------------------------------------
 // fp32 orchestration
 // ---------------------------------------------------------------------------------------------------------
-static void encoder_fp32(const oetr_handle* h, const Workspace& w, int B, int L1, int L2, cudaStream_t s,
-                         LaunchCounter& lc) {
+static void encoder_fp32(const oetr_handle* h, const Workspace& w, int B, int L1, int L2, const float* mask1,
+                         const float* mask2, cudaStream_t s, LaunchCounter& lc) {
     const float* W = h->d_w;
     const int R1 = B * L1, R2 = B * L2, R = R1 + R2;
     float* const pos1 = w.pos;
@@ -180,6 +180,12 @@ static void encoder_fp32(const oetr_handle* h, const Workspace& w, int B, int L1
         ln_pos(w.X + (size_t)R1 * C, g, b, with_pos ? pos2 : nullptr, L2, out + (size_t)R1 * C, R2, s, lc);
     };
     const bool linear = h->attn_mode == OETR_ATTN_LINEAR;
+    // q / kv masks of LinearAttention: a row's own mask scales its phi(q), phi(k) and v (cross layers read the
+    // partner's summaries, which were built from the partner's masked rows)
+    auto mask_rows = [&](float* buf) {
+        row_scale(buf, mask1, R1, s, lc);
+        row_scale(buf + (size_t)R1 * C, mask2, R2, s, lc);
+    };
     for (int i = 0; i < N_ENC; ++i) {
         const EncW& e = h->L.enc[i];
         // key/value side: ONE normalised source (+pos) feeds k_proj and v_proj (transformer.py:119-126)
@@ -187,6 +193,8 @@ static void encoder_fp32(const oetr_handle* h, const Workspace& w, int B, int L1
         gemm_nt(w.T, C, W + e.wk, C, nullptr, w.KF, C, R, C, C, linear ? ACT_ELU1 : ACT_NONE, 0, s, lc);
         gemm_nt(w.T, C, W + e.wv, C, nullptr, w.V, C, R, C, C, ACT_NONE, 0, s, lc);
         if (linear) {
+            mask_rows(w.KF);
+            mask_rows(w.V);
             kv_reduce(w.KF, w.V, w.kvs, B, L1, s, lc);
             kv_reduce(w.KF + (size_t)R1 * C, w.V + (size_t)R1 * C, w.kvs + (size_t)B * KVS, B, L2, s, lc);
         }
@@ -195,6 +203,7 @@ static void encoder_fp32(const oetr_handle* h, const Workspace& w, int B, int L1
         gemm_nt(w.T, C, W + e.wq, C, nullptr, w.Q, C, R, C, C, linear ? ACT_ELU1 : ACT_NONE, 0, s, lc);
         const bool cross = (i & 1) != 0;   // ['self','cross']*4; cross layers read the partner's PRE-update state
         if (linear) {
+            mask_rows(w.Q);
             const float* kv_for_1 = w.kvs + (cross ? (size_t)B * KVS : 0);
             const float* kv_for_2 = w.kvs + (cross ? 0 : (size_t)B * KVS);
             linattn_apply(w.Q, kv_for_1, w.O, R1, L1, s, lc);
@@ -250,7 +259,7 @@ static void decoder_fp32(const oetr_handle* h, const Workspace& w, int B, cudaSt
 }
 
 static void decoder_kv_fp32(const oetr_handle* h, const Workspace& w, int j, int B, int L1, int L2,
-                            cudaStream_t s, LaunchCounter& lc) {
+                            const float* mask1, const float* mask2, cudaStream_t s, LaunchCounter& lc) {
     const float* W = h->d_w;
     const DecW& d = h->L.dec[j];
     const int R1 = B * L1, R2 = B * L2, R = R1 + R2;
@@ -258,6 +267,8 @@ static void decoder_kv_fp32(const oetr_handle* h, const Workspace& w, int j, int
     ln_pos(w.X + (size_t)R1 * C, nullptr, nullptr, w.pos + (size_t)L1 * C, L2, w.T + (size_t)R1 * C, R2, s, lc);
     gemm_nt(w.T, C, W + d.ca.wk, C, W + d.ca.bk, w.KF, C, R, C, C, ACT_ELU1, 0, s, lc);
     gemm_nt(w.X, C, W + d.ca.wv, C, W + d.ca.bv, w.V, C, R, C, C, ACT_NONE, 0, s, lc);
+    row_scale(w.KF, mask1, R1, s, lc); row_scale(w.KF + (size_t)R1 * C, mask2, R2, s, lc);      // memory_mask (transformer.py:361-381)
+    row_scale(w.V, mask1, R1, s, lc);  row_scale(w.V + (size_t)R1 * C, mask2, R2, s, lc);
     kv_reduce(w.KF, w.V, w.dkvs, B, L1, s, lc);
     kv_reduce(w.KF + (size_t)R1 * C, w.V + (size_t)R1 * C, w.dkvs + (size_t)B * KVS, B, L2, s, lc);
 }
@@ -481,6 +492,7 @@ struct EventSet { cudaEvent_t fork; cudaEvent_t* join; bool join_caller; int* n_
 struct FwdArgs {
     int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
     float *dbg_hs, *dbg_memory, *dbg_cxy, *dbg_tlbr;
+    const float *mask1, *mask2;     // nullable [batch][hf*wf] device masks of the WHOLE batch (sub-batches offset them)
 };
 
 // one (sub-)batch of B pairs on stream s with workspace slice w
@@ -495,16 +507,17 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
         k_gather_pos<<<(L2 * (C / 4) + 255) / 256, 256, 0, s>>>(h->d_pe, h->max_w, wf2, L2, w.pos + (size_t)L1 * C); lc.n++;
         nchw_to_tokens(feat1, w.X, B, L1, s, lc);
         nchw_to_tokens(feat2, w.X + (size_t)R1 * C, B, L2, s, lc);
-        encoder_fp32(h, w, B, L1, L2, s, lc);
-        decoder_fp32(h, w, B, s, lc, [&](int j) { decoder_kv_fp32(h, w, j, B, L1, L2, s, lc); });
+        encoder_fp32(h, w, B, L1, L2, a.mask1, a.mask2, s, lc);
+        decoder_fp32(h, w, B, s, lc, [&](int j) { decoder_kv_fp32(h, w, j, B, L1, L2, a.mask1, a.mask2, s, lc); });
     } else {
         // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
         // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
         char msg[256] = "";
         if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
+                       a.mask1, a.mask2,
                        a.dbg_memory ? w.X : nullptr, h->d_flag, profile ? &h->prof : nullptr, s, lc, msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
-        const HeadGeom hg{B, hf1, wf1, hf2, wf2, a.img_h1, a.img_w1, a.img_h2, a.img_w2, a.clamp};
+        const HeadGeom hg{B, hf1, wf1, hf2, wf2, a.img_h1, a.img_w1, a.img_h2, a.img_w2, a.clamp, a.mask1, a.mask2};
         if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, hg, w.dt, w.O, boxes1, boxes2, a.dbg_cxy, a.dbg_tlbr, h->d_flag, s, lc,
                             msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
@@ -524,10 +537,11 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
         p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;
         p.batch = B; p.clamp = a.clamp;
         p.Y = Y; p.hs = w.dt; p.hf = hf1; p.wf = wf1; p.img_h = a.img_h1; p.img_w = a.img_w1;
-        p.boxes = boxes1; p.dbg_cxy = a.dbg_cxy; p.dbg_tlbr = a.dbg_tlbr;
+        p.boxes = boxes1; p.dbg_cxy = a.dbg_cxy; p.dbg_tlbr = a.dbg_tlbr; p.mask = a.mask1;
         head_finalize(p, s, lc);
         p.Y = Y + (size_t)R1 * C; p.hs = w.dt + (size_t)B * C; p.hf = hf2; p.wf = wf2; p.img_h = a.img_h2; p.img_w = a.img_w2;
         p.boxes = boxes2; p.dbg_cxy = a.dbg_cxy ? a.dbg_cxy + 2 * B : nullptr; p.dbg_tlbr = a.dbg_tlbr ? a.dbg_tlbr + 4 * B : nullptr;
+        p.mask = a.mask2;
         head_finalize(p, s, lc);
     }
     return OETR_OK;
@@ -580,6 +594,8 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
             const int Bc = sizes[c];
             cudaStream_t sc = es.streams[c];
             CU(cudaStreamWaitEvent(sc, es.fork, 0));
+            FwdArgs ac = a;                                  // the sub-batch's slice of the masks
+            if (a.mask1) { ac.mask1 = a.mask1 + (size_t)b0 * L1; ac.mask2 = a.mask2 + (size_t)b0 * L2; }
             const float* f1c = feat1 + (size_t)b0 * C * L1;
             const float* f2c = feat2 + (size_t)b0 * C * L2;
             float* b1c = boxes1 + (size_t)b0 * 4;
@@ -608,7 +624,7 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
                     cudaGraph_t graph = nullptr;
                     CU(cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal));
                     const Workspace wg = carve(base, h, Bc, L1, L2);
-                    const int rcg = run_batch(h, wg, f1c, f2c, Bc, a, b1c, b2c, false, sc, lg);
+                    const int rcg = run_batch(h, wg, f1c, f2c, Bc, ac, b1c, b2c, false, sc, lg);
                     const cudaError_t ec = cudaStreamEndCapture(sc, &graph);
                     if (rcg == OETR_OK && ec == cudaSuccess && graph &&
                         cudaGraphInstantiate(&cg->exec, graph, 0) == cudaSuccess) cg->launches = lg.n;
@@ -625,7 +641,7 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
             const Workspace w = carve(base, h, Bc, L1, L2);
             base += (w.bytes + 1023) & ~size_t(1023);
             if (!replayed) {
-                int rc = run_batch(h, w, f1c, f2c, Bc, a, b1c, b2c, false, sc, lc);
+                int rc = run_batch(h, w, f1c, f2c, Bc, ac, b1c, b2c, false, sc, lc);
                 if (rc) return rc;
             }
             if (hio) {
@@ -650,6 +666,15 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
                  int wf2, int img_h1, int img_w1, int img_h2, int img_w2, int clamp, float* boxes1, float* boxes2,
                  float* dbg_hs, float* dbg_memory, float* dbg_cxy, float* dbg_tlbr, void* workspace,
                  size_t workspace_bytes, void* stream) {
+    return oetr_forward_masked(h, feat1, feat2, nullptr, nullptr, batch, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2,
+                               img_w2, clamp, boxes1, boxes2, dbg_hs, dbg_memory, dbg_cxy, dbg_tlbr, workspace,
+                               workspace_bytes, stream);
+}
+
+int oetr_forward_masked(oetr_handle* h, const float* feat1, const float* feat2, const float* mask1, const float* mask2,
+                        int batch, int hf1, int wf1, int hf2, int wf2, int img_h1, int img_w1, int img_h2, int img_w2,
+                        int clamp, float* boxes1, float* boxes2, float* dbg_hs, float* dbg_memory, float* dbg_cxy,
+                        float* dbg_tlbr, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_shapes(h, batch, hf1, wf1, hf2, wf2);
     if (rc) return rc;
     if (batch == 0) { h->last_launches = 0; return OETR_OK; }              // empty batch: nothing to do
@@ -660,7 +685,12 @@ int oetr_forward(oetr_handle* h, const float* feat1, const float* feat2, int bat
                     img_w1, img_h2, img_w2);
     if (reinterpret_cast<uintptr_t>(workspace) & 255)
         return fail(OETR_E_ARG, "oetr_forward: workspace must be 256-byte aligned");
-    const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, dbg_hs, dbg_memory, dbg_cxy, dbg_tlbr};
+    if ((mask1 == nullptr) != (mask2 == nullptr))
+        return fail(OETR_E_ARG, "oetr_forward_masked: give both masks or neither (reference src/model.py:167-171)");
+    if (mask1 && h->attn_mode != OETR_ATTN_LINEAR)
+        return fail(OETR_E_ARG, "oetr_forward_masked: masks are implemented for linear attention only");
+    const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, dbg_hs, dbg_memory, dbg_cxy, dbg_tlbr,
+                    mask1, mask2};
     std::lock_guard<std::mutex> lock(h->mu);
     const EventSet es{h->ev_fork, h->ev_join, true, nullptr, h->aux};
     return forward_core(h, feat1, feat2, batch, a, boxes1, boxes2, workspace, workspace_bytes,
@@ -710,7 +740,8 @@ int oetr_forward_host_submit(oetr_handle* h, const float* feat1_host, const floa
                 return fail(OETR_E_NOMEM, "oetr_forward_host_submit: pinned staging allocation failed");
             sl.boxes_pin_n = (size_t)batch * 8;
         }
-        const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, nullptr, nullptr, nullptr, nullptr};
+        const FwdArgs a{hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp, nullptr, nullptr, nullptr, nullptr,
+                        nullptr, nullptr};
         const HostIO hio{feat1_host, feat2_host, sl.boxes_pin, sl.boxes_pin + (size_t)batch * 4, sl.flag_pin, sl.cg};
         const EventSet es{sl.ev_fork, sl.ev_join, false, &sl.n_join, sl.aux};
         rc = forward_core(h, sl.feat1, sl.feat2, batch, a, sl.boxes, sl.boxes + (size_t)batch * 4, sl.ws, sl.ws_n, s, &hio, es);

@@ -94,8 +94,11 @@ struct HeadParams {
     const float *gn_g, *gn_b, *w3, *b3, *tl_w0, *tl_w2, *tl_b2;
     int batch, hf, wf, img_h, img_w, clamp;
     float *boxes, *dbg_cxy, *dbg_tlbr;   // dbg nullable
+    const float* mask;     // nullable [batch][hf*wf]: logits where mask == 0 are filled with -1e9 (src/model.py:167-171)
 };
 // GroupNorm(32)+ReLU+1x1 conv+softmax+soft-argmax, tlbr MLP+sigmoid, box assembly; one CTA per image
 void head_finalize(const HeadParams& p, cudaStream_t s, LaunchCounter& lc);
+// X[r][:] *= mask[r] for r < rows (256 channels): the q / kv masks of LinearAttention (linear_attention.py:36-41)
+void row_scale(float* X, const float* mask, int rows, cudaStream_t s, LaunchCounter& lc);
 
 }  // namespace oetr

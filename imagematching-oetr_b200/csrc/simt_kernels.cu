@@ -382,7 +382,7 @@ k_head_finalize(HeadParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc = fmaf(w3[i], fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f), acc);
         acc = warp_sum(acc);
-        if (lane == 0) z[l] = acc + b3;
+        if (lane == 0) z[l] = (p.mask && p.mask[(size_t)b * L + l] == 0.f) ? -1e9f : acc + b3;
     }
     __syncthreads();
     // ---- softmax + soft-argmax over the (x+0.5, y+0.5)*stride grid; stride = img_h / hf for both axes (:176-181)
@@ -431,6 +431,20 @@ k_head_finalize(HeadParams p) {
         if (p.dbg_tlbr) { for (int i = 0; i < 4; ++i) p.dbg_tlbr[b * 4 + i] = tl[i]; }
     }
 }
+__global__ void k_row_scale(float* __restrict__ X, const float* __restrict__ mask, int rows) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // one float4 per thread
+    if (idx >= rows * (C / 4)) return;
+    const float m = mask[idx / (C / 4)];
+    float4 v = reinterpret_cast<float4*>(X)[idx];
+    v.x *= m; v.y *= m; v.z *= m; v.w *= m;
+    reinterpret_cast<float4*>(X)[idx] = v;
+}
+void row_scale(float* X, const float* mask, int rows, cudaStream_t s, LaunchCounter& lc) {
+    if (rows <= 0 || mask == nullptr) return;
+    k_row_scale<<<(rows * (C / 4) + 255) / 256, 256, 0, s>>>(X, mask, rows);
+    lc.n++;
+}
+
 void head_finalize(const HeadParams& p, cudaStream_t s, LaunchCounter& lc) {
     if (p.batch <= 0) return;
     const size_t smem = (size_t)p.hf * p.wf * sizeof(float);

@@ -17,6 +17,8 @@ struct EncParams {
     const float* feat2;
     float* xt;                  // tile-blocked residual stream (read unless load_feat; written when store_x)
     const float *post1, *post2; // tile-blocked positional rows of set 0 / set 1
+    const float *mask1, *mask2; // nullable [B][L] float masks of set 0 / set 1: a row's mask scales its phi(q), phi(k)
+                                // and v (linear_attention.py:36-41; k and v of a row always belong to its own image)
     int load_feat, store_x, do_q, do_kv;
     // query phase (encoder layer i)
     const float *lnq_g, *lnq_b, *ln2_g, *ln2_b;
@@ -135,6 +137,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         uint8_t* img_hi = smem + SM_AHI;
         uint8_t* img_lo = smem + SM_ALO;
         const float* post = (et.set == 0 ? p.post1 : p.post2);
+        const float* maskp = (et.set == 0 ? p.mask1 : p.mask2);
+        const bool has_mask = maskp != nullptr;
+        const float mrow = (has_mask && valid) ? __ldg(maskp + (size_t)rb * et.L + rl) : 1.f;
         uint32_t ns0 = 0, ns1 = 0;
         auto wait_s = [&](int b) {
             mbar_wait(&bars->s_full[b], (b ? ns1++ : ns0++) & 1, p.flag);
@@ -243,6 +248,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     v[e4 * 4 + 2] = elu1(v[e4 * 4 + 2]); den = fmaf(v[e4 * 4 + 2], k4.z, den);
                     v[e4 * 4 + 3] = elu1(v[e4 * 4 + 3]); den = fmaf(v[e4 * 4 + 3], k4.w, den);
                 }
+                if (has_mask) {                           // Q = phi(q) * q_mask, before Z (linear_attention.py:37,46)
+                    den *= mrow;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] *= mrow;
+                }
                 const float inv = 1.f / (den + eps_s);
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] *= inv;
@@ -339,6 +349,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 if (!valid) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = 0.f;
+                } else if (has_mask) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] *= mrow;
                 }
                 if (pass == 1) wait_s(0);                               // KV of half 0 has consumed the images
                 store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e]) : 0.f;
+                for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e]) * mrow : 0.f;
                 store_row32_split(img_hi + KF_OFF, img_lo + KF_OFF, r, ch, v);
                 publish(pass);
                 // Ksum[c0 + j] = sum over the tile's rows of Kf[:, c0 + j] (fp32, exact operands): butterfly

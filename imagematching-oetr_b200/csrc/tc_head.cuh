@@ -238,6 +238,7 @@ struct BoxParams {
     TileGeom g;
     int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
     const float* z;             // tile-blocked logits
+    const float *mask1, *mask2; // nullable [B][L]: logits where the mask is 0 count as -1e9 (src/model.py:167-171)
     const float* tlbr;          // [2B][4] sigmoid(top,left,bottom,right) from k_decoder
     float *boxes1, *boxes2, *dbg_cxy, *dbg_tlbr;
 };
@@ -248,6 +249,9 @@ __global__ void __launch_bounds__(256) k_box(const BoxParams p) {
     const int img_h = set == 0 ? p.img_h1 : p.img_h2, img_w = set == 0 ? p.img_w1 : p.img_w2;
     const int first = set == 0 ? b * p.g.T1 : p.g.B * p.g.T1 + b * p.g.T2;
     const float* z = p.z + (size_t)first * TILE;
+    const float* mk = set == 0 ? p.mask1 : p.mask2;
+    if (mk) mk += (size_t)b * L;
+    auto logit = [&](int l) { return (mk && mk[l] == 0.f) ? -1e9f : z[l]; };
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     auto block_reduce = [&](float v, bool is_max) {
 #pragma unroll
@@ -261,12 +265,12 @@ __global__ void __launch_bounds__(256) k_box(const BoxParams p) {
         return r;
     };
     float mx = -INFINITY;
-    for (int l = tid; l < L; l += 256) mx = fmaxf(mx, z[l]);
+    for (int l = tid; l < L; l += 256) mx = fmaxf(mx, logit(l));
     mx = block_reduce(mx, true);
     const float stride = (float)(img_h / hf);
     float se = 0.f, sx = 0.f, sy = 0.f;
     for (int l = tid; l < L; l += 256) {
-        const float e = expf(z[l] - mx);
+        const float e = expf(logit(l) - mx);
         se += e;
         sx = fmaf(e, ((float)(l % wf) + 0.5f) * stride, sx);
         sy = fmaf(e, ((float)(l / wf) + 0.5f) * stride, sy);

@@ -373,6 +373,7 @@ void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cuda
 
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
+               const float* mask1, const float* mask2,
                float* X_out, int* flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len) {
     if (set_attrs(msg, msg_len)) return -1;
     const int L1 = hf1 * wf1, L2 = hf2 * wf2;
@@ -389,6 +390,10 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
     // OETR_ENC=2 selects the experimental CTA-pair kernel (k_enc2, see its header: correct, but slower than k_enc
     // as measured in round 1); default: one CTA per tile (k_enc)
     static const bool pairs = tc_pair_kernel_selected();
+    if (pairs && (mask1 || mask2)) {
+        snprintf(msg, msg_len, "masks are not implemented in the experimental CTA-pair kernel (OETR_ENC=2)");
+        return -1;
+    }
     const EncGeom eg = make_enc_geom(B, L1, L2, pairs);
     const int ppt = (pairs || eg.flat) ? 2 : 1;
     const int enc_tiles = eg.flat ? eg.F1 + eg.F2 : tiles;
@@ -398,7 +403,8 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         lc.n++;
     };
     EncParams base{};
-    base.g = g; base.eg = eg; base.feat1 = feat1; base.feat2 = feat2; base.xt = eg.flat ? ws.xt_enc : ws.xt; base.post1 = post1; base.post2 = post2;
+    base.g = g; base.eg = eg; base.feat1 = feat1; base.feat2 = feat2; base.xt = eg.flat ? ws.xt_enc : ws.xt;
+    base.mask1 = mask1; base.mask2 = mask2; base.post1 = post1; base.post2 = post2;
     base.mimg = ws.mimg; base.ksum = ws.ksum; base.kv_part = ws.kv_part; base.flag = flag;
     auto set_kv_enc = [&](EncParams& p, int layer) {
         const EncW& e = L.enc[layer];
@@ -518,7 +524,7 @@ int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, con
     BoxParams bp{};
     bp.g = g; bp.hf1 = hg.hf1; bp.wf1 = hg.wf1; bp.hf2 = hg.hf2; bp.wf2 = hg.wf2;
     bp.img_h1 = hg.img_h1; bp.img_w1 = hg.img_w1; bp.img_h2 = hg.img_h2; bp.img_w2 = hg.img_w2; bp.clamp = hg.clamp;
-    bp.z = ws.z; bp.tlbr = ws.tlbr; bp.boxes1 = boxes1; bp.boxes2 = boxes2; bp.dbg_cxy = dbg_cxy; bp.dbg_tlbr = dbg_tlbr;
+    bp.z = ws.z; bp.tlbr = ws.tlbr; bp.mask1 = hg.mask1; bp.mask2 = hg.mask2; bp.boxes1 = boxes1; bp.boxes2 = boxes2; bp.dbg_cxy = dbg_cxy; bp.dbg_tlbr = dbg_tlbr;
     k_box<<<2 * B, 256, 0, s>>>(bp); lc.n++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -59,8 +59,9 @@ size_t tc_pos_tile_floats(int L);
 void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cudaStream_t s, LaunchCounter& lc);
 int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
+               const float* mask1, const float* mask2,
                float* X_out, int* timeout_flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
-struct HeadGeom { int B, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp; };
+struct HeadGeom { int B, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp; const float *mask1, *mask2; };
 // fused fp32 query decoder (+ tlbr regression) -> hs_out [2B][256]; tcgen05 3x3 heat-map convolution -> Y scratch
 // [B*L1+B*L2][256]; GroupNorm/ReLU/1x1 logits; softmax + soft-argmax + box assembly -> boxes1/boxes2 [B][4]
 int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const HeadGeom& hg,

@@ -75,9 +75,10 @@ class OverlapHotPath:
     def last_launch_count(self):
         return self._lib.oetr_last_launch_count(self._handle)
 
-    def forward(self, feat1, feat2, img_hw1, img_hw2, clamp=True, debug=False):
+    def forward(self, feat1, feat2, img_hw1, img_hw2, clamp=True, debug=False, mask1=None, mask2=None):
         """feat1 [B,256,hf1,wf1], feat2 [B,256,hf2,wf2]: fp32 CUDA tensors (NCHW).  Returns (box1, box2) [B,4]
         xyxy pixels; with debug=True also a dict of the stage boundaries (hs, memory, cxy, tlbr).
+        mask1 [B,hf1,wf1], mask2 [B,hf2,wf2]: the optional masks of the reference's forward_dummy (both or neither).
         Stream-ordered on torch's current stream; no synchronisation."""
         if feat1.dim() != 4 or feat2.dim() != 4 or feat1.shape[1] != 256 or feat2.shape[1] != 256:
             raise ValueError("features must be [B,256,h,w], got %s and %s" % (tuple(feat1.shape), tuple(feat2.shape)))
@@ -89,6 +90,14 @@ class OverlapHotPath:
         feat2 = feat2.contiguous().float()
         b, _, hf1, wf1 = feat1.shape
         _, _, hf2, wf2 = feat2.shape
+        if (mask1 is None) != (mask2 is None):
+            raise ValueError("give both masks or neither")
+        if mask1 is not None:
+            if tuple(mask1.shape) != (b, hf1, wf1) or tuple(mask2.shape) != (b, hf2, wf2):
+                raise ValueError("masks must be [B,hf,wf] like the feature maps, got %s and %s" % (
+                    tuple(mask1.shape), tuple(mask2.shape)))
+            mask1 = mask1.to(device=self.device, dtype=torch.float32).contiguous()
+            mask2 = mask2.to(device=self.device, dtype=torch.float32).contiguous()
         box1 = torch.empty(b, 4, dtype=torch.float32, device=self.device)
         box2 = torch.empty(b, 4, dtype=torch.float32, device=self.device)
         dbg = None
@@ -100,8 +109,8 @@ class OverlapHotPath:
         with torch.cuda.device(self.device):
             ws = self._workspace(b, hf1, wf1, hf2, wf2)
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            cabi.check(self._lib.oetr_forward(
-                self._handle, ptr(feat1), ptr(feat2), b, hf1, wf1, hf2, wf2,
+            cabi.check(self._lib.oetr_forward_masked(
+                self._handle, ptr(feat1), ptr(feat2), ptr(mask1), ptr(mask2), b, hf1, wf1, hf2, wf2,
                 int(img_hw1[0]), int(img_hw1[1]), int(img_hw2[0]), int(img_hw2[1]), int(bool(clamp)),
                 ptr(box1), ptr(box2),
                 ptr(dbg["hs"]) if debug else None, ptr(dbg["memory"]) if debug else None,

@@ -128,17 +128,18 @@ class OETR(nn.Module):
             feats.append(f)
         return feats[0], feats[1]
 
-    def feature_correlation_and_regression(self, feat1, feat2, hw1, hw2, clamp=True, debug=False):
-        return self.hot_path.forward(feat1, feat2, hw1, hw2, clamp=clamp, debug=debug)
+    def feature_correlation_and_regression(self, feat1, feat2, hw1, hw2, clamp=True, debug=False, mask1=None,
+                                           mask2=None):
+        return self.hot_path.forward(feat1, feat2, hw1, hw2, clamp=clamp, debug=debug, mask1=mask1, mask2=mask2)
 
     @torch.no_grad()
     def forward_dummy(self, image1, image2, mask1=None, mask2=None):
-        """Inference entry (model.py:229-252): NHWC fp32 images in [0,1] -> (box1, box2) clamped xyxy."""
-        if mask1 is not None or mask2 is not None:
-            raise NotImplementedError("masks are None on every shipped path of the reference (SURVEY 8(a)-Q6)")
+        """Inference entry (model.py:229-252): NHWC fp32 images in [0,1] -> (box1, box2) clamped xyxy.
+        mask1 / mask2 [B,hf,wf] (feature-map resolution, float; both or neither): the masks the reference hands to
+        feature_correlation and center_estimation (model.py:240-247); linear attention only."""
         hw1, hw2 = tuple(image1.shape[1:3]), tuple(image2.shape[1:3])
         feat1, feat2 = self.feature_extraction(image1, image2)
-        return self.feature_correlation_and_regression(feat1, feat2, hw1, hw2, clamp=True)
+        return self.feature_correlation_and_regression(feat1, feat2, hw1, hw2, clamp=True, mask1=mask1, mask2=mask2)
 
     @torch.no_grad()
     def forward(self, data, validation=False):

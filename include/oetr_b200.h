@@ -118,6 +118,21 @@ OETR_API int oetr_forward(oetr_handle* h,
                  float* dbg_hs, float* dbg_memory, float* dbg_cxy, float* dbg_tlbr,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* oetr_forward with the optional float masks of the reference's direct callers (forward_dummy(image1, image2, mask1,
+ * mask2), src/model.py:229-250): mask1 [batch,hf1,wf1], mask2 [batch,hf2,wf2] fp32 device, or both NULL.  A position's
+ * mask scales its phi(q), phi(k) and v in every encoder layer and in the decoder's cross-attention
+ * (src/models/linear_attention.py:36-41, transformer.py:341-381), and heat-map logits where the mask is 0 are filled
+ * with -1e9 before the softmax (src/model.py:167-171).  Linear attention only.  No shipped path of the reference
+ * passes masks. */
+OETR_API int oetr_forward_masked(oetr_handle* h,
+                 const float* feat1, const float* feat2, const float* mask1, const float* mask2,
+                 int batch, int hf1, int wf1, int hf2, int wf2,
+                 int img_h1, int img_w1, int img_h2, int img_w2,
+                 int clamp,
+                 float* boxes1, float* boxes2,
+                 float* dbg_hs, float* dbg_memory, float* dbg_cxy, float* dbg_tlbr,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* Sub-batch scheduling of the FP16 path (default: automatic, about 56 encoder tiles per sub-batch = 8 pairs at
  * 640x640; env OETR_CHUNK_PAIRS overrides at create; < 0 = automatic): a batch larger
  * than `pairs_per_chunk` is cut into up to 8 balanced sub-batches that run on handle-owned streams, forked from and

@@ -66,8 +66,8 @@ def test_hot_path_fails_loudly_without_cuda(model):
     img = torch.rand(1, 64, 64, 3)
     with pytest.raises(RuntimeError):
         model.forward_dummy(img, img)
-    with pytest.raises(NotImplementedError):
-        model.forward_dummy(img, img, mask1=torch.ones(1, 2, 2))
+    with pytest.raises(RuntimeError):
+        model.forward_dummy(img, img, mask1=torch.ones(1, 2, 2), mask2=torch.ones(1, 2, 2))
 
 
 def test_plugin_convention():

@@ -12,8 +12,8 @@ import numpy as np
 import pytest
 import torch
 
-from cases import CASES, MEMORY_STRIDE
-from conftest import load_case, rel_err
+from cases import CASES, MASK_CASES, MEMORY_STRIDE
+from conftest import load_case, load_masks, rel_err
 from oracle import oetr_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -272,4 +272,31 @@ def test_host_requests_in_flight():
         g_ = hot.wait_host(tickets.pop(0))
         assert np.array_equal(g_[0], req[4]) and np.array_equal(g_[1], req[5])
     hot.poll_error()
+    hot.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", sorted(MASK_CASES))
+def test_masked_parity_with_oracle_and_golden(name, precision):
+    """Float padding masks on both images (oetr_forward_masked): stage parity against the oracle and the committed
+    outputs of the reference run with the same masks; sub-batches slice the masks like the features."""
+    W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case(name)
+    m1, m2 = load_masks(name)
+    want = orc.hot_path(W, f1, f2, hw1, hw2, mask1=m1, mask2=m2)
+    tol = TOL[precision]
+    hot = oetr_b200.OverlapHotPath(W, precision=precision)
+    t = lambda a: torch.from_numpy(a).cuda()
+    for pairs in (0, 1):
+        hot.set_chunk_pairs(pairs)
+        b1, b2, dbg = hot.forward(t(f1), t(f2), hw1, hw2, clamp=False, debug=(pairs == 0), mask1=t(m1), mask2=t(m2)) \
+            if pairs == 0 else hot.forward(t(f1), t(f2), hw1, hw2, clamp=False, mask1=t(m1), mask2=t(m2)) + (None,)
+        for i, (got, hw) in enumerate(((b1, hw1), (b2, hw2)), 1):
+            assert np.abs(got.cpu().numpy() - want["box%d_raw" % i]).max() / max(hw) < tol["box"], (pairs, i)
+            assert np.abs(got.cpu().numpy() - g["box%d_raw" % i]).max() / max(hw) < tol["box"] + 2e-5, (pairs, i)
+        if dbg is not None:
+            for k in ("memory1", "memory2", "hs1", "hs2", "tlbr1", "tlbr2"):
+                assert rel_err(dbg[k].cpu().numpy(), want[k]) < tol["mid"], k
+    hot.poll_error()
+    with pytest.raises(ValueError):
+        hot.forward(t(f1), t(f2), hw1, hw2, mask1=t(m1))
     hot.close()

@@ -47,8 +47,19 @@ def test_forward_dummy_and_forward_match_the_oracle_on_backbone_features(precisi
         r1, r2, _, _ = _oracle_boxes(model, img1, img2, clamp=False)
         assert np.abs(out["pred_bbox1"].cpu().numpy() - r1).max() / max(hw1) < tol
         assert np.abs(out["pred_bbox2"].cpu().numpy() - r2).max() / max(hw2) < tol
-    with pytest.raises(NotImplementedError):
-        model.forward_dummy(img1, img2, mask1=torch.ones(2, 20, 20))
+    with pytest.raises(ValueError):
+        model.forward_dummy(img1, img2, mask1=torch.ones(2, 20, 20))            # both masks or neither
+    # masks at feature-map resolution (reference model.py:229-250): against the oracle with the same masks
+    from oetr_b200 import weights
+    m1 = torch.from_numpy(weights.synthetic_mask(2, 20, 20, tag="mask1")).cuda()
+    m2 = torch.from_numpy(weights.synthetic_mask(2, 20, 20, tag="mask2")).cuda()
+    b1, b2 = model.forward_dummy(img1, img2, mask1=m1, mask2=m2)
+    with torch.no_grad():
+        f1, f2 = model.feature_extraction(img1, img2)
+    W = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    o = orc.hot_path(W, f1.cpu().numpy(), f2.cpu().numpy(), (640, 640), (640, 640), mask1=m1.cpu().numpy(),
+                     mask2=m2.cpu().numpy())
+    assert np.abs(b1.cpu().numpy() - o["box1"]).max() / 640 < tol and np.abs(b2.cpu().numpy() - o["box2"]).max() / 640 < tol
 
 
 def test_dloc_plugin_runs_like_the_reference_plugin(tmp_path):
