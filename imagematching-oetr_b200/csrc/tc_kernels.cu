@@ -10,8 +10,8 @@
 //   warps 0-15  "row" warps: thread <-> (token row, one quarter of the columns).  Warp w owns TMEM lanes
 //               32*(w%4).. and the 32-column chunks {w/4, w/4+4}.  The fp32 residual stream of the tile lives in
 //               their REGISTERS (64 per thread) for the whole kernel.
-//   warp 16     weight producer: streams pre-swizzled 16 KB fp16 stages global->shared with cp.async.bulk
-//               through a 4-stage mbarrier ring (2 MB per encoder layer per CTA, L2 resident)
+//   warp 16     weight producer: streams pre-swizzled fp16 stages (16 KB each, two per copy) global->shared with cp.async.bulk
+//               through a ring of 3 x 32 KB units guarded by mbarriers (2 MB per encoder layer per CTA, L2 resident)
 //   warp 17     MMA issuer: one lane issues tcgen05.mma M=128 N=256 K=16 (fp16 x fp16 -> fp32)
 // TMEM holds two 128x256 fp32 accumulators S0 | S1 (all 512 columns).  Shared memory holds ONE operand image
 // of the tile (hi and lo, 128 KB), written by the row warps in two column passes so that the next GEMM starts

@@ -33,7 +33,7 @@ constexpr uint32_t IDESC_KV = umma_idesc_f16(128, 128, 1, 1);      // both opera
 // shared-memory map (dynamic, 1024-byte aligned)
 constexpr uint32_t SM_AHI = 0;                                     // operand image, hi part (64 KB)
 constexpr uint32_t SM_ALO = SM_AHI + IMG_BYTES;                    // operand image, lo part (64 KB)
-constexpr uint32_t SM_RING = SM_ALO + IMG_BYTES;                   // 4 x 16 KB weight stages
+constexpr uint32_t SM_RING = SM_ALO + IMG_BYTES;                   // weight ring: RING stages of 16 KB (3 units of 32 KB)
 constexpr uint32_t SM_X = SM_RING + RING * STAGE_BYTES;            // float[512] scratch of the row warps: LayerNorm
                                                                    // partials -> (gamma | beta) -> Ksum of the source
                                                                    // image -> Ksum exchange (one user at a time)

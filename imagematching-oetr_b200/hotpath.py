@@ -62,7 +62,7 @@ class OverlapHotPath:
         cabi.check(self._lib.oetr_profile_enable(self._handle, int(bool(enable))), self._lib)
 
     def profile_read(self):
-        """(average k_tc_layer launch duration in ms, launches) since the last read; synchronises."""
+        """(average k_enc launch duration in ms, launches) since the last read; synchronises."""
         ms, n = ctypes.c_float(), ctypes.c_int()
         cabi.check(self._lib.oetr_profile_read(self._handle, ctypes.byref(ms), ctypes.byref(n)), self._lib)
         return ms.value, n.value

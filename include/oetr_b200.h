@@ -145,7 +145,7 @@ OETR_API int oetr_set_chunk_pairs(oetr_handle* h, int pairs_per_chunk);
 OETR_API int oetr_last_launch_count(const oetr_handle* h);
 
 /* Measurement hook (bench.py's roofline leg): when enabled, every launch of the dominant kernel of the FP16 path
- * (k_tc_layer, one per encoder layer) is bracketed by CUDA events on the launching stream.  oetr_profile_read
+ * (k_enc with a query phase, one per encoder layer; the profiler pass runs the batch unsplit on one stream) is bracketed by CUDA events on the launching stream.  oetr_profile_read
  * synchronises, returns the average launch duration since the last read and the number of launches, and resets. */
 OETR_API int oetr_profile_enable(oetr_handle* h, int enable);
 OETR_API int oetr_profile_read(oetr_handle* h, float* avg_ms, int* n_launches);
