@@ -6,7 +6,8 @@
 // accumulated in fp32 in TMEM (the dropped a_lo.w_lo term is ~2^-22 relative).  Everything row-wise (LayerNorm,
 // elu+1, 1/Z, GELU, residual adds) is fp32 on the CUDA cores.
 //
-// Work decomposition: one CTA = one tile of 128 tokens of one image; 18 warps:
+// Work decomposition: one CTA = one tile of 128 token rows (of one image, or of two consecutive images with the flat
+// tiling, see tc_tiles.cuh); 18 warps:
 //   warps 0-15  "row" warps: thread <-> (token row, one quarter of the columns).  Warp w owns TMEM lanes
 //               32*(w%4).. and the 32-column chunks {w/4, w/4+4}.  The fp32 residual stream of the tile lives in
 //               their REGISTERS (64 per thread) for the whole kernel.
