@@ -15,7 +15,7 @@ EXPORTS = (
     "oetr_workspace_bytes", "oetr_forward", "oetr_forward_masked", "oetr_last_launch_count", "oetr_poll_error", "oetr_forward_host",
     "oetr_forward_host_submit", "oetr_forward_host_wait",
     "oetr_profile_enable", "oetr_profile_read", "oetr_set_chunk_pairs",
-    "oetr_selftest_tcgen05", "oetr_selftest_geometry",
+    "oetr_selftest_tcgen05", "oetr_selftest_geometry", "oetr_debug_cycles",
 )
 
 
@@ -71,6 +71,8 @@ def load_library(path=None):
     lib.oetr_forward_host_wait.argtypes = [vp, c.c_int, vp, vp]
     lib.oetr_selftest_geometry.restype = c.c_int
     lib.oetr_selftest_geometry.argtypes = [c.c_int] * 5 + [c.POINTER(c.c_int)]
+    lib.oetr_debug_cycles.restype = c.c_int
+    lib.oetr_debug_cycles.argtypes = [c.POINTER(c.c_ulonglong), c.c_int, c.c_int]
     lib.oetr_selftest_tcgen05.restype = c.c_int
     lib.oetr_selftest_tcgen05.argtypes = [f32p, c.c_int]
     if path == LIB_PATH:

@@ -412,7 +412,7 @@ static int chunk_plan(const oetr_handle* h, int B, int L1, int L2, int* sizes) {
         cp = (2 * 56 + tiles16 / 2) / (tiles16 > 0 ? tiles16 : 1);
         if (cp < 1) cp = 1;
     }
-    if (h->prec == OETR_PREC_FP16 && cp > 0 && B > cp && !tc_pair_kernel_selected())
+    if (h->prec == OETR_PREC_FP16 && cp > 0 && B > cp)
         n = (B + cp - 1) / cp;
     if (n > MAX_CHUNKS) n = MAX_CHUNKS;
     for (int i = 0; i < n; ++i) sizes[i] = B / n + (i < B % n ? 1 : 0);
@@ -799,6 +799,11 @@ int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat
                                       img_w2, clamp, stream, &ticket);
     if (rc) return rc;
     return oetr_forward_host_wait(h, ticket, boxes1_host, boxes2_host);
+}
+
+int oetr_debug_cycles(unsigned long long* out, int n, int reset) {
+    if (!out || n < 1) return fail(OETR_E_ARG, "oetr_debug_cycles: bad arguments");
+    return tc_debug_read(out, n, reset);
 }
 
 int oetr_selftest_geometry(int batch, int hf1, int wf1, int hf2, int wf2, int* flat_tiles) {

@@ -12,7 +12,7 @@ using namespace tc;
 // ---------------------------------------------------------------------------------------------------------
 struct EncParams {
     TileGeom g;
-    EncGeom eg;                 // row mapping of the tiles (k_enc only; k_enc2 always uses the per-image tiles of g)
+    EncGeom eg;                 // row mapping of the tiles
     const float* feat1;         // NCHW inputs, read when load_feat
     const float* feat2;
     float* xt;                  // tile-blocked residual stream (read unless load_feat; written when store_x)
@@ -33,7 +33,7 @@ struct EncParams {
     const __half* w_kv;         // Wv | Wk                    (32 stages)
     float* kv_part;             // [tiles][KVS] per-tile partial summaries
     int* flag;
-    long long* dbg_clock;       // nullable: per CTA {total, MMA wait on operand image, MMA wait on weights, 0} cycles
+    unsigned long long* dbg_acc;   // nullable: global cycle accumulators (OETR_TIMING=1), see DBG_* in tc_tiles.cuh
     // L2 prefetch: every layer's weights are read once per forward, so without it each stage is a DRAM-latency
     // miss for the whole first wave.  The grid spreads these ranges (the NEXT launch's weights) in 16 KB pieces.
     const void* pf_ptr[3];
@@ -115,9 +115,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     umma_commit(&bars->s_full[half]);
                 }
             }
-            if (p.dbg_clock) {
-                long long* o = p.dbg_clock + (size_t)blockIdx.x * 4;
-                o[0] = clock64() - t_begin; o[1] = ms.t_a; o[2] = ms.t_ring; o[3] = 0;
+            if (p.dbg_acc) {
+                atomicAdd(p.dbg_acc + DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
+                atomicAdd(p.dbg_acc + DBG_MMA_WAIT_A, (unsigned long long)ms.t_a);
+                atomicAdd(p.dbg_acc + DBG_MMA_WAIT_W, (unsigned long long)ms.t_ring);
+                atomicAdd(p.dbg_acc + DBG_TILES, 1ull);
             }
         }
         __syncwarp();
@@ -141,6 +143,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         const bool has_mask = maskp != nullptr;
         const float mrow = (has_mask && valid) ? __ldg(maskp + (size_t)rb * et.L + rl) : 1.f;
         uint32_t ns0 = 0, ns1 = 0;
+        long long t_prev = clock64();
+        auto stamp = [&](int i) {                         // OETR_TIMING=1: stage durations of row-warp thread 0
+            if (p.dbg_acc && tid == 0) {
+                const long long t = clock64();
+                atomicAdd(p.dbg_acc + DBG_STAGE0 + i, (unsigned long long)(t - t_prev));
+                t_prev = t;
+            }
+        };
         auto wait_s = [&](int b) {
             mbar_wait(&bars->s_full[b], (b ? ns1++ : ns0++) & 1, p.flag);
             tc_fence_after();
@@ -223,9 +233,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             }
         };
 
+        stamp(0);
         if (p.do_q) {
             // (E0) A = LNq(x) + pos
             image_from_x(p.lnq_g, p.lnq_b, true);
+            stamp(1);
             // Ksum of the source image -> X (every thread is done with gamma/beta after the barrier)
             named_bar_sync(1, N_ROW_THREADS);
             if (tid < 256 || two) X[tid] = __ldg(p.ksum + (size_t)(src_img + (tid >> 8)) * C + (tid & 255));   // [256, 512): second image
@@ -233,6 +245,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             const float* Xk = X + rel * 256;
             // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
             wait_s(0);
+            stamp(2);
             const float eps_s = ATTN_EPS / (float)src_len;    // summaries arrive scaled by 1/S (k_fold)
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
@@ -259,9 +272,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 store_row32_split(img_hi, img_lo, r, c0, v);
                 publish(pass);
             }
+            stamp(3);
             // (E2) x += msg ; A = LN2(x)   (two-image tile: rows of the second image take the product with its M_img, S0)
             wait_s(1);
             if (two) wait_s(0);
+            stamp(4);
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 float v[32];
@@ -276,11 +291,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
             }
             image_from_x(p.ln2_g, p.ln2_b, false);
+            stamp(5);
             // (E3) A = gelu(h_a): needs h_a (S0) and, for the image to be free, h_b complete (S1)
             // (E4) A = gelu(h_b): the image is free once y = gelu(h_a) W2a^T has completed (S0 commit)
 #pragma unroll 1
             for (int which = 0; which < 2; ++which) {
-                if (which == 0) wait_s(0);
+                if (which == 0) { wait_s(0); stamp(6); }
                 const uint32_t S = which ? S1 : S0;
 #pragma unroll 1
                 for (int pass = 0; pass < 2; ++pass) {
@@ -298,9 +314,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     store_row32_split(img_hi, img_lo, r, c0, v);
                 }
                 publish(1);
+                stamp(7 + which);
             }
             // (E5) x += y
             wait_s(0);
+            stamp(9);
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 float v[32];
@@ -320,9 +338,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                         make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
             }
         }
+        stamp(10);
         if (p.do_kv) {
             if (!dec_mode) {
                 image_from_x(p.lnkv_g, p.lnkv_b, true);        // k and v share LN_kv(x)+pos (transformer.py:119-126)
+                stamp(11);
                 wait_s(0);
                 wait_s(1);
             } else {
@@ -331,6 +351,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 image_from_x(nullptr, nullptr, true);          // k = (x+pos) Wk^T + bk
                 wait_s(1);
             }
+            stamp(12);
             // half images (tokens = K dimension): V and Kf = elu(k)+1; padded rows are zero
             // partial summaries of this tile: one slot per image of the tile when the tiling is flat
             float* part = p.kv_part + (size_t)blockIdx.x * (p.eg.flat ? 2 : 1) * KVS;
@@ -393,8 +414,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     named_bar_sync(1, N_ROW_THREADS);
                 }
             }
+            stamp(13);
             // results: KV diagonal blocks (this warp's TMEM lanes are the d-channels of head 4*half + q)
             wait_s(1);
+            stamp(14);
             if (cq < 2) {
                 const int half = cq, h = half * 4 + q;
                 for (int im = 0; im < (two ? 2 : 1); ++im) {
@@ -406,6 +429,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 }
             }
             tc_fence_before();
+            stamp(15);
         }
     }
     // teardown

@@ -48,7 +48,7 @@ struct ConvParams {
     float* Y;                   // token-major [B*L1 + B*L2][256]
     float* gstat;               // [tiles][32 groups][2]: per-tile GroupNorm partials (mean, M2) over the valid rows
     int* flag;
-    long long* dbg_clock;       // nullable, like EncParams::dbg_clock
+    unsigned long long* dbg_acc;   // nullable, like EncParams::dbg_acc (slots 24..27)
 };
 
 __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
@@ -72,9 +72,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
             const long long t_begin = clock64();
             for (int tap = 0; tap < 9; ++tap) gemm_issue(smem_base, bars, p.flag, ms, S0, tap > 0, true, true);
             umma_commit(&bars->s_full[0]);
-            if (p.dbg_clock) {
-                long long* o = p.dbg_clock + (size_t)blockIdx.x * 4;
-                o[0] = clock64() - t_begin; o[1] = ms.t_a; o[2] = ms.t_ring; o[3] = 0;
+            if (p.dbg_acc) {
+                atomicAdd(p.dbg_acc + 24, (unsigned long long)(clock64() - t_begin));
+                atomicAdd(p.dbg_acc + 25, (unsigned long long)ms.t_a);
+                atomicAdd(p.dbg_acc + 26, (unsigned long long)ms.t_ring);
+                atomicAdd(p.dbg_acc + 27, 1ull);
             }
         }
         __syncwarp();

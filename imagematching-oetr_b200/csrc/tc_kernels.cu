@@ -29,17 +29,17 @@
 // Files (one translation unit -- the kernels are launched from the host code at the end of this file):
 //   tc_common.cuh     sm_100a primitives (mbarrier, bulk TMA, TMEM, UMMA descriptors, swizzled slabs)
 //   tc_tiles.cuh      tile constants, shared-memory map, operand-image stores, tile geometry, producer / MMA issue
-//   tc_enc.cuh        k_enc            tc_enc_pairs.cuh  k_enc2 (experimental CTA pairs)
+//   tc_enc.cuh        k_enc
 //   tc_head.cuh       k_att, k_conv, k_logits, k_box, k_decoder
 //   tc_kernels.cu     weight images, k_fold, layout kernels, workspace, launch sequences, self-tests
 #include "tc_tiles.cuh"
 #include "tc_enc.cuh"
-#include "tc_enc_pairs.cuh"
 #include "tc_head.cuh"
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace oetr {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
     __shared__ __align__(16) float kvT[HD][HD + 4];        // [e][d]
     const int img = blockIdx.x >> 3, h = blockIdx.x & 7;
     const int set = img / g.B, b = img % g.B;
-    // the image's partial summaries (per tile; k_enc2: per CTA of a pair; flat tiling: per (tile, image)), fixed order
+    // the image's partial summaries (per tile; flat tiling: per (tile, image)), fixed order
     const int T = enc_parts(g, eg, ppt, set, b);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // both summaries are scaled by 1/S (S = source length) like the reference's v / v_length
@@ -269,7 +269,7 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
     };
     w.xt = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));
     w.xt_enc = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));      // flat tiles <= per-image tiles
-    w.kv_part = static_cast<float*>(take((size_t)g.tiles() * 2 * KVS * sizeof(float)));   // k_enc2: one partial per CTA of a pair
+    w.kv_part = static_cast<float*>(take((size_t)g.tiles() * 2 * KVS * sizeof(float)));   // flat tiling: one partial per (tile, image)
     w.dec_kvs = static_cast<float*>(take((size_t)N_DEC * 2 * B * KVS * sizeof(float)));
     w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
     w.ksum = static_cast<float*>(take((size_t)2 * B * C * sizeof(float)));
@@ -279,41 +279,53 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
     w.tlbr = static_cast<float*>(take((size_t)2 * B * 4 * sizeof(float)));
 }
 
-static bool g_attr_set = false;
+// cudaFuncSetAttribute is per device (per context): opt every device in once, under a mutex (oetr_forward may be
+// called from several threads, and one process may hold handles on several GPUs)
+static std::mutex g_attr_mu;
+static bool g_attr_set[64] = {};
 static int set_attrs(char* msg, size_t msg_len) {
-    if (g_attr_set) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { snprintf(msg, msg_len, "cudaGetDevice failed"); return -1; }
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    if (g_attr_set[dev]) return 0;
     cudaError_t e1 = cudaFuncSetAttribute(k_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_enc2, cudaFuncAttributeMaxDynamicSharedMemorySize, E2_TOTAL);
-    // two CTAs per SM need the full shared-memory carve-out (the driver sizes it for ONE block otherwise)
-    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_enc2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_decoder, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
     if (e1 != cudaSuccess) {
         snprintf(msg, msg_len, "cudaFuncSetAttribute(max dynamic smem %u): %s", SM_TOTAL, cudaGetErrorString(e1));
         return -1;
     }
-    if (getenv("OETR_TIMING")) {
-        int nb = 0, nc = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_enc2, E2_THREADS, E2_TOTAL);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(512); cfg.blockDim = dim3(E2_THREADS); cfg.dynamicSmemBytes = E2_TOTAL;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, k_enc2, &cfg);
-        fprintf(stderr, "[oetr timing] k_enc2 occupancy: %d blocks/SM, %d active clusters (%s), smem %u B\n", nb, nc,
-                cudaGetErrorString(e), E2_TOTAL);
-    }
-    g_attr_set = true;
+    g_attr_set[dev] = true;
     return 0;
+}
+
+// OETR_TIMING=1: device-side cycle accumulators (DBG_* in tc_tiles.cuh), one buffer per process, no host synchronisation
+static unsigned long long* g_dbg_acc = nullptr;
+static unsigned long long* dbg_acc_buffer() {
+    static const bool on = getenv("OETR_TIMING") != nullptr;
+    if (!on) return nullptr;
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    if (!g_dbg_acc) {
+        if (cudaMalloc(&g_dbg_acc, DBG_SLOTS * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+        cudaMemset(g_dbg_acc, 0, DBG_SLOTS * sizeof(unsigned long long));
+    }
+    return g_dbg_acc;
+}
+int tc_debug_read(unsigned long long* out, int n, int reset) {
+    if (!g_dbg_acc) return 0;
+    if (n > DBG_SLOTS) n = DBG_SLOTS;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_dbg_acc, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(g_dbg_acc, 0, DBG_SLOTS * sizeof(unsigned long long));
+    return n;
 }
 
 // flat encoder tiling (EncGeom): on unless OETR_FLAT=0; needs both maps to have >= 128 tokens (a tile then holds at
 // most two images) and the one-CTA-per-tile kernel
-static EncGeom make_enc_geom(int B, int L1, int L2, bool pairs) {
+static EncGeom make_enc_geom(int B, int L1, int L2) {
     static const bool off = getenv("OETR_FLAT") && atoi(getenv("OETR_FLAT")) == 0;
     EncGeom eg{};
-    if (off || pairs || L1 < 128 || L2 < 128) return eg;
+    if (off || L1 < 128 || L2 < 128) return eg;
     eg.flat = 1;
     eg.Lp1 = (L1 + 15) / 16 * 16; eg.Lp2 = (L2 + 15) / 16 * 16;
     eg.F1 = (B * eg.Lp1 + TILE - 1) / TILE; eg.F2 = (B * eg.Lp2 + TILE - 1) / TILE;
@@ -325,7 +337,7 @@ static EncGeom make_enc_geom(int B, int L1, int L2, bool pairs) {
 // pairs that hold rows of it.  Used by the CPU test suite (no GPU needed).
 int tc_check_geometry(int B, int L1, int L2, char* msg, size_t msg_len) {
     const TileGeom g = make_geom(B, L1, L2);
-    const EncGeom eg = make_enc_geom(B, L1, L2, false);
+    const EncGeom eg = make_enc_geom(B, L1, L2);
     const int tiles = eg.flat ? eg.F1 + eg.F2 : g.tiles();
     const int ppt = eg.flat ? 2 : 1;
     std::vector<int> hits((size_t)B * (L1 + L2), 0);
@@ -361,11 +373,6 @@ int tc_check_geometry(int B, int L1, int L2, char* msg, size_t msg_len) {
     return eg.flat ? tiles : -2 - tiles;     // > 0: flat tiles; <= -2: per-image tiling with (-ret - 2) tiles
 }
 
-bool tc_pair_kernel_selected() {
-    static const bool pairs = getenv("OETR_ENC") && atoi(getenv("OETR_ENC")) == 2;
-    return pairs;
-}
-
 size_t tc_pos_tile_floats(int L) { return (size_t)((L + TILE - 1) / TILE) * TILE * C; }
 void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cudaStream_t s, LaunchCounter& lc) {
     k_pos_tiles<<<(L + TILE - 1) / TILE, 256, 0, s>>>(d_pe, max_w, wf, L, post);
@@ -380,27 +387,12 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
     const int L1 = hf1 * wf1, L2 = hf2 * wf2;
     const TileGeom g = make_geom(B, L1, L2);
     const int tiles = g.tiles();
-    // OETR_TIMING=1: print where the MMA thread of encoder layer 4 waits (debugging aid; synchronises)
-    static long long* dbg_clock_buf = nullptr;
-    static int dbg_clock_tiles = 0;
-    long long* dbg_clock = nullptr;
-    if (getenv("OETR_TIMING")) {
-        if (dbg_clock_tiles < tiles) { cudaFree(dbg_clock_buf); cudaMalloc(&dbg_clock_buf, (size_t)tiles * 4 * sizeof(long long)); dbg_clock_tiles = tiles; }
-        dbg_clock = dbg_clock_buf;
-    }
-    // OETR_ENC=2 selects the experimental CTA-pair kernel (k_enc2, see its header: correct, but slower than k_enc
-    // as measured in round 1); default: one CTA per tile (k_enc)
-    static const bool pairs = tc_pair_kernel_selected();
-    if (pairs && (mask1 || mask2)) {
-        snprintf(msg, msg_len, "masks are not implemented in the experimental CTA-pair kernel (OETR_ENC=2)");
-        return -1;
-    }
-    const EncGeom eg = make_enc_geom(B, L1, L2, pairs);
-    const int ppt = (pairs || eg.flat) ? 2 : 1;
+    unsigned long long* dbg_acc = dbg_acc_buffer();
+    const EncGeom eg = make_enc_geom(B, L1, L2);
+    const int ppt = eg.flat ? 2 : 1;
     const int enc_tiles = eg.flat ? eg.F1 + eg.F2 : tiles;
     auto launch_enc = [&](const EncParams& p) {
-        if (pairs) k_enc2<<<2 * tiles, E2_THREADS, E2_TOTAL, s>>>(p);
-        else k_enc<<<enc_tiles, N_THREADS, SM_TOTAL, s>>>(p);
+        k_enc<<<enc_tiles, N_THREADS, SM_TOTAL, s>>>(p);
         lc.n++;
     };
     EncParams base{};
@@ -448,7 +440,7 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         p.w_q = img; p.w_mlp = img + GEMM_HALFS;
         if (i + 1 < N_ENC) set_kv_enc(p, i + 1); else set_kv_dec(p, 0);
         set_prefetch_for(p, i + 1);
-        if (i == 4 && dbg_clock) p.dbg_clock = dbg_clock;
+        if (i + 1 < N_ENC) p.dbg_acc = dbg_acc;
         if (prof) prof->mark(s);
         launch_enc(p);
         if (prof) prof->mark(s);
@@ -464,15 +456,6 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
     }
     if (eg.flat) { k_retile<<<tiles, 256, 0, s>>>(ws.xt_enc, g, eg, ws.xt); lc.n++; }
     if (X_out) { k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++; }
-    if (dbg_clock) {
-        std::vector<long long> hbuf((size_t)tiles * 4);
-        cudaStreamSynchronize(s);
-        cudaMemcpy(hbuf.data(), dbg_clock, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double sum[3] = {0, 0, 0};
-        for (int t = 0; t < tiles; ++t) for (int k = 0; k < 3; ++k) sum[k] += (double)hbuf[(size_t)t * 4 + k];
-        fprintf(stderr, "[oetr timing] layer 4, %d tiles: MMA thread total %.0f cycles, waiting on operand image %.0f, on weights %.0f (means)\n",
-                tiles, sum[0] / tiles, sum[1] / tiles, sum[2] / tiles);
-    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(msg, msg_len, "tcgen05 encoder launch: %s", cudaGetErrorString(e));
@@ -505,22 +488,8 @@ int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, con
     ConvParams cp{};
     cp.g = g; cp.hf1 = hg.hf1; cp.wf1 = hg.wf1; cp.hf2 = hg.hf2; cp.wf2 = hg.wf2; cp.xt = ws.xt; cp.att = ws.att;
     cp.w = tw.head_img; cp.bias = d_w + L.hm_b0; cp.Y = Y; cp.gstat = ws.gstat; cp.flag = flag;
-    static long long* conv_clock = nullptr;
-    static int conv_clock_tiles = 0;
-    if (getenv("OETR_TIMING")) {
-        if (conv_clock_tiles < g.tiles()) { cudaFree(conv_clock); cudaMalloc(&conv_clock, (size_t)g.tiles() * 4 * sizeof(long long)); conv_clock_tiles = g.tiles(); }
-        cp.dbg_clock = conv_clock;
-    }
+    cp.dbg_acc = dbg_acc_buffer();
     k_conv<<<g.tiles(), N_THREADS, SM_TOTAL, s>>>(cp); lc.n++;
-    if (cp.dbg_clock) {
-        std::vector<long long> hbuf((size_t)g.tiles() * 4);
-        cudaStreamSynchronize(s);
-        cudaMemcpy(hbuf.data(), conv_clock, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double sum[3] = {0, 0, 0};
-        for (int t = 0; t < g.tiles(); ++t) for (int k = 0; k < 3; ++k) sum[k] += (double)hbuf[(size_t)t * 4 + k];
-        fprintf(stderr, "[oetr timing] k_conv, %d tiles: MMA thread total %.0f cycles, waiting on operand image %.0f, on weights %.0f (means)\n",
-                g.tiles(), sum[0] / g.tiles(), sum[1] / g.tiles(), sum[2] / g.tiles());
-    }
     k_logits<<<g.tiles(), 256, 0, s>>>(Y, ws.gstat, g, d_w + L.hm_gn_g, d_w + L.hm_gn_b, d_w + L.hm_w3, d_w + L.hm_b3, ws.z); lc.n++;
     BoxParams bp{};
     bp.g = g; bp.hf1 = hg.hf1; bp.wf1 = hg.wf1; bp.hf2 = hg.hf2; bp.wf2 = hg.wf2;

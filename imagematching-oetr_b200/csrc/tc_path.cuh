@@ -50,8 +50,8 @@ int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, Tc
 void tc_free_weights(TcWeights& w);
 // runs the 8 encoder layers and the decoder's cross-attention K/V summaries; writes token-major memory to X_out
 // tile-blocked positional rows of one (hf,wf) geometry (cached by the handle, see oetr_abi.cu)
-// OETR_ENC=2: the experimental CTA-pair encoder kernel is in use (sub-batch scheduling is then switched off)
-bool tc_pair_kernel_selected();
+// OETR_TIMING=1: copies the device-side cycle accumulators (DBG_* in tc_tiles.cuh) to out; returns the slots copied
+int tc_debug_read(unsigned long long* out, int n, int reset);
 // host-only consistency check of the encoder tiling; returns the number of flat tiles (> 0), -2 - tiles for the
 // per-image tiling, or -1 with a message
 int tc_check_geometry(int B, int L1, int L2, char* msg, size_t msg_len);

@@ -45,6 +45,9 @@ static_assert(sizeof(uint64_t) * (2 * RING + 6) + 8 <= 256, "Bars must fit its r
 constexpr uint32_t KF_OFF = 0;                                     // Kf half image: 2 slabs (32 KB) inside hi / lo
 constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
 
+// OETR_TIMING=1: global cycle accumulators of the k_enc launches with a query and a source phase (atomicAdd per CTA)
+enum { DBG_MMA_TOTAL = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_W = 2, DBG_TILES = 3, DBG_STAGE0 = 8, DBG_SLOTS = 32 };
+
 struct Bars {
     uint64_t full[RING], empty[RING];
     uint64_t a_full[2];   // row warps -> MMA: column pass p of the operand image written (count 512)

@@ -183,6 +183,11 @@ OETR_API int oetr_forward_host(oetr_handle* h,
  * Returns OETR_OK when the kernels ran (inspect errs for the numeric outcome). */
 OETR_API int oetr_selftest_tcgen05(float* errs_host, int n_errs);
 
+/* Debugging aid (OETR_TIMING=1 in the environment at the first forward): copies up to n device-side cycle
+ * accumulators of the tcgen05 kernels (MMA-lane busy / wait cycles, row-warp stage durations) to out and optionally
+ * resets them.  Returns the number of slots copied (0 when timing is off).  Synchronises the device. */
+OETR_API int oetr_debug_cycles(unsigned long long* out, int n, int reset);
+
 /* Host-only (no GPU needed) consistency check of the encoder's tile geometry for a problem size: every token is one
  * row of exactly one 128-token tile and the partial attention summaries gathered per image are exactly those of the
  * tiles holding its rows.  *flat_tiles = number of tiles of the flat tiling, 0 when per-image tiles are used (maps
