@@ -75,6 +75,7 @@ struct oetr_handle {
     std::mutex mu;             // fork/launch/join section (the events are shared by all callers of this handle)
     WLayout L;
     float* d_w = nullptr;      // packed fp32 weights (canonical order)
+    std::vector<float> h_w;    // host copy (LayerNorm vectors / biases travel to the kernels as launch parameters)
     float* d_w9 = nullptr;     // heatmap_conv.0.weight repacked per tap: [9][256 out][256 in]
     float* d_pe = nullptr;     // PositionEncodingSine table, channel-last: [max_h][max_w][256]
     TcWeights tc;              // fp16 UMMA operand images (FP16 path only)
@@ -332,6 +333,8 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
     CUH(cudaMalloc(&h->d_w, L.total * sizeof(float)));
     CUH(cudaMemcpy(h->d_w, weights, L.total * sizeof(float),
                    weights_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    h->h_w.resize(L.total);
+    CUH(cudaMemcpy(h->h_w.data(), h->d_w, L.total * sizeof(float), cudaMemcpyDeviceToHost));
     CUH(cudaMalloc(&h->d_w9, (size_t)9 * C * C * sizeof(float)));
     k_repack_conv<<<(9 * C * C + 255) / 256, 256>>>(h->d_w + L.hm_w0, h->d_w9);
     std::vector<float> pe;
@@ -513,7 +516,7 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
         // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
         // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
         char msg[256] = "";
-        if (tc_encoder(h->tc, h->d_w, h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
+        if (tc_encoder(h->tc, h->d_w, h->h_w.data(), h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
                        a.mask1, a.mask2,
                        a.dbg_memory ? w.X : nullptr, h->d_flag, profile ? &h->prof : nullptr, s, lc, msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);

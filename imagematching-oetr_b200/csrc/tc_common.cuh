@@ -41,22 +41,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
-// Bounded wait: a protocol bug must never hang the GPU.  On timeout the flag is raised and the wait returns;
-// results are then garbage and the host reports the failure.
+// Bounded wait: a protocol bug must never hang the GPU.  On timeout the flag (nullable) is raised for the host's
+// diagnostics and the kernel TRAPS: the launch fails with a CUDA error that every later call on the context reports,
+// so garbage results can never be returned silently (and a stale flag cannot shorten the waits of later launches).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* timeout_flag) {
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(a), "r"(parity)
             : "memory");
         if (done) return;
-        // somebody already timed out: the launch is lost anyway, drain quickly
-        if ((spin & 1023) == 1023 && timeout_flag && *reinterpret_cast<volatile int*>(timeout_flag)) return;
     }
     if (timeout_flag) atomicExch(timeout_flag, 1);
+    __threadfence_system();
+    __trap();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -133,6 +134,27 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
         "r"(__float_as_uint(v[31]))
         : "memory");
+}
+// 32 lanes x 2 columns (row-statistics exchange between the four column-quarter threads of a token row)
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)),
+                 "r"(__float_as_uint(b))
+                 : "memory");
+}
+// four 2-column loads (columns c, c+32, c+64, c+96 of the thread's lane) completed by one wait
+__device__ __forceinline__ void tmem_ld2x4(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%8];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%2,%3}, [%9];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%4,%5}, [%10];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%6,%7}, [%11];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr), "r"(taddr + 32), "r"(taddr + 64), "r"(taddr + 96)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

@@ -10,6 +10,10 @@ using namespace tc;
 // ---------------------------------------------------------------------------------------------------------
 // k_enc
 // ---------------------------------------------------------------------------------------------------------
+// Operand precision per contraction (tests/precision_map.py; box error of the whole map 5e-5 of the image side):
+//   q = (LNq(x)+pos) Wq^T            1 term   (a hi, w hi)          k = (LNkv(x)+pos) Wk^T   2 terms (a split, w hi)
+//   v, merge, W1, W2, K^T V          3 terms  (both split)
+//   decoder: v = x Wv^T              2 terms  (a hi, w split)       k = (x+pos) Wk^T 1 term; K^T V 1 term
 struct EncParams {
     TileGeom g;
     EncGeom eg;                 // row mapping of the tiles
@@ -21,33 +25,35 @@ struct EncParams {
                                 // and v (linear_attention.py:36-41; k and v of a row always belong to its own image)
     int load_feat, store_x, do_q, do_kv;
     // query phase (encoder layer i)
-    const float *lnq_g, *lnq_b, *ln2_g, *ln2_b;
-    const __half* w_q;          // Wq                         (16 stages)
-    const __half* w_mlp;        // W1a | W1b | W2a | W2b      (64 stages)
+    const __half* w_q;          // Wq                         (hi units only)
+    const __half* w_mlp;        // W1a | W1b | W2a | W2b      (4 GEMM images)
     const __half* mimg;         // [2B images][GEMM_HALFS] folded merge weights of the source image
     const float* ksum;          // [2B images][256]
     int cross;                  // 1: the source is the partner image (transformer.py:354-358)
-    // kv phase (encoder layer i+1, or a decoder layer's cross-attention when lnkv_g == nullptr)
-    const float *lnkv_g, *lnkv_b;   // nullptr: decoder mode: k = (x+pos) Wk^T + bk, v = x Wv^T + bv
-    const float *bk, *bv;
-    const __half* w_kv;         // Wv | Wk                    (32 stages)
-    float* kv_part;             // [tiles][KVS] per-tile partial summaries
+    // kv phase (encoder layer i+1, or a decoder layer's cross-attention when dec_mode)
+    int dec_mode;               // decoder: k = (x+pos) Wk^T + bk, v = x Wv^T + bv, no LayerNorm (transformer.py:243-249)
+    const __half* w_kv;         // Wv | Wk
+    float* kv_part;             // [tiles][ppt][PART_FLOATS] per-tile partial summaries
     int* flag;
     unsigned long long* dbg_acc;   // nullable: global cycle accumulators (OETR_TIMING=1), see DBG_* in tc_tiles.cuh
     // L2 prefetch: every layer's weights are read once per forward, so without it each stage is a DRAM-latency
     // miss for the whole first wave.  The grid spreads these ranges (the NEXT launch's weights) in 16 KB pieces.
     const void* pf_ptr[3];
     uint32_t pf_bytes[3];
+    // LayerNorm vectors and decoder biases travel in the kernel parameters (constant bank): every lane of a warp
+    // reads the same column's value, and nothing has to be staged through shared memory (which is full)
+    float lnq_g[C], lnq_b[C], ln2_g[C], ln2_b[C];
+    float lnkv_g[C], lnkv_b[C];     // dec_mode: bv | bk
 };
 
-__global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
+__global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ EncParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const EncTile et = enc_tile(p.g, p.eg, blockIdx.x);
     const bool two = et.two != 0;                      // the tile holds rows of two images (flat tiling only)
     const uint32_t smem_base = smem_u32(smem);
-    const bool dec_mode = p.lnkv_g == nullptr;
+    const bool dec_mode = p.dec_mode != 0;
 
     const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
     const uint32_t S0 = tmem, S1 = tmem + 256;
@@ -57,21 +63,31 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
     if (p.cross) { src_img = et.set == 0 ? p.g.B + et.b0 : et.b0; src_len = et.set == 0 ? p.g.L2 : p.g.L1; }
 
     if (warp == WARP_PRODUCER) {
-        // ------------------------------------------------------------------ weight stream
+        // ------------------------------------------------------------------ residual stream + weight stream
         if (lane == 0) {
+            if (!p.load_feat) {   // the tile's residual stream [64 quads][128 rows][4] fp32 = 128 KB, into the (still free) image area
+                mbar_arrive_expect_tx(&bars->x_full, 2 * IMG_BYTES);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xt + xt_off(blockIdx.x, 0, 0));
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i)
+                    bulk_g2s(smem + SM_AHI + i * (IMG_BYTES / 2), src + (size_t)i * (IMG_BYTES / 2), IMG_BYTES / 2, &bars->x_full);
+            }
 #pragma unroll 1
             for (int k = 0; k < 3; ++k)
                 for (uint32_t off = blockIdx.x * STAGE_BYTES; off < p.pf_bytes[k]; off += gridDim.x * STAGE_BYTES)
                     bulk_prefetch_l2(static_cast<const uint8_t*>(p.pf_ptr[k]) + off, min(STAGE_BYTES, p.pf_bytes[k] - off));
             uint32_t g = 0;
-            auto stream = [&](const __half* src, int nstages) { ring_stream(smem, bars, p.flag, g, src, nstages); };
+            auto stream = [&](const __half* src, int nunits, int stride) { ring_stream(smem, bars, p.flag, g, src, nunits, stride); };
             if (p.do_q) {
-                stream(p.w_q, GEMM_STAGES);
-                stream(p.mimg + (size_t)src_img * GEMM_HALFS, GEMM_STAGES);
-                if (two) stream(p.mimg + (size_t)(src_img + 1) * GEMM_HALFS, GEMM_STAGES);
-                stream(p.w_mlp, 4 * GEMM_STAGES);
+                stream(p.w_q, 4, 4);                                                  // hi units only
+                stream(p.mimg + (size_t)src_img * GEMM_HALFS, 8, 2);
+                if (two) stream(p.mimg + (size_t)(src_img + 1) * GEMM_HALFS, 8, 2);
+                stream(p.w_mlp, 32, 2);
             }
-            if (p.do_kv) stream(p.w_kv, 2 * GEMM_STAGES);
+            if (p.do_kv) {
+                stream(p.w_kv, 8, 2);                                                 // Wv: hi and lo
+                stream(p.w_kv + GEMM_HALFS, 4, 4);                                    // Wk: hi only
+            }
         }
         __syncwarp();
     } else if (warp == WARP_MMA) {
@@ -80,28 +96,34 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             MmaState ms;
             const long long t_begin = clock64();
             auto wait_a = [&](int pass) { mma_wait_a(bars, p.flag, ms, pass); };
-            auto gemm = [&](uint32_t d, bool accumulate, bool wait) { gemm_issue(smem_base, bars, p.flag, ms, d, accumulate, wait, false); };
+            auto gemm = [&](uint32_t d, bool accumulate, bool wait, int terms) { gemm_issue(smem_base, bars, p.flag, ms, d, accumulate, wait, false, terms); };
             if (p.do_q) {
-                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
-                gemm(S1, false, true);  umma_commit(&bars->s_full[1]);     // msg = (phi(q)/Z) M_img^T
-                if (two) { gemm(S0, false, false); umma_commit(&bars->s_full[0]); }   // ... with the second image's M_img
-                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // h_a = LN2(x) W1a^T
-                gemm(S1, false, false); umma_commit(&bars->s_full[1]);     // h_b = LN2(x) W1b^T
-                gemm(S0, false, true);  umma_commit(&bars->s_full[0]);     // y   = gelu(h_a) W2a^T
-                gemm(S0, true, true);   umma_commit(&bars->s_full[0]);     // y  += gelu(h_b) W2b^T
+                gemm(S0, false, true, T_HH);   umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
+                gemm(S1, false, true, T_ALL);  umma_commit(&bars->s_full[1]);     // msg = (phi(q)/Z) M_img^T
+                if (two) { gemm(S0, false, false, T_ALL); umma_commit(&bars->s_full[0]); }   // ... with the second image's M_img
+                gemm(S0, false, true, T_ALL);  umma_commit(&bars->s_full[0]);     // h_a = LN2(x) W1a^T
+                gemm(S1, false, false, T_ALL); umma_commit(&bars->s_full[1]);     // h_b = LN2(x) W1b^T
+                gemm(S0, false, true, T_ALL);  umma_commit(&bars->s_full[0]);     // y   = gelu(h_a) W2a^T
+                gemm(S0, true, true, T_ALL);   umma_commit(&bars->s_full[0]);     // y  += gelu(h_b) W2b^T
             }
             if (p.do_kv) {
-                gemm(S0, false, true);      umma_commit(&bars->s_full[0]); // v
-                gemm(S1, false, dec_mode);  umma_commit(&bars->s_full[1]); // k (decoder: from a second image)
+                if (!dec_mode) {
+                    gemm(S0, false, true, T_ALL);           umma_commit(&bars->s_full[0]);   // v
+                    gemm(S1, false, false, T_HH | T_LH);    umma_commit(&bars->s_full[1]);   // k (same image)
+                } else {
+                    gemm(S0, false, true, T_HH | T_HL);     umma_commit(&bars->s_full[0]);   // v = x Wv^T
+                    gemm(S1, false, true, T_HH);            umma_commit(&bars->s_full[1]);   // k = (x+pos) Wk^T
+                }
                 // per 128-channel half: KV = Kf^T V (diagonal 32x32 blocks are the heads); Ksum is reduced by the row warps
                 // the token rows are the K dimension, 16 per MMA: a two-image tile splits the k-steps at the image
                 // boundary (a multiple of 16 rows) and accumulates the second image's product in S1's columns
                 const int ksplit = two ? et.split / 16 : TILE / 16;
+                const int nterms = dec_mode ? 1 : 3;
                 for (int half = 0; half < 2; ++half) {
                     wait_a(half);
                     const uint32_t kf_hi = smem_base + SM_AHI + KF_OFF, kf_lo = smem_base + SM_ALO + KF_OFF;
                     const uint32_t v_hi = smem_base + SM_AHI + V_OFF, v_lo = smem_base + SM_ALO + V_OFF;
-                    for (int term = 0; term < 3; ++term) {
+                    for (int term = 0; term < nterms; ++term) {
                         const uint32_t a = term == 1 ? kf_lo : kf_hi, bb = term == 2 ? v_lo : v_hi;
 #pragma unroll
                         for (int k = 0; k < TILE / 16; ++k) {
@@ -115,7 +137,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     umma_commit(&bars->s_full[half]);
                 }
             }
-            if (p.dbg_acc) {
+            if (p.dbg_acc && p.do_q && p.do_kv) {
                 atomicAdd(p.dbg_acc + DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
                 atomicAdd(p.dbg_acc + DBG_MMA_WAIT_A, (unsigned long long)ms.t_a);
                 atomicAdd(p.dbg_acc + DBG_MMA_WAIT_W, (unsigned long long)ms.t_ring);
@@ -135,7 +157,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         const int pl = valid ? rl : 0;                     // row of the position table
         const bool warp_has_rel1 = two && et.split < q * 32 + 32;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float* X = reinterpret_cast<float*>(smem + SM_X);       // 512-float scratch, see the shared-memory map
+        float* X = reinterpret_cast<float*>(smem + SM_X);       // 512-float scratch: Ksum of the source image(s)
         uint8_t* img_hi = smem + SM_AHI;
         uint8_t* img_lo = smem + SM_ALO;
         const float* post = (et.set == 0 ? p.post1 : p.post2);
@@ -145,7 +167,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
         uint32_t ns0 = 0, ns1 = 0;
         long long t_prev = clock64();
         auto stamp = [&](int i) {                         // OETR_TIMING=1: stage durations of row-warp thread 0
-            if (p.dbg_acc && tid == 0) {
+            if (p.dbg_acc && p.do_q && p.do_kv && tid == 0) {
                 const long long t = clock64();
                 atomicAdd(p.dbg_acc + DBG_STAGE0 + i, (unsigned long long)(t - t_prev));
                 t_prev = t;
@@ -160,54 +182,75 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
             fence_async_smem();
             mbar_arrive(&bars->a_full[pass]);
         };
+        // positional rows of this token: 8 x 16 bytes of column pass `pass` (tile-blocked table: coalesced per warp)
+        auto load_pos = [&](int pass, float4 (&ps)[8]) {
+            const int c0 = pass * 128 + cq * 32;
+#pragma unroll
+            for (int jq = 0; jq < 8; ++jq)
+                ps[jq] = __ldg(reinterpret_cast<const float4*>(post + xt_off(pl >> 7, (c0 >> 2) + jq, pl & 127)));
+        };
         // ---- the residual stream of this thread: columns [32*cq, +32) and [128 + 32*cq, +32) of row r
         float x[2][32];
+        if (p.load_feat) {
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int c0 = pass * 128 + cq * 32;
-            if (p.load_feat) {
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
                 const float* feat = et.set == 0 ? p.feat1 : p.feat2;
                 const float* f = feat + ((size_t)(valid ? rb : 0) * C + c0) * et.L + pl;
 #pragma unroll
                 for (int e = 0; e < 32; ++e) x[pass][e] = valid ? f[(size_t)e * et.L] : 0.f;
-            } else {
+            }
+        } else {
+            mbar_wait(&bars->x_full, 0, p.flag);           // the bulk copy has landed (complete_tx makes it visible)
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int quad0 = pass * 32 + cq * 8;
 #pragma unroll
                 for (int jq = 0; jq < 8; ++jq) {
-                    const float4 v = *reinterpret_cast<const float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r));
+                    const float4 v = *reinterpret_cast<const float4*>(smem + SM_AHI + ((size_t)(quad0 + jq) * TILE + r) * 16);
                     x[pass][jq * 4 + 0] = v.x; x[pass][jq * 4 + 1] = v.y; x[pass][jq * 4 + 2] = v.z; x[pass][jq * 4 + 3] = v.w;
                 }
             }
+            named_bar_sync(1, N_ROW_THREADS);              // every thread has its rows: the image area may be overwritten
         }
-        // two-pass LayerNorm statistics of the row (4 threads per row, combined through X), then (gamma | beta) are
-        // staged into X for the normalisation pass (their global loads are issued before the statistics)
-        auto ln_stats = [&](const float* __restrict__ gamma, const float* __restrict__ beta, float& mean, float& rstd) {
-            const float gb = tid < 256 ? __ldg(gamma + tid) : __ldg(beta + tid - 256);
+        // LayerNorm statistics of the row.  Each of the row's four threads (one per column quarter, in four different
+        // warps of the same TMEM lane quarter) reduces its 64 values exactly (local mean, local M2); the (mean, M2) pairs
+        // are exchanged through two TMEM columns per thread -- columns of accumulator `scr` that this thread has already
+        // consumed (its own chunk [32*cq, +32)) -- and merged with Chan's formula.  One 128-thread barrier per LayerNorm.
+        auto row_stats = [&](uint32_t scr, float& mean, float& rstd) {
             float s = 0.f;
 #pragma unroll
             for (int e = 0; e < 32; ++e) s += x[0][e] + x[1][e];
-            X[cq * TILE + r] = s;
-            named_bar_sync(1, N_ROW_THREADS);
-            mean = (X[0 * TILE + r] + X[1 * TILE + r] + X[2 * TILE + r] + X[3 * TILE + r]) * (1.f / C);
-            float sq = 0.f;
+            const float m_i = s * (1.f / 64.f);
+            float m2 = 0.f;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-                const float d0 = x[0][e] - mean, d1 = x[1][e] - mean;
-                sq = fmaf(d0, d0, sq);
-                sq = fmaf(d1, d1, sq);
+                const float d0 = x[0][e] - m_i, d1 = x[1][e] - m_i;
+                m2 = fmaf(d0, d0, m2);
+                m2 = fmaf(d1, d1, m2);
             }
-            named_bar_sync(1, N_ROW_THREADS);              // every thread has read the sums
-            X[cq * TILE + r] = sq;
-            named_bar_sync(1, N_ROW_THREADS);
-            const float var = (X[0 * TILE + r] + X[1 * TILE + r] + X[2 * TILE + r] + X[3 * TILE + r]) * (1.f / C);
-            rstd = rsqrtf(var + LN_EPS);
-            named_bar_sync(1, N_ROW_THREADS);
-            X[tid] = gb;                                   // X[0,256) = gamma, X[256,512) = beta
-            named_bar_sync(1, N_ROW_THREADS);
+            tmem_st2(scr + lane_addr + cq * 32, m_i, m2);
+            tmem_st_wait();
+            tc_fence_before();
+            named_bar_sync(2 + q, 128);
+            tc_fence_after();
+            float v[8];
+            tmem_ld2x4(scr + lane_addr, v);
+            mean = (v[0] + v[2] + v[4] + v[6]) * 0.25f;
+            float M2 = (v[1] + v[3]) + (v[5] + v[7]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float d = v[2 * i] - mean;
+                M2 = fmaf(64.f * d, d, M2);
+            }
+            rstd = rsqrtf(M2 * (1.f / C) + LN_EPS);
         };
-        // operand image <- [LN](x) [+ pos], both column passes (gamma == nullptr: no LayerNorm)
-        auto image_from_x = [&](const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos) {
-            float mean = 0.f, rstd = 1.f;
-            if (gamma) ln_stats(gamma, beta, mean, rstd);
+        // operand image <- LN(x) [+ pos], both column passes; split: (hi, lo) image, else one fp16 value per element
+        auto ln_image = [&](const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos, uint32_t scr, bool split) {
+            float4 ps[8];
+            if (with_pos) load_pos(0, ps);                 // in flight during the statistics
+            float mean, rstd;
+            row_stats(scr, mean, rstd);
             const float shift = -mean * rstd;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
@@ -215,33 +258,48 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 float v[32];
 #pragma unroll
                 for (int jq = 0; jq < 8; ++jq) {
-                    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (with_pos) ps = *reinterpret_cast<const float4*>(post + xt_off(pl >> 7, (c0 >> 2) + jq, pl & 127));
-                    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gamma) {
-                        g4 = *reinterpret_cast<const float4*>(X + c0 + jq * 4);
-                        b4 = *reinterpret_cast<const float4*>(X + 256 + c0 + jq * 4);
-                    }
+                    const float4 pz = with_pos ? ps[jq] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int c = c0 + jq * 4;
                     // (x - mean) * rstd * g + b + pos  ==  fma(fma(x, rstd, shift), g, b + pos)
-                    v[jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), g4.x, b4.x + ps.x);
-                    v[jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), g4.y, b4.y + ps.y);
-                    v[jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), g4.z, b4.z + ps.z);
-                    v[jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), g4.w, b4.w + ps.w);
+                    v[jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), gamma[c + 0], beta[c + 0] + pz.x);
+                    v[jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), gamma[c + 1], beta[c + 1] + pz.y);
+                    v[jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), gamma[c + 2], beta[c + 2] + pz.z);
+                    v[jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), gamma[c + 3], beta[c + 3] + pz.w);
                 }
-                store_row32_split(img_hi, img_lo, r, c0, v);
+                if (with_pos && pass == 0) load_pos(1, ps);    // in flight during the split + stores of pass 0
+                if (split) store_row32_split(img_hi, img_lo, r, c0, v);
+                else store_row32_hi(img_hi, r, c0, v);
+                publish(pass);
+            }
+        };
+        // operand image <- x [+ pos] (decoder K/V projections: no LayerNorm), one fp16 value per element
+        auto raw_image = [&](bool with_pos) {
+            float4 ps[8];
+            if (with_pos) load_pos(0, ps);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+                float v[32];
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq) {
+                    const float4 pz = with_pos ? ps[jq] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[jq * 4 + 0] = x[pass][jq * 4 + 0] + pz.x; v[jq * 4 + 1] = x[pass][jq * 4 + 1] + pz.y;
+                    v[jq * 4 + 2] = x[pass][jq * 4 + 2] + pz.z; v[jq * 4 + 3] = x[pass][jq * 4 + 3] + pz.w;
+                }
+                if (with_pos && pass == 0) load_pos(1, ps);
+                store_row32_hi(img_hi, r, c0, v);
                 publish(pass);
             }
         };
 
         stamp(0);
         if (p.do_q) {
-            // (E0) A = LNq(x) + pos
-            image_from_x(p.lnq_g, p.lnq_b, true);
-            stamp(1);
-            // Ksum of the source image -> X (every thread is done with gamma/beta after the barrier)
-            named_bar_sync(1, N_ROW_THREADS);
+            // Ksum of the source image(s) -> X (nobody else uses X during the query phase)
             if (tid < 256 || two) X[tid] = __ldg(p.ksum + (size_t)(src_img + (tid >> 8)) * C + (tid & 255));   // [256, 512): second image
-            named_bar_sync(1, N_ROW_THREADS);
+            // (E0) A = LNq(x) + pos   (one fp16 value per element: the q GEMM is a 1-term product)
+            ln_image(p.lnq_g, p.lnq_b, true, S0, false);
+            stamp(1);
+            named_bar_sync(1, N_ROW_THREADS);              // Ksum visible to every row thread
             const float* Xk = X + rel * 256;
             // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
             wait_s(0);
@@ -290,7 +348,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
             }
-            image_from_x(p.ln2_g, p.ln2_b, false);
+            ln_image(p.ln2_g, p.ln2_b, false, S1, true);
             stamp(5);
             // (E3) A = gelu(h_a): needs h_a (S0) and, for the image to be free, h_b complete (S1)
             // (E4) A = gelu(h_b): the image is free once y = gelu(h_a) W2a^T has completed (S0 commit)
@@ -327,6 +385,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                 for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
             }
             tc_fence_before();
+            stamp(10);
         }
         if (p.store_x) {
 #pragma unroll
@@ -338,34 +397,33 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                         make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
             }
         }
-        stamp(10);
+        stamp(11);
         if (p.do_kv) {
             if (!dec_mode) {
-                image_from_x(p.lnkv_g, p.lnkv_b, true);        // k and v share LN_kv(x)+pos (transformer.py:119-126)
-                stamp(11);
+                ln_image(p.lnkv_g, p.lnkv_b, true, S0, true);  // k and v share LN_kv(x)+pos (transformer.py:119-126)
+                stamp(12);
                 wait_s(0);
                 wait_s(1);
             } else {
-                image_from_x(nullptr, nullptr, false);         // v = x Wv^T + bv      (transformer.py:243-249)
+                raw_image(false);                              // v = x Wv^T + bv      (transformer.py:243-249)
                 wait_s(0);
-                image_from_x(nullptr, nullptr, true);          // k = (x+pos) Wk^T + bk
+                raw_image(true);                               // k = (x+pos) Wk^T + bk
                 wait_s(1);
             }
-            stamp(12);
+            stamp(13);
             // half images (tokens = K dimension): V and Kf = elu(k)+1; padded rows are zero
             // partial summaries of this tile: one slot per image of the tile when the tiling is flat
-            float* part = p.kv_part + (size_t)blockIdx.x * (p.eg.flat ? 2 : 1) * KVS;
+            float* part = p.kv_part + (size_t)blockIdx.x * (p.eg.flat ? 2 : 1) * PART_FLOATS;
+            const float* bvp = p.lnkv_g;                       // dec_mode: bv | bk ride in the lnkv slots
+            const float* bkp = p.lnkv_b;
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32, ch = cq * 32;      // ch: column inside the 128-channel half
                 float v[32];
                 tmem_ld32(S0 + lane_addr + c0, v);
-                if (p.bv) {
+                if (dec_mode) {
 #pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bv + c0) + e4);
-                        v[e4 * 4] += b4.x; v[e4 * 4 + 1] += b4.y; v[e4 * 4 + 2] += b4.z; v[e4 * 4 + 3] += b4.w;
-                    }
+                    for (int e = 0; e < 32; ++e) v[e] += bvp[c0 + e];
                 }
                 if (!valid) {
 #pragma unroll
@@ -375,22 +433,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                     for (int e = 0; e < 32; ++e) v[e] *= mrow;
                 }
                 if (pass == 1) wait_s(0);                               // KV of half 0 has consumed the images
-                store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
+                if (dec_mode) store_row32_hi(img_hi + V_OFF, r, ch, v);
+                else store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
                 tmem_ld32(S1 + lane_addr + c0, v);
-                if (p.bk) {
+                if (dec_mode) {
 #pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bk + c0) + e4);
-                        v[e4 * 4] += b4.x; v[e4 * 4 + 1] += b4.y; v[e4 * 4 + 2] += b4.z; v[e4 * 4 + 3] += b4.w;
-                    }
+                    for (int e = 0; e < 32; ++e) v[e] += bkp[c0 + e];
                 }
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = valid ? elu1(v[e]) * mrow : 0.f;
-                store_row32_split(img_hi + KF_OFF, img_lo + KF_OFF, r, ch, v);
+                if (dec_mode) store_row32_hi(img_hi + KF_OFF, r, ch, v);
+                else store_row32_split(img_hi + KF_OFF, img_lo + KF_OFF, r, ch, v);
                 publish(pass);
                 // Ksum[c0 + j] = sum over the tile's rows of Kf[:, c0 + j] (fp32, exact operands): butterfly
-                // transpose-reduce inside the warp (lane j ends with column j summed over the warp's 32 rows),
-                // then across the 4 row quarters through X; per image of the tile (rows of the other image masked)
+                // transpose-reduce inside the warp (lane j ends with column j summed over the warp's 32 rows); the four
+                // row quarters write their partial sums to four slots that k_fold / k_sum_partials add in fixed order
+                // (no barrier, deterministic); per image of the tile (rows of the other image masked)
 #pragma unroll 1
                 for (int im = 0; im < (two ? 2 : 1); ++im) {
                     float w[32];
@@ -406,30 +464,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const EncParams p) {
                             w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                         }
                     }
-                    X[(cq * 4 + q) * 32 + lane] = w[0];
-                    named_bar_sync(1, N_ROW_THREADS);
-                    if (q == 0)
-                        part[im * KVS + NH * HD * HD + c0 + lane] = X[(cq * 4 + 0) * 32 + lane] + X[(cq * 4 + 1) * 32 + lane] +
-                                                                    X[(cq * 4 + 2) * 32 + lane] + X[(cq * 4 + 3) * 32 + lane];
-                    named_bar_sync(1, N_ROW_THREADS);
+                    part[im * PART_FLOATS + NH * HD * HD + q * C + c0 + lane] = w[0];
                 }
             }
-            stamp(13);
+            stamp(14);
             // results: KV diagonal blocks (this warp's TMEM lanes are the d-channels of head 4*half + q)
             wait_s(1);
-            stamp(14);
+            stamp(15);
             if (cq < 2) {
                 const int half = cq, h = half * 4 + q;
                 for (int im = 0; im < (two ? 2 : 1); ++im) {
                     float v[32];
                     tmem_ld32((im ? S1 : S0) + lane_addr + half * 128 + q * 32, v);
-                    float* o = part + im * KVS + h * HD * HD + lane * HD;
+                    float* o = part + im * PART_FLOATS + h * HD * HD + lane * HD;
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
                 }
             }
             tc_fence_before();
-            stamp(15);
+            stamp(16);
         }
     }
     // teardown

@@ -48,7 +48,7 @@ struct ConvParams {
     float* Y;                   // token-major [B*L1 + B*L2][256]
     float* gstat;               // [tiles][32 groups][2]: per-tile GroupNorm partials (mean, M2) over the valid rows
     int* flag;
-    unsigned long long* dbg_acc;   // nullable, like EncParams::dbg_acc (slots 24..27)
+    unsigned long long* dbg_acc;   // nullable, like EncParams::dbg_acc (slots DBG_CONV..)
 };
 
 __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
     if (warp == WARP_PRODUCER) {
         if (lane == 0) {
             uint32_t g = 0;
-            ring_stream(smem, bars, p.flag, g, p.w, 9 * GEMM_STAGES);
+            ring_stream(smem, bars, p.flag, g, p.w, 9 * GEMM_STAGES / 2);
         }
         __syncwarp();
     } else if (warp == WARP_MMA) {
@@ -73,10 +73,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
             for (int tap = 0; tap < 9; ++tap) gemm_issue(smem_base, bars, p.flag, ms, S0, tap > 0, true, true);
             umma_commit(&bars->s_full[0]);
             if (p.dbg_acc) {
-                atomicAdd(p.dbg_acc + 24, (unsigned long long)(clock64() - t_begin));
-                atomicAdd(p.dbg_acc + 25, (unsigned long long)ms.t_a);
-                atomicAdd(p.dbg_acc + 26, (unsigned long long)ms.t_ring);
-                atomicAdd(p.dbg_acc + 27, 1ull);
+                atomicAdd(p.dbg_acc + DBG_CONV + 0, (unsigned long long)(clock64() - t_begin));
+                atomicAdd(p.dbg_acc + DBG_CONV + 1, (unsigned long long)ms.t_a);
+                atomicAdd(p.dbg_acc + DBG_CONV + 2, (unsigned long long)ms.t_ring);
+                atomicAdd(p.dbg_acc + DBG_CONV + 3, 1ull);
             }
         }
         __syncwarp();

@@ -39,6 +39,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -143,14 +144,17 @@ __global__ void __launch_bounds__(256) k_fold(const float* __restrict__ part, Ti
         const int i = tid * 4, d = i >> 5, e0 = i & 31;    // 4 consecutive e of KV_h[d][:]
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < T; ++t) {
-            const float4 v = *reinterpret_cast<const float4*>(part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * KVS + h * HD * HD + i);
+            const float4 v = *reinterpret_cast<const float4*>(part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * PART_FLOATS + h * HD * HD + i);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         kvT[e0][d] = acc.x * inv_s; kvT[e0 + 1][d] = acc.y * inv_s; kvT[e0 + 2][d] = acc.z * inv_s; kvT[e0 + 3][d] = acc.w * inv_s;
     }
     if (tid < HD) {
         float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc += part[(size_t)enc_part_index(g, eg, ppt, set, b, t) * KVS + NH * HD * HD + h * HD + tid];
+        for (int t = 0; t < T; ++t) {
+            const float* ks = part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * PART_FLOATS + NH * HD * HD + h * HD + tid;
+            acc += (ks[0] + ks[C]) + (ks[2 * C] + ks[3 * C]);      // the four row quarters of the tile, fixed order
+        }
         ksum[(size_t)img * C + h * HD + tid] = acc * inv_s;
     }
 #pragma unroll 8
@@ -242,8 +246,16 @@ __global__ void __launch_bounds__(256) k_sum_partials(const float* __restrict__ 
     const int i = (blockIdx.y * 256 + threadIdx.x) * 4;
     if (i >= KVS) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool is_ksum = i >= NH * HD * HD;          // Ksum: four row-quarter slots per partial
     for (int t = 0; t < T; ++t) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * KVS + i);
+        const float* src = part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * PART_FLOATS + i;
+        float4 v = *reinterpret_cast<const float4*>(src);
+        if (is_ksum) {
+            const float4 v1 = *reinterpret_cast<const float4*>(src + C), v2 = *reinterpret_cast<const float4*>(src + 2 * C),
+                         v3 = *reinterpret_cast<const float4*>(src + 3 * C);
+            v.x = (v.x + v1.x) + (v2.x + v3.x); v.y = (v.y + v1.y) + (v2.y + v3.y);
+            v.z = (v.z + v1.z) + (v2.z + v3.z); v.w = (v.w + v1.w) + (v2.w + v3.w);
+        }
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     *reinterpret_cast<float4*>(out + (size_t)img * KVS + i) = acc;
@@ -269,7 +281,7 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
     };
     w.xt = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));
     w.xt_enc = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));      // flat tiles <= per-image tiles
-    w.kv_part = static_cast<float*>(take((size_t)g.tiles() * 2 * KVS * sizeof(float)));   // flat tiling: one partial per (tile, image)
+    w.kv_part = static_cast<float*>(take((size_t)g.tiles() * 2 * PART_FLOATS * sizeof(float)));   // flat tiling: one partial per (tile, image)
     w.dec_kvs = static_cast<float*>(take((size_t)N_DEC * 2 * B * KVS * sizeof(float)));
     w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
     w.ksum = static_cast<float*>(take((size_t)2 * B * C * sizeof(float)));
@@ -379,7 +391,7 @@ void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cuda
     lc.n++;
 }
 
-int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
+int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
                const float* mask1, const float* mask2,
                float* X_out, int* flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len) {
@@ -399,14 +411,15 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
     base.g = g; base.eg = eg; base.feat1 = feat1; base.feat2 = feat2; base.xt = eg.flat ? ws.xt_enc : ws.xt;
     base.mask1 = mask1; base.mask2 = mask2; base.post1 = post1; base.post2 = post2;
     base.mimg = ws.mimg; base.ksum = ws.ksum; base.kv_part = ws.kv_part; base.flag = flag;
+    auto vec = [&](float (&dst)[C], size_t off) { memcpy(dst, h_w + off, C * sizeof(float)); };
     auto set_kv_enc = [&](EncParams& p, int layer) {
         const EncW& e = L.enc[layer];
-        p.do_kv = 1; p.lnkv_g = d_w + e.lnkv_g; p.lnkv_b = d_w + e.lnkv_b; p.bk = nullptr; p.bv = nullptr;
+        p.do_kv = 1; p.dec_mode = 0; vec(p.lnkv_g, e.lnkv_g); vec(p.lnkv_b, e.lnkv_b);
         p.w_kv = tw.enc_img + (size_t)layer * ENC_LAYER_HALFS + 5 * GEMM_HALFS;
     };
     auto set_kv_dec = [&](EncParams& p, int layer) {
         const DecW& d = L.dec[layer];
-        p.do_kv = 1; p.lnkv_g = nullptr; p.lnkv_b = nullptr; p.bk = d_w + d.ca.bk; p.bv = d_w + d.ca.bv;
+        p.do_kv = 1; p.dec_mode = 1; vec(p.lnkv_g, d.ca.bv); vec(p.lnkv_b, d.ca.bk);     // the biases ride in the lnkv slots
         p.w_kv = tw.dec_img + (size_t)layer * DEC_LAYER_HALFS;
     };
     const uint32_t G = (uint32_t)(GEMM_HALFS * sizeof(__half));
@@ -436,7 +449,7 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const Tc
         const __half* img = tw.enc_img + (size_t)i * ENC_LAYER_HALFS;
         EncParams p = base;
         p.store_x = 1; p.do_q = 1; p.cross = i & 1;
-        p.lnq_g = d_w + e.lnq_g; p.lnq_b = d_w + e.lnq_b; p.ln2_g = d_w + e.ln2_g; p.ln2_b = d_w + e.ln2_b;
+        vec(p.lnq_g, e.lnq_g); vec(p.lnq_b, e.lnq_b); vec(p.ln2_g, e.ln2_g); vec(p.ln2_b, e.ln2_b);
         p.w_q = img; p.w_mlp = img + GEMM_HALFS;
         if (i + 1 < N_ENC) set_kv_enc(p, i + 1); else set_kv_dec(p, 0);
         set_prefetch_for(p, i + 1);
@@ -537,7 +550,7 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
 #define ST(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(msg, msg_len, "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
     ST(cudaMalloc(&d_feat, feat.size() * 4)); ST(cudaMalloc(&d_wm, wm.size() * 4)); ST(cudaMalloc(&d_tmp, (size_t)FF * C * 4));
     ST(cudaMalloc(&d_ln, 6 * C * 4)); ST(cudaMalloc(&d_xt, (size_t)2 * TILE * C * 4)); ST(cudaMalloc(&d_post, pos.size() * 4));
-    ST(cudaMalloc(&d_part, (size_t)2 * KVS * 4)); ST(cudaMalloc(&d_ksum, 2 * C * 4));
+    ST(cudaMalloc(&d_part, (size_t)2 * PART_FLOATS * 4)); ST(cudaMalloc(&d_ksum, 2 * C * 4));
     ST(cudaMalloc(&d_img, ENC_LAYER_HALFS * 2)); ST(cudaMalloc(&d_mimg, 2 * GEMM_HALFS * 2)); ST(cudaMalloc(&d_flag, 4));
     ST(cudaMemcpy(d_feat, feat.data(), feat.size() * 4, cudaMemcpyHostToDevice));
     ST(cudaMemcpy(d_wm, wm.data(), wm.size() * 4, cudaMemcpyHostToDevice));
@@ -631,10 +644,12 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
     EncParams base{};
     base.g = g; base.feat1 = d_feat; base.feat2 = d_feat + (size_t)C * L; base.xt = d_xt; base.post1 = d_post; base.post2 = d_post;
     base.mimg = d_mimg; base.ksum = d_ksum; base.kv_part = d_part; base.flag = d_flag;
-    base.lnq_g = d_ln + 0 * C; base.lnq_b = d_ln + 3 * C; base.lnkv_g = d_ln + 1 * C; base.lnkv_b = d_ln + 4 * C;
-    base.ln2_g = d_ln + 2 * C; base.ln2_b = d_ln + 5 * C;
+    memcpy(base.lnq_g, lng.data() + 0 * C, C * 4); memcpy(base.lnq_b, lnb.data() + 0 * C, C * 4);
+    memcpy(base.lnkv_g, lng.data() + 1 * C, C * 4); memcpy(base.lnkv_b, lnb.data() + 1 * C, C * 4);
+    memcpy(base.ln2_g, lng.data() + 2 * C, C * 4); memcpy(base.ln2_b, lnb.data() + 2 * C, C * 4);
     base.w_q = d_img; base.w_mlp = d_img + GEMM_HALFS; base.w_kv = d_img + 5 * GEMM_HALFS;
-    std::vector<float> part((size_t)2 * KVS), xt((size_t)2 * TILE * C);
+    std::vector<float> part((size_t)2 * PART_FLOATS), xt((size_t)2 * TILE * C);
+    std::vector<float> ksum_got(2 * NH * HD);
     // (1) source phase from the NCHW features
     {
         EncParams p = base;
@@ -642,9 +657,14 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
         k_enc<<<2, N_THREADS, SM_TOTAL>>>(p);
         ST(cudaDeviceSynchronize());
         ST(cudaMemcpy(part.data(), d_part, part.size() * 4, cudaMemcpyDeviceToHost));
-        errs[0] = std::max(max_rel(part.data(), kvs0.data(), NH * HD * HD), max_rel(part.data() + KVS, kvs1.data(), NH * HD * HD));
-        if (n_errs > 1) errs[1] = std::max(max_rel(part.data() + NH * HD * HD, kvs0.data() + NH * HD * HD, NH * HD),
-                                           max_rel(part.data() + KVS + NH * HD * HD, kvs1.data() + NH * HD * HD, NH * HD));
+        errs[0] = std::max(max_rel(part.data(), kvs0.data(), NH * HD * HD), max_rel(part.data() + PART_FLOATS, kvs1.data(), NH * HD * HD));
+        for (int im = 0; im < 2; ++im)
+            for (int c = 0; c < NH * HD; ++c) {
+                const float* ks = part.data() + (size_t)im * PART_FLOATS + NH * HD * HD + c;
+                ksum_got[im * NH * HD + c] = (ks[0] + ks[C]) + (ks[2 * C] + ks[3 * C]);
+            }
+        if (n_errs > 1) errs[1] = std::max(max_rel(ksum_got.data(), kvs0.data() + NH * HD * HD, NH * HD),
+                                           max_rel(ksum_got.data() + NH * HD, kvs1.data() + NH * HD * HD, NH * HD));
     }
     // (2) fold
     k_fold<<<2 * NH, 256>>>(d_part, g, EncGeom{}, 1, d_wm, d_mimg, d_ksum);
@@ -689,7 +709,7 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
         errs[3] = compare_x(x0, x1);
         summary(x0, kvs0);
         summary(x1, kvs1);
-        if (n_errs > 5) errs[5] = std::max(max_rel(part.data(), kvs0.data(), NH * HD * HD), max_rel(part.data() + KVS, kvs1.data(), NH * HD * HD));
+        if (n_errs > 5) errs[5] = std::max(max_rel(part.data(), kvs0.data(), NH * HD * HD), max_rel(part.data() + PART_FLOATS, kvs1.data(), NH * HD * HD));
     }
     // (4) cross layer (each image reads the partner's summary), query phase only
     if (n_errs > 6) {

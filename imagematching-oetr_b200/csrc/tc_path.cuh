@@ -57,7 +57,7 @@ int tc_debug_read(unsigned long long* out, int n, int reset);
 int tc_check_geometry(int B, int L1, int L2, char* msg, size_t msg_len);
 size_t tc_pos_tile_floats(int L);
 void tc_pos_tiles(const float* d_pe, int max_w, int wf, int L, float* post, cudaStream_t s, LaunchCounter& lc);
-int tc_encoder(const TcWeights& tw, const float* d_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
+int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
                const float* mask1, const float* mask2,
                float* X_out, int* timeout_flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);

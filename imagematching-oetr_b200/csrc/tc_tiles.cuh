@@ -27,6 +27,9 @@ constexpr size_t ENC_LAYER_HALFS = ENC_LAYER_GEMMS * GEMM_HALFS;
 constexpr size_t DEC_LAYER_HALFS = DEC_LAYER_GEMMS * GEMM_HALFS;
 constexpr size_t DEC_T_FLOATS = (size_t)6 * C * C + (size_t)2 * FF * C;   // transposed fp32 decoder weights per layer
 
+// one partial linear-attention summary of a (tile, image): KV[8][32][32] | Ksum of the four row quarters [4][256]
+constexpr int PART_FLOATS = NH * HD * HD + 4 * C;
+
 constexpr uint32_t IDESC_N256 = umma_idesc_f16(128, 256, 0, 0);
 constexpr uint32_t IDESC_KV = umma_idesc_f16(128, 128, 1, 1);      // both operands MN-major (token = K)
 
@@ -40,19 +43,20 @@ constexpr uint32_t SM_X = SM_RING + RING * STAGE_BYTES;            // float[512]
 constexpr uint32_t SM_BAR = SM_X + 512 * 4;                        // mbarriers + tmem pointer
 constexpr uint32_t SM_TOTAL = SM_BAR + 256;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(uint64_t) * (2 * RING + 6) + 8 <= 256, "Bars must fit its reservation");
+static_assert(sizeof(uint64_t) * (2 * RING + 7) + 8 <= 256, "Bars must fit its reservation");
 // the kv phase re-uses the operand image space for the MN-major half images (tokens = K dimension)
 constexpr uint32_t KF_OFF = 0;                                     // Kf half image: 2 slabs (32 KB) inside hi / lo
 constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
 
 // OETR_TIMING=1: global cycle accumulators of the k_enc launches with a query and a source phase (atomicAdd per CTA)
-enum { DBG_MMA_TOTAL = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_W = 2, DBG_TILES = 3, DBG_STAGE0 = 8, DBG_SLOTS = 32 };
+enum { DBG_MMA_TOTAL = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_W = 2, DBG_TILES = 3, DBG_STAGE0 = 8, DBG_CONV = 40, DBG_SLOTS = 48 };
 
 struct Bars {
     uint64_t full[RING], empty[RING];
     uint64_t a_full[2];   // row warps -> MMA: column pass p of the operand image written (count 512)
     uint64_t s_full[2];   // MMA -> row warps: accumulator S0 / S1 complete (tcgen05.commit)
     uint64_t a_free[2];   // MMA -> row warps (k_conv): the MMAs reading column pass p of the image have completed
+    uint64_t x_full;      // producer -> row warps (k_enc): the tile's residual stream has landed in the image area
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -87,6 +91,15 @@ __device__ __forceinline__ void store_row32_split(uint8_t* img_hi, uint8_t* img_
         *reinterpret_cast<uint4*>(img_hi + off) = h;
         *reinterpret_cast<uint4*>(img_lo + off) = l;
     }
+}
+
+// the same, hi part only (operands the precision map keeps as ONE fp16 value)
+__device__ __forceinline__ void store_row32_hi(uint8_t* img_hi, uint32_t r, uint32_t c0, const float (&v)[32]) {
+    const uint32_t slab = (c0 >> 6) * SLAB_BYTES;
+    const uint32_t j0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(img_hi + slab + slab_chunk_off(r, j0 + j)) = pack8_f16(&v[8 * j]);
 }
 
 // columns [c0, c0+16) (c0 % 16 == 0)
@@ -205,6 +218,7 @@ __device__ __forceinline__ uint32_t cta_setup(Bars* bars, int alloc_warp) {
             mbar_init(&bars->s_full[i], 1);
             mbar_init(&bars->a_free[i], 1);
         }
+        mbar_init(&bars->x_full, 1);
         fence_mbar_init();
     }
     if ((int)(threadIdx.x >> 5) == alloc_warp) tmem_alloc(&bars->tmem_base, 512);
@@ -213,17 +227,20 @@ __device__ __forceinline__ uint32_t cta_setup(Bars* bars, int alloc_warp) {
     tc_fence_after();
     return bars->tmem_base;
 }
-// producer: nstages (even) consecutive 16 KB stages global -> ring, ONE 32 KB bulk copy per pair of stages.  The
-// issuing thread pays ~480 cycles per copy whatever its size (measured, tools/bulk_bw.cu: 16 KB copies stream at
-// 34 B/cycle/SM, 32 KB copies at 68), and the 3-term MMAs consume 43 B/cycle: 16 KB copies starve the tensor core.
-// Only the even stage's full barrier is used; both empty barriers are still committed by the consumer.
-__device__ __forceinline__ void ring_stream(uint8_t* smem, Bars* bars, int* flag, uint32_t& g, const __half* src, int nstages) {
-    for (int i = 0; i < nstages; i += 2, g += 2) {
+// producer: `nunits` 32 KB units (two adjacent 16 KB stages = one [256 N x 64 K] B tile) global -> ring, ONE bulk copy
+// per unit.  The issuing thread pays ~480 cycles per copy whatever its size (measured, tools/bulk_bw.cu: 16 KB copies
+// stream at 34 B/cycle/SM, 32 KB copies at 68), and the 3-term MMAs consume 43 B/cycle: 16 KB copies starve the
+// tensor core.  unit_stride: distance between consecutive units in stages (2 = every unit of a GEMM image: hi and lo;
+// 4 = the hi units only, for GEMMs whose weight operand is not split).  Only the even stage's full barrier is used;
+// both empty barriers are still committed by the consumer.
+__device__ __forceinline__ void ring_stream(uint8_t* smem, Bars* bars, int* flag, uint32_t& g, const __half* src, int nunits,
+                                            int unit_stride = 2) {
+    for (int i = 0; i < nunits; ++i, g += 2) {
         const int st = g % RING;
         mbar_wait(&bars->empty[st], ((g / RING) & 1) ^ 1, flag);
         mbar_wait(&bars->empty[st + 1], ((g / RING) & 1) ^ 1, flag);
         mbar_arrive_expect_tx(&bars->full[st], 2 * STAGE_BYTES);
-        bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * STAGE_HALFS, 2 * STAGE_BYTES, &bars->full[st]);
+        bulk_g2s(smem + SM_RING + st * STAGE_BYTES, src + (size_t)i * unit_stride * STAGE_HALFS, 2 * STAGE_BYTES, &bars->full[st]);
     }
 }
 struct MmaState { uint32_t g = 0, na0 = 0, na1 = 0; long long t_a = 0, t_ring = 0; };   // t_*: cycles spent waiting (profiling aid)
@@ -233,11 +250,14 @@ __device__ __forceinline__ void mma_wait_a(Bars* bars, int* flag, MmaState& ms, 
     ms.t_a += clock64() - t0;
     tc_fence_after();
 }
-// D[128 x 256] (tmem columns d..d+255) (+)= A[128 x 256] . W^T with the 3-term split; consumes 16 ring stages.
-// wait: the operand image is (re)written for this GEMM -> wait for column pass 0 before k-slab 0 and pass 1
-// before k-slab 2.  signal_free: commit a_free[p] once the MMAs reading pass p have been issued (k_conv).
+// Terms of a split product a.w = (a_hi + a_lo).(w_hi + w_lo): which ones a GEMM issues is decided per contraction by
+// the precision map (tests/precision_map.py); a_lo.w_lo (2^-22 relative) is never issued.
+enum { T_HH = 1, T_LH = 2, T_HL = 4, T_ALL = 7 };     // a_hi.w_hi | a_lo.w_hi | a_hi.w_lo
+// D[128 x 256] (tmem columns d..d+255) (+)= A[128 x 256] . W^T; consumes 4 ring units (w_hi), or 8 with T_HL (w_hi,
+// w_lo alternating).  wait: the operand image is (re)written for this GEMM -> wait for column pass 0 before k-slab 0
+// and pass 1 before k-slab 2.  signal_free: commit a_free[p] once the MMAs reading pass p have been issued (k_conv).
 __device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* flag, MmaState& ms, uint32_t d,
-                                           bool accumulate, bool wait, bool signal_free) {
+                                           bool accumulate, bool wait, bool signal_free, int terms = T_ALL) {
     for (int ks = 0; ks < 4; ++ks) {
         if (wait && ks == 0) mma_wait_a(bars, flag, ms, 0);
         if (wait && ks == 2) mma_wait_a(bars, flag, ms, 1);
@@ -254,15 +274,17 @@ __device__ __forceinline__ void gemm_issue(uint32_t smem_base, Bars* bars, int* 
             for (int k = 0; k < 4; ++k)
                 umma_f16(d, umma_desc(a_hi + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
                          IDESC_N256, (accumulate || ks > 0 || k > 0) ? 1u : 0u);
+            if (terms & T_LH) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma_f16(d, umma_desc(a_lo + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                         IDESC_N256, 1u);
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(d, umma_desc(a_lo + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                             IDESC_N256, 1u);
+            }
             umma_commit(&bars->empty[st]);
             umma_commit(&bars->empty[st + 1]);
             ms.g += 2;
         }
-        {   // w_lo
+        if (terms & T_HL) {   // w_lo
             const int st = ms.g % RING;
             const long long t0 = clock64();
             mbar_wait(&bars->full[st], (ms.g / RING) & 1, flag);

@@ -16,8 +16,9 @@ import oetr_b200  # noqa: E402
 from oetr_b200 import cabi, weights  # noqa: E402
 
 STAGES = ["x load", "E0 LNq image", "wait q", "E1 phi(q)/Z", "wait msg", "E2 x+=msg, LN2 image", "wait h_a",
-          "E3 gelu(h_a) (+wait h_b)", "E4 gelu(h_b) (+wait y_a)", "wait y", "E5 x+=y, store x", "LNkv image",
+          "E3 gelu(h_a) (+wait h_b)", "E4 gelu(h_b) (+wait y_a)", "wait y", "E5 x+=y", "store x", "LNkv image",
           "wait v,k", "kv epilogue (+wait KV half 0)", "wait KV", "KV out"]
+NS = 48
 
 
 def main():
@@ -38,7 +39,7 @@ def main():
     f1 = torch.from_numpy(weights.synthetic_features(a.batch, fm, fm, seed=1, tag="a")).cuda()
     f2 = torch.from_numpy(weights.synthetic_features(a.batch, fm, fm, seed=1, tag="b")).cuda()
     lib = cabi.load_library()
-    buf = (ctypes.c_ulonglong * 32)()
+    buf = (ctypes.c_ulonglong * NS)()
 
     def run(n):
         for i in range(n):
@@ -47,14 +48,14 @@ def main():
         torch.cuda.synchronize()
 
     run(4)
-    lib.oetr_debug_cycles(buf, 32, 1)
+    lib.oetr_debug_cycles(buf, NS, 1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     run(a.steps)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / a.steps
-    n = lib.oetr_debug_cycles(buf, 32, 1)
+    n = lib.oetr_debug_cycles(buf, NS, 1)
     v = np.array(list(buf), dtype=np.float64)
     print("batch %d, %dx%d, %d in flight: %.3f ms/step, %.0f pairs/s (timing build perturbs little: atomics only)" % (
         a.batch, a.side, a.side, a.in_flight, ms, a.batch / ms * 1e3))
@@ -65,14 +66,14 @@ def main():
     print("k_enc q+kv launches: %d tiles sampled; per tile (cycles):" % t)
     print("  MMA lane total %8.0f   waiting operand image %8.0f   waiting weights %8.0f   issuing/executing %8.0f" % (
         v[0] / t, v[1] / t, v[2] / t, (v[0] - v[1] - v[2]) / t))
-    tot = v[8:24].sum() / t
+    tot = v[8:8 + len(STAGES)].sum() / t
     print("  row warp 0 stages (sum %.0f):" % tot)
     for i, name in enumerate(STAGES):
         print("    %2d %-34s %8.0f  %5.1f %%" % (i, name, v[8 + i] / t, 100 * v[8 + i] / t / tot))
-    if v[27]:
-        c = v[27]
+    if v[43]:
+        c = v[43]
         print("k_conv: %d tiles; MMA lane total %.0f, waiting operand image %.0f, waiting weights %.0f" % (
-            c, v[24] / c, v[25] / c, v[26] / c))
+            c, v[40] / c, v[41] / c, v[42] / c))
 
 
 if __name__ == "__main__":
