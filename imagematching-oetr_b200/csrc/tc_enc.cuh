@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
     const bool dec_mode = p.dec_mode != 0;
 
     const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
-    const uint32_t S0 = tmem, S1 = tmem + 256;
+    const uint32_t T = tmem, XA = tmem + 256;
 
     // source image of the tile's first image (the second one's is src_img + 1) and its length
     int src_img = et.set * p.g.B + et.b0, src_len = et.L;
@@ -92,31 +92,40 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
         __syncwarp();
     } else if (warp == WARP_MMA) {
         // ------------------------------------------------------------------ MMA issue
+        // TMEM: T = columns [0,256): working accumulator (q, h_a, h_b; v in the source phase);
+        //       XA = columns [256,512): THE RESIDUAL STREAM of the tile.  The merge and W2 GEMMs accumulate onto it in
+        //       place (x += msg, x += y are done by the tensor core); in the source phase x is dead and XA takes k.
         if (lane == 0) {
             MmaState ms;
             const long long t_begin = clock64();
             auto wait_a = [&](int pass) { mma_wait_a(bars, p.flag, ms, pass); };
             auto gemm = [&](uint32_t d, bool accumulate, bool wait, int terms) { gemm_issue(smem_base, bars, p.flag, ms, d, accumulate, wait, false, terms); };
             if (p.do_q) {
-                gemm(S0, false, true, T_HH);   umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
-                gemm(S1, false, true, T_ALL);  umma_commit(&bars->s_full[1]);     // msg = (phi(q)/Z) M_img^T
-                if (two) { gemm(S0, false, false, T_ALL); umma_commit(&bars->s_full[0]); }   // ... with the second image's M_img
-                gemm(S0, false, true, T_ALL);  umma_commit(&bars->s_full[0]);     // h_a = LN2(x) W1a^T
-                gemm(S1, false, false, T_ALL); umma_commit(&bars->s_full[1]);     // h_b = LN2(x) W1b^T
-                gemm(S0, false, true, T_ALL);  umma_commit(&bars->s_full[0]);     // y   = gelu(h_a) W2a^T
-                gemm(S0, true, true, T_ALL);   umma_commit(&bars->s_full[0]);     // y  += gelu(h_b) W2b^T
+                gemm(T, false, true, T_HH);    umma_commit(&bars->s_full[0]);     // q   = (LNq(x)+pos) Wq^T
+                gemm(XA, true, true, T_ALL);   umma_commit(&bars->s_full[1]);     // x  += (phi(q)/Z) M_img^T
+                if (two) { gemm(XA, true, true, T_ALL); umma_commit(&bars->s_full[1]); }   // rows of the second image, its M_img
+                gemm(T, false, true, T_ALL);   umma_commit(&bars->s_full[0]);     // h_a = LN2(x) W1a^T
+                {   // h_b overwrites T: every row thread must have read h_a
+                    const long long t0 = clock64();
+                    mbar_wait(&bars->s_free, 0, p.flag);
+                    ms.t_a += clock64() - t0;
+                    tc_fence_after();
+                }
+                gemm(T, false, false, T_ALL);  umma_commit(&bars->s_full[0]);     // h_b = LN2(x) W1b^T
+                gemm(XA, true, true, T_ALL);   umma_commit(&bars->s_full[1]);     // x  += gelu(h_a) W2a^T
+                gemm(XA, true, true, T_ALL);   umma_commit(&bars->s_full[1]);     // x  += gelu(h_b) W2b^T
             }
             if (p.do_kv) {
                 if (!dec_mode) {
-                    gemm(S0, false, true, T_ALL);           umma_commit(&bars->s_full[0]);   // v
-                    gemm(S1, false, false, T_HH | T_LH);    umma_commit(&bars->s_full[1]);   // k (same image)
+                    gemm(T, false, true, T_ALL);            umma_commit(&bars->s_full[0]);   // v
+                    gemm(XA, false, false, T_HH | T_LH);    umma_commit(&bars->s_full[1]);   // k (same image)
                 } else {
-                    gemm(S0, false, true, T_HH | T_HL);     umma_commit(&bars->s_full[0]);   // v = x Wv^T
-                    gemm(S1, false, true, T_HH);            umma_commit(&bars->s_full[1]);   // k = (x+pos) Wk^T
+                    gemm(T, false, true, T_HH | T_HL);      umma_commit(&bars->s_full[0]);   // v = x Wv^T
+                    gemm(XA, false, true, T_HH);            umma_commit(&bars->s_full[1]);   // k = (x+pos) Wk^T
                 }
                 // per 128-channel half: KV = Kf^T V (diagonal 32x32 blocks are the heads); Ksum is reduced by the row warps
                 // the token rows are the K dimension, 16 per MMA: a two-image tile splits the k-steps at the image
-                // boundary (a multiple of 16 rows) and accumulates the second image's product in S1's columns
+                // boundary (a multiple of 16 rows) and accumulates the second image's product in XA's columns
                 const int ksplit = two ? et.split / 16 : TILE / 16;
                 const int nterms = dec_mode ? 1 : 3;
                 for (int half = 0; half < 2; ++half) {
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
 #pragma unroll
                         for (int k = 0; k < TILE / 16; ++k) {
                             const bool second = k >= ksplit;
-                            const uint32_t dkv = (second ? S1 : S0) + half * 128;
+                            const uint32_t dkv = (second ? XA : T) + half * 128;
                             const uint32_t first_of_group = (term == 0 && (k == 0 || k == ksplit)) ? 0u : 1u;
                             umma_f16(dkv, umma_desc(a + k * 2048, SLAB_BYTES, ATOM_BYTES),
                                      umma_desc(bb + k * 2048, SLAB_BYTES, ATOM_BYTES), IDESC_KV, first_of_group);
@@ -147,6 +156,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
         __syncwarp();
     } else if (warp < WARP_PRODUCER) {
         // ------------------------------------------------------------------ row warps
+        // thread <-> (token row r, column chunks [32*cq, +32) and [128 + 32*cq, +32)).  At most 64 tile values live in a
+        // thread's registers at any time (the residual stream lives in TMEM), so the 96-register budget holds.
         const int q = warp & 3, cq = warp >> 2;            // TMEM lane quarter, column quarter
         const int r = q * 32 + lane;                       // token row of the tile
         // which image / token this row is (enc_tile): rows >= split belong to the tile's second image
@@ -155,7 +166,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
         const int rl = rel ? r - et.split : et.l0 + r;     // token inside the image
         const bool valid = rb < et.B && rl < et.L;
         const int pl = valid ? rl : 0;                     // row of the position table
-        const bool warp_has_rel1 = two && et.split < q * 32 + 32;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float* X = reinterpret_cast<float*>(smem + SM_X);       // 512-float scratch: Ksum of the source image(s)
         uint8_t* img_hi = smem + SM_AHI;
@@ -182,6 +192,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             fence_async_smem();
             mbar_arrive(&bars->a_full[pass]);
         };
+        // the thread's 64 columns of an accumulator (both column passes), one wait
+        auto load_acc = [&](uint32_t acc, float (&v)[2][32]) {
+            tmem_ld32x2(acc + lane_addr + cq * 32, v[0], v[1]);
+        };
         // positional rows of this token: 8 x 16 bytes of column pass `pass` (tile-blocked table: coalesced per warp)
         auto load_pos = [&](int pass, float4 (&ps)[8]) {
             const int c0 = pass * 128 + cq * 32;
@@ -189,8 +203,96 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             for (int jq = 0; jq < 8; ++jq)
                 ps[jq] = __ldg(reinterpret_cast<const float4*>(post + xt_off(pl >> 7, (c0 >> 2) + jq, pl & 127)));
         };
-        // ---- the residual stream of this thread: columns [32*cq, +32) and [128 + 32*cq, +32) of row r
-        float x[2][32];
+        // LayerNorm statistics of the row.  Each of the row's four threads (one per column quarter, in four different
+        // warps of the same TMEM lane quarter) reduces its 64 values exactly (local mean, local M2); the (mean, M2) pairs
+        // are exchanged through two columns per thread of accumulator T -- columns of the thread's own chunk, which it
+        // has consumed -- and merged with Chan's formula.  One 128-thread barrier per LayerNorm.
+        auto row_stats = [&](const float (&x)[2][32], float& mean, float& rstd) {
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) s += x[0][e] + x[1][e];
+            const float m_i = s * (1.f / 64.f);
+            float m2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float d0 = x[0][e] - m_i, d1 = x[1][e] - m_i;
+                m2 = fmaf(d0, d0, m2);
+                m2 = fmaf(d1, d1, m2);
+            }
+            tmem_st2(T + lane_addr + cq * 32, m_i, m2);
+            tmem_st_wait();
+            tc_fence_before();
+            named_bar_sync(2 + q, 128);
+            tc_fence_after();
+            float v[8];
+            tmem_ld2x4(T + lane_addr, v);
+            mean = (v[0] + v[2] + v[4] + v[6]) * 0.25f;
+            float M2 = (v[1] + v[3]) + (v[5] + v[7]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float d = v[2 * i] - mean;
+                M2 = fmaf(64.f * d, d, M2);
+            }
+            rstd = rsqrtf(M2 * (1.f / C) + LN_EPS);
+        };
+        // operand image <- LN(x) [+ pos], both column passes, computed in place in x (x is dead afterwards);
+        // split: (hi, lo) image, else one fp16 value per element
+        auto ln_image = [&](float (&x)[2][32], const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos, bool split) {
+            float4 ps[8];
+            if (with_pos) load_pos(0, ps);                 // in flight during the statistics
+            float mean, rstd;
+            row_stats(x, mean, rstd);
+            const float shift = -mean * rstd;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq) {
+                    const float4 pz = with_pos ? ps[jq] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int c = c0 + jq * 4;
+                    // (x - mean) * rstd * g + b + pos  ==  fma(fma(x, rstd, shift), g, b + pos)
+                    x[pass][jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), gamma[c + 0], beta[c + 0] + pz.x);
+                    x[pass][jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), gamma[c + 1], beta[c + 1] + pz.y);
+                    x[pass][jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), gamma[c + 2], beta[c + 2] + pz.z);
+                    x[pass][jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), gamma[c + 3], beta[c + 3] + pz.w);
+                }
+                if (with_pos && pass == 0) load_pos(1, ps);    // in flight during the split + stores of pass 0
+                if (split) store_row32_split(img_hi, img_lo, r, c0, x[pass]);
+                else store_row32_hi(img_hi, r, c0, x[pass]);
+                publish(pass);
+            }
+        };
+        // operand image <- x [+ pos] (decoder K/V projections: no LayerNorm), one fp16 value per element; x is kept
+        auto raw_image = [&](const float (&x)[2][32], bool with_pos) {
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+                float4 ps[8];
+                if (with_pos) load_pos(pass, ps);
+                float v[32];
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq) {
+                    const float4 pz = with_pos ? ps[jq] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[jq * 4 + 0] = x[pass][jq * 4 + 0] + pz.x; v[jq * 4 + 1] = x[pass][jq * 4 + 1] + pz.y;
+                    v[jq * 4 + 2] = x[pass][jq * 4 + 2] + pz.z; v[jq * 4 + 3] = x[pass][jq * 4 + 3] + pz.w;
+                }
+                store_row32_hi(img_hi, r, c0, v);
+                publish(pass);
+            }
+        };
+        auto store_x = [&](const float (&x)[2][32]) {      // tile-blocked residual stream for the next launch
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c0 = pass * 128 + cq * 32;
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq)
+                    *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r)) =
+                        make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
+            }
+        };
+
+        float x[2][32];                                    // the one 64-value register tile of this thread
+        // ---- the residual stream of this thread's row
         if (p.load_feat) {
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
@@ -213,201 +315,112 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             }
             named_bar_sync(1, N_ROW_THREADS);              // every thread has its rows: the image area may be overwritten
         }
-        // LayerNorm statistics of the row.  Each of the row's four threads (one per column quarter, in four different
-        // warps of the same TMEM lane quarter) reduces its 64 values exactly (local mean, local M2); the (mean, M2) pairs
-        // are exchanged through two TMEM columns per thread -- columns of accumulator `scr` that this thread has already
-        // consumed (its own chunk [32*cq, +32)) -- and merged with Chan's formula.  One 128-thread barrier per LayerNorm.
-        auto row_stats = [&](uint32_t scr, float& mean, float& rstd) {
-            float s = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) s += x[0][e] + x[1][e];
-            const float m_i = s * (1.f / 64.f);
-            float m2 = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float d0 = x[0][e] - m_i, d1 = x[1][e] - m_i;
-                m2 = fmaf(d0, d0, m2);
-                m2 = fmaf(d1, d1, m2);
-            }
-            tmem_st2(scr + lane_addr + cq * 32, m_i, m2);
-            tmem_st_wait();
-            tc_fence_before();
-            named_bar_sync(2 + q, 128);
-            tc_fence_after();
-            float v[8];
-            tmem_ld2x4(scr + lane_addr, v);
-            mean = (v[0] + v[2] + v[4] + v[6]) * 0.25f;
-            float M2 = (v[1] + v[3]) + (v[5] + v[7]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float d = v[2 * i] - mean;
-                M2 = fmaf(64.f * d, d, M2);
-            }
-            rstd = rsqrtf(M2 * (1.f / C) + LN_EPS);
-        };
-        // operand image <- LN(x) [+ pos], both column passes; split: (hi, lo) image, else one fp16 value per element
-        auto ln_image = [&](const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos, uint32_t scr, bool split) {
-            float4 ps[8];
-            if (with_pos) load_pos(0, ps);                 // in flight during the statistics
-            float mean, rstd;
-            row_stats(scr, mean, rstd);
-            const float shift = -mean * rstd;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-                float v[32];
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    const float4 pz = with_pos ? ps[jq] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int c = c0 + jq * 4;
-                    // (x - mean) * rstd * g + b + pos  ==  fma(fma(x, rstd, shift), g, b + pos)
-                    v[jq * 4 + 0] = fmaf(fmaf(x[pass][jq * 4 + 0], rstd, shift), gamma[c + 0], beta[c + 0] + pz.x);
-                    v[jq * 4 + 1] = fmaf(fmaf(x[pass][jq * 4 + 1], rstd, shift), gamma[c + 1], beta[c + 1] + pz.y);
-                    v[jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), gamma[c + 2], beta[c + 2] + pz.z);
-                    v[jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), gamma[c + 3], beta[c + 3] + pz.w);
-                }
-                if (with_pos && pass == 0) load_pos(1, ps);    // in flight during the split + stores of pass 0
-                if (split) store_row32_split(img_hi, img_lo, r, c0, v);
-                else store_row32_hi(img_hi, r, c0, v);
-                publish(pass);
-            }
-        };
-        // operand image <- x [+ pos] (decoder K/V projections: no LayerNorm), one fp16 value per element
-        auto raw_image = [&](bool with_pos) {
-            float4 ps[8];
-            if (with_pos) load_pos(0, ps);
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-                float v[32];
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq) {
-                    const float4 pz = with_pos ? ps[jq] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[jq * 4 + 0] = x[pass][jq * 4 + 0] + pz.x; v[jq * 4 + 1] = x[pass][jq * 4 + 1] + pz.y;
-                    v[jq * 4 + 2] = x[pass][jq * 4 + 2] + pz.z; v[jq * 4 + 3] = x[pass][jq * 4 + 3] + pz.w;
-                }
-                if (with_pos && pass == 0) load_pos(1, ps);
-                store_row32_hi(img_hi, r, c0, v);
-                publish(pass);
-            }
-        };
-
         stamp(0);
         if (p.do_q) {
+            // the residual stream moves into TMEM (XA) for the whole query phase
+            tmem_st32(XA + lane_addr + cq * 32, x[0]);
+            tmem_st32(XA + lane_addr + 128 + cq * 32, x[1]);
+            tmem_st_wait();
             // Ksum of the source image(s) -> X (nobody else uses X during the query phase)
             if (tid < 256 || two) X[tid] = __ldg(p.ksum + (size_t)(src_img + (tid >> 8)) * C + (tid & 255));   // [256, 512): second image
             // (E0) A = LNq(x) + pos   (one fp16 value per element: the q GEMM is a 1-term product)
-            ln_image(p.lnq_g, p.lnq_b, true, S0, false);
+            ln_image(x, p.lnq_g, p.lnq_b, true, false);
             stamp(1);
             named_bar_sync(1, N_ROW_THREADS);              // Ksum visible to every row thread
             const float* Xk = X + rel * 256;
             // (E1) A = phi(q) / Z   (linear_attention.py:33,46; the KV product is folded into M_img)
             wait_s(0);
             stamp(2);
+            load_acc(T, x);
             const float eps_s = ATTN_EPS / (float)src_len;    // summaries arrive scaled by 1/S (k_fold)
-#pragma unroll 1
+#pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32;      // one head per 32-column chunk
-                float v[32];
-                tmem_ld32(S0 + lane_addr + c0, v);
                 float den = 0.f;
 #pragma unroll
                 for (int e4 = 0; e4 < 8; ++e4) {
                     const float4 k4 = *reinterpret_cast<const float4*>(Xk + c0 + e4 * 4);
-                    v[e4 * 4 + 0] = elu1(v[e4 * 4 + 0]); den = fmaf(v[e4 * 4 + 0], k4.x, den);
-                    v[e4 * 4 + 1] = elu1(v[e4 * 4 + 1]); den = fmaf(v[e4 * 4 + 1], k4.y, den);
-                    v[e4 * 4 + 2] = elu1(v[e4 * 4 + 2]); den = fmaf(v[e4 * 4 + 2], k4.z, den);
-                    v[e4 * 4 + 3] = elu1(v[e4 * 4 + 3]); den = fmaf(v[e4 * 4 + 3], k4.w, den);
+                    x[pass][e4 * 4 + 0] = elu1(x[pass][e4 * 4 + 0]); den = fmaf(x[pass][e4 * 4 + 0], k4.x, den);
+                    x[pass][e4 * 4 + 1] = elu1(x[pass][e4 * 4 + 1]); den = fmaf(x[pass][e4 * 4 + 1], k4.y, den);
+                    x[pass][e4 * 4 + 2] = elu1(x[pass][e4 * 4 + 2]); den = fmaf(x[pass][e4 * 4 + 2], k4.z, den);
+                    x[pass][e4 * 4 + 3] = elu1(x[pass][e4 * 4 + 3]); den = fmaf(x[pass][e4 * 4 + 3], k4.w, den);
                 }
-                if (has_mask) {                           // Q = phi(q) * q_mask, before Z (linear_attention.py:37,46)
-                    den *= mrow;
+                // Q = phi(q) * q_mask before Z (linear_attention.py:37,46): phi(q) m / (m den + eps)
+                const float inv = mrow / (den * mrow + eps_s);
+                // two-image tile: the GEMM with the first image's M_img must see zero rows for the second image's tokens
+                const float sc = (two && rel) ? 0.f : inv;
+                float v[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] *= mrow;
-                }
-                const float inv = 1.f / (den + eps_s);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] *= inv;
+                for (int e = 0; e < 32; ++e) { v[e] = x[pass][e] * sc; x[pass][e] *= inv; }
                 store_row32_split(img_hi, img_lo, r, c0, v);
                 publish(pass);
             }
-            stamp(3);
-            // (E2) x += msg ; A = LN2(x)   (two-image tile: rows of the second image take the product with its M_img, S0)
-            wait_s(1);
-            if (two) wait_s(0);
-            stamp(4);
+            if (two) {                                    // ... and the GEMM with the second image's M_img zero rows for the first's
+                wait_s(1);                                // the first GEMM has consumed the image
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                tmem_ld32(S1 + lane_addr + pass * 128 + cq * 32, v);
-                if (warp_has_rel1) {
-                    float v2[32];
-                    tmem_ld32(S0 + lane_addr + pass * 128 + cq * 32, v2);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = rel ? v2[e] : v[e];
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
-            }
-            ln_image(p.ln2_g, p.ln2_b, false, S1, true);
-            stamp(5);
-            // (E3) A = gelu(h_a): needs h_a (S0) and, for the image to be free, h_b complete (S1)
-            // (E4) A = gelu(h_b): the image is free once y = gelu(h_a) W2a^T has completed (S0 commit)
-#pragma unroll 1
-            for (int which = 0; which < 2; ++which) {
-                if (which == 0) { wait_s(0); stamp(6); }
-                const uint32_t S = which ? S1 : S0;
-#pragma unroll 1
                 for (int pass = 0; pass < 2; ++pass) {
-                    const int c0 = pass * 128 + cq * 32;
                     float v[32];
-                    tmem_ld32(S + lane_addr + c0, v);
-                    // the GEMM that consumes pass 0 overwrites ALL of S0 (h_a): release pass 0 only once this
-                    // thread has also read its pass-1 columns
-                    if (pass == 1) publish(0);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = gelu_erf(v[e]);
-                    // the image is free once the GEMM still reading it has completed: h_b (S1 commit) before
-                    // gelu(h_a) is stored, y = gelu(h_a) W2a^T (S0 commit) before gelu(h_b) is stored
-                    if (pass == 0) wait_s(which == 0 ? 1 : 0);
-                    store_row32_split(img_hi, img_lo, r, c0, v);
+                    for (int e = 0; e < 32; ++e) v[e] = rel ? x[pass][e] : 0.f;
+                    store_row32_split(img_hi, img_lo, r, pass * 128 + cq * 32, v);
+                    publish(pass);
                 }
-                publish(1);
-                stamp(7 + which);
             }
-            // (E5) x += y
+            stamp(3);
+            // (E2) A = LN2(x), x = x + msg as accumulated by the tensor core
+            wait_s(1);
+            stamp(4);
+            load_acc(XA, x);
+            ln_image(x, p.ln2_g, p.ln2_b, false, true);
+            stamp(5);
+            // (E3) gelu(h_a): T is read at once (h_b may then overwrite it), the values wait in registers until the GEMMs
+            // reading the LN2 image have completed (h_b commit); then h_b is read BEFORE the image is published, because
+            // the GEMM it feeds is followed by nothing that protects T ... and x += gelu(h_a) W2a^T runs under (E4)
             wait_s(0);
-            stamp(9);
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                tmem_ld32(S0 + lane_addr + pass * 128 + cq * 32, v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) x[pass][e] += v[e];
-            }
+            stamp(6);
+            load_acc(T, x);
             tc_fence_before();
+            mbar_arrive(&bars->s_free);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) x[pass][e] = gelu_erf(x[pass][e]);
+            wait_s(0);                                     // h_b complete: the LN2 image is free, T holds h_b
+            store_row32_split(img_hi, img_lo, r, cq * 32, x[0]);
+            store_row32_split(img_hi, img_lo, r, 128 + cq * 32, x[1]);
+            load_acc(T, x);
+            publish(0);
+            publish(1);
+            stamp(7);
+            // (E4) gelu(h_b) under the W2a GEMM; its image is written once that GEMM has completed
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) x[pass][e] = gelu_erf(x[pass][e]);
+            wait_s(1);
+            store_row32_split(img_hi, img_lo, r, cq * 32, x[0]);
+            publish(0);
+            store_row32_split(img_hi, img_lo, r, 128 + cq * 32, x[1]);
+            publish(1);
+            stamp(8);
+            // (E5) x = x + y as accumulated by the tensor core
+            wait_s(1);
+            stamp(9);
+            load_acc(XA, x);
             stamp(10);
         }
-        if (p.store_x) {
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c0 = pass * 128 + cq * 32;
-#pragma unroll
-                for (int jq = 0; jq < 8; ++jq)
-                    *reinterpret_cast<float4*>(p.xt + xt_off(blockIdx.x, (c0 >> 2) + jq, r)) =
-                        make_float4(x[pass][jq * 4], x[pass][jq * 4 + 1], x[pass][jq * 4 + 2], x[pass][jq * 4 + 3]);
-            }
-        }
+        if (p.store_x) store_x(x);
         stamp(11);
         if (p.do_kv) {
             if (!dec_mode) {
-                ln_image(p.lnkv_g, p.lnkv_b, true, S0, true);  // k and v share LN_kv(x)+pos (transformer.py:119-126)
+                ln_image(x, p.lnkv_g, p.lnkv_b, true, true);   // k and v share LN_kv(x)+pos (transformer.py:119-126)
                 stamp(12);
                 wait_s(0);
                 wait_s(1);
             } else {
-                raw_image(false);                              // v = x Wv^T + bv      (transformer.py:243-249)
+                raw_image(x, false);                           // v = x Wv^T + bv      (transformer.py:243-249)
                 wait_s(0);
-                raw_image(true);                               // k = (x+pos) Wk^T + bk
+                raw_image(x, true);                            // k = (x+pos) Wk^T + bk
                 wait_s(1);
             }
             stamp(13);
@@ -420,7 +433,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32, ch = cq * 32;      // ch: column inside the 128-channel half
                 float v[32];
-                tmem_ld32(S0 + lane_addr + c0, v);
+                tmem_ld32(T + lane_addr + c0, v);
                 if (dec_mode) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] += bvp[c0 + e];
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
                 if (pass == 1) wait_s(0);                               // KV of half 0 has consumed the images
                 if (dec_mode) store_row32_hi(img_hi + V_OFF, r, ch, v);
                 else store_row32_split(img_hi + V_OFF, img_lo + V_OFF, r, ch, v);
-                tmem_ld32(S1 + lane_addr + c0, v);
+                tmem_ld32(XA + lane_addr + c0, v);
                 if (dec_mode) {
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] += bkp[c0 + e];
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
                 const int half = cq, h = half * 4 + q;
                 for (int im = 0; im < (two ? 2 : 1); ++im) {
                     float v[32];
-                    tmem_ld32((im ? S1 : S0) + lane_addr + half * 128 + q * 32, v);
+                    tmem_ld32((im ? XA : T) + lane_addr + half * 128 + q * 32, v);
                     float* o = part + im * PART_FLOATS + h * HD * HD + lane * HD;
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);

@@ -43,7 +43,7 @@ constexpr uint32_t SM_X = SM_RING + RING * STAGE_BYTES;            // float[512]
 constexpr uint32_t SM_BAR = SM_X + 512 * 4;                        // mbarriers + tmem pointer
 constexpr uint32_t SM_TOTAL = SM_BAR + 256;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(uint64_t) * (2 * RING + 7) + 8 <= 256, "Bars must fit its reservation");
+static_assert(sizeof(uint64_t) * (2 * RING + 8) + 8 <= 256, "Bars must fit its reservation");
 // the kv phase re-uses the operand image space for the MN-major half images (tokens = K dimension)
 constexpr uint32_t KF_OFF = 0;                                     // Kf half image: 2 slabs (32 KB) inside hi / lo
 constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
@@ -57,6 +57,7 @@ struct Bars {
     uint64_t s_full[2];   // MMA -> row warps: accumulator S0 / S1 complete (tcgen05.commit)
     uint64_t a_free[2];   // MMA -> row warps (k_conv): the MMAs reading column pass p of the image have completed
     uint64_t x_full;      // producer -> row warps (k_enc): the tile's residual stream has landed in the image area
+    uint64_t s_free;      // row warps -> MMA (k_enc): accumulator T has been read by every row thread (count 512)
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -219,6 +220,7 @@ __device__ __forceinline__ uint32_t cta_setup(Bars* bars, int alloc_warp) {
             mbar_init(&bars->a_free[i], 1);
         }
         mbar_init(&bars->x_full, 1);
+        mbar_init(&bars->s_free, N_ROW_THREADS);
         fence_mbar_init();
     }
     if ((int)(threadIdx.x >> 5) == alloc_warp) tmem_alloc(&bars->tmem_base, 512);
