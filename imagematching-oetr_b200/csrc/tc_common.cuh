@@ -44,20 +44,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // Bounded wait: a protocol bug must never hang the GPU.  On timeout the flag (nullable) is raised for the host's
 // diagnostics and the kernel TRAPS: the launch fails with a CUDA error that every later call on the context reports,
 // so garbage results can never be returned silently (and a stale flag cannot shorten the waits of later launches).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* timeout_flag) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t a, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return done;
+}
+// ONE copy of the spin loop per kernel (inlined at ~60 call sites it was 40 % of k_enc's instruction stream, and the
+// row-warp code is instruction-fetch bound)
+__device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity, int* timeout_flag) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin)
+        if (mbar_try(a, parity)) return;
     if (timeout_flag) atomicExch(timeout_flag, 1);
     __threadfence_system();
     __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* timeout_flag) {
+    const uint32_t a = smem_u32(bar);
+    if (mbar_try(a, parity)) return;
+    mbar_wait_slow(a, parity, timeout_flag);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -196,12 +196,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
         auto load_acc = [&](uint32_t acc, float (&v)[2][32]) {
             tmem_ld32x2(acc + lane_addr + cq * 32, v[0], v[1]);
         };
-        // positional rows of this token: 8 x 16 bytes of column pass `pass` (tile-blocked table: coalesced per warp)
-        auto load_pos = [&](int pass, float4 (&ps)[8]) {
-            const int c0 = pass * 128 + cq * 32;
+        // Positional rows of this token (tile-blocked table: coalesced per warp).  PositionEncodingSine's frequencies are
+        // exp(-2k), k = channel / 4 (models/utils.py:188-190 with its precedence quirk): from channel 64 on the angles
+        // are below max_w * e^-32 < 4e-11, i.e. the rows are (sin, cos, sin, cos) = (0, 1, 0, 1) to far below fp32
+        // resolution of the sum LN(x) + pos.  Only the two chunks with channels < 64 read the table (pass 0 of the
+        // column quarters 0 and 1); everywhere else the constant pattern is added: 1/8 of the position-row traffic.
+        const bool pos_chunk = cq < 2;                     // warp-uniform
+        auto load_pos = [&](float4 (&ps)[8]) {
+            if (pos_chunk) {
 #pragma unroll
-            for (int jq = 0; jq < 8; ++jq)
-                ps[jq] = __ldg(reinterpret_cast<const float4*>(post + xt_off(pl >> 7, (c0 >> 2) + jq, pl & 127)));
+                for (int jq = 0; jq < 8; ++jq)
+                    ps[jq] = __ldg(reinterpret_cast<const float4*>(post + xt_off(pl >> 7, cq * 8 + jq, pl & 127)));
+            } else {
+#pragma unroll
+                for (int jq = 0; jq < 8; ++jq) ps[jq] = make_float4(0.f, 1.f, 0.f, 1.f);
+            }
         };
         // LayerNorm statistics of the row.  Each of the row's four threads (one per column quarter, in four different
         // warps of the same TMEM lane quarter) reduces its 64 values exactly (local mean, local M2); the (mean, M2) pairs
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
         // split: (hi, lo) image, else one fp16 value per element
         auto ln_image = [&](float (&x)[2][32], const float* __restrict__ gamma, const float* __restrict__ beta, bool with_pos, bool split) {
             float4 ps[8];
-            if (with_pos) load_pos(0, ps);                 // in flight during the statistics
+            if (with_pos) load_pos(ps);                    // pass 0's rows, in flight during the statistics
             float mean, rstd;
             row_stats(x, mean, rstd);
             const float shift = -mean * rstd;
@@ -256,7 +265,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
                     x[pass][jq * 4 + 2] = fmaf(fmaf(x[pass][jq * 4 + 2], rstd, shift), gamma[c + 2], beta[c + 2] + pz.z);
                     x[pass][jq * 4 + 3] = fmaf(fmaf(x[pass][jq * 4 + 3], rstd, shift), gamma[c + 3], beta[c + 3] + pz.w);
                 }
-                if (with_pos && pass == 0) load_pos(1, ps);    // in flight during the split + stores of pass 0
+                if (with_pos && pass == 0) {               // pass 1: channels >= 128, the constant pattern
+#pragma unroll
+                    for (int jq = 0; jq < 8; ++jq) ps[jq] = make_float4(0.f, 1.f, 0.f, 1.f);
+                }
                 if (split) store_row32_split(img_hi, img_lo, r, c0, x[pass]);
                 else store_row32_hi(img_hi, r, c0, x[pass]);
                 publish(pass);
@@ -268,7 +280,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             for (int pass = 0; pass < 2; ++pass) {
                 const int c0 = pass * 128 + cq * 32;
                 float4 ps[8];
-                if (with_pos) load_pos(pass, ps);
+                if (with_pos) {
+                    if (pass == 0) load_pos(ps);
+                    else {
+#pragma unroll
+                        for (int jq = 0; jq < 8; ++jq) ps[jq] = make_float4(0.f, 1.f, 0.f, 1.f);
+                    }
+                }
                 float v[32];
 #pragma unroll
                 for (int jq = 0; jq < 8; ++jq) {

@@ -29,7 +29,6 @@ def main():
     ap.add_argument("--in-flight", type=int, default=2)
     ap.add_argument("--chunk-pairs", type=int, default=-1)
     a = ap.parse_args()
-    os.environ.setdefault("OETR_TIMING", "1")
     fm = a.side // 32
     W = weights.synthetic_hot_path_weights(0)
     hots = [oetr_b200.OverlapHotPath(W) for _ in range(a.in_flight)]
