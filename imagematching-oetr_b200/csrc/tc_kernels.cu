@@ -541,7 +541,8 @@ int tc_selftest(float* errs, int n_errs, char* msg, size_t msg_len) {
     for (auto& v : lng) v = 1.f + 0.5f * frand(seed);
     for (auto& v : lnb) v = 0.4f * frand(seed);
     std::vector<float> posrow((size_t)L * C);
-    for (auto& v : posrow) v = 2.f * frand(seed);
+    // like PositionEncodingSine: free values in channels < 64, the constant (0, 1, 0, 1) pattern above (see k_enc load_pos)
+    for (size_t i = 0; i < posrow.size(); ++i) posrow[i] = (i % C) < 64 ? 2.f * frand(seed) : (float)((i % C) & 1);
     for (int l = 0; l < L; ++l) for (int c = 0; c < C; ++c) pos[xt_off(0, c / 4, l) + c % 4] = posrow[(size_t)l * C + c];
 
     float *d_feat, *d_wm, *d_tmp, *d_ln, *d_xt, *d_post, *d_part, *d_ksum;
