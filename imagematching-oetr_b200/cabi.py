@@ -16,7 +16,10 @@ EXPORTS = (
     "oetr_forward_host_submit", "oetr_forward_host_wait",
     "oetr_profile_enable", "oetr_profile_read", "oetr_set_chunk_pairs",
     "oetr_selftest_tcgen05", "oetr_selftest_geometry", "oetr_debug_cycles",
+    "oetr_gather_create", "oetr_gather_connect", "oetr_gather_submit", "oetr_gather_collect", "oetr_gather_destroy",
+    "oetr_gather_last_error",
 )
+IPC_HANDLE_BYTES = 64
 
 
 class OetrError(RuntimeError):
@@ -71,6 +74,17 @@ def load_library(path=None):
     lib.oetr_forward_host_wait.argtypes = [vp, c.c_int, vp, vp]
     lib.oetr_selftest_geometry.restype = c.c_int
     lib.oetr_selftest_geometry.argtypes = [c.c_int] * 5 + [c.POINTER(c.c_int)]
+    lib.oetr_gather_create.restype = c.c_int
+    lib.oetr_gather_create.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(vp), vp]
+    lib.oetr_gather_connect.restype = c.c_int
+    lib.oetr_gather_connect.argtypes = [vp, vp]
+    lib.oetr_gather_submit.restype = c.c_int
+    lib.oetr_gather_submit.argtypes = [vp, vp, vp, vp]
+    lib.oetr_gather_collect.restype = c.c_int
+    lib.oetr_gather_collect.argtypes = [vp, vp, vp]
+    lib.oetr_gather_destroy.restype = c.c_int
+    lib.oetr_gather_destroy.argtypes = [vp]
+    lib.oetr_gather_last_error.restype = c.c_char_p
     lib.oetr_debug_cycles.restype = c.c_int
     lib.oetr_debug_cycles.argtypes = [c.POINTER(c.c_ulonglong), c.c_int, c.c_int]
     lib.oetr_selftest_tcgen05.restype = c.c_int

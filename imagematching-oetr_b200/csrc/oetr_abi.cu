@@ -805,6 +805,7 @@ int oetr_forward_host(oetr_handle* h, const float* feat1_host, const float* feat
 }
 
 int oetr_debug_cycles(unsigned long long* out, int n, int reset) {
+    if (n < 0) { tc_debug_enable(reset != 0); return 0; }          // n < 0: switch the accumulators on / off
     if (!out || n < 1) return fail(OETR_E_ARG, "oetr_debug_cycles: bad arguments");
     return tc_debug_read(out, n, reset);
 }

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
         if (lane == 0) {
             MmaState ms;
             const long long t_begin = clock64();
+            const unsigned long long ns_begin = p.dbg_acc ? global_ns() : 0ull;
             auto wait_a = [&](int pass) { mma_wait_a(bars, p.flag, ms, pass); };
             auto gemm = [&](uint32_t d, bool accumulate, bool wait, int terms) { gemm_issue(smem_base, bars, p.flag, ms, d, accumulate, wait, false, terms); };
             if (p.do_q) {
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
                 atomicAdd(p.dbg_acc + DBG_MMA_WAIT_A, (unsigned long long)ms.t_a);
                 atomicAdd(p.dbg_acc + DBG_MMA_WAIT_W, (unsigned long long)ms.t_ring);
                 atomicAdd(p.dbg_acc + DBG_TILES, 1ull);
+                atomicAdd(p.dbg_acc + DBG_TILE_NS, global_ns() - ns_begin);
             }
         }
         __syncwarp();

@@ -313,9 +313,10 @@ static int set_attrs(char* msg, size_t msg_len) {
 
 // OETR_TIMING=1: device-side cycle accumulators (DBG_* in tc_tiles.cuh), one buffer per process, no host synchronisation
 static unsigned long long* g_dbg_acc = nullptr;
+static bool g_dbg_on = getenv("OETR_TIMING") != nullptr;
+void tc_debug_enable(bool on) { g_dbg_on = on; }
 static unsigned long long* dbg_acc_buffer() {
-    static const bool on = getenv("OETR_TIMING") != nullptr;
-    if (!on) return nullptr;
+    if (!g_dbg_on) return nullptr;
     std::lock_guard<std::mutex> lock(g_attr_mu);
     if (!g_dbg_acc) {
         if (cudaMalloc(&g_dbg_acc, DBG_SLOTS * sizeof(unsigned long long)) != cudaSuccess) return nullptr;

@@ -52,6 +52,7 @@ void tc_free_weights(TcWeights& w);
 // tile-blocked positional rows of one (hf,wf) geometry (cached by the handle, see oetr_abi.cu)
 // OETR_TIMING=1: copies the device-side cycle accumulators (DBG_* in tc_tiles.cuh) to out; returns the slots copied
 int tc_debug_read(unsigned long long* out, int n, int reset);
+void tc_debug_enable(bool on);
 // host-only consistency check of the encoder tiling; returns the number of flat tiles (> 0), -2 - tiles for the
 // per-image tiling, or -1 with a message
 int tc_check_geometry(int B, int L1, int L2, char* msg, size_t msg_len);

@@ -49,7 +49,8 @@ constexpr uint32_t KF_OFF = 0;                                     // Kf half im
 constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
 
 // OETR_TIMING=1: global cycle accumulators of the k_enc launches with a query and a source phase (atomicAdd per CTA)
-enum { DBG_MMA_TOTAL = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_W = 2, DBG_TILES = 3, DBG_STAGE0 = 8, DBG_CONV = 40, DBG_SLOTS = 48 };
+enum { DBG_MMA_TOTAL = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_W = 2, DBG_TILES = 3, DBG_TILE_NS = 4, DBG_STAGE0 = 8, DBG_CONV = 40, DBG_SLOTS = 48 };
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 struct Bars {
     uint64_t full[RING], empty[RING];

@@ -183,9 +183,31 @@ OETR_API int oetr_forward_host(oetr_handle* h,
  * Returns OETR_OK when the kernels ran (inspect errs for the numeric outcome). */
 OETR_API int oetr_selftest_tcgen05(float* errs_host, int n_errs);
 
-/* Debugging aid (OETR_TIMING=1 in the environment at the first forward): copies up to n device-side cycle
- * accumulators of the tcgen05 kernels (MMA-lane busy / wait cycles, row-warp stage durations) to out and optionally
- * resets them.  Returns the number of slots copied (0 when timing is off).  Synchronises the device. */
+/* ---- boxes of every rank on every rank (BASELINE configs[2]) ------------------------------------------
+ * One process per GPU.  Instead of a collective, every rank stores its [pairs][2][4] boxes straight into its peers'
+ * communication buffers over NVLink (CUDA IPC mapped peer memory, one tiny stream-ordered kernel) and publishes a
+ * per-(slot, source rank) step flag; oetr_gather_collect waits (on the device, stream-ordered) for the flags of all
+ * ranks of the oldest outstanding step and copies the gathered [world*pairs][2][4] boxes (global pair order: rank
+ * major) to `all_boxes`.  Up to `slots` steps may be in flight; ranks never rendezvous.  Every submit must be
+ * followed by a collect on every rank (a peer that stops collecting makes its writers trap after ~10 s).
+ *   create : allocates this rank's buffer, returns its CUDA IPC handle (OETR_IPC_HANDLE_BYTES bytes)
+ *   connect: all_handles = the handles of ranks 0..world-1, concatenated (exchange them with any host transport,
+ *            e.g. torch.distributed.all_gather_object); world == 1 needs no connect
+ * Replaces the reference-side nothing: the reference has no inference-time communication (train.py:59-74 is DDP). */
+#define OETR_IPC_HANDLE_BYTES 64
+typedef struct oetr_gather oetr_gather;
+OETR_API int oetr_gather_create(int world, int rank, int pairs_per_rank, int slots, oetr_gather** out, void* ipc_handle_out);
+OETR_API int oetr_gather_connect(oetr_gather* g, const void* all_handles);
+OETR_API int oetr_gather_submit(oetr_gather* g, const float* boxes1, const float* boxes2, void* stream);
+OETR_API int oetr_gather_collect(oetr_gather* g, float* all_boxes, void* stream);
+OETR_API int oetr_gather_destroy(oetr_gather* g);
+OETR_API const char* oetr_gather_last_error(void);
+
+/* Measurement aid: device-side accumulators of the tcgen05 kernels (per-tile MMA-lane busy / wait cycles, wall
+ * nanoseconds per tile, row-warp stage durations; one atomicAdd per tile, no host synchronisation).  Switched on by
+ * OETR_TIMING=1 in the environment or by oetr_debug_cycles(NULL, -1, 1) (off: (NULL, -1, 0)).  With n > 0: copies up
+ * to n accumulators to out, optionally resets them, returns the number copied (0 when off); synchronises the device.
+ * bench.py derives the dominant kernel's per-SM tile time inside the timed region from them. */
 OETR_API int oetr_debug_cycles(unsigned long long* out, int n, int reset);
 
 /* Host-only (no GPU needed) consistency check of the encoder's tile geometry for a problem size: every token is one

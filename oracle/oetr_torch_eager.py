@@ -29,14 +29,22 @@ def _lin_attn(q, k, v):
     return torch.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z) * s_len
 
 
-def _encoder_layer(W, p, x, src, x_pos, s_pos):
+def _full_attn(q, k, v):
+    """linear_attention.py:59-87 (masks None, dropout off): softmax(q k^T / sqrt(D)) v per head."""
+    QK = torch.einsum("nlhd,nshd->nlsh", q, k)
+    A = torch.softmax(QK / q.size(3) ** 0.5, dim=2)
+    return torch.einsum("nlsh,nshd->nlhd", A, v)
+
+
+def _encoder_layer(W, p, x, src, x_pos, s_pos, attention="linear"):
     n, l, _ = x.shape
     query = F.layer_norm(x, (C,), W[p + "pre_norm_q.weight"], W[p + "pre_norm_q.bias"]) + x_pos
     kv = F.layer_norm(src, (C,), W[p + "pre_norm_kv.weight"], W[p + "pre_norm_kv.bias"]) + s_pos
     q = F.linear(query, W[p + "q_proj.weight"]).view(n, l, NH, HD)
     k = F.linear(kv, W[p + "k_proj.weight"]).view(n, -1, NH, HD)
     v = F.linear(kv, W[p + "v_proj.weight"]).view(n, -1, NH, HD)
-    x = x + F.linear(_lin_attn(q, k, v).reshape(n, l, C), W[p + "merge.weight"])
+    att = _lin_attn(q, k, v) if attention == "linear" else _full_attn(q, k, v)
+    x = x + F.linear(att.reshape(n, l, C), W[p + "merge.weight"])
     h = F.gelu(F.linear(F.layer_norm(x, (C,), W[p + "norm2.weight"], W[p + "norm2.bias"]), W[p + "mlp.0.weight"]))
     return x + F.linear(h, W[p + "mlp.2.weight"])
 
@@ -92,7 +100,7 @@ def prepare(weights, device, dtype=torch.float32, max_shape=(100, 100)):
 
 
 @torch.no_grad()
-def hot_path(W, feat1, feat2, img_hw1, img_hw2, clamp=True):
+def hot_path(W, feat1, feat2, img_hw1, img_hw2, clamp=True, attention="linear"):
     """feat1 [N,256,hf1,wf1], feat2 [N,256,hf2,wf2] tensors on W's device.  Returns (box1, box2) [N,4]."""
     n = feat1.size(0)
     hf1, wf1 = feat1.shape[2:]
@@ -102,9 +110,9 @@ def hot_path(W, feat1, feat2, img_hw1, img_hw2, clamp=True):
     for i in range(orc.N_ENCODER):
         p = "transformer.encoder.%d." % i
         if i % 2 == 0:
-            x = [_encoder_layer(W, p, x[0], x[0], pos[0], pos[0]), _encoder_layer(W, p, x[1], x[1], pos[1], pos[1])]
+            x = [_encoder_layer(W, p, x[0], x[0], pos[0], pos[0], attention), _encoder_layer(W, p, x[1], x[1], pos[1], pos[1], attention)]
         else:
-            x = [_encoder_layer(W, p, x[0], x[1], pos[0], pos[1]), _encoder_layer(W, p, x[1], x[0], pos[1], pos[0])]
+            x = [_encoder_layer(W, p, x[0], x[1], pos[0], pos[1], attention), _encoder_layer(W, p, x[1], x[0], pos[1], pos[0], attention)]
     out = []
     geo = ((hf1, wf1, img_hw1), (hf2, wf2, img_hw2))
     for k in range(2):

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oetr_b200.distributed import ShardedOverlapEstimator, shard_range
+from oetr_b200.distributed import BoxGather, ShardedOverlapEstimator, shard_range
 
 
 def test_shard_ranges_cover_batch():
@@ -48,4 +48,34 @@ def test_gather_two_ranks(batch):
         port = s.getsockname()[1]
     ok = mp.get_context("spawn").Array("i", [0, 0])
     mp.spawn(_worker, args=(2, port, batch, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+
+
+def _gather_worker(rank, world, port, pairs, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = BoxGather(pairs, "cpu", slots=3)
+        assert g.mode == "collective"
+        good = True
+        for step in range(7):                               # more steps than slots: the ring wraps
+            b1 = torch.arange(pairs * 4, dtype=torch.float32).view(pairs, 4) + 1000 * rank + 10000 * step
+            g.submit(b1, -b1)
+            got = g.result()
+            for r in range(world):
+                want = torch.arange(pairs * 4, dtype=torch.float32).view(pairs, 4) + 1000 * r + 10000 * step
+                good &= bool(torch.equal(got[r * pairs:(r + 1) * pairs, 0], want))
+                good &= bool(torch.equal(got[r * pairs:(r + 1) * pairs, 1], -want))
+        ok[rank] = int(good)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_box_gather_ring_two_ranks_gloo():
+    """BoxGather (collective mode on CPU): every rank ends every step with the boxes of all ranks in global order."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(_gather_worker, args=(2, port, 3, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]
