@@ -102,19 +102,45 @@ def synthetic_tensor(name, shape, seed=0):
     return _uniform(rng, shape, float(np.sqrt(6.0 / (shape[-1] + shape[0]))))
 
 
-def synthetic_hot_path_weights(seed=0, include_unused=False):
-    """{name: fp32 ndarray} for every hot-path tensor (random-init weights of the reference architecture)."""
+def _default_init_tensor(name, shape, seed):
+    """PyTorch's default initialisation of nn.Linear / nn.Conv2d / nn.GroupNorm (what the reference's tlbr_reg and
+    heatmap_conv get: src/model.py:59-77 are outside the xavier loop of transformer.py:308-311): kaiming_uniform
+    (a = sqrt(5)) -> bound 1/sqrt(fan_in) for weights and biases; GroupNorm weight 1, bias 0."""
+    shape = tuple(shape)
+    if name.startswith("heatmap_conv.1."):
+        return np.ones(shape, np.float32) if name.endswith("weight") else np.zeros(shape, np.float32)
+    fan_in = {"tlbr_reg.0": 256, "tlbr_reg.2": 256, "heatmap_conv.0": 256 * 9, "heatmap_conv.3": 256}[name.rsplit(".", 1)[0]]
+    return _uniform(_rng_for(name + "/default", seed), shape, 1.0 / float(np.sqrt(fan_in)))
+
+
+def synthetic_hot_path_weights(seed=0, include_unused=False, ln_gain=None, head_default_init=False):
+    """{name: fp32 ndarray} for every hot-path tensor (random-init weights of the reference architecture).
+    Stress variants (tests/golden STRESS_CASES): ln_gain = (lo, hi) multiplies every LayerNorm weight by a deterministic
+    per-channel factor in [lo, hi] (trained-like gains); head_default_init uses PyTorch's default initialisation for
+    tlbr_reg / heatmap_conv instead of the test-friendly scales of synthetic_tensor."""
     names = list(CANONICAL_ORDER) + (UNUSED_NAMES if include_unused else [])
-    return {n: synthetic_tensor(n, s, seed) for n, s in names}
+    out = {n: synthetic_tensor(n, s, seed) for n, s in names}
+    if ln_gain is not None:
+        lo, hi = ln_gain
+        for n, s in names:
+            if "norm" in n and n.endswith("weight") and n.startswith("transformer."):
+                u = _uniform(_rng_for(n + "/gain", seed), s, 1.0).astype(np.float64) * 0.5 + 0.5        # [0, 1)
+                out[n] = (out[n] * (lo + (hi - lo) * u)).astype(np.float32)
+    if head_default_init:
+        for n, s in names:
+            if n.startswith(("tlbr_reg.", "heatmap_conv.")):
+                out[n] = _default_init_tensor(n, s, seed)
+    return out
 
 
-def synthetic_features(batch, hf, wf, seed=1, tag="feat"):
-    """Stand-in for input_proj2 outputs: 0.3*N(0,1)-like (real features have std ~0.30)."""
+def synthetic_features(batch, hf, wf, seed=1, tag="feat", scale=1.0):
+    """Stand-in for input_proj2 outputs: 0.3*N(0,1)-like (real features have std ~0.30); `scale`
+    multiplies them (stress cases)."""
     rng = _rng_for("%s/%d/%d/%d" % (tag, batch, hf, wf), seed)
     shape = (batch, D_MODEL, hf, wf)
     # sum of 4 uniforms: bell-shaped, exactly reproducible
     acc = sum(_uniform(rng, shape, 1.0).astype(np.float64) for _ in range(4))
-    return (acc * (0.3 / np.sqrt(4.0 / 3.0))).astype(np.float32)
+    return (acc * (scale * 0.3 / np.sqrt(4.0 / 3.0))).astype(np.float32)
 
 
 def synthetic_mask(batch, hf, wf, tag="mask"):

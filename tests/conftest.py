@@ -48,3 +48,14 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def load_stress_case(name):
+    """(weights dict, feat1, feat2, case dict, golden npz) for a tests/golden STRESS_CASES case (trained-like scales)."""
+    from cases import STRESS_CASES
+    from oetr_b200 import weights
+    c = STRESS_CASES[name]
+    W = weights.synthetic_hot_path_weights(c["wseed"], ln_gain=c["ln_gain"], head_default_init=c["head_default_init"])
+    f1 = weights.synthetic_features(c["batch"], *c["fm1"], seed=c["fseed"], tag="feat1", scale=c["feat_scale"])
+    f2 = weights.synthetic_features(c["batch"], *c["fm2"], seed=c["fseed"], tag="feat2", scale=c["feat_scale"])
+    return W, f1, f2, c, np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))

@@ -20,13 +20,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 import ref_loader  # noqa: E402
-from cases import CASES, MASK_CASES, MEMORY_STRIDE  # noqa: E402
+from cases import CASES, MASK_CASES, MEMORY_STRIDE, STRESS_CASES  # noqa: E402
 
 from oetr_b200 import weights  # noqa: E402
 
 
-def load_synthetic(net, seed):
-    sd = weights.synthetic_hot_path_weights(seed, include_unused=True)
+def load_synthetic(net, seed, **variant):
+    sd = weights.synthetic_hot_path_weights(seed, include_unused=True, **variant)
     missing, unexpected = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
     assert not unexpected, unexpected
     assert all(k.startswith(("backbone.", "input_proj", "patchmerging.")) for k in missing), missing
@@ -64,8 +64,31 @@ def run_reference(net, full_tf, feat1, feat2, hw1, hw2, attention, dtype, mask1=
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
+def make_stress(net):
+    for name, c in STRESS_CASES.items():
+        load_synthetic(net, c["wseed"], ln_gain=c["ln_gain"], head_default_init=c["head_default_init"])
+        feat1 = weights.synthetic_features(c["batch"], *c["fm1"], seed=c["fseed"], tag="feat1", scale=c["feat_scale"])
+        feat2 = weights.synthetic_features(c["batch"], *c["fm2"], seed=c["fseed"], tag="feat2", scale=c["feat_scale"])
+        net.float()
+        o32 = run_reference(net, None, feat1, feat2, c["hw1"], c["hw2"], "linear", torch.float32)
+        net.double()
+        o64 = run_reference(net, None, feat1, feat2, c["hw1"], c["hw2"], "linear", torch.float64)
+        net.float()
+        blob = {k: v for k, v in o32.items()}
+        blob.update({k + "_f64": v for k, v in o64.items() if not k.startswith("memory")})
+        if c["batch"] > 4:                                # big batch: keep memory of 4 pairs only
+            for k in ("memory1_sub", "memory2_sub"):
+                blob[k] = blob[k][::8]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        print("%-20s box1_raw=%s  |fp32-fp64|=%.2e  tlbr1=%s" % (name, o64["box1_raw"][0].round(3),
+              np.abs(o32["box1_raw"] - o64["box1_raw"]).max(), o64["tlbr1"][0].round(4)))
+
+
 def main():
     net = ref_loader.build_reference_oetr(seed=0)
+    if "--stress-only" in sys.argv:                    # leaves the other committed files untouched
+        make_stress(net)
+        return
     only_masked = "--masked-only" in sys.argv          # leaves the other committed files untouched
     if not only_masked:
         np.savez_compressed(os.path.join(HERE, "pe_table.npz"),
@@ -108,6 +131,9 @@ def main():
         d = np.abs(o32["box1_raw"] - o64["box1_raw"]).max()
         print("%-16s box1_raw=%s  |fp32-fp64|=%.2e  tlbr1=%s" % (name, o64["box1_raw"][0].round(3), d,
                                                                  o64["tlbr1"][0].round(4)))
+
+
+    make_stress(net)
 
 
 if __name__ == "__main__":

@@ -5,8 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES, MASK_CASES, MEMORY_STRIDE
-from conftest import ROOT, load_case, load_masks, rel_err
+from cases import CASES, MASK_CASES, MEMORY_STRIDE, STRESS_CASES
+from conftest import ROOT, load_case, load_masks, load_stress_case, rel_err
 from oracle import oetr_oracle as orc
 
 
@@ -89,3 +89,26 @@ def test_oracle_matches_reference_with_masks(name):
     # the masks matter: the unmasked result is a different box
     u = orc.hot_path(W, f1, f2, hw1, hw2)
     assert np.abs(u["box1_raw"] - o["box1_raw"]).max() > 1.0
+
+
+@pytest.mark.parametrize("name", sorted(n for n in STRESS_CASES if n != "b32_640"))
+def test_oracle_matches_reference_on_stress_scales(name):
+    """Trained-like scales (features x3 / x0.1, LayerNorm gains up to 3, PyTorch-default head init): the oracle still
+    agrees with the reference run in double precision at fp64 noise level, and with the reference as shipped (fp32)."""
+    W, f1, f2, c, g = load_stress_case(name)
+    o = orc.hot_path(W, f1, f2, c["hw1"], c["hw2"])
+    for k in ("hs1", "hs2", "cxy1", "cxy2", "tlbr1", "tlbr2", "box1_raw", "box2_raw"):
+        assert rel_err(o[k], g[k + "_f64"]) < 1e-7, k
+    for k, side in (("box1", max(c["hw1"])), ("box2", max(c["hw2"])), ("box1_raw", max(c["hw1"])), ("box2_raw", max(c["hw2"]))):
+        assert np.abs(o[k] - g[k]).max() / side < 2e-5, k
+    assert rel_err(o["memory1"][:, ::MEMORY_STRIDE], g["memory1_sub"]) < 5e-5
+
+
+def test_oracle_matches_reference_full_batch_32_sample():
+    """BASELINE config 2's full batch (32 pairs of 640x640) was run through the reference once; the oracle reproduces a
+    sample of its pairs (pairs are independent) -- the GPU suite checks all 32."""
+    W, f1, f2, c, g = load_stress_case("b32_640")
+    idx = [0, 13, 31]
+    o = orc.hot_path(W, f1[idx], f2[idx], c["hw1"], c["hw2"])
+    for k in ("box1_raw", "box2_raw", "tlbr1", "cxy2"):
+        assert rel_err(o[k], g[k + "_f64"][idx]) < 1e-7, k
