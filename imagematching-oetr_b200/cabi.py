@@ -17,7 +17,7 @@ EXPORTS = (
     "oetr_profile_enable", "oetr_profile_read", "oetr_set_chunk_pairs",
     "oetr_selftest_tcgen05", "oetr_selftest_geometry", "oetr_debug_cycles",
     "oetr_gather_create", "oetr_gather_connect", "oetr_gather_submit", "oetr_gather_collect", "oetr_gather_destroy",
-    "oetr_gather_last_error",
+    "oetr_gather_last_error", "oetr_head_forward",
 )
 IPC_HANDLE_BYTES = 64
 
@@ -74,6 +74,8 @@ def load_library(path=None):
     lib.oetr_forward_host_wait.argtypes = [vp, c.c_int, vp, vp]
     lib.oetr_selftest_geometry.restype = c.c_int
     lib.oetr_selftest_geometry.argtypes = [c.c_int] * 5 + [c.POINTER(c.c_int)]
+    lib.oetr_head_forward.restype = c.c_int
+    lib.oetr_head_forward.argtypes = [vp] * 7 + [c.c_int] * 10 + [vp] * 4 + [vp, c.c_size_t, vp]
     lib.oetr_gather_create.restype = c.c_int
     lib.oetr_gather_create.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(vp), vp]
     lib.oetr_gather_connect.restype = c.c_int

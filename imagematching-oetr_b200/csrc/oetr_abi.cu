@@ -81,10 +81,11 @@ struct oetr_handle {
     TcWeights tc;              // fp16 UMMA operand images (FP16 path only)
     KernelProfiler prof;       // optional CUDA-event brackets around the dominant kernel
     int* d_flag = nullptr;     // raised by a device-side mbarrier wait that timed out (protocol bug guard)
-    // FP16 path: tile-blocked positional rows of the two most recent geometries (regenerated only on change)
-    float* d_post[2] = {nullptr, nullptr};
-    size_t post_cap[2] = {0, 0};
-    int post_hw[2][2] = {{0, 0}, {0, 0}};
+    // FP16 path: tile-blocked positional rows per feature-map geometry.  Entries are IMMUTABLE once generated (a forward
+    // on another stream may still be reading them): a new geometry gets a new buffer, and every forward makes its
+    // stream wait for the generating kernel through the entry's event.
+    struct PosEntry { int hf = 0, wf = 0; float* rows = nullptr; cudaEvent_t ready = nullptr; };
+    std::vector<PosEntry> pos_cache;
     int last_launches = 0;
     // staging owned by the handle for the host-buffer entry points only: HOST_SLOTS requests can be in flight
     HostSlot slot[HOST_SLOTS];
@@ -371,7 +372,7 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
 int oetr_destroy(oetr_handle* h) {
     if (!h) return OETR_OK;
     cudaFree(h->d_w); cudaFree(h->d_w9); cudaFree(h->d_pe); cudaFree(h->d_flag);
-    cudaFree(h->d_post[0]); cudaFree(h->d_post[1]);
+    for (auto& e : h->pos_cache) { cudaFree(e.rows); if (e.ready) cudaEventDestroy(e.ready); }
     tc_free_weights(h->tc);
     for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -496,6 +497,7 @@ struct FwdArgs {
     int hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp;
     float *dbg_hs, *dbg_memory, *dbg_cxy, *dbg_tlbr;
     const float *mask1, *mask2;     // nullable [batch][hf*wf] device masks of the WHOLE batch (sub-batches offset them)
+    const float *post1 = nullptr, *post2 = nullptr;   // FP16 path: tile-blocked positional rows of the two geometries
 };
 
 // one (sub-)batch of B pairs on stream s with workspace slice w
@@ -516,7 +518,7 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
         // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
         // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
         char msg[256] = "";
-        if (tc_encoder(h->tc, h->d_w, h->h_w.data(), h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, h->d_post[0], h->d_post[1],
+        if (tc_encoder(h->tc, h->d_w, h->h_w.data(), h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, a.post1, a.post2,
                        a.mask1, a.mask2,
                        a.dbg_memory ? w.X : nullptr, h->d_flag, profile ? &h->prof : nullptr, s, lc, msg, sizeof(msg)) != 0)
             return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
@@ -550,30 +552,43 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
     return OETR_OK;
 }
 
-int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int batch, const FwdArgs& a, float* boxes1,
+int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int batch, const FwdArgs& a_in, float* boxes1,
                  float* boxes2, void* workspace, size_t workspace_bytes, cudaStream_t s, const HostIO* hio,
                  const EventSet& es) {
+    FwdArgs a = a_in;
     const int B = batch, L1 = a.hf1 * a.wf1, L2 = a.hf2 * a.wf2;
+    int cur_dev = -1;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev != h->device)
+        return fail(OETR_E_ARG, "oetr_forward: the handle lives on device %d but the current device is %d", h->device, cur_dev);
     LaunchCounter lc;
+    const float* post[2] = {nullptr, nullptr};
     if (h->prec == OETR_PREC_FP16) {
-        // positional rows, tile-blocked, cached per geometry (the only state a forward keeps between calls; a
-        // geometry change regenerates it on `s`, growing the buffer with cudaMalloc if needed)
+        // positional rows, tile-blocked, cached per geometry (the only state a forward adds to the handle)
         const int geo[2][2] = {{a.hf1, a.wf1}, {a.hf2, a.wf2}};
         for (int k = 0; k < 2; ++k) {
-            if (h->post_hw[k][0] == geo[k][0] && h->post_hw[k][1] == geo[k][1]) continue;
-            const int Lk = geo[k][0] * geo[k][1];
-            const size_t need = tc_pos_tile_floats(Lk);
-            // requests still in flight on the handle's own streams (host submit/wait) read the rows being replaced
-            for (HostSlot& sl : h->slot)
-                if (sl.busy) for (int c = 0; c < sl.n_join; ++c) cudaEventSynchronize(sl.ev_join[c]);
-            if (h->post_cap[k] < need) {
-                cudaFree(h->d_post[k]); h->d_post[k] = nullptr; h->post_cap[k] = 0; h->post_hw[k][0] = h->post_hw[k][1] = 0;
-                CU(cudaMalloc(&h->d_post[k], need * sizeof(float)));
-                h->post_cap[k] = need;
+            oetr_handle::PosEntry* hit = nullptr;
+            for (auto& e : h->pos_cache) if (e.hf == geo[k][0] && e.wf == geo[k][1]) hit = &e;
+            if (!hit) {
+                if (h->pos_cache.size() >= 32) {               // many geometries: start over once nothing can be reading
+                    CU(cudaDeviceSynchronize());
+                    for (auto& e : h->pos_cache) { cudaFree(e.rows); cudaEventDestroy(e.ready); }
+                    h->pos_cache.clear();
+                    for (HostSlot& sl : h->slot) for (ChunkGraph& g : sl.cg) g.uses = 0, g.ptr[5] = g.ptr[6] = nullptr;
+                }
+                oetr_handle::PosEntry e;
+                e.hf = geo[k][0]; e.wf = geo[k][1];
+                const int Lk = e.hf * e.wf;
+                CU(cudaMalloc(&e.rows, tc_pos_tile_floats(Lk) * sizeof(float)));
+                CU(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming));
+                tc_pos_tiles(h->d_pe, h->max_w, e.wf, Lk, e.rows, s, lc);
+                CU(cudaEventRecord(e.ready, s));
+                h->pos_cache.push_back(e);
+                hit = &h->pos_cache.back();
             }
-            tc_pos_tiles(h->d_pe, h->max_w, geo[k][1], Lk, h->d_post[k], s, lc);
-            h->post_hw[k][0] = geo[k][0]; h->post_hw[k][1] = geo[k][1];
+            CU(cudaStreamWaitEvent(s, hit->ready, 0));         // no-op once the generating kernel has finished
+            post[k] = hit->rows;
         }
+        a.post1 = post[0]; a.post2 = post[1];
     }
     int sizes[MAX_CHUNKS];
     int nc = chunk_plan(h, B, L1, L2, sizes);
@@ -615,7 +630,7 @@ int forward_core(oetr_handle* h, const float* feat1, const float* feat2, int bat
             bool replayed = false;
             if (cg) {
                 const int key[11] = {Bc, a.hf1, a.wf1, a.hf2, a.wf2, a.img_h1, a.img_w1, a.img_h2, a.img_w2, a.clamp, nc};
-                const void* ptr[7] = {f1c, f2c, b1c, b2c, base, h->d_post[0], h->d_post[1]};
+                const void* ptr[7] = {f1c, f2c, b1c, b2c, base, post[0], post[1]};
                 const bool same = memcmp(key, cg->key, sizeof(key)) == 0 && memcmp(ptr, cg->ptr, sizeof(ptr)) == 0;
                 if (!same) {
                     if (cg->exec) { cudaGraphExecDestroy(cg->exec); cg->exec = nullptr; }
@@ -698,6 +713,44 @@ int oetr_forward_masked(oetr_handle* h, const float* feat1, const float* feat2, 
     const EventSet es{h->ev_fork, h->ev_join, true, nullptr, h->aux};
     return forward_core(h, feat1, feat2, batch, a, boxes1, boxes2, workspace, workspace_bytes,
                         static_cast<cudaStream_t>(stream), nullptr, es);
+}
+
+int oetr_head_forward(oetr_handle* h, const float* memory1, const float* memory2, const float* hs1, const float* hs2,
+                      const float* mask1, const float* mask2, int batch, int hf1, int wf1, int hf2, int wf2, int img_h1,
+                      int img_w1, int img_h2, int img_w2, int clamp, float* boxes1, float* boxes2, float* cxy,
+                      float* tlbr, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_shapes(h, batch, hf1, wf1, hf2, wf2);
+    if (rc) return rc;
+    if (batch == 0) return OETR_OK;
+    if (!memory1 || !memory2 || !hs1 || !hs2 || !boxes1 || !boxes2 || !workspace)
+        return fail(OETR_E_ARG, "oetr_head_forward: null buffer");
+    if ((mask1 == nullptr) != (mask2 == nullptr)) return fail(OETR_E_ARG, "oetr_head_forward: give both masks or neither");
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(OETR_E_ARG, "oetr_head_forward: workspace must be 256-byte aligned");
+    const int B = batch, L1 = hf1 * wf1, L2 = hf2 * wf2, R1 = B * L1, R2 = B * L2;
+    const Workspace w = carve(workspace, h, B, L1, L2);
+    if (w.bytes > workspace_bytes) return fail(OETR_E_NOMEM, "oetr_head_forward: workspace %zu B < required %zu B", workspace_bytes, w.bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LaunchCounter lc;
+    const float* W = h->d_w;
+    // heat = memory * <memory, hs>; conv3x3 (+bias) -> Y; GroupNorm/ReLU/1x1/softmax/soft-argmax + tlbr + box assembly:
+    // the fp32 CUDA-core kernels of either precision's handle (this entry serves the stage-wise Python signatures)
+    float *G = w.T, *Gs = w.Q, *Y = w.O;
+    heat_scale(memory1, hs1, G, R1, L1, s, lc);
+    heat_scale(memory2, hs2, G + (size_t)R1 * C, R2, L2, s, lc);
+    head_conv_fp32(h, w, B, hf1, wf1, hf2, wf2, G, Gs, Y, s, lc);
+    HeadParams p{};
+    p.gn_g = W + h->L.hm_gn_g; p.gn_b = W + h->L.hm_gn_b; p.w3 = W + h->L.hm_w3; p.b3 = W + h->L.hm_b3;
+    p.tl_w0 = W + h->L.tl_w0; p.tl_w2 = W + h->L.tl_w2; p.tl_b2 = W + h->L.tl_b2;
+    p.batch = B; p.clamp = clamp;
+    p.Y = Y; p.hs = hs1; p.hf = hf1; p.wf = wf1; p.img_h = img_h1; p.img_w = img_w1;
+    p.boxes = boxes1; p.dbg_cxy = cxy; p.dbg_tlbr = tlbr; p.mask = mask1;
+    head_finalize(p, s, lc);
+    p.Y = Y + (size_t)R1 * C; p.hs = hs2; p.hf = hf2; p.wf = wf2; p.img_h = img_h2; p.img_w = img_w2;
+    p.boxes = boxes2; p.dbg_cxy = cxy ? cxy + 2 * B : nullptr; p.dbg_tlbr = tlbr ? tlbr + 4 * B : nullptr; p.mask = mask2;
+    head_finalize(p, s, lc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(OETR_E_CUDA, "oetr_head_forward: launch failed: %s", cudaGetErrorString(e));
+    return OETR_OK;
 }
 
 static int grow(float** p, size_t* have, size_t need) {

@@ -3,9 +3,13 @@ the reference plugin (reference dloc/core/overlaps/oetr.py:15-46), so `--overlap
 (evaluation.py:41-45,77-80; dloc/core/overlap_features.py:267-294) work unchanged."""
 import torch
 
-from ....config import get_cfg_defaults
-from ....model import build_detectors
-from ..utils.base_model import BaseModel
+# Absolute imports only: this file works where it lies (oetr_b200.dloc.core.overlaps.oetr) AND copied / linked into the
+# reference tree as dloc/core/overlaps/<name>.py, where the host's `dynamic_load` must find exactly one subclass of the
+# HOST's BaseModel in it (reference dloc/core/utils/base_model.py:37-46).  `oetr_b200` must be importable (repo root on
+# sys.path).
+from oetr_b200.config import get_cfg_defaults
+from oetr_b200.dloc.core.utils.base_model import BaseModel        # the host tree's class when `dloc` is importable
+from oetr_b200.model import build_detectors
 
 
 class OETR(BaseModel):

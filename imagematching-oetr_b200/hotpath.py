@@ -25,7 +25,11 @@ class OverlapHotPath:
         self._lib = cabi.load_library()
         if not torch.cuda.is_available():
             raise cabi.OetrError(cabi.OETR_E_ARCH, "no CUDA device: the OETR hot path has no CPU fallback")
-        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise cabi.OetrError(cabi.OETR_E_ARCH, "device %s: the OETR hot path has no CPU fallback" % (self.device,))
+        if self.device.index is None:                      # 'cuda' -> the current device, so tensor.device compares equal
+            self.device = torch.device("cuda", torch.cuda.current_device())
         packed = pack_hot_path_weights(state_dict)
         assert packed.size == PACKED_COUNT == self._lib.oetr_packed_weight_count()
         self.attention, self.precision, self.max_shape = attention, precision, tuple(max_shape)
@@ -34,7 +38,7 @@ class OverlapHotPath:
             cabi.check(self._lib.oetr_create(packed.ctypes.data_as(ctypes.c_void_p), packed.size, 0,
                                              _ATTN[attention], _PREC[precision], int(max_shape[0]),
                                              int(max_shape[1]), ctypes.byref(self._handle)), self._lib)
-        self._ws = None
+        self._ws = {}                                      # one workspace per CUDA stream (concurrent forwards)
         self._inflight = {}
 
     def close(self):
@@ -48,15 +52,19 @@ class OverlapHotPath:
         need = ctypes.c_size_t()
         cabi.check(self._lib.oetr_workspace_bytes(self._handle, batch, hf1, wf1, hf2, wf2, ctypes.byref(need)),
                    self._lib)
-        if self._ws is None or self._ws.numel() < need.value:
-            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
-        return self._ws
+        # one block per stream: forwards on two streams of one handle must not share activations, and a block is
+        # allocated (and later freed) under the stream that uses it, so the caching allocator's reuse is stream-safe
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need.value:
+            ws = self._ws[key] = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        return ws
 
     def set_chunk_pairs(self, pairs):
         """Pairs per concurrently scheduled sub-batch of the fp16 path (0 = never split; < 0 = automatic, the default:
         about 56 encoder tiles per sub-batch, i.e. 8 pairs at 640x640)."""
         cabi.check(self._lib.oetr_set_chunk_pairs(self._handle, int(pairs)), self._lib)
-        self._ws = None
+        self._ws = {}
 
     def profile(self, enable=True):
         cabi.check(self._lib.oetr_profile_enable(self._handle, int(bool(enable))), self._lib)
@@ -124,6 +132,33 @@ class OverlapHotPath:
                    memory1=dbg["memory"][: b * l1].view(b, l1, 256),
                    memory2=dbg["memory"][b * l1:].view(b, hf2 * wf2, 256))
         return box1, box2, out
+
+    def head(self, hs1, hs2, memory1, memory2, hf1, wf1, hf2, wf2, img_hw1, img_hw2, clamp=True, mask1=None, mask2=None):
+        """The overlap head alone (oetr_head_forward): hs [B,1,256] or [B,256], memory [B,L,256] CUDA fp32 tensors ->
+        (box1, box2 [B,4], cxy1, cxy2 [B,2], tlbr1, tlbr2 [B,4]).  Serves the reference's stage-wise signatures
+        (center_estimation / size_regression, src/model.py:145-191)."""
+        b = memory1.shape[0]
+        f = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        hs1, hs2, memory1, memory2 = f(hs1).reshape(b, 256), f(hs2).reshape(b, 256), f(memory1), f(memory2)
+        if tuple(memory1.shape) != (b, hf1 * wf1, 256) or tuple(memory2.shape) != (b, hf2 * wf2, 256):
+            raise ValueError("memory must be [B,hf*wf,256], got %s and %s" % (tuple(memory1.shape), tuple(memory2.shape)))
+        if (mask1 is None) != (mask2 is None):
+            raise ValueError("give both masks or neither")
+        if mask1 is not None:
+            mask1, mask2 = f(mask1.float()), f(mask2.float())
+        box1 = torch.empty(b, 4, dtype=torch.float32, device=self.device)
+        box2 = torch.empty(b, 4, dtype=torch.float32, device=self.device)
+        cxy = torch.empty(2, b, 2, dtype=torch.float32, device=self.device)
+        tlbr = torch.empty(2, b, 4, dtype=torch.float32, device=self.device)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() else ctypes.c_void_p(0)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(b, hf1, wf1, hf2, wf2)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            cabi.check(self._lib.oetr_head_forward(
+                self._handle, ptr(memory1), ptr(memory2), ptr(hs1), ptr(hs2), ptr(mask1), ptr(mask2), b, hf1, wf1, hf2, wf2,
+                int(img_hw1[0]), int(img_hw1[1]), int(img_hw2[0]), int(img_hw2[1]), int(bool(clamp)), ptr(box1), ptr(box2),
+                ptr(cxy), ptr(tlbr), ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(stream)), self._lib)
+        return box1, box2, cxy[0], cxy[1], tlbr[0], tlbr[1]
 
     def submit_host(self, feat1, feat2, img_hw1, img_hw2, clamp=True):
         """Queue a host-buffer request (oetr_forward_host_submit) and return a ticket for `wait_host`.  At most four

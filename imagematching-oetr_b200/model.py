@@ -2,6 +2,8 @@
 same parameter names (strict load_state_dict of reference checkpoints), same `forward_dummy` / `forward`
 signatures and return types.  feature_extraction stays PyTorch; everything after it (feature_correlation,
 center_estimation, size_regression, box assembly) is one call into the CUDA library."""
+import math
+
 import torch
 import torch.nn as nn
 
@@ -49,8 +51,34 @@ class _DecoderParams(nn.Module):
         self.layers = nn.ModuleList(_DecoderLayerParams(d) for _ in range(n))
 
 
+class PositionEncodingSine(nn.Module):
+    """The constant table of reference src/models/utils.py:174-205, restated from its definition (SURVEY.md Appendix
+    A.1): frequencies exp(-2k) (the reference's `-log(1e4)/d_model // 2` evaluates to -1), positions from 1, channels
+    4k..4k+3 = sin(x d), cos(x d), sin(y d), cos(y d).  Non-persistent buffer (absent from checkpoints).  The CUDA path
+    has its own copy of this table; this module exists so that feature_extraction returns the reference's 8-tuple."""
+
+    def __init__(self, d_model, max_shape=(100, 100)):
+        super().__init__()
+        h, w = max_shape
+        ys = torch.arange(1, h + 1, dtype=torch.float32)[:, None].expand(h, w)
+        xs = torch.arange(1, w + 1, dtype=torch.float32)[None, :].expand(h, w)
+        factor = (-math.log(10000.0) / d_model // 2)                     # == -1.0
+        div = torch.exp(torch.arange(0, d_model // 2, 2).float() * factor)[:, None, None]
+        pe = torch.zeros(d_model, h, w)
+        pe[0::4], pe[1::4] = torch.sin(xs * div), torch.cos(xs * div)
+        pe[2::4], pe[3::4] = torch.sin(ys * div), torch.cos(ys * div)
+        self.register_buffer("pe", pe[None], persistent=False)
+
+    def forward(self, x):
+        return self.pe[:, :, :x.size(2), :x.size(3)]
+
+
+def _versions(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
 class QueryTransformer(nn.Module):
-    """Weights of the reference QueryTransformer (transformer.py:287-311).  It holds parameters only: the
+    """Weights of the reference QueryTransformer (transformer.py:287-311) with its forward signature; the
     arithmetic lives in liboetr_b200.so.  `attention_mode` selects linear (shipped default) or full attention."""
 
     def __init__(self, d_model=256, nhead=8, num_layers=4, attention_mode="linear"):
@@ -63,9 +91,31 @@ class QueryTransformer(nn.Module):
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
 
-    def forward(self, *args, **kwargs):
-        raise RuntimeError("QueryTransformer here is a parameter container; call OETR.forward_dummy / "
-                           "OETR.feature_correlation_and_regression (CUDA hot path)")
+        self._hot, self._hot_key = None, None
+        self.precision = "fp16"
+
+    def forward(self, feat0, feat1, query_embed0, query_embed1, pos0=None, pos1=None, mask0=None, mask1=None):
+        """reference transformer.py:313-383: feat* [N,C,h,w], query_embed* [1,C] -> (hs0, hs1 [N,1,C], memory0, memory1
+        [N,L,C]).  pos0 / pos1 are accepted for signature compatibility; the CUDA path uses its own
+        PositionEncodingSine table (the only encoding the reference ever passes, src/model.py:126-127).
+        Stand-alone use builds a CUDA handle from this module's weights and the given query embeddings (head weights
+        zero) and rebuilds it when any of them changes; inside OETR the model's own handle is used instead."""
+        from .weights import CANONICAL_ORDER
+        params = list(self.parameters()) + [query_embed0, query_embed1]
+        key = _versions(params)
+        if self._hot is None or self._hot_key != key:
+            if self._hot is not None:
+                self._hot.close()
+            sd = {"transformer." + k: v for k, v in self.state_dict().items()}
+            sd["query_embed1.weight"], sd["query_embed2.weight"] = query_embed0.detach(), query_embed1.detach()
+            for name, shape in CANONICAL_ORDER:
+                if name not in sd:
+                    sd[name] = torch.zeros(shape)
+            self._hot = OverlapHotPath(sd, attention=self.attention_mode, precision=self.precision, device=feat0.device)
+            self._hot_key = key
+        hw0, hw1 = (32 * feat0.shape[2], 32 * feat0.shape[3]), (32 * feat1.shape[2], 32 * feat1.shape[3])
+        _, _, dbg = self._hot.forward(feat0, feat1, hw0, hw1, clamp=False, debug=True, mask1=mask0, mask2=mask1)
+        return dbg["hs1"][:, None], dbg["hs2"][:, None], dbg["memory1"], dbg["memory2"]
 
 
 class OETR(nn.Module):
@@ -85,10 +135,12 @@ class OETR(nn.Module):
         self.query_embed2 = nn.Embedding(1, self.d_model)
         self.transformer = QueryTransformer(self.d_model, nhead=8, num_layers=4, attention_mode=attention_mode)
         self.max_shape = tuple(cfg.NECK.MAX_SHAPE)
+        self.pos_encoding = PositionEncodingSine(self.d_model, max_shape=self.max_shape)
         self.cycle = cfg.LOSS.CYCLE_OVERLAP
         self.softmax_temperature = 1
         self.precision = precision
-        self._hot = None
+        self._hot, self._hot_key = None, None
+        self.h1 = self.w1 = self.h2 = self.w2 = None         # set by forward_dummy / forward like the reference (model.py:232-233)
 
     # ---- hot-path handle management ---------------------------------------------------------------------
     def refresh_hot_path(self):
@@ -103,7 +155,14 @@ class OETR(nn.Module):
                                "call .cuda() first")
         self._hot = OverlapHotPath(sd, attention=self.transformer.attention_mode, precision=self.precision,
                                    max_shape=self.max_shape, device=dev)
+        self._hot_key = _versions(self._hot_params())
         return self._hot
+
+    def _hot_params(self):
+        if getattr(self, "_hot_param_list", None) is None:
+            names = {n for n, _ in CANONICAL_ORDER}
+            self._hot_param_list = [p for n, p in self.named_parameters() if n in names]
+        return self._hot_param_list
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -117,16 +176,56 @@ class OETR(nn.Module):
 
     @property
     def hot_path(self):
-        return self._hot if self._hot is not None else self.refresh_hot_path()
+        """The CUDA handle snapshots the weights: it is rebuilt when a hot-path parameter was replaced or modified in
+        place (optimizer.step, param.data.copy_) since the snapshot -- a cheap (data_ptr, _version) check per call."""
+        if self._hot is None or self._hot_key != _versions(self._hot_params()):
+            self.refresh_hot_path()
+        return self._hot
 
     # ---- stages ---------------------------------------------------------------------------------------
     def feature_extraction(self, image1, image2, mask1=None, mask2=None):
-        """backbone -> input_proj -> patchmerging -> input_proj2 for both images (model.py:109-130)."""
-        feats = []
-        for img in (image1, image2):
-            f = self.input_proj2(self.patchmerging(self.input_proj(self.backbone(img))))
-            feats.append(f)
-        return feats[0], feats[1]
+        """backbone -> input_proj -> patchmerging -> input_proj2 for both images and the position encodings: the
+        reference's 8-tuple (feat1, feat2, pos1, pos2, hf1, wf1, hf2, wf2), model.py:109-130."""
+        feat1 = self.input_proj2(self.patchmerging(self.input_proj(self.backbone(image1))))
+        feat2 = self.input_proj2(self.patchmerging(self.input_proj(self.backbone(image2))))
+        hf1, wf1 = feat1.shape[2:]
+        hf2, wf2 = feat2.shape[2:]
+        return feat1, feat2, self.pos_encoding(feat1), self.pos_encoding(feat2), hf1, wf1, hf2, wf2
+
+    @torch.no_grad()
+    def feature_correlation(self, feat1, feat2, pos1=None, pos2=None, mask1=None, mask2=None):
+        """model.py:132-143 -> (hs1, hs2 [N,1,256], memory1, memory2 [N,L,256]) from the CUDA path's stage taps.  pos1 /
+        pos2 are the PositionEncodingSine slices the reference passes; the kernels read their own copy of that table."""
+        hw1 = (self.h1 or 32 * feat1.shape[2], self.w1 or 32 * feat1.shape[3])
+        hw2 = (self.h2 or 32 * feat2.shape[2], self.w2 or 32 * feat2.shape[3])
+        _, _, dbg = self.hot_path.forward(feat1, feat2, hw1, hw2, clamp=False, debug=True, mask1=mask1, mask2=mask2)
+        return dbg["hs1"][:, None], dbg["hs2"][:, None], dbg["memory1"], dbg["memory2"]
+
+    def _head(self, hs1, hs2, memory1, memory2, hf1, wf1, hf2, wf2, mask1, mask2):
+        if self.h1 is None:
+            raise RuntimeError("set self.h1, w1, h2, w2 (image sizes) first, as forward_dummy does (model.py:232-233)")
+        return self.hot_path.head(hs1, hs2, memory1, memory2, hf1, wf1, hf2, wf2, (self.h1, self.w1), (self.h2, self.w2),
+                                  clamp=False, mask1=mask1, mask2=mask2)
+
+    @torch.no_grad()
+    def center_estimation(self, hs1, hs2, memory1, memory2, hf1, wf1, hf2, wf2, mask1=None, mask2=None):
+        """model.py:145-186 -> (box_cxy1, box_cxy2) [N,2] pixels; uses self.h1 / self.h2 for the grid stride."""
+        out = self._head(hs1, hs2, memory1, memory2, hf1, wf1, hf2, wf2, mask1, mask2)
+        return out[2], out[3]
+
+    @torch.no_grad()
+    def size_regression(self, hs1, hs2):
+        """model.py:188-191 -> (tlbr1, tlbr2) [N,4] in (0,1)."""
+        n = hs1.shape[0]
+        z = torch.zeros(n, 1, 256, device=hs1.device)
+        h1, w1, h2, w2 = self.h1, self.w1, self.h2, self.w2
+        if h1 is None:
+            self.h1 = self.w1 = self.h2 = self.w2 = 32
+        try:
+            out = self._head(hs1, hs2, z, z, 1, 1, 1, 1, None, None)
+        finally:
+            self.h1, self.w1, self.h2, self.w2 = h1, w1, h2, w2
+        return out[4], out[5]
 
     def feature_correlation_and_regression(self, feat1, feat2, hw1, hw2, clamp=True, debug=False, mask1=None,
                                            mask2=None):
@@ -138,7 +237,9 @@ class OETR(nn.Module):
         mask1 / mask2 [B,hf,wf] (feature-map resolution, float; both or neither): the masks the reference hands to
         feature_correlation and center_estimation (model.py:240-247); linear attention only."""
         hw1, hw2 = tuple(image1.shape[1:3]), tuple(image2.shape[1:3])
-        feat1, feat2 = self.feature_extraction(image1, image2)
+        self.h1, self.w1 = hw1
+        self.h2, self.w2 = hw2
+        feat1, feat2 = self.feature_extraction(image1, image2)[:2]
         return self.feature_correlation_and_regression(feat1, feat2, hw1, hw2, clamp=True, mask1=mask1, mask2=mask2)
 
     @torch.no_grad()
@@ -146,12 +247,17 @@ class OETR(nn.Module):
         """Training-signature entry (model.py:255-376) restricted to its inference half: unclamped boxes
         (model.py:193-211) and, when ground truth is given, the IoU metrics.  Losses are training-only and
         out of scope."""
+        if self.training:
+            raise NotImplementedError("oetr_b200.OETR is an inference drop-in: the CUDA hot path has no backward pass and the "
+                                      "losses of reference src/model.py:300-376 are out of scope; call .eval()")
         valid = data["overlap_valid"] if "overlap_valid" in data else slice(None)
         image1, image2 = data["image1"][valid], data["image2"][valid]
         if "resize_mask1" in data:
             raise NotImplementedError("resize_mask inputs are never produced by the reference datasets")
         hw1, hw2 = tuple(image1.shape[1:3]), tuple(image2.shape[1:3])
-        feat1, feat2 = self.feature_extraction(image1, image2)
+        self.h1, self.w1 = hw1
+        self.h2, self.w2 = hw2
+        feat1, feat2 = self.feature_extraction(image1, image2)[:2]
         box1, box2 = self.feature_correlation_and_regression(feat1, feat2, hw1, hw2, clamp=False)
         out = {"pred_bbox1": box1, "pred_bbox2": box2}
         if "overlap_box1" in data:

@@ -183,6 +183,16 @@ OETR_API int oetr_forward_host(oetr_handle* h,
  * Returns OETR_OK when the kernels ran (inspect errs for the numeric outcome). */
 OETR_API int oetr_selftest_tcgen05(float* errs_host, int n_errs);
 
+/* The overlap head alone, for callers that use the reference's stage-wise methods (OETR.center_estimation,
+ * src/model.py:145-186, OETR.size_regression :188-191, box_tlbr_to_xyxy src/models/utils.py:16-28) with their own
+ * hs / memory tensors: memory1 [batch*hf1*wf1][256], memory2, hs1 [batch][256], hs2 (device, fp32, token-major),
+ * optional masks [batch][hf*wf] -> boxes1/boxes2 [batch][4], cxy [2][batch][2] (nullable), tlbr [2][batch][4]
+ * (nullable).  fp32 CUDA-core kernels for handles of either precision; workspace as for oetr_forward. */
+OETR_API int oetr_head_forward(oetr_handle* h, const float* memory1, const float* memory2, const float* hs1, const float* hs2,
+                               const float* mask1, const float* mask2, int batch, int hf1, int wf1, int hf2, int wf2,
+                               int img_h1, int img_w1, int img_h2, int img_w2, int clamp, float* boxes1, float* boxes2,
+                               float* cxy, float* tlbr, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- boxes of every rank on every rank (BASELINE configs[2]) ------------------------------------------
  * One process per GPU.  Instead of a collective, every rank stores its [pairs][2][4] boxes straight into its peers'
  * communication buffers over NVLink (CUDA IPC mapped peer memory, one tiny stream-ordered kernel) and publishes a

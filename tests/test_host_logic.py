@@ -9,6 +9,8 @@ from oetr_b200 import weights
 from oetr_b200.dloc.core import overlap_features, overlaps
 from oetr_b200.dloc.core.utils.base_model import BaseModel, dynamic_load
 
+from conftest import ROOT as ROOT_DIR
+
 try:
     import ref_loader
     HAVE_REF = ref_loader.reference_available()
@@ -110,6 +112,44 @@ def test_strict_load_and_feature_extraction_match_reference(model):
     torch.manual_seed(1)
     a, b = torch.rand(1, 192, 256, 3), torch.rand(1, 256, 192, 3)
     with torch.no_grad():
-        f1, f2 = model.feature_extraction(a, b)
+        m = model.feature_extraction(a, b)
         r = ref.feature_extraction(a, b)
-    assert torch.equal(f1, r[0]) and torch.equal(f2, r[1])
+    assert len(m) == len(r) == 8                              # (feat1, feat2, pos1, pos2, hf1, wf1, hf2, wf2), model.py:130
+    assert torch.equal(m[0], r[0]) and torch.equal(m[1], r[1])
+    assert torch.allclose(m[2], r[2], atol=1e-6, rtol=0) and torch.allclose(m[3], r[3], atol=1e-6, rtol=0)
+    assert tuple(m[4:]) == tuple(r[4:])
+    assert torch.allclose(model.pos_encoding.pe, ref.pos_encoding.pe, atol=1e-6, rtol=0)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present (GPU box)")
+def test_plugin_is_found_by_the_reference_dynamic_load(tmp_path, model):
+    """The plugin file, placed FIRST on the reference's `dloc.core.overlaps` package path (= copied over
+    dloc/core/overlaps/oetr.py), is what the reference's own dynamic_load returns for `--overlaper oetr`: one subclass of
+    the HOST's BaseModel, same default_conf keys and tuple-returning `_forward` (reference evaluation.py:41-45)."""
+    import importlib
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys, os, torch
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests', 'golden')); sys.path.insert(0, %r)
+import ref_loader                                   # installs the kornia / timm / yacs shims the reference needs
+sys.path.insert(0, '/root/reference')
+import dloc.core.overlaps as host_overlaps
+from dloc.core.utils.base_model import BaseModel as HostBase, dynamic_load as host_dynamic_load
+import oetr_b200
+plug_dir = os.path.join(os.path.dirname(oetr_b200.__path__[0]), 'imagematching-oetr_b200', 'dloc', 'core', 'overlaps')
+host_overlaps.__path__.insert(0, plug_dir)
+cls = host_dynamic_load(host_overlaps, 'oetr')
+assert cls.__module__ == 'dloc.core.overlaps.oetr' and issubclass(cls, HostBase), cls.__mro__
+assert os.path.samefile(sys.modules[cls.__module__].__file__, os.path.join(plug_dir, 'oetr.py'))
+from oetr_b200.dloc.core import overlap_features
+conf = dict(overlap_features.confs['oetr']['model'], weights='oetr/x.pth')
+plug = cls(conf, __import__('pathlib').Path(%r))
+assert isinstance(plug.net, oetr_b200.OETR) and {'model', 'num_layers', 'stride', 'last_layer', 'weights'} <= set(cls.default_conf)
+print('OK')
+""" % (ROOT_DIR, ROOT_DIR, ROOT_DIR, str(tmp_path))
+    (tmp_path / "oetr").mkdir()
+    torch.save(model.state_dict(), tmp_path / "oetr" / "x.pth")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stderr[-3000:]

@@ -22,7 +22,7 @@ def _model(precision="fp16"):
 
 def _oracle_boxes(model, img1, img2, clamp):
     with torch.no_grad():
-        f1, f2 = model.feature_extraction(img1, img2)
+        f1, f2 = model.feature_extraction(img1, img2)[:2]
     W = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     hw1, hw2 = tuple(img1.shape[1:3]), tuple(img2.shape[1:3])
     o = orc.hot_path(W, f1.cpu().numpy(), f2.cpu().numpy(), hw1, hw2, clamp=clamp)
@@ -55,7 +55,7 @@ def test_forward_dummy_and_forward_match_the_oracle_on_backbone_features(precisi
     m2 = torch.from_numpy(weights.synthetic_mask(2, 20, 20, tag="mask2")).cuda()
     b1, b2 = model.forward_dummy(img1, img2, mask1=m1, mask2=m2)
     with torch.no_grad():
-        f1, f2 = model.feature_extraction(img1, img2)
+        f1, f2 = model.feature_extraction(img1, img2)[:2]
     W = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     o = orc.hot_path(W, f1.cpu().numpy(), f2.cpu().numpy(), (640, 640), (640, 640), mask1=m1.cpu().numpy(),
                      mask2=m2.cpu().numpy())
@@ -80,3 +80,46 @@ def test_dloc_plugin_runs_like_the_reference_plugin(tmp_path):
     assert np.abs(box1.cpu().numpy() - w1).max() / max(hw1) < 1e-3
     scales = torch.tensor([1.5, 2.0, 1.5, 2.0], device=box0.device)
     assert (box0 * scales)[0].int().shape == (4,)
+
+
+def test_stage_wise_signatures_of_the_reference():
+    """The reference's own stage methods (src/model.py:109-191, transformer.py:313-383) on the mirror: the 8-tuple of
+    feature_extraction, feature_correlation -> (hs1, hs2, memory1, memory2), center_estimation, size_regression, and the
+    stand-alone QueryTransformer.forward -- the sequence forward_dummy (model.py:236-250) runs, against the oracle."""
+    from oetr_b200.model import QueryTransformer
+    model = _model("fp16")
+    g = torch.Generator().manual_seed(3)
+    img1, img2 = torch.rand((2, 320, 416, 3), generator=g).cuda(), torch.rand((2, 384, 288, 3), generator=g).cuda()
+    model.h1, model.w1 = img1.shape[1:3]
+    model.h2, model.w2 = img2.shape[1:3]
+    with torch.no_grad():
+        feat1, feat2, pos1, pos2, hf1, wf1, hf2, wf2 = model.feature_extraction(img1, img2)
+    assert pos1.shape == (1, 256, hf1, wf1) and (hf1, wf1, hf2, wf2) == (10, 13, 12, 9)
+    hs1, hs2, mem1, mem2 = model.feature_correlation(feat1, feat2, pos1, pos2, None, None)
+    assert hs1.shape == (2, 1, 256) and mem1.shape == (2, hf1 * wf1, 256) and mem2.shape == (2, hf2 * wf2, 256)
+    cxy1, cxy2 = model.center_estimation(hs1, hs2, mem1, mem2, hf1, wf1, hf2, wf2, None, None)
+    tlbr1, tlbr2 = model.size_regression(hs1, hs2)
+    W = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    o = orc.hot_path(W, feat1.cpu().numpy(), feat2.cpu().numpy(), (320, 416), (384, 288), clamp=False)
+    rel = lambda a, b: float(np.abs(a.cpu().numpy() - b).max() / np.abs(b).max())
+    assert rel(hs1[:, 0], o["hs1"]) < 3e-3 and rel(mem2, o["memory2"]) < 3e-3
+    assert np.abs(cxy1.cpu().numpy() - o["cxy1"]).max() / 416 < 1e-3 and np.abs(cxy2.cpu().numpy() - o["cxy2"]).max() / 384 < 1e-3
+    assert rel(tlbr1, o["tlbr1"]) < 3e-3 and rel(tlbr2, o["tlbr2"]) < 3e-3
+    # the head takes ANY hs / memory (here: the oracle's), like the reference's method
+    c1, _ = model.center_estimation(torch.from_numpy(o["hs1"][:, None]).float().cuda(), hs2,
+                                    torch.from_numpy(o["memory1"]).float().cuda(), mem2, hf1, wf1, hf2, wf2)
+    assert np.abs(c1.cpu().numpy() - o["cxy1"]).max() / 416 < 2e-5
+    # stand-alone transformer with the reference's forward signature
+    qt = QueryTransformer(256, 8, 4).cuda().eval()
+    qt.load_state_dict(model.transformer.state_dict())
+    h1, h2, m1, m2 = qt(feat1, feat2, model.query_embed1.weight, model.query_embed2.weight, pos1, pos2, None, None)
+    assert rel(h1[:, 0], o["hs1"]) < 3e-3 and rel(m1, o["memory1"]) < 3e-3
+    # in-place weight updates are seen (the CUDA handle snapshots the weights; it is rebuilt on a version change)
+    b_before, _ = model.forward_dummy(img1, img2)
+    with torch.no_grad():
+        model.tlbr_reg[2].bias.add_(0.5)
+    b_after, _ = model.forward_dummy(img1, img2)
+    assert (b_after - b_before).abs().max() > 1.0
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model({"image1": img1, "image2": img2})
