@@ -162,7 +162,7 @@ Workspace carve(void* base, const oetr_handle* h, int B, int L1, int L2) {
     w.dt = c.take<float>(D); w.du = c.take<float>(D); w.dqk = c.take<float>(D); w.dq = c.take<float>(D);
     w.dk = c.take<float>(D); w.dv = c.take<float>(D); w.dob = c.take<float>(D); w.dh = c.take<float>(2 * D);
     w.dkvs = c.take<float>((size_t)2 * B * KVS);
-    if (h->prec == OETR_PREC_FP16) tc_carve(c.off, base, B, L1, L2, w.tc);
+    if (h->prec == OETR_PREC_FP16) tc_carve(c.off, base, B, L1, L2, w.tc, h->attn_mode == OETR_ATTN_FULL);
     w.bytes = (c.off + 255) & ~size_t(255);
     return w;
 }
@@ -317,8 +317,6 @@ int oetr_create(const float* weights, size_t n_floats, int weights_on_device, in
     if (prop.major != 10)
         return fail(OETR_E_ARCH, "oetr_create: device %d is sm_%d%d; this library is sm_100a-only (no fallback)",
                     dev, prop.major, prop.minor);
-    if (operand_precision == OETR_PREC_FP16 && attention_mode == OETR_ATTN_FULL)
-        return fail(OETR_E_ARG, "oetr_create: full attention is implemented on the fp32 path only (round 1)");
     oetr_handle* h = new (std::nothrow) oetr_handle();
     if (!h) return fail(OETR_E_NOMEM, "oetr_create: host allocation failed");
     h->attn_mode = attention_mode; h->prec = operand_precision; h->max_h = max_h; h->max_w = max_w;
@@ -518,10 +516,13 @@ int run_batch(oetr_handle* h, const Workspace& w, const float* feat1, const floa
         // tcgen05 encoder + decoder K/V summaries (memory stays tile-blocked in w.tc.xt; token-major copy only for
         // the debug output), fused fp32 decoder, tcgen05 heat-map convolution
         char msg[256] = "";
-        if (tc_encoder(h->tc, h->d_w, h->h_w.data(), h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, a.post1, a.post2,
-                       a.mask1, a.mask2,
-                       a.dbg_memory ? w.X : nullptr, h->d_flag, profile ? &h->prof : nullptr, s, lc, msg, sizeof(msg)) != 0)
-            return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
+        const int erc = h->attn_mode == OETR_ATTN_FULL
+            ? tc_encoder_full(h->tc, h->d_w, h->h_w.data(), h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, a.post1, a.post2,
+                              a.dbg_memory ? w.X : nullptr, h->d_flag, s, lc, msg, sizeof(msg))
+            : tc_encoder(h->tc, h->d_w, h->h_w.data(), h->L, w.tc, feat1, feat2, B, hf1, wf1, hf2, wf2, a.post1, a.post2,
+                         a.mask1, a.mask2,
+                         a.dbg_memory ? w.X : nullptr, h->d_flag, profile ? &h->prof : nullptr, s, lc, msg, sizeof(msg));
+        if (erc != 0) return fail(OETR_E_CUDA, "oetr_forward: %s", msg);
         const HeadGeom hg{B, hf1, wf1, hf2, wf2, a.img_h1, a.img_w1, a.img_h2, a.img_w2, a.clamp, a.mask1, a.mask2};
         if (tc_decoder_head(h->tc, h->d_w, h->L, w.tc, hg, w.dt, w.O, boxes1, boxes2, a.dbg_cxy, a.dbg_tlbr, h->d_flag, s, lc,
                             msg, sizeof(msg)) != 0)

@@ -35,6 +35,7 @@
 #include "tc_tiles.cuh"
 #include "tc_enc.cuh"
 #include "tc_head.cuh"
+#include "tc_full.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -91,6 +92,7 @@ int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, Tc
         make_gemm_image(d_w + e.w2, FF, 0, 256, o + 4 * GEMM_HALFS);        // W2[:, 256:512]
         make_gemm_image(d_w + e.wv, C, 0, 0, o + 5 * GEMM_HALFS);
         make_gemm_image(d_w + e.wk, C, 0, 0, o + 6 * GEMM_HALFS);
+        make_gemm_image(d_w + e.wm, C, 0, 0, o + 7 * GEMM_HALFS);
     }
     for (int j = 0; j < N_DEC; ++j) {
         const DecW& d = L.dec[j];
@@ -270,7 +272,7 @@ static TileGeom make_geom(int B, int L1, int L2) {
     return g;
 }
 
-void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
+void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w, bool full_attention) {
     const TileGeom g = make_geom(B, L1, L2);
     char* b = static_cast<char*>(base);
     auto take = [&](size_t nbytes) {
@@ -289,6 +291,9 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w) {
     w.gstat = static_cast<float*>(take((size_t)g.tiles() * 64 * sizeof(float)));
     w.z = static_cast<float*>(take((size_t)g.tiles() * TILE * sizeof(float)));
     w.tlbr = static_cast<float*>(take((size_t)2 * B * 4 * sizeof(float)));
+    if (full_attention) {   // q, k, v, o operand images exchanged between k_proj_mlp and k_attn: 128 KB per tile each
+        for (__half** img : {&w.qimg, &w.kimg, &w.vimg, &w.oimg}) *img = static_cast<__half*>(take((size_t)g.tiles() * TILE_IMG_HALFS * sizeof(__half)));
+    }
 }
 
 // cudaFuncSetAttribute is per device (per context): opt every device in once, under a mutex (oetr_forward may be
@@ -302,6 +307,8 @@ static int set_attrs(char* msg, size_t msg_len) {
     if (g_attr_set[dev]) return 0;
     cudaError_t e1 = cudaFuncSetAttribute(k_enc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_proj_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_TOTAL);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_decoder, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
     if (e1 != cudaSuccess) {
         snprintf(msg, msg_len, "cudaFuncSetAttribute(max dynamic smem %u): %s", SM_TOTAL, cudaGetErrorString(e1));
@@ -478,6 +485,63 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WL
     return 0;
 }
 
+
+// Full-attention encoder (attention_mode = 'full'): per-image 128-token tiles; k_proj_mlp (projections) -> 8 x [k_attn ->
+// k_proj_mlp (merge + MLP, next layer's projections)] -> the decoder's linear-attention K/V summaries as in tc_encoder.
+int tc_encoder_full(const TcWeights& tw, const float* d_w, const float* h_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
+                    const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
+                    float* X_out, int* flag, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len) {
+    if (set_attrs(msg, msg_len)) return -1;
+    const int L1 = hf1 * wf1, L2 = hf2 * wf2;
+    const TileGeom g = make_geom(B, L1, L2);
+    const int tiles = g.tiles();
+    auto vec = [&](float (&dst)[C], size_t off) { memcpy(dst, h_w + off, C * sizeof(float)); };
+    ProjParams base{};
+    base.g = g; base.feat1 = feat1; base.feat2 = feat2; base.xt = ws.xt; base.post1 = post1; base.post2 = post2;
+    base.oimg = ws.oimg; base.qimg = ws.qimg; base.kimg = ws.kimg; base.vimg = ws.vimg; base.flag = flag;
+    auto set_proj = [&](ProjParams& p, int layer) {
+        const EncW& e = L.enc[layer];
+        const __half* img = tw.enc_img + (size_t)layer * ENC_LAYER_HALFS;
+        p.do_proj = 1; p.w_q = img; p.w_kv = img + 5 * GEMM_HALFS;
+        vec(p.lnq_g, e.lnq_g); vec(p.lnq_b, e.lnq_b); vec(p.lnkv_g, e.lnkv_g); vec(p.lnkv_b, e.lnkv_b);
+    };
+    {
+        ProjParams p = base;
+        p.load_feat = 1;
+        set_proj(p, 0);
+        k_proj_mlp<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
+    }
+    for (int i = 0; i < N_ENC; ++i) {
+        AttnParams ap{};
+        ap.g = g; ap.qimg = ws.qimg; ap.kimg = ws.kimg; ap.vimg = ws.vimg; ap.oimg = ws.oimg; ap.cross = i & 1; ap.flag = flag;
+        k_attn<<<dim3(tiles, 4), AT_THREADS, AT_TOTAL, s>>>(ap); lc.n++;
+        const EncW& e = L.enc[i];
+        const __half* img = tw.enc_img + (size_t)i * ENC_LAYER_HALFS;
+        ProjParams p = base;
+        p.do_merge = 1; p.w_merge = img + 7 * GEMM_HALFS; p.w_mlp = img + GEMM_HALFS;
+        vec(p.ln2_g, e.ln2_g); vec(p.ln2_b, e.ln2_b);
+        if (i + 1 < N_ENC) set_proj(p, i + 1);
+        k_proj_mlp<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
+    }
+    // decoder cross-attention summaries (the decoder's MultiHeadAttention is always linear attention, transformer.py:32,200-201)
+    const EncGeom eg{};
+    for (int j = 0; j < N_DEC; ++j) {
+        const DecW& d = L.dec[j];
+        EncParams p{};
+        p.g = g; p.eg = eg; p.xt = ws.xt; p.post1 = post1; p.post2 = post2; p.kv_part = ws.kv_part; p.flag = flag;
+        p.do_kv = 1; p.dec_mode = 1; vec(p.lnkv_g, d.ca.bv); vec(p.lnkv_b, d.ca.bk);
+        p.w_kv = tw.dec_img + (size_t)j * DEC_LAYER_HALFS;
+        k_enc<<<tiles, N_THREADS, SM_TOTAL, s>>>(p); lc.n++;
+        k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, eg, 1, ws.dec_kvs + (size_t)j * 2 * B * KVS); lc.n++;
+    }
+    if (X_out) { k_untile<<<tiles, 256, 0, s>>>(ws.xt, g, X_out); lc.n++; }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(msg, msg_len, "full-attention encoder launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
 
 // query decoder + size regression (fp32, one fused kernel), heat-map 3x3 convolution (tcgen05) with GroupNorm
 // partials, logits, soft-argmax + box assembly.  hs_out [2B][256], Y scratch [B*L1+B*L2][256].

@@ -26,6 +26,7 @@ struct TcWorkspace {
     float* gstat = nullptr;        // [tiles][32][2] per-tile GroupNorm partials (mean, M2)
     float* z = nullptr;            // [tiles][128] heat-map logits
     float* tlbr = nullptr;         // [2B][4]
+    __half *qimg = nullptr, *kimg = nullptr, *vimg = nullptr, *oimg = nullptr;   // full attention: per-tile operand images
 };
 
 // CUDA-event bracket around every launch of the dominant kernel (k_enc with a query phase); read back by bench.py through
@@ -45,7 +46,7 @@ struct KernelProfiler {
     }
 };
 
-void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w);
+void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w, bool full_attention);
 int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, TcWeights& out, char* msg, size_t msg_len);
 void tc_free_weights(TcWeights& w);
 // runs the 8 encoder layers and the decoder's cross-attention K/V summaries; writes token-major memory to X_out
@@ -62,6 +63,9 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WL
                const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
                const float* mask1, const float* mask2,
                float* X_out, int* timeout_flag, KernelProfiler* prof, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
+int tc_encoder_full(const TcWeights& tw, const float* d_w, const float* h_w, const WLayout& L, const TcWorkspace& ws, const float* feat1,
+                    const float* feat2, int B, int hf1, int wf1, int hf2, int wf2, const float* post1, const float* post2,
+                    float* X_out, int* timeout_flag, cudaStream_t s, LaunchCounter& lc, char* msg, size_t msg_len);
 struct HeadGeom { int B, hf1, wf1, hf2, wf2, img_h1, img_w1, img_h2, img_w2, clamp; const float *mask1, *mask2; };
 // fused fp32 query decoder (+ tlbr regression) -> hs_out [2B][256]; tcgen05 3x3 heat-map convolution -> Y scratch
 // [B*L1+B*L2][256]; GroupNorm/ReLU/1x1 logits; softmax + soft-argmax + box assembly -> boxes1/boxes2 [B][4]

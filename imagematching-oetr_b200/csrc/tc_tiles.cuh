@@ -21,8 +21,9 @@ constexpr int GEMM_STAGES = 16;                 // a 256x256 weight block: 4 k-s
 constexpr size_t GEMM_HALFS = (size_t)GEMM_STAGES * STAGE_HALFS;      // 256 KB
 constexpr uint32_t SLAB_BYTES = TILE * 128;     // one [128 x 64] fp16 operand slab = 16 KB
 constexpr uint32_t IMG_BYTES = 4 * SLAB_BYTES;  // a [128 x 256] fp16 operand image = 64 KB
-// per encoder layer: Wq | W1a | W1b | W2a | W2b | Wv | Wk ; per decoder layer: Wv | Wk
-constexpr int ENC_LAYER_GEMMS = 7, DEC_LAYER_GEMMS = 2;
+// per encoder layer: Wq | W1a | W1b | W2a | W2b | Wv | Wk | Wm (the last only for full attention: linear attention folds
+// the merge projection into per-image weights, k_fold) ; per decoder layer: Wv | Wk
+constexpr int ENC_LAYER_GEMMS = 8, DEC_LAYER_GEMMS = 2;
 constexpr size_t ENC_LAYER_HALFS = ENC_LAYER_GEMMS * GEMM_HALFS;
 constexpr size_t DEC_LAYER_HALFS = DEC_LAYER_GEMMS * GEMM_HALFS;
 constexpr size_t DEC_T_FLOATS = (size_t)6 * C * C + (size_t)2 * FF * C;   // transposed fp32 decoder weights per layer

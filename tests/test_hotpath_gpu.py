@@ -37,14 +37,12 @@ def _run(W, f1, f2, hw1, hw2, attention, precision, clamp):
 
 
 def _cases(precision):
-    return [n for n in sorted(CASES) if precision == "fp32" or CASES[n][5] == "linear"]
+    return sorted(CASES)            # both attention modes run on both precision paths (round 2: tcgen05 full attention)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_stage_parity_with_oracle_and_golden(name, precision):
-    if name not in _cases(precision):
-        pytest.skip("full attention runs on the fp32 path only in round 1")
     W, f1, f2, (b, fm1, fm2, hw1, hw2, attention, _, _), g = load_case(name)
     want = orc.hot_path(W, f1, f2, hw1, hw2, attention=attention)
     got = _run(W, f1, f2, hw1, hw2, attention, precision, clamp=False)
@@ -321,3 +319,22 @@ def test_stress_scales_against_reference_outputs(name, precision):
     clamped = _run(W, f1, f2, c["hw1"], c["hw2"], "linear", precision, clamp=True)
     for i, hw in ((1, c["hw1"]), (2, c["hw2"])):
         assert np.abs(clamped["box%d" % i] - g["box%d" % i]).max() / max(hw) < tol["box"] + 2e-5
+
+
+def test_full_attention_tensor_core_path_properties():
+    """attention_mode='full' on the tcgen05 path (k_proj_mlp + k_attn): agreement with the fp32 CUDA-core path and the
+    oracle on shapes the golden files do not cover (key counts that are not a multiple of the 64-key chunk, more than
+    one key tile, ragged pairs, batch > 1), and determinism."""
+    W = weights.synthetic_hot_path_weights(0)
+    for b, fm1, fm2 in ((2, (9, 7), (5, 13)), (3, (13, 11), (20, 20)), (1, (26, 26), (4, 4))):
+        hw1, hw2 = (fm1[0] * 32, fm1[1] * 32), (fm2[0] * 32, fm2[1] * 32)
+        f1 = weights.synthetic_features(b, *fm1, seed=6, tag="fa1")
+        f2 = weights.synthetic_features(b, *fm2, seed=6, tag="fa2")
+        want = orc.hot_path(W, f1, f2, hw1, hw2, attention="full")
+        got = _run(W, f1, f2, hw1, hw2, "full", "fp16", clamp=False)
+        again = _run(W, f1, f2, hw1, hw2, "full", "fp16", clamp=False)
+        for i, hw in ((1, hw1), (2, hw2)):
+            err = np.abs(got["box%d" % i] - want["box%d_raw" % i]).max() / max(hw)
+            assert err < TOL["fp16"]["box"], (fm1, fm2, i, err)
+            assert rel_err(got["memory%d" % i], want["memory%d" % i]) < TOL["fp16"]["mid"]
+            assert np.array_equal(got["box%d" % i], again["box%d" % i])
