@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
     const uint32_t smem_base = smem_u32(smem);
     const bool dec_mode = p.dec_mode != 0;
 
+    const unsigned long long cta_t0 = (p.dbg_acc && tid == 0) ? global_ns() : 0ull;
     const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
     const uint32_t T = tmem, XA = tmem + 256;
 
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
                     umma_commit(&bars->s_full[half]);
                 }
             }
-            if (p.dbg_acc && p.do_q && p.do_kv) {
+            if (p.dbg_acc && p.do_q && p.do_kv && !p.dec_mode) {
                 atomicAdd(p.dbg_acc + DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
                 atomicAdd(p.dbg_acc + DBG_MMA_WAIT_A, (unsigned long long)ms.t_a);
                 atomicAdd(p.dbg_acc + DBG_MMA_WAIT_W, (unsigned long long)ms.t_ring);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
         uint32_t ns0 = 0, ns1 = 0;
         long long t_prev = clock64();
         auto stamp = [&](int i) {                         // OETR_TIMING=1: stage durations of row-warp thread 0
-            if (p.dbg_acc && p.do_q && p.do_kv && tid == 0) {
+            if (p.dbg_acc && p.do_q && p.do_kv && !p.dec_mode && tid == 0) {
                 const long long t = clock64();
                 atomicAdd(p.dbg_acc + DBG_STAGE0 + i, (unsigned long long)(t - t_prev));
                 t_prev = t;
@@ -522,6 +523,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
     tc_fence_before();
     __syncthreads();
     if (warp == WARP_PRODUCER) tmem_dealloc(tmem, 512);
+    if (tid == 0) dbg_log_cta(p.dbg_acc, p.do_q ? 2 : (p.dec_mode ? 3 : 1), cta_t0);
 }
 
 }  // namespace oetr

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const TileInfo ti = tile_info(p.g, blockIdx.x);
     const uint32_t smem_base = smem_u32(smem);
+    const unsigned long long cta_t0 = (p.dbg_acc && tid == 0) ? global_ns() : 0ull;
     const uint32_t tmem = cta_setup(bars, WARP_PRODUCER);
     const uint32_t S0 = tmem;
 
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_conv(const ConvParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == WARP_PRODUCER) tmem_dealloc(tmem, 512);
+    if (tid == 0) dbg_log_cta(p.dbg_acc, 4, cta_t0);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -326,16 +326,20 @@ static unsigned long long* dbg_acc_buffer() {
     if (!g_dbg_on) return nullptr;
     std::lock_guard<std::mutex> lock(g_attr_mu);
     if (!g_dbg_acc) {
-        if (cudaMalloc(&g_dbg_acc, DBG_SLOTS * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
-        cudaMemset(g_dbg_acc, 0, DBG_SLOTS * sizeof(unsigned long long));
+        const size_t n = DBG_SLOTS + 8 + (size_t)DBG_LOG_CAP * 4;
+        if (cudaMalloc(&g_dbg_acc, n * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+        cudaMemset(g_dbg_acc, 0, n * sizeof(unsigned long long));
+        const char* env = getenv("OETR_TIMING");
+        if (env && atoi(env) >= 2) { const unsigned long long one = 1; cudaMemcpy(g_dbg_acc + DBG_SLOTS, &one, sizeof(one), cudaMemcpyHostToDevice); }
     }
     return g_dbg_acc;
 }
 int tc_debug_read(unsigned long long* out, int n, int reset) {
     if (!g_dbg_acc) return 0;
-    if (n > DBG_SLOTS) n = DBG_SLOTS;
+    const int cap = DBG_SLOTS + 8 + DBG_LOG_CAP * 4;       // accumulators | log header | CTA log (OETR_TIMING=2)
+    if (n > cap) n = cap;
     cudaDeviceSynchronize();
-    cudaMemcpy(out, g_dbg_acc, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, g_dbg_acc, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     if (reset) cudaMemset(g_dbg_acc, 0, DBG_SLOTS * sizeof(unsigned long long));
     return n;
 }
@@ -418,7 +422,7 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WL
     EncParams base{};
     base.g = g; base.eg = eg; base.feat1 = feat1; base.feat2 = feat2; base.xt = eg.flat ? ws.xt_enc : ws.xt;
     base.mask1 = mask1; base.mask2 = mask2; base.post1 = post1; base.post2 = post2;
-    base.mimg = ws.mimg; base.ksum = ws.ksum; base.kv_part = ws.kv_part; base.flag = flag;
+    base.mimg = ws.mimg; base.ksum = ws.ksum; base.kv_part = ws.kv_part; base.flag = flag; base.dbg_acc = dbg_acc;
     auto vec = [&](float (&dst)[C], size_t off) { memcpy(dst, h_w + off, C * sizeof(float)); };
     auto set_kv_enc = [&](EncParams& p, int layer) {
         const EncW& e = L.enc[layer];
@@ -461,7 +465,6 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WL
         p.w_q = img; p.w_mlp = img + GEMM_HALFS;
         if (i + 1 < N_ENC) set_kv_enc(p, i + 1); else set_kv_dec(p, 0);
         set_prefetch_for(p, i + 1);
-        if (i + 1 < N_ENC) p.dbg_acc = dbg_acc;
         if (prof) prof->mark(s);
         launch_enc(p);
         if (prof) prof->mark(s);

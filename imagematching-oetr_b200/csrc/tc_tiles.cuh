@@ -50,8 +50,18 @@ constexpr uint32_t KF_OFF = 0;                                     // Kf half im
 constexpr uint32_t V_OFF = 2 * SLAB_BYTES;                         // V  half image: 2 slabs (32 KB) inside hi / lo
 
 // OETR_TIMING=1: global cycle accumulators of the k_enc launches with a query and a source phase (atomicAdd per CTA)
-enum { DBG_MMA_TOTAL = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_W = 2, DBG_TILES = 3, DBG_TILE_NS = 4, DBG_STAGE0 = 8, DBG_CONV = 40, DBG_SLOTS = 48 };
+// DBG_LOG: optional CTA log (OETR_TIMING=2): slot DBG_LOG_N counts entries of {smid, kernel id, t_start ns, t_end ns} appended after the
+// accumulators (tools/sm_timeline.py reconstructs per-SM busy time from it)
+enum { DBG_MMA_TOTAL = 0, DBG_MMA_WAIT_A = 1, DBG_MMA_WAIT_W = 2, DBG_TILES = 3, DBG_TILE_NS = 4, DBG_STAGE0 = 8, DBG_CONV = 40, DBG_LOG_N = 47, DBG_SLOTS = 48, DBG_LOG_CAP = 1 << 18 };
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint32_t sm_id() { uint32_t s; asm volatile("mov.u32 %0, %smid;" : "=r"(s)); return s; }
+__device__ __forceinline__ void dbg_log_cta(unsigned long long* acc, int kernel_id, unsigned long long t0) {
+    if (!acc || !acc[DBG_LOG_N + 1]) return;               // slot 48 (first word after the accumulators) = logging enabled
+    const unsigned long long i = atomicAdd(acc + DBG_LOG_N, 1ull);
+    if (i >= DBG_LOG_CAP) return;
+    unsigned long long* e = acc + DBG_SLOTS + 8 + i * 4;
+    e[0] = sm_id(); e[1] = (unsigned long long)kernel_id; e[2] = t0; e[3] = global_ns();
+}
 
 struct Bars {
     uint64_t full[RING], empty[RING];
