@@ -4,4 +4,5 @@ package at the repo root) or via importlib.import_module("imagematching-oetr_b20
 from . import cabi, weights  # noqa: F401
 from .config import get_cfg_defaults  # noqa: F401
 from .hotpath import OverlapHotPath  # noqa: F401
+from .neck import NeckB200  # noqa: F401
 from .model import OETR, QueryTransformer, build_detectors  # noqa: F401

@@ -18,6 +18,8 @@ EXPORTS = (
     "oetr_selftest_tcgen05", "oetr_selftest_geometry", "oetr_debug_cycles",
     "oetr_gather_create", "oetr_gather_connect", "oetr_gather_submit", "oetr_gather_collect", "oetr_gather_destroy",
     "oetr_gather_last_error", "oetr_head_forward",
+    "oetr_neck_packed_weight_count", "oetr_neck_create", "oetr_neck_destroy", "oetr_neck_workspace_bytes", "oetr_neck_forward",
+    "oetr_neck_last_launch_count", "oetr_neck_geometry", "oetr_neck_last_error",
 )
 IPC_HANDLE_BYTES = 64
 
@@ -87,6 +89,20 @@ def load_library(path=None):
     lib.oetr_gather_destroy.restype = c.c_int
     lib.oetr_gather_destroy.argtypes = [vp]
     lib.oetr_gather_last_error.restype = c.c_char_p
+    lib.oetr_neck_packed_weight_count.restype = c.c_size_t
+    lib.oetr_neck_create.restype = c.c_int
+    lib.oetr_neck_create.argtypes = [vp, c.c_size_t, c.POINTER(vp)]
+    lib.oetr_neck_destroy.restype = c.c_int
+    lib.oetr_neck_destroy.argtypes = [vp]
+    lib.oetr_neck_workspace_bytes.restype = c.c_int
+    lib.oetr_neck_workspace_bytes.argtypes = [vp, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_size_t)]
+    lib.oetr_neck_forward.restype = c.c_int
+    lib.oetr_neck_forward.argtypes = [vp, vp, c.c_int, c.c_int, c.c_int, vp, vp, c.c_size_t, vp]
+    lib.oetr_neck_last_launch_count.restype = c.c_int
+    lib.oetr_neck_last_launch_count.argtypes = [vp]
+    lib.oetr_neck_geometry.restype = c.c_int
+    lib.oetr_neck_geometry.argtypes = [c.c_int] * 4 + [c.POINTER(c.c_int)]
+    lib.oetr_neck_last_error.restype = c.c_char_p
     lib.oetr_debug_cycles.restype = c.c_int
     lib.oetr_debug_cycles.argtypes = [c.POINTER(c.c_ulonglong), c.c_int, c.c_int]
     lib.oetr_selftest_tcgen05.restype = c.c_int

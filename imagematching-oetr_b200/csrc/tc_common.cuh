@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t a, uint32_t parity) {
 }
 // ONE copy of the spin loop per kernel (inlined at ~60 call sites it was 40 % of k_enc's instruction stream, and the
 // row-warp code is instruction-fetch bound)
-__device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity, int* timeout_flag) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity, int* timeout_flag) {
 #pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 22); ++spin)
         if (mbar_try(a, parity)) return;

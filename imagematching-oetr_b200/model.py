@@ -1,7 +1,8 @@
 """Drop-in mirror of the reference model class (reference src/model.py:38-384): same constructor argument,
 same parameter names (strict load_state_dict of reference checkpoints), same `forward_dummy` / `forward`
-signatures and return types.  feature_extraction stays PyTorch; everything after it (feature_correlation,
-center_estimation, size_regression, box assembly) is one call into the CUDA library."""
+signatures and return types.  The ResNet trunk stays PyTorch; the neck (input_proj -> patchmerging -> input_proj2) is one
+call into the CUDA library (oetr_neck_forward) and everything after it (feature_correlation, center_estimation,
+size_regression, box assembly) another (oetr_forward)."""
 import math
 
 import torch
@@ -9,7 +10,8 @@ import torch.nn as nn
 
 from .backbone import PatchMerging, ResnetEncoder
 from .hotpath import OverlapHotPath
-from .weights import CANONICAL_ORDER, UNUSED_NAMES
+from .neck import NeckB200
+from .weights import CANONICAL_ORDER, NECK_ORDER, UNUSED_NAMES
 
 
 def _linear(i, o, bias):
@@ -119,8 +121,15 @@ class QueryTransformer(nn.Module):
 
 
 class OETR(nn.Module):
-    def __init__(self, cfg, attention_mode="linear", precision="fp16", pretrained_backbone=False):
+    def __init__(self, cfg, attention_mode="linear", precision="fp16", pretrained_backbone=False, neck="cuda"):
+        """neck: "cuda" runs input_proj -> patchmerging -> input_proj2 in liboetr_b200.so (oetr_neck_forward; ResNet-50
+        layer3 features only, no fallback), "torch" keeps the reference's PyTorch modules (needed for training the neck
+        or for backbones with another channel count)."""
         super().__init__()
+        if neck not in ("cuda", "torch"):
+            raise ValueError("neck %r not in ('cuda', 'torch')" % (neck,))
+        self.neck_mode = neck
+        self._neck, self._neck_key = None, None
         self.backbone = ResnetEncoder(cfg, pretrained=pretrained_backbone)
         self.d_model = self.backbone.last_layer // 4
         self.input_proj = nn.Conv2d(self.backbone.last_layer, self.d_model, kernel_size=1)
@@ -166,13 +175,37 @@ class OETR(nn.Module):
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
-        self._hot = None
+        self._hot = self._neck = None
         return out
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._hot = None
+        self._hot = self._neck = None
         return out
+
+    def _neck_params(self):
+        if getattr(self, "_neck_param_list", None) is None:
+            names = {n for n, _ in NECK_ORDER}
+            self._neck_param_list = [p for n, p in self.named_parameters() if n in names]
+        return self._neck_param_list
+
+    @property
+    def neck_path(self):
+        """The CUDA neck handle (a snapshot of input_proj / patchmerging / input_proj2), rebuilt like `hot_path` when one
+        of those parameters changed."""
+        if self._neck is None or self._neck_key != _versions(self._neck_params()):
+            if self._neck is not None:
+                self._neck.close()
+            dev = self.input_proj.weight.device
+            if dev.type != "cuda":
+                raise RuntimeError("the CUDA neck needs the module on a CUDA device (there is no CPU fallback); call .cuda() "
+                                   "or build the model with neck='torch'")
+            if self.backbone.last_layer != 1024:
+                raise RuntimeError("the CUDA neck is specialised for 1024-channel backbone features (ResNet-50 layer3), got "
+                                   "%d; build the model with neck='torch'" % self.backbone.last_layer)
+            self._neck = NeckB200({n: p for n, p in self.state_dict().items()}, device=dev)
+            self._neck_key = _versions(self._neck_params())
+        return self._neck
 
     @property
     def hot_path(self):
@@ -186,8 +219,16 @@ class OETR(nn.Module):
     def feature_extraction(self, image1, image2, mask1=None, mask2=None):
         """backbone -> input_proj -> patchmerging -> input_proj2 for both images and the position encodings: the
         reference's 8-tuple (feat1, feat2, pos1, pos2, hf1, wf1, hf2, wf2), model.py:109-130."""
-        feat1 = self.input_proj2(self.patchmerging(self.input_proj(self.backbone(image1))))
-        feat2 = self.input_proj2(self.patchmerging(self.input_proj(self.backbone(image2))))
+        x1, x2 = self.backbone(image1), self.backbone(image2)
+        if self.neck_mode == "cuda" and not (torch.is_grad_enabled() and self.training):
+            if x1.shape == x2.shape:                         # one launch sequence for both image sets
+                f = self.neck_path.forward(torch.cat([x1, x2], dim=0))
+                feat1, feat2 = f[: x1.shape[0]], f[x1.shape[0]:]
+            else:
+                feat1, feat2 = self.neck_path.forward(x1), self.neck_path.forward(x2)
+        else:
+            feat1 = self.input_proj2(self.patchmerging(self.input_proj(x1)))
+            feat2 = self.input_proj2(self.patchmerging(self.input_proj(x2)))
         hf1, wf1 = feat1.shape[2:]
         hf2, wf2 = feat2.shape[2:]
         return feat1, feat2, self.pos_encoding(feat1), self.pos_encoding(feat2), hf1, wf1, hf2, wf2

@@ -153,3 +153,59 @@ def synthetic_mask(batch, hf, wf, tag="mask"):
         c = min(wf - 1, (2 * b + 1 + off) % 5)
         m[b, : hf - r, : wf - c] = 1.0
     return m
+
+
+# --------------------------------------------------------------------------------------------------------
+# neck: input_proj -> PatchMerging -> input_proj2, reference src/model.py:45-56,
+# src/models/backbone.py:28-51.  NECK_ORDER is the packing order of oetr_neck_create (include/oetr_b200.h).
+# --------------------------------------------------------------------------------------------------------
+BACKBONE_CH = 1024
+NECK_ORDER = [
+    ("input_proj.weight", (256, 1024, 1, 1)), ("input_proj.bias", (256,)),
+    ("patchmerging.norm.weight", (256,)), ("patchmerging.norm.bias", (256,)),
+    ("patchmerging.reductions.0.weight", (256, 256, 4, 4)), ("patchmerging.reductions.0.bias", (256,)),
+    ("patchmerging.reductions.1.weight", (128, 256, 8, 8)), ("patchmerging.reductions.1.bias", (128,)),
+    ("patchmerging.reductions.2.weight", (128, 256, 16, 16)), ("patchmerging.reductions.2.bias", (128,)),
+    ("input_proj2.weight", (256, 512, 1, 1)), ("input_proj2.bias", (256,)),
+]
+NECK_PACKED_COUNT = sum(int(np.prod(s)) for _, s in NECK_ORDER)      # 11 929 088
+
+
+def pack_neck_weights(state_dict):
+    """state_dict (reference key names) -> one fp32 ndarray in NECK_ORDER."""
+    parts = []
+    for name, shape in NECK_ORDER:
+        if name not in state_dict:
+            raise KeyError("neck weight %r missing from state dict" % name)
+        v = state_dict[name]
+        if hasattr(v, "detach"):
+            v = v.detach().to("cpu").float().numpy()
+        v = np.asarray(v, dtype=np.float32)
+        if tuple(v.shape) != tuple(shape):
+            raise ValueError("weight %r has shape %s, expected %s" % (name, tuple(v.shape), shape))
+        parts.append(v.reshape(-1))
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
+def synthetic_neck_weights(seed=0, gain=1.0):
+    """{name: fp32 ndarray}: PyTorch's default nn.Conv2d initialisation (bound 1/sqrt(fan_in) for weight and bias --
+    what the reference's neck gets, it is outside the xavier loop) times `gain`; LayerNorm scale around 1."""
+    out = {}
+    for name, shape in NECK_ORDER:
+        rng = _rng_for(name, seed)
+        if ".norm." in name:
+            out[name] = (1.0 + _uniform(rng, shape, 0.25)) if name.endswith("weight") else _uniform(rng, shape, 0.2)
+            out[name] = out[name].astype(np.float32)
+            continue
+        wshape = dict(NECK_ORDER)[name.rsplit(".", 1)[0] + ".weight"]
+        fan_in = int(np.prod(wshape[1:]))
+        out[name] = (_uniform(rng, shape, 1.0 / float(np.sqrt(fan_in))) * np.float32(gain)).astype(np.float32)
+    return out
+
+
+def synthetic_backbone_features(batch, h, w, seed=1, tag="layer3", scale=1.0):
+    """Stand-in for ResNet-50 layer3 outputs [batch,1024,h,w]: post-ReLU, about half the entries zero."""
+    rng = _rng_for("%s/%d/%d/%d" % (tag, batch, h, w), seed)
+    shape = (batch, BACKBONE_CH, h, w)
+    acc = sum(_uniform(rng, shape, 1.0).astype(np.float64) for _ in range(3))
+    return (np.maximum(acc, 0.0) * scale).astype(np.float32)

@@ -213,6 +213,31 @@ OETR_API int oetr_gather_collect(oetr_gather* g, float* all_boxes, void* stream)
 OETR_API int oetr_gather_destroy(oetr_gather* g);
 OETR_API const char* oetr_gather_last_error(void);
 
+/* ---- the neck: what the reference runs between the backbone and the hot path ----------------------
+ * Replaces, in OETR.feature_extraction (src/model.py:116-124): input_proj (1x1 conv 1024 -> 256, src/model.py:45-47),
+ * PatchMerging (LayerNorm over channels + three stride-2 convolutions k = 4/8/16, padding (k-2)/2, 256 -> 256/128/128,
+ * concatenated; src/models/backbone.py:28-67) and input_proj2 (1x1 conv 512 -> 256, src/model.py:48-50), for ONE image
+ * set: backbone_out [n][1024][height][width] fp32 NCHW (ResNet-50 layer3) -> feat_out [n][256][height/2][width/2] fp32
+ * NCHW (what oetr_forward reads).  tcgen05 kernels, single fp16 operands with fp32 accumulation; the convolution operands
+ * are fetched with TMA tensor loads.  Stream-ordered, no allocation; workspace from oetr_neck_workspace_bytes.
+ * Packed weights (fp32, host pointer), each tensor as torch's state_dict stores it:
+ *   input_proj.weight[256,1024,1,1] input_proj.bias[256] patchmerging.norm.weight[256] patchmerging.norm.bias[256]
+ *   patchmerging.reductions.0.weight[256,256,4,4] .0.bias[256] .1.weight[128,256,8,8] .1.bias[128]
+ *   .2.weight[128,256,16,16] .2.bias[128] input_proj2.weight[256,512,1,1] input_proj2.bias[256]      (11 929 088 floats)
+ * height, width in 2..200 (the position table of the hot path allows feature maps up to 100 x 100). */
+typedef struct oetr_neck oetr_neck;
+OETR_API size_t oetr_neck_packed_weight_count(void);
+OETR_API int oetr_neck_create(const float* weights_host, size_t n_floats, oetr_neck** out);
+OETR_API int oetr_neck_destroy(oetr_neck* h);
+OETR_API int oetr_neck_workspace_bytes(const oetr_neck* h, int n_images, int height, int width, size_t* out);
+OETR_API int oetr_neck_forward(oetr_neck* h, const float* backbone_out, int n_images, int height, int width, float* feat_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+OETR_API int oetr_neck_last_launch_count(const oetr_neck* h);
+/* host-only: the convolution tiling of a problem on a GPU of `sms` SMs: out5 = {tiles, rows per tile (<= 128), output rows
+ * per tile, images per tile, split-K parts} */
+OETR_API int oetr_neck_geometry(int n_images, int height, int width, int sms, int* out5);
+OETR_API const char* oetr_neck_last_error(void);
+
 /* Measurement aid: device-side accumulators of the tcgen05 kernels (per-tile MMA-lane busy / wait cycles, wall
  * nanoseconds per tile, row-warp stage durations; one atomicAdd per tile, no host synchronisation).  Switched on by
  * OETR_TIMING=1 in the environment or by oetr_debug_cycles(NULL, -1, 1) (off: (NULL, -1, 0)).  With n > 0: copies up

@@ -7,4 +7,5 @@ __path__ = [os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file_
 from . import cabi, weights  # noqa: E402,F401
 from .config import get_cfg_defaults  # noqa: E402,F401
 from .hotpath import OverlapHotPath  # noqa: E402,F401
+from .neck import NeckB200  # noqa: E402,F401
 from .model import OETR, QueryTransformer, build_detectors  # noqa: E402,F401

@@ -26,7 +26,7 @@ def model():
 
 def test_state_dict_has_every_hot_path_name(model):
     sd = model.state_dict()
-    for name, shape in weights.CANONICAL_ORDER + weights.UNUSED_NAMES:
+    for name, shape in weights.CANONICAL_ORDER + weights.UNUSED_NAMES + weights.NECK_ORDER:
         assert name in sd and tuple(sd[name].shape) == tuple(shape), name
     assert "pos_encoding.pe" not in sd          # non-persistent in the reference (models/utils.py:196)
 
@@ -112,7 +112,11 @@ def test_strict_load_and_feature_extraction_match_reference(model):
     torch.manual_seed(1)
     a, b = torch.rand(1, 192, 256, 3), torch.rand(1, 256, 192, 3)
     with torch.no_grad():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model.feature_extraction(a, b)                    # the default CUDA neck refuses to run on the CPU
+        model.neck_mode = "torch"                             # the reference's PyTorch modules (bit-exact check below)
         m = model.feature_extraction(a, b)
+        model.neck_mode = "cuda"
         r = ref.feature_extraction(a, b)
     assert len(m) == len(r) == 8                              # (feat1, feat2, pos1, pos2, hf1, wf1, hf2, wf2), model.py:130
     assert torch.equal(m[0], r[0]) and torch.equal(m[1], r[1])

@@ -123,3 +123,30 @@ def test_stage_wise_signatures_of_the_reference():
     model.train()
     with pytest.raises(NotImplementedError):
         model({"image1": img1, "image2": img2})
+
+
+def test_cuda_neck_matches_the_pytorch_neck_modules():
+    """feature_extraction with the CUDA neck (oetr_neck_forward, the default) against the reference's PyTorch modules on the
+    SAME weights and backbone features (fp32, TF32 off): features within the neck's fp16-operand bar, boxes within 1e-3."""
+    model = _model()
+    assert model.neck_mode == "cuda"
+    g = torch.Generator().manual_seed(5)
+    for shape1, shape2 in (((2, 640, 640, 3), (2, 640, 640, 3)), ((1, 480, 640, 3), (1, 608, 416, 3))):
+        img1, img2 = torch.rand(shape1, generator=g).cuda(), torch.rand(shape2, generator=g).cuda()
+        with torch.no_grad():
+            f1, f2 = model.feature_extraction(img1, img2)[:2]
+            b1, b2 = model.forward_dummy(img1, img2)
+            model.neck_mode = "torch"
+            t1, t2 = model.feature_extraction(img1, img2)[:2]
+            c1, c2 = model.forward_dummy(img1, img2)
+            model.neck_mode = "cuda"
+        for f, t in ((f1, t1), (f2, t2)):
+            assert f.shape == t.shape
+            std = float(t.std())
+            assert float((f - t).abs().max()) < 4e-3 * std and float((f - t).pow(2).mean().sqrt()) < 1e-3 * std
+        assert float((b1 - c1).abs().max()) / max(shape1[1:3]) < 1e-3 and float((b2 - c2).abs().max()) / max(shape2[1:3]) < 1e-3
+    # the neck handle snapshots its weights and follows in-place updates
+    with torch.no_grad():
+        model.input_proj2.bias.add_(0.25)
+        f1b = model.feature_extraction(img1, img2)[0]
+    assert float((f1b - f1).abs().max()) > 0.2
