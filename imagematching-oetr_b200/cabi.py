@@ -20,6 +20,7 @@ EXPORTS = (
     "oetr_gather_last_error", "oetr_head_forward",
     "oetr_neck_packed_weight_count", "oetr_neck_create", "oetr_neck_destroy", "oetr_neck_workspace_bytes", "oetr_neck_forward",
     "oetr_neck_last_launch_count", "oetr_neck_geometry", "oetr_neck_last_error",
+    "oetr_crop_resize", "oetr_crop_last_error",
 )
 IPC_HANDLE_BYTES = 64
 
@@ -103,6 +104,9 @@ def load_library(path=None):
     lib.oetr_neck_geometry.restype = c.c_int
     lib.oetr_neck_geometry.argtypes = [c.c_int] * 4 + [c.POINTER(c.c_int)]
     lib.oetr_neck_last_error.restype = c.c_char_p
+    lib.oetr_crop_resize.restype = c.c_int
+    lib.oetr_crop_resize.argtypes = [vp, c.c_int, vp]
+    lib.oetr_crop_last_error.restype = c.c_char_p
     lib.oetr_debug_cycles.restype = c.c_int
     lib.oetr_debug_cycles.argtypes = [c.POINTER(c.c_ulonglong), c.c_int, c.c_int]
     lib.oetr_selftest_tcgen05.restype = c.c_int

@@ -238,6 +238,28 @@ OETR_API int oetr_neck_last_launch_count(const oetr_neck* h);
 OETR_API int oetr_neck_geometry(int n_images, int height, int width, int sms, int* out5);
 OETR_API const char* oetr_neck_last_error(void);
 
+/* ---- post-box plumbing on the device -------------------------------------------------------------
+ * Replaces the host round trip of dloc/core/utils/utils.py:510-564 `tensor_overlap_crop` (called from evaluation.py:104-111):
+ * image[0, :, y0:y1, x0:x1] -> * 255 -> cv2.resize(float32, (new_w, new_h), INTER_CUBIC) -> / 255.  One job = one resize
+ * of one crop; all jobs of a call run in ONE kernel launch (up to 32 per launch), stream-ordered, no allocation.
+ * src = the whole image [channels][src_h][src_w] fp32 (device); the crop is [y0, min(y1, src_h)) x [x0, min(x1, src_w))
+ * like Python slicing; dst [channels][new_h][new_w] fp32 (device).  flags: OETR_CROP_MUL255 scales the source by 255
+ * before interpolating, OETR_CROP_DIV255 divides the result by 255 (a two-pass resize sets MUL on the first pass and DIV on
+ * the second).  Bicubic arithmetic = cv2 4.13 INTER_CUBIC on float32 (A = -0.75, clamped taps); results agree with cv2
+ * to float32 rounding (2e-4 on the 0..255 scale). */
+#define OETR_CROP_MUL255 1
+#define OETR_CROP_DIV255 2
+typedef struct oetr_crop_job {
+    const float* src;
+    float* dst;
+    int channels, src_h, src_w;
+    int x0, y0, x1, y1;
+    int new_w, new_h;
+    int flags;
+} oetr_crop_job;
+OETR_API int oetr_crop_resize(const oetr_crop_job* jobs, int n_jobs, void* stream);
+OETR_API const char* oetr_crop_last_error(void);
+
 /* Measurement aid: device-side accumulators of the tcgen05 kernels (per-tile MMA-lane busy / wait cycles, wall
  * nanoseconds per tile, row-warp stage durations; one atomicAdd per tile, no host synchronisation).  Switched on by
  * OETR_TIMING=1 in the environment or by oetr_debug_cycles(NULL, -1, 1) (off: (NULL, -1, 0)).  With n > 0: copies up

@@ -97,3 +97,14 @@ def build_reference_full_transformer(net):
     full = QueryTransformer(256, 8, 4, attention_mode="full")
     full.load_state_dict(net.transformer.state_dict())
     return full.eval()
+
+
+def install_dloc():
+    """Additionally stub matplotlib (not installed here; reference dloc/core/utils/utils.py:53-58 imports it for its
+    plotting helpers only) so that the reference's dloc.core.utils.utils can be imported."""
+    install()
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+        except ImportError:
+            _mod("matplotlib", use=lambda *a, **k: None, pyplot=_mod("matplotlib.pyplot"), cm=_mod("matplotlib.cm"))
