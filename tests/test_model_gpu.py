@@ -150,3 +150,29 @@ def test_cuda_neck_matches_the_pytorch_neck_modules():
         model.input_proj2.bias.add_(0.25)
         f1b = model.feature_extraction(img1, img2)[0]
     assert float((f1b - f1).abs().max()) > 0.2
+
+
+def test_backbone_execution_modes():
+    """channels_last / TF32 / bf16 / CUDA-graph execution of the PyTorch trunk against the reference's eager
+    fp32 execution; graph replay equals the uncaptured run of the same mode bit for bit and follows new inputs."""
+    model = _model()
+    g = torch.Generator().manual_seed(7)
+    img, img_b = torch.rand((2, 320, 416, 3), generator=g).cuda(), torch.rand((2, 320, 416, 3), generator=g).cuda()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    with torch.no_grad():
+        ref = model.backbone(img)
+        for mode, tol in (("channels_last", 1e-4), ("tf32", 2e-2), ("bf16", 1e-1)):
+            model.backbone.set_execution_mode(mode)
+            f = model.backbone(img)
+            assert f.shape == ref.shape and f.dtype == torch.float32 and f.is_contiguous() and rel(f, ref) < tol, (mode, rel(f, ref))
+            model.backbone.set_execution_mode(mode, graphs=True)
+            f1 = model.backbone(img)            # captures
+            f2 = model.backbone(img_b)          # replays on new data
+            f3 = model.backbone(img)
+            assert torch.equal(f1, f3) and rel(f1, ref) < tol and not torch.equal(f1, f2)
+            model.backbone.set_execution_mode(mode)
+            assert torch.equal(model.backbone(img_b), f2) or rel(model.backbone(img_b), f2) < 1e-5
+        model.backbone.set_execution_mode("eager")
+        assert torch.equal(model.backbone(img), ref)
+    with pytest.raises(ValueError):
+        model.backbone.set_execution_mode("int4")
