@@ -40,7 +40,8 @@ def test_full_size_properties():
     im = torch.from_numpy(synthetic_image(1, 1200, 1600, 9)).cuda()
     full = torch.tensor([[0.0, 0.0, 1600.0, 1200.0]]).cuda()
     l, r, r1, r2 = U.tensor_overlap_crop(im, full, im, full, "superpoint")
-    assert torch.equal(l, im * 255 / 255) and r1 == [[1.0, 1.0]]
+    want_id = im.cpu().numpy() * np.float32(255) / np.float32(255)          # numpy's true division, like the reference (torch multiplies by 1/255)
+    assert np.array_equal(l.cpu().numpy(), want_id) and r1 == [[1.0, 1.0]]
     box = torch.tensor([[100.7, 50.2, 1300.1, 1100.9]]).cuda()
     a, _, ra, _ = U.tensor_overlap_crop(im, box, im, full, "superpoint")
     b, _, _, _ = U.tensor_overlap_crop(im, box, im, full, "superpoint")
