@@ -21,6 +21,7 @@ EXPORTS = (
     "oetr_neck_packed_weight_count", "oetr_neck_create", "oetr_neck_destroy", "oetr_neck_workspace_bytes", "oetr_neck_forward",
     "oetr_neck_last_launch_count", "oetr_neck_geometry", "oetr_neck_last_error",
     "oetr_crop_resize", "oetr_crop_last_error",
+    "oetr_sg_attention", "oetr_sg_transport_workspace_bytes", "oetr_sg_optimal_transport", "oetr_sg_last_error",
 )
 IPC_HANDLE_BYTES = 64
 
@@ -107,6 +108,13 @@ def load_library(path=None):
     lib.oetr_crop_resize.restype = c.c_int
     lib.oetr_crop_resize.argtypes = [vp, c.c_int, vp]
     lib.oetr_crop_last_error.restype = c.c_char_p
+    lib.oetr_sg_attention.restype = c.c_int
+    lib.oetr_sg_attention.argtypes = [vp, vp, vp, vp, c.c_int, c.c_int, c.c_int, vp]
+    lib.oetr_sg_transport_workspace_bytes.restype = c.c_size_t
+    lib.oetr_sg_transport_workspace_bytes.argtypes = [c.c_int, c.c_int, c.c_int]
+    lib.oetr_sg_optimal_transport.restype = c.c_int
+    lib.oetr_sg_optimal_transport.argtypes = [vp, c.c_float, c.c_int, vp, c.c_int, c.c_int, c.c_int, vp, c.c_size_t, vp]
+    lib.oetr_sg_last_error.restype = c.c_char_p
     lib.oetr_debug_cycles.restype = c.c_int
     lib.oetr_debug_cycles.argtypes = [c.POINTER(c.c_ulonglong), c.c_int, c.c_int]
     lib.oetr_selftest_tcgen05.restype = c.c_int

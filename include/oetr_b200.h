@@ -260,6 +260,21 @@ typedef struct oetr_crop_job {
 OETR_API int oetr_crop_resize(const oetr_crop_job* jobs, int n_jobs, void* stream);
 OETR_API const char* oetr_crop_last_error(void);
 
+/* ---- SuperGlue's two hot operators ---------------------------------------------------------------
+ * oetr_sg_attention replaces `attention(query, key, value)` of third_party/SuperGluePretrainedNetwork/models/superglue.py:86-90
+ * as called by MultiHeadedAttention.forward (:100-108): query [batch][256][n], key / value [batch][256][m] fp32 device
+ * tensors in the reference's Conv1d layout, channel c = d * 4 + head (4 heads x 64 dims) -> out [batch][256][n]
+ * = softmax_m(Q_h^T K_h / 8) V_h per head, online softmax (no [n, m] matrix in memory).  fp32 arithmetic.
+ * oetr_sg_optimal_transport replaces `log_optimal_transport(scores, alpha, iters)` (:150-184): scores [batch][m][n] fp32,
+ * alpha = bin_score -> out [batch][m+1][n+1] (log assignment matrix incl. dustbins, multiplied by m + n like the
+ * reference).  workspace: oetr_sg_transport_workspace_bytes.  Both are stream-ordered and allocate nothing. */
+OETR_API int oetr_sg_attention(const float* query, const float* key, const float* value, float* out, int batch, int n, int m,
+                               void* stream);
+OETR_API size_t oetr_sg_transport_workspace_bytes(int batch, int m, int n);
+OETR_API int oetr_sg_optimal_transport(const float* scores, float alpha, int iters, float* out, int batch, int m, int n,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+OETR_API const char* oetr_sg_last_error(void);
+
 /* Measurement aid: device-side accumulators of the tcgen05 kernels (per-tile MMA-lane busy / wait cycles, wall
  * nanoseconds per tile, row-warp stage durations; one atomicAdd per tile, no host synchronisation).  Switched on by
  * OETR_TIMING=1 in the environment or by oetr_debug_cycles(NULL, -1, 1) (off: (NULL, -1, 0)).  With n > 0: copies up

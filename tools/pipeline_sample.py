@@ -113,6 +113,10 @@ def phase_prepare():
         for i in (1, 2):
             shutil.copyfile(os.path.join(REF, "third_party", "D2Net", "qualitative", "images", pair, "%d.jpg" % i),
                             os.path.join(SAMPLES, pair, "%d.jpg" % i))
+    wdir = os.path.join(ROOT, "oracle", "_ref", "weights")          # in-tree matcher weights for the GPU tests of oetr_b200.superglue
+    os.makedirs(wdir, exist_ok=True)
+    shutil.copyfile(os.path.join(REF, "third_party", "SuperGluePretrainedNetwork", "models", "weights", "superglue_outdoor.pth"),
+                    os.path.join(wdir, "superglue_outdoor.pth"))
     print("samples in", SAMPLES)
 
 
