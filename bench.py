@@ -2,6 +2,7 @@
 """Benchmark of the OETR hot path (feature-correlation transformer + overlap-box head) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 640|840] [--attention linear|full]
+                    [--path hot|neck]
 
 A step = one pass of the hot path over one batch of synthetic input: 32 pairs of 640x640 images, i.e. two
 [32,256,20,20] fp32 feature maps (BASELINE.json configs[1]; --config 840: 16 pairs of 840x840, configs[3]); with N
@@ -465,6 +466,110 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_neck(args):
+    """--path neck: the same contract for the neck (input_proj -> PatchMerging -> input_proj2 on the two
+    image sets of a batch; NOT the headline metric).  value: backbone features resident in HBM, CUDA events, median of the
+    regions; e2e: oetr_neck_forward fed from pinned host buffers every step (H2D of the 1024-channel features inside the
+    timed region, D2H of the 256-channel output); roofline: the whole neck's algorithmic FLOPs against the measured tensor
+    peak (k_neck_conv holds 76 % of the device time, profiles/r02_neck_launches.txt); cpu_baseline: the reference's own
+    PyTorch modules' arithmetic (torch conv2d / layer_norm, fp32) on the host cores, bounded sample."""
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import torch.nn.functional as F
+
+    from oetr_b200 import weights
+    from oetr_b200.neck import NeckB200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and rank > 0:
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    side, fm, B, _, _ = CONFIGS[args.config]
+    h = w = side // 16
+    n = 2 * B
+    K, Wm, R = args.steps, args.warmup, max(1, args.regions)
+    W = weights.synthetic_neck_weights(0)
+    neck = NeckB200(W, device=dev)
+    host = [torch.from_numpy(weights.synthetic_backbone_features(n, h, w, seed=60 + i)).pin_memory() for i in range(2)]
+    xs = [t.to(dev) for t in host]                            # 2 x 420 MB at 640: a step never finds its input in L2
+    out = torch.empty(n, 256, h // 2, w // 2, device=dev)
+    out_host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+    for i in range(Wm):
+        neck.forward(xs[i & 1], out=out)
+    torch.cuda.synchronize()
+    regions = []
+    with ClockSampler(0) as clk:
+        for _ in range(R):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for i in range(K):
+                neck.forward(xs[i & 1], out=out)
+            ev1.record()
+            torch.cuda.synchronize()
+            regions.append(ev0.elapsed_time(ev1))
+    ms = statistics.median(regions)
+    staging = torch.empty_like(xs[0])
+    e2e = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            staging.copy_(host[i & 1], non_blocking=True)
+            neck.forward(staging, out=out)
+            out_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e.append(time.perf_counter() - t0)
+    e2e_s = statistics.median(e2e)
+    t, o = h * w, (h // 2) * (w // 2)
+    flops_img = 2.0 * (t * 1024 * 256 + o * 256 * (256 * 16 + 128 * 64 + 128 * 256) + o * 512 * 256)
+    peak, peak_src = _peaks(ms * 1e-3)
+    ach = flops_img * n * K / (ms * 1e-3) / 1e12
+    # parity spot check against the oracle (2 images) and the CPU baseline (torch fp32 on the host cores, bounded sample)
+    from oracle import neck_oracle as nk
+    got = neck.forward(xs[0][:2].contiguous()).cpu().numpy()
+    want = nk.neck(W, host[0][:2].numpy())
+    perr = float(np.abs(got - want).max() / want.std())
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    xc = host[0][:8]
+
+    def torch_neck(x):
+        p = F.conv2d(x, Wt["input_proj.weight"], Wt["input_proj.bias"])
+        p = F.layer_norm(p.permute(0, 2, 3, 1), (256,), Wt["patchmerging.norm.weight"], Wt["patchmerging.norm.bias"]).permute(0, 3, 1, 2)
+        outs = [F.conv2d(p, Wt["patchmerging.reductions.%d.weight" % i], Wt["patchmerging.reductions.%d.bias" % i], stride=2,
+                         padding=(k - 2) // 2) for i, k in enumerate((4, 8, 16))]
+        return F.conv2d(torch.cat(outs, 1), Wt["input_proj2.weight"], Wt["input_proj2.bias"])
+    with torch.no_grad():
+        torch_neck(xc[:2])
+        t0 = time.perf_counter()
+        torch_neck(xc)
+        cpu_dt = time.perf_counter() - t0
+    line = {
+        "metric": "neck image-pairs/sec at %dx%d" % (side, side), "value": B * K / (ms * 1e-3), "unit": "pairs/s", "n_gpus": 1,
+        "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+        "config": {"workload": "batch=%d %dx%d pairs: neck (input_proj -> PatchMerging -> input_proj2) on [%d,1024,%d,%d] fp32 backbone "
+                               "features -> [%d,256,%d,%d]" % (B, side, side, n, h, w, n, h // 2, w // 2),
+                   "regions": "%d regions of %d steps, median reported" % (R, K),
+                   "l2": "inputs alternate between two resident batches (%.0f MB each > 126 MB L2)" % (xs[0].numel() * 4 / 1e6)},
+        "clocks": clk.summary(),
+        "e2e": {"value": B * K / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(xs[0].numel() * 4), "d2h_bytes_per_step": int(out.numel() * 4),
+                "api": "oetr_neck_forward (C ABI via NeckB200.forward) fed from pinned host buffers, one request at a time"},
+        "gpu_launches": neck.last_launch_count * K,
+        "roofline": {"bound": "tensor", "kernel": "whole neck (k_neck_proj + k_neck_conv + k_neck_out)", "achieved": ach, "peak": peak,
+                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "flops_per_step": flops_img * n, "note": "algorithmic FLOPs; single fp16 products, so the cap is 1.0"},
+        "cpu_baseline": {"value": 4 / cpu_dt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "8 images (4 pairs), %.1f s, torch conv2d / layer_norm fp32 on the host cores (the reference modules' "
+                                   "arithmetic)" % cpu_dt},
+        "parity": {"feature_err_over_std": perr, "bar": 4e-3, "images_checked": 2},
+    }
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def gpu_baselines(torch, dev, Wts, feats, hw, B, attention, hot):
     """The same path as eager PyTorch on this GPU (the bar SURVEY.md 2b names): fp32 with TF32 off, and TF32 on +
     CUDA-graph replay (no launch overhead).  Measurement aid only."""
@@ -532,10 +637,14 @@ def main():
                     help="independent batches kept in flight in the device-resident timed region")
     ap.add_argument("--e2e-in-flight", type=int, default=4, help="host requests kept in flight in the e2e leg (1..4)")
     ap.add_argument("--precision", default=os.environ.get("OETR_BENCH_PRECISION", "fp16"), choices=["fp16", "fp32"])
+    ap.add_argument("--path", default="hot", choices=["hot", "neck"], help="hot: the headline hot path (default); neck: the same "
+                    "contract for the neck kernels (SURVEY 8(f1)), one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.path == "neck":
+        run_neck(args)
     else:
         run_b200(args)
 

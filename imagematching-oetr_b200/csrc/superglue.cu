@@ -6,11 +6,12 @@
 //                    cores: exact-parity arithmetic (SuperGlue's match decisions are mutual-argmax + a threshold on
 //                    exp(score)); the contraction sizes are tiny next to OETR's (<= 38 GFLOP for 2048 keypoints over all
 //                    layers), a tcgen05 version with split operands is listed as next work in DESIGN.md.
-//   k_sg_rows / k_sg_cols / k_sg_finish   `log_optimal_transport` (superglue.py:150-184): log-space Sinkhorn iterations on
-//                    the score matrix augmented by the dustbin row / column.  The augmented matrix is never built (the
+//   k_sg_half / k_sg_transpose / k_sg_finish   `log_optimal_transport` (superglue.py:150-184): log-space Sinkhorn iterations
+//                    on the score matrix augmented by the dustbin row / column.  The augmented matrix is never built (the
 //                    dustbin entries are the scalar alpha), u and v live in a small workspace, every half-iteration is one
-//                    pass over the scores with an online log-sum-exp (rows: a warp per row; columns: 32 columns per block,
-//                    rows strided over 8 warps), all launches stream-ordered.
+//                    pass over the L2-resident scores with a chunked log-sum-exp (a warp per row, 8 independent loads and
+//                    exponentials per lane and step); the column update runs the same kernel on a transposed copy made
+//                    once per call, so both passes are coalesced.  All launches stream-ordered.
 // Layout: channel-major like the reference's Conv1d tensors, q [batch][256][N] with channel c = d * 4 + h
 // (`.view(batch, dim, heads, -1)`, superglue.py:103-104).
 #include "../../include/oetr_b200.h"
@@ -130,54 +131,66 @@ __global__ void __launch_bounds__(256) k_sg_attention(const float* __restrict__ 
 
 // ---- log-space optimal transport ------------------------------------------------------------------------------------
 struct LSE { float m, s; };
-__device__ __forceinline__ void lse_add(LSE& a, float x) {
-    if (x > a.m) { a.s = a.s * expf(a.m - x) + 1.f; a.m = x; }
-    else a.s += expf(x - a.m);
-}
 __device__ __forceinline__ void lse_merge(LSE& a, const LSE& b) {
-    if (b.m == -INFINITY) return;
-    if (b.m > a.m) { a.s = a.s * expf(a.m - b.m) + b.s; a.m = b.m; }
-    else a.s += b.s * expf(b.m - a.m);
+    const float m = fmaxf(a.m, b.m);
+    if (m == -INFINITY) return;
+    a.s = a.s * expf(a.m - m) + b.s * expf(b.m - m);
+    a.m = m;
+}
+// one chunk of 8 independent elements: local maximum first, then 8 independent exponentials (no serial rescale chain)
+__device__ __forceinline__ void lse_chunk(LSE& a, const float (&x)[8]) {
+    float cm = x[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cm = fmaxf(cm, x[i]);
+    if (cm == -INFINITY) return;
+    const float m = fmaxf(a.m, cm);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += expf(x[i] - m);
+    a.s = a.s * expf(a.m - m) + sum;
+    a.m = m;
 }
 
-// u[i] = log_mu[i] - logsumexp_j (Z[i][j] + v[j]), i in [0, m], j in [0, n]; Z = scores inside, alpha in the dustbins
-__global__ void __launch_bounds__(256) k_sg_rows(const float* __restrict__ scores, float alpha, const float* __restrict__ vv,
-                                                 float* __restrict__ u, int m, int n, float norm, int first) {
+// One half-iteration: out[r] = log_marg[r] - logsumexp_c (Z[r][c] + in[c]) for the R+1 rows of the augmented matrix whose
+// inner part `mat` is [R][Cn] row-major (the scores for the u-update, their transpose for the v-update) and whose dustbin
+// row / column is the scalar alpha.  A warp per row: coalesced loads, 8 independent loads in flight per lane.
+__global__ void __launch_bounds__(256) k_sg_half(const float* __restrict__ mat, float alpha, const float* __restrict__ in,
+                                                 float* __restrict__ out, int R, int Cn, float norm, float log_other, int first) {
     const int b = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row > m) return;
-    const float* sc = scores + (size_t)b * m * n + (size_t)row * n;
-    const float* v = vv + (size_t)b * (n + 1);
+    if (row > R) return;
+    const float* mr = mat + (size_t)b * R * Cn + (size_t)row * Cn;
+    const float* iv = in + (size_t)b * (Cn + 1);
+    const bool inner = row < R;
     LSE a{-INFINITY, 0.f};
-    for (int j = lane; j <= n; j += 32) {
-        const float z = (row < m && j < n) ? sc[j] : alpha;
-        lse_add(a, z + (first ? 0.f : v[j]));
+    for (int c0 = 0; c0 <= Cn; c0 += 256) {
+        float x[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = c0 + t * 32 + lane;
+            float z = -INFINITY;
+            if (c <= Cn) z = ((inner && c < Cn) ? __ldg(mr + c) : alpha) + (first ? 0.f : iv[c]);
+            x[t] = z;
+        }
+        lse_chunk(a, x);
     }
 #pragma unroll
     for (int w = 16; w > 0; w >>= 1) {
         LSE o{__shfl_xor_sync(0xffffffffu, a.m, w), __shfl_xor_sync(0xffffffffu, a.s, w)};
         lse_merge(a, o);
     }
-    if (lane == 0) u[(size_t)b * (m + 1) + row] = (row < m ? norm : logf((float)n) + norm) - (a.m + logf(a.s));
+    if (lane == 0) out[(size_t)b * (R + 1) + row] = (inner ? norm : log_other + norm) - (a.m + logf(a.s));
 }
-// v[j] = log_nu[j] - logsumexp_i (Z[i][j] + u[i])
-__global__ void __launch_bounds__(256) k_sg_cols(const float* __restrict__ scores, float alpha, const float* __restrict__ uu,
-                                                 float* __restrict__ v, int m, int n, float norm) {
-    __shared__ float sm_m[8][33], sm_s[8][33];
-    const int b = blockIdx.y, lane = threadIdx.x & 31, ty = threadIdx.x >> 5, col = blockIdx.x * 32 + lane;
-    const float* sc = scores + (size_t)b * m * n;
-    const float* u = uu + (size_t)b * (m + 1);
-    LSE a{-INFINITY, 0.f};
-    if (col <= n)
-        for (int i = ty; i <= m; i += 8) {
-            const float z = (i < m && col < n) ? sc[(size_t)i * n + col] : alpha;
-            lse_add(a, z + u[i]);
-        }
-    sm_m[ty][lane] = a.m; sm_s[ty][lane] = a.s;
+// scores [m][n] -> transposed copy [n][m] (32 x 32 tiles through shared memory), once per call
+__global__ void __launch_bounds__(256) k_sg_transpose(const float* __restrict__ src, float* __restrict__ dst, int m, int n) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z, j0 = blockIdx.x * 32, i0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* s = src + (size_t)b * m * n;
+    float* d = dst + (size_t)b * m * n;
+    for (int r = ty; r < 32; r += 8)
+        if (i0 + r < m && j0 + tx < n) t[r][tx] = s[(size_t)(i0 + r) * n + j0 + tx];
     __syncthreads();
-    if (ty == 0 && col <= n) {
-        for (int t = 1; t < 8; ++t) { LSE o{sm_m[t][lane], sm_s[t][lane]}; lse_merge(a, o); }
-        v[(size_t)b * (n + 1) + col] = (col < n ? norm : logf((float)m) + norm) - (a.m + logf(a.s));
-    }
+    for (int r = ty; r < 32; r += 8)
+        if (j0 + r < n && i0 + tx < m) d[(size_t)(j0 + r) * m + i0 + tx] = t[tx][r];
 }
 // out[i][j] = Z[i][j] + u[i] + v[j] - norm        ([m+1][n+1], the matrix the reference returns)
 __global__ void __launch_bounds__(256) k_sg_finish(const float* __restrict__ scores, float alpha, const float* __restrict__ uu,
@@ -224,8 +237,10 @@ int oetr_sg_attention(const float* query, const float* key, const float* value, 
     return OETR_OK;
 }
 
+// u [batch][m+1] | v [batch][n+1] | transposed scores [batch][n][m]
 size_t oetr_sg_transport_workspace_bytes(int batch, int m, int n) {
-    return (size_t)(batch > 0 ? batch : 0) * (size_t)(m + n + 2) * sizeof(float);
+    if (batch < 1 || m < 1 || n < 1) return 0;
+    return (size_t)batch * ((size_t)(m + n + 2) + (size_t)m * n) * sizeof(float);
 }
 
 int oetr_sg_optimal_transport(const float* scores, float alpha, int iters, float* out, int batch, int m, int n, void* workspace,
@@ -239,14 +254,17 @@ int oetr_sg_optimal_transport(const float* scores, float alpha, int iters, float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float* u = static_cast<float*>(workspace);
     float* v = u + (size_t)batch * (m + 1);
+    float* st = v + (size_t)batch * (n + 1);
     const float norm = -logf((float)(m + n));
     if (iters == 0) {
-        const cudaError_t e0 = cudaMemsetAsync(workspace, 0, oetr_sg_transport_workspace_bytes(batch, m, n), s);
+        const cudaError_t e0 = cudaMemsetAsync(workspace, 0, (size_t)batch * (m + n + 2) * sizeof(float), s);
         if (e0 != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_optimal_transport: %s", cudaGetErrorString(e0));
+    } else {
+        k_sg_transpose<<<dim3((n + 31) / 32, (m + 31) / 32, batch), 256, 0, s>>>(scores, st, m, n);
     }
     for (int it = 0; it < iters; ++it) {
-        k_sg_rows<<<dim3((m + 1 + 7) / 8, batch), 256, 0, s>>>(scores, alpha, v, u, m, n, norm, it == 0);
-        k_sg_cols<<<dim3((n + 1 + 31) / 32, batch), 256, 0, s>>>(scores, alpha, u, v, m, n, norm);
+        k_sg_half<<<dim3((m + 1 + 7) / 8, batch), 256, 0, s>>>(scores, alpha, v, u, m, n, norm, logf((float)n), it == 0);
+        k_sg_half<<<dim3((n + 1 + 7) / 8, batch), 256, 0, s>>>(st, alpha, u, v, n, m, norm, logf((float)m), 0);
     }
     k_sg_finish<<<dim3((n + 1 + 255) / 256, m + 1, batch), 256, 0, s>>>(scores, alpha, u, v, out, m, n, norm);
     const cudaError_t e = cudaGetLastError();
