@@ -109,7 +109,7 @@ def load_library(path=None):
     lib.oetr_crop_resize.argtypes = [vp, c.c_int, vp]
     lib.oetr_crop_last_error.restype = c.c_char_p
     lib.oetr_sg_attention.restype = c.c_int
-    lib.oetr_sg_attention.argtypes = [vp, vp, vp, vp, c.c_int, c.c_int, c.c_int, vp]
+    lib.oetr_sg_attention.argtypes = [vp, vp, vp, vp, c.c_int, c.c_int, c.c_int, c.c_int, vp]
     lib.oetr_sg_transport_workspace_bytes.restype = c.c_size_t
     lib.oetr_sg_transport_workspace_bytes.argtypes = [c.c_int, c.c_int, c.c_int]
     lib.oetr_sg_optimal_transport.restype = c.c_int

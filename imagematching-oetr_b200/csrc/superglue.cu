@@ -1,20 +1,21 @@
 // SuperGlue's two hot operators on the device, the heaviest consumer downstream of the overlap
 // boxes in the reference's pipeline (evaluation.py:125-224 -> third_party/SuperGluePretrainedNetwork/models/superglue.py):
-//   k_sg_attention   `attention(query, key, value)` (superglue.py:86-90) for the 4 heads x 64 dims of MultiHeadedAttention
-//                    (:93-108): softmax(Q K^T / 8) V with an online softmax over 64-key tiles -- the [N, M] score matrix
-//                    never exists in memory (the reference materialises it twice per layer, 18 layers).  fp32 on the CUDA
-//                    cores: exact-parity arithmetic (SuperGlue's match decisions are mutual-argmax + a threshold on
-//                    exp(score)); the contraction sizes are tiny next to OETR's (<= 38 GFLOP for 2048 keypoints over all
-//                    layers), a tcgen05 version with split operands is listed as next work in DESIGN.md.
-//   k_sg_half / k_sg_transpose / k_sg_finish   `log_optimal_transport` (superglue.py:150-184): log-space Sinkhorn iterations
-//                    on the score matrix augmented by the dustbin row / column.  The augmented matrix is never built (the
-//                    dustbin entries are the scalar alpha), u and v live in a small workspace, every half-iteration is one
-//                    pass over the L2-resident scores with a chunked log-sum-exp (a warp per row, 8 independent loads and
-//                    exponentials per lane and step); the column update runs the same kernel on a transposed copy made
-//                    once per call, so both passes are coalesced.  All launches stream-ordered.
+//   k_sg_attention_tc / k_sg_attention   `attention(query, key, value)` (superglue.py:86-90) for the 4 heads x 64 dims of
+//                    MultiHeadedAttention (:93-108): softmax(Q K^T / 8) V with an online softmax over key chunks -- the
+//                    [N, M] score matrix never exists in memory (the reference materialises it twice per layer, 18 layers).
+//                    _tc (default): QK^T and PV on tcgen05 with 3-term split fp16 operands, S and O in TMEM; the second
+//                    kernel is the same operator in fp32 on the CUDA cores (mode OETR_SG_FP32; cross-check and baseline).
+//   k_sg_sinkhorn / k_sg_transpose / k_sg_finish   `log_optimal_transport` (superglue.py:150-184): log-space Sinkhorn
+//                    iterations on the score matrix augmented by the dustbin row / column.  The augmented matrix is never
+//                    built (the dustbin entries are the scalar alpha), u and v live in a small workspace, every
+//                    half-iteration is one pass over the L2-resident scores with a chunked log-sum-exp (a warp per row, 8
+//                    independent loads and exponentials per lane and step); the column update reads a transposed copy made
+//                    once per call, so both passes are coalesced.  ALL iterations run inside ONE persistent cooperative
+//                    kernel with a grid barrier between half-iterations (one launch instead of 2 x iters).
 // Layout: channel-major like the reference's Conv1d tensors, q [batch][256][N] with channel c = d * 4 + h
 // (`.view(batch, dim, heads, -1)`, superglue.py:103-104).
 #include "../../include/oetr_b200.h"
+#include "tc_common.cuh"
 
 #include <cuda_runtime.h>
 
@@ -129,6 +130,206 @@ __global__ void __launch_bounds__(256) k_sg_attention(const float* __restrict__ 
     }
 }
 
+// ---- attention on the tensor cores ----------------------------------------------------------------------------------
+// k_sg_attention_tc: one CTA per (128 queries, head, batch element); keys in chunks of 128.  Per chunk:
+//   row threads (one per query row = TMEM lane) transpose the chunk's K [key][dim] and V [dim][key] into 128-byte-swizzled
+//   K-major fp16 (hi, lo) operand slabs -> S = Q K^T on tcgen05 (M 128, N 128, K 64) into TMEM -> each row thread reads
+//   its S row twice (row maximum, then p = exp2(s - max) and the row sum), rescales its O row in TMEM when the maximum
+//   moved, writes P as the next A operand -> O += P V on tcgen05 (M 128, N 64, K 128).
+// Every product is the 3-term split (a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32 accumulation): 2^-22 relative, so the match
+// decisions downstream see fp32-grade attention.  Q is pre-scaled by log2(e) / 8.
+namespace tca {
+using namespace oetr::tc;
+constexpr int THREADS = 160;                       // warps 0-3: query rows; warp 4: MMA issue
+constexpr uint32_t SLAB16 = 128 * 128;             // [128 rows x 64 fp16]
+constexpr uint32_t SLAB8 = 64 * 128;               // [64 rows x 64 fp16]
+constexpr uint32_t SM_QH = 0, SM_QL = SM_QH + SLAB16, SM_KH = SM_QL + SLAB16, SM_KL = SM_KH + SLAB16;
+constexpr uint32_t SM_VH = SM_KL + SLAB16, SM_VL = SM_VH + 2 * SLAB8;
+constexpr uint32_t SM_PH = SM_VL + 2 * SLAB8, SM_PL = SM_PH + 2 * SLAB16;
+constexpr uint32_t SM_BAR = SM_PL + 2 * SLAB16;    // 160 KB
+constexpr uint32_t SM_TOTAL = SM_BAR + 64;
+struct Bars { uint64_t kv, s, p, o; uint32_t tmem, pad; };
+constexpr uint32_t IDESC_S = umma_idesc_f16(128, 128, 0, 0), IDESC_O = umma_idesc_f16(128, 64, 0, 0);
+constexpr float Q_SCALE = 0.125f * 1.4426950408889634f;
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// 64 consecutive K-columns of row r of a (hi, lo) slab pair
+__device__ __forceinline__ void store_row64(uint8_t* hi, uint8_t* lo, uint32_t r, const float (&v)[64]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint4 h, l;
+        split8(&v[8 * j], h, l);
+        const uint32_t off = slab_chunk_off(r, j);
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+}
+}  // namespace tca
+
+__global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float* __restrict__ q, const float* __restrict__ k,
+                                                                     const float* __restrict__ v, float* __restrict__ out, int N, int M) {
+    using namespace tca;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, b = blockIdx.z, n0 = blockIdx.x * 128;
+    const uint32_t sb = smem_u32(smem);
+    if (tid == 0) {
+        mbar_init(&bars->kv, 128); mbar_init(&bars->s, 1); mbar_init(&bars->p, 128); mbar_init(&bars->o, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc(&bars->tmem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem, TS = tmem, TO = tmem + 128;
+    const int chunks = (M + 127) / 128;
+    const float* kb = k + (size_t)b * SG_C * M;
+    const float* vb = v + (size_t)b * SG_C * M;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int c = 0; c < chunks; ++c) {
+                mbar_wait(&bars->kv, c & 1, nullptr);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {                                   // Qhi.Khi, Qlo.Khi, Qhi.Klo
+                    const uint32_t a = sb + (t == 1 ? SM_QL : SM_QH), bb = sb + (t == 2 ? SM_KL : SM_KH);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(TS, umma_desc(a + ks * 32, 16, ATOM_BYTES), umma_desc(bb + ks * 32, 16, ATOM_BYTES), IDESC_S,
+                                 (t > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&bars->s);
+                mbar_wait(&bars->p, c & 1, nullptr);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {                                   // Phi.Vhi, Plo.Vhi, Phi.Vlo
+                    const uint32_t a = sb + (t == 1 ? SM_PL : SM_PH), bb = sb + (t == 2 ? SM_VL : SM_VH);
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16(TO, umma_desc(a + sl * SLAB16 + ks * 32, 16, ATOM_BYTES),
+                                     umma_desc(bb + sl * SLAB8 + ks * 32, 16, ATOM_BYTES), IDESC_O,
+                                     (c > 0 || t > 0 || sl > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&bars->o);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int r = tid;                                                      // query row = TMEM lane
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        {
+            const float* qb = q + (size_t)b * SG_C * N;
+            const int n = n0 + r;
+            float x[64];
+#pragma unroll
+            for (int d = 0; d < 64; ++d) x[d] = n < N ? __ldg(qb + (size_t)(d * SG_H + h) * N + n) * Q_SCALE : 0.f;
+            store_row64(smem + SM_QH, smem + SM_QL, r, x);
+        }
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int c = 0; c < chunks; ++c) {
+            const int m0 = c * 128;
+            if (c > 0) { mbar_wait(&bars->o, (c - 1) & 1, nullptr); tc_fence_after(); }   // P, V and O of the previous chunk are free
+            {   // K chunk: key m0 + r -> row r
+                const int key = m0 + r;
+                float x[64];
+#pragma unroll
+                for (int d = 0; d < 64; ++d) x[d] = key < M ? __ldg(kb + (size_t)(d * SG_H + h) * M + key) : 0.f;
+                store_row64(smem + SM_KH, smem + SM_KL, r, x);
+            }
+            {   // V chunk: row = dim r >> 1, slab = r & 1 (keys m0 + 64 slab ..)
+                const int d = r >> 1, sl = r & 1;
+                const float* src = vb + (size_t)(d * SG_H + h) * M;
+                float x[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) { const int key = m0 + sl * 64 + j; x[j] = key < M ? __ldg(src + key) : 0.f; }
+                store_row64(smem + SM_VH + sl * SLAB8, smem + SM_VL + sl * SLAB8, d, x);
+            }
+            fence_async_smem();
+            mbar_arrive(&bars->kv);
+            mbar_wait(&bars->s, c & 1, nullptr);
+            tc_fence_after();
+            const int valid = M - m0 < 128 ? M - m0 : 128;
+            float rmax = -INFINITY;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                float sv[32];
+                tmem_ld32(TS + lane_addr + cc * 32, sv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (cc * 32 + j < valid) rmax = fmaxf(rmax, sv[j]);
+            }
+            const float m_new = fmaxf(m_run, rmax);
+            const float sc = exp2f(m_run - m_new);                              // 0 on the first chunk
+            float rsum = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                float sv[32];
+                tmem_ld32(TS + lane_addr + cc * 32, sv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { sv[j] = cc * 32 + j < valid ? exp2f(sv[j] - m_new) : 0.f; rsum += sv[j]; }
+                uint8_t* ph = smem + SM_PH + (cc >> 1) * SLAB16;
+                uint8_t* pl = smem + SM_PL + (cc >> 1) * SLAB16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 hh, ll;
+                    split8(&sv[8 * j], hh, ll);
+                    const uint32_t off = slab_chunk_off(r, (cc & 1) * 4 + j);
+                    *reinterpret_cast<uint4*>(ph + off) = hh;
+                    *reinterpret_cast<uint4*>(pl + off) = ll;
+                }
+            }
+            l_run = l_run * sc + rsum;
+            m_run = m_new;
+            if (c > 0) {                                                        // rescale the O row in TMEM
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    float ov[32];
+                    tmem_ld32(TO + lane_addr + cc * 32, ov);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) ov[j] *= sc;
+                    tmem_st32(TO + lane_addr + cc * 32, ov);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(&bars->p);
+        }
+        mbar_wait(&bars->o, (chunks - 1) & 1, nullptr);
+        tc_fence_after();
+        const float inv = 1.f / l_run;
+        float* ob = out + (size_t)b * SG_C * N;
+        const int n = n0 + r;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            float ov[32];
+            tmem_ld32(TO + lane_addr + cc * 32, ov);
+            if (n < N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ob[(size_t)((cc * 32 + j) * SG_H + h) * N + n] = ov[j] * inv;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
 // ---- log-space optimal transport ------------------------------------------------------------------------------------
 struct LSE { float m, s; };
 __device__ __forceinline__ void lse_merge(LSE& a, const LSE& b) {
@@ -151,16 +352,12 @@ __device__ __forceinline__ void lse_chunk(LSE& a, const float (&x)[8]) {
     a.m = m;
 }
 
-// One half-iteration: out[r] = log_marg[r] - logsumexp_c (Z[r][c] + in[c]) for the R+1 rows of the augmented matrix whose
-// inner part `mat` is [R][Cn] row-major (the scores for the u-update, their transpose for the v-update) and whose dustbin
-// row / column is the scalar alpha.  A warp per row: coalesced loads, 8 independent loads in flight per lane.
-__global__ void __launch_bounds__(256) k_sg_half(const float* __restrict__ mat, float alpha, const float* __restrict__ in,
-                                                 float* __restrict__ out, int R, int Cn, float norm, float log_other, int first) {
-    const int b = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row > R) return;
-    const float* mr = mat + (size_t)b * R * Cn + (size_t)row * Cn;
-    const float* iv = in + (size_t)b * (Cn + 1);
-    const bool inner = row < R;
+// One row of a half-iteration: out[row] = log_marg[row] - logsumexp_c (Z[row][c] + in[c]) for the R+1 rows of the augmented
+// matrix whose inner part `mat` is [R][Cn] row-major (the scores for the u-update, their transpose for the v-update) and
+// whose dustbin row / column is the scalar alpha.  A warp per row: coalesced loads, 8 independent loads in flight per lane.
+// `in` was written by other CTAs of the same launch: read through L2 (ld.cg), never the non-coherent path.
+__device__ __forceinline__ void sg_row(const float* __restrict__ mr, bool inner, float alpha, const float* iv, float* out_row,
+                                       int Cn, float log_marg, int first, int lane) {
     LSE a{-INFINITY, 0.f};
     for (int c0 = 0; c0 <= Cn; c0 += 256) {
         float x[8];
@@ -168,7 +365,7 @@ __global__ void __launch_bounds__(256) k_sg_half(const float* __restrict__ mat, 
         for (int t = 0; t < 8; ++t) {
             const int c = c0 + t * 32 + lane;
             float z = -INFINITY;
-            if (c <= Cn) z = ((inner && c < Cn) ? __ldg(mr + c) : alpha) + (first ? 0.f : iv[c]);
+            if (c <= Cn) z = ((inner && c < Cn) ? __ldg(mr + c) : alpha) + (first ? 0.f : __ldcg(iv + c));
             x[t] = z;
         }
         lse_chunk(a, x);
@@ -178,7 +375,43 @@ __global__ void __launch_bounds__(256) k_sg_half(const float* __restrict__ mat, 
         LSE o{__shfl_xor_sync(0xffffffffu, a.m, w), __shfl_xor_sync(0xffffffffu, a.s, w)};
         lse_merge(a, o);
     }
-    if (lane == 0) out[(size_t)b * (R + 1) + row] = (inner ? norm : log_other + norm) - (a.m + logf(a.s));
+    if (lane == 0) *out_row = log_marg - (a.m + logf(a.s));
+}
+// all CTAs of a cooperative launch: monotonic ticket barrier on a zero-initialised counter
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+// ALL Sinkhorn iterations in one persistent cooperative kernel: rows are strided over the warps of the grid, a grid barrier
+// separates the half-iterations (200 launches of a few microseconds each were bound by the host's launch rate)
+__global__ void __launch_bounds__(256) k_sg_sinkhorn(const float* __restrict__ scores, const float* __restrict__ scores_t, float alpha,
+                                                     float* u, float* v, int batch, int m, int n, float norm, int iters,
+                                                     unsigned int* counter) {
+    const int lane = threadIdx.x & 31, wid = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    const float log_m = logf((float)m), log_n = logf((float)n);
+    unsigned int phase = 0;
+    for (int it = 0; it < iters; ++it) {
+        for (int r = wid; r < batch * (m + 1); r += nw) {
+            const int b = r / (m + 1), row = r - b * (m + 1);
+            sg_row(scores + (size_t)b * m * n + (size_t)row * n, row < m, alpha, v + (size_t)b * (n + 1), u + r, n,
+                   row < m ? norm : log_n + norm, it == 0, lane);
+        }
+        grid_barrier(counter, ++phase * gridDim.x);
+        for (int r = wid; r < batch * (n + 1); r += nw) {
+            const int b = r / (n + 1), row = r - b * (n + 1);
+            sg_row(scores_t + (size_t)b * m * n + (size_t)row * m, row < n, alpha, u + (size_t)b * (m + 1), v + r, m,
+                   row < n ? norm : log_m + norm, 0, lane);
+        }
+        grid_barrier(counter, ++phase * gridDim.x);
+    }
 }
 // scores [m][n] -> transposed copy [n][m] (32 x 32 tiles through shared memory), once per call
 __global__ void __launch_bounds__(256) k_sg_transpose(const float* __restrict__ src, float* __restrict__ dst, int m, int n) {
@@ -218,7 +451,8 @@ extern "C" {
 
 const char* oetr_sg_last_error(void) { return g_serr; }
 
-int oetr_sg_attention(const float* query, const float* key, const float* value, float* out, int batch, int n, int m, void* stream) {
+int oetr_sg_attention(const float* query, const float* key, const float* value, float* out, int batch, int n, int m, int mode,
+                      void* stream) {
     if (!query || !key || !value || !out) return sfail(OETR_E_ARG, "oetr_sg_attention: null argument");
     if (batch < 1 || n < 1 || m < 1 || batch > 65535) return sfail(OETR_E_SHAPE, "oetr_sg_attention: batch %d, %d queries, %d keys", batch, n, m);
     int dev = 0;
@@ -227,20 +461,25 @@ int oetr_sg_attention(const float* query, const float* key, const float* value, 
         std::lock_guard<std::mutex> lk(g_sg_mu);
         if (dev < 64 && !g_sg_attr[dev]) {
             e = cudaFuncSetAttribute(k_sg_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sg_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tca::SM_TOTAL);
             if (e == cudaSuccess) g_sg_attr[dev] = true;
         }
     }
     if (e != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_attention: %s", cudaGetErrorString(e));
-    k_sg_attention<<<dim3((n + BQ - 1) / BQ, SG_H, batch), 256, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(query, key, value, out, n, m);
+    if (mode != OETR_SG_TENSOR && mode != OETR_SG_FP32) return sfail(OETR_E_ARG, "oetr_sg_attention: mode %d", mode);
+    if (mode == OETR_SG_TENSOR)
+        k_sg_attention_tc<<<dim3((n + 127) / 128, SG_H, batch), tca::THREADS, tca::SM_TOTAL, static_cast<cudaStream_t>(stream)>>>(query, key, value, out, n, m);
+    else
+        k_sg_attention<<<dim3((n + BQ - 1) / BQ, SG_H, batch), 256, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(query, key, value, out, n, m);
     e = cudaGetLastError();
     if (e != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_attention: %s", cudaGetErrorString(e));
     return OETR_OK;
 }
 
-// u [batch][m+1] | v [batch][n+1] | transposed scores [batch][n][m]
+// barrier counter (256 B) | u [batch][m+1] | v [batch][n+1] | transposed scores [batch][n][m]
 size_t oetr_sg_transport_workspace_bytes(int batch, int m, int n) {
     if (batch < 1 || m < 1 || n < 1) return 0;
-    return (size_t)batch * ((size_t)(m + n + 2) + (size_t)m * n) * sizeof(float);
+    return 256 + (size_t)batch * ((size_t)(m + n + 2) + (size_t)m * n) * sizeof(float);
 }
 
 int oetr_sg_optimal_transport(const float* scores, float alpha, int iters, float* out, int batch, int m, int n, void* workspace,
@@ -252,19 +491,28 @@ int oetr_sg_optimal_transport(const float* scores, float alpha, int iters, float
         return sfail(OETR_E_NOMEM, "oetr_sg_optimal_transport: workspace of %zu bytes, %zu needed", workspace_bytes,
                      oetr_sg_transport_workspace_bytes(batch, m, n));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    float* u = static_cast<float*>(workspace);
+    unsigned int* counter = static_cast<unsigned int*>(workspace);
+    float* u = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
     float* v = u + (size_t)batch * (m + 1);
     float* st = v + (size_t)batch * (n + 1);
     const float norm = -logf((float)(m + n));
-    if (iters == 0) {
-        const cudaError_t e0 = cudaMemsetAsync(workspace, 0, (size_t)batch * (m + n + 2) * sizeof(float), s);
-        if (e0 != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_optimal_transport: %s", cudaGetErrorString(e0));
-    } else {
+    cudaError_t e0 = cudaMemsetAsync(workspace, 0, 256 + (iters == 0 ? (size_t)batch * (m + n + 2) * sizeof(float) : 0), s);
+    if (e0 != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_optimal_transport: %s", cudaGetErrorString(e0));
+    if (iters > 0) {
         k_sg_transpose<<<dim3((n + 31) / 32, (m + 31) / 32, batch), 256, 0, s>>>(scores, st, m, n);
-    }
-    for (int it = 0; it < iters; ++it) {
-        k_sg_half<<<dim3((m + 1 + 7) / 8, batch), 256, 0, s>>>(scores, alpha, v, u, m, n, norm, logf((float)n), it == 0);
-        k_sg_half<<<dim3((n + 1 + 7) / 8, batch), 256, 0, s>>>(st, alpha, u, v, n, m, norm, logf((float)m), 0);
+        int dev = 0, sms = 0, per_sm = 0;
+        e0 = cudaGetDevice(&dev);
+        if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e0 == cudaSuccess) e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sg_sinkhorn, 256, 0);
+        if (e0 != cudaSuccess || per_sm < 1) return sfail(OETR_E_CUDA, "oetr_sg_optimal_transport: occupancy query failed");
+        const long rows = (long)batch * ((m > n ? m : n) + 1);
+        long grid = (rows + 7) / 8;
+        if (grid > (long)sms * (per_sm > 2 ? 2 : per_sm)) grid = (long)sms * (per_sm > 2 ? 2 : per_sm);
+        const float* sc_ = scores; const float* st_ = st;
+        void* kargs[] = {(void*)&sc_, (void*)&st_, (void*)&alpha, (void*)&u, (void*)&v, (void*)&batch, (void*)&m, (void*)&n,
+                         (void*)&norm, (void*)&iters, (void*)&counter};
+        e0 = cudaLaunchCooperativeKernel((const void*)k_sg_sinkhorn, dim3((unsigned)grid), dim3(256), kargs, 0, s);
+        if (e0 != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_optimal_transport: cooperative launch: %s", cudaGetErrorString(e0));
     }
     k_sg_finish<<<dim3((n + 1 + 255) / 256, m + 1, batch), 256, 0, s>>>(scores, alpha, u, v, out, m, n, norm);
     const cudaError_t e = cudaGetLastError();

@@ -23,9 +23,13 @@ def _need_cuda(t, what):
         raise cabi.OetrError(cabi.OETR_E_ARCH, "%s on %s: the SuperGlue operators have no CPU fallback" % (what, t.device))
 
 
-def attention(query, key, value):
+MODES = {"tensor": 0, "fp32": 1}
+
+
+def attention(query, key, value, mode="tensor"):
     """reference superglue.py:86-90: query [b, dim=64, heads=4, n], key / value [b, 64, 4, m] -> [b, 64, 4, n].  The
-    probability tensor the reference also returns is never used by its callers and is not produced."""
+    probability tensor the reference also returns is never used by its callers and is not produced.  mode: "tensor" =
+    tcgen05 with split fp16 operands (default), "fp32" = the CUDA-core kernel."""
     _need_cuda(query, "attention")
     b, d, h, n = query.shape
     m = key.shape[3]
@@ -36,7 +40,7 @@ def attention(query, key, value):
     lib = cabi.load_library()
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
     with torch.cuda.device(q.device):
-        _check(lib.oetr_sg_attention(vp(q), vp(k), vp(v), vp(out), b, n, m, ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)), lib)
+        _check(lib.oetr_sg_attention(vp(q), vp(k), vp(v), vp(out), b, n, m, MODES[mode], ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)), lib)
     return out
 
 

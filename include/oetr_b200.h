@@ -264,12 +264,14 @@ OETR_API const char* oetr_crop_last_error(void);
  * oetr_sg_attention replaces `attention(query, key, value)` of third_party/SuperGluePretrainedNetwork/models/superglue.py:86-90
  * as called by MultiHeadedAttention.forward (:100-108): query [batch][256][n], key / value [batch][256][m] fp32 device
  * tensors in the reference's Conv1d layout, channel c = d * 4 + head (4 heads x 64 dims) -> out [batch][256][n]
- * = softmax_m(Q_h^T K_h / 8) V_h per head, online softmax (no [n, m] matrix in memory).  fp32 arithmetic.
+ * = softmax_m(Q_h^T K_h / 8) V_h per head, online softmax (no [n, m] matrix in memory); `mode` selects the arithmetic.
  * oetr_sg_optimal_transport replaces `log_optimal_transport(scores, alpha, iters)` (:150-184): scores [batch][m][n] fp32,
  * alpha = bin_score -> out [batch][m+1][n+1] (log assignment matrix incl. dustbins, multiplied by m + n like the
  * reference).  workspace: oetr_sg_transport_workspace_bytes.  Both are stream-ordered and allocate nothing. */
+#define OETR_SG_TENSOR 0   /* QK^T and PV on tcgen05, 3-term split fp16 operands, fp32 accumulation in TMEM (default) */
+#define OETR_SG_FP32   1   /* the same operator in fp32 on the CUDA cores */
 OETR_API int oetr_sg_attention(const float* query, const float* key, const float* value, float* out, int batch, int n, int m,
-                               void* stream);
+                               int mode, void* stream);
 OETR_API size_t oetr_sg_transport_workspace_bytes(int batch, int m, int n);
 OETR_API int oetr_sg_optimal_transport(const float* scores, float alpha, int iters, float* out, int batch, int m, int n,
                                        void* workspace, size_t workspace_bytes, void* stream);

@@ -1,7 +1,8 @@
 """Parity of SuperGlue's CUDA operators (oetr_sg_attention, oetr_sg_optimal_transport through ctypes) and of the SuperGlue
 mirror built on them against the CPU oracle and the committed outputs of the reference module.
-Tolerances (fp32 kernels against an fp32 reference / an fp64 oracle): attention 2e-5 absolute on O(1) outputs, transport 2e-4
-on log-scores, full model 2e-3 on log-scores with identical matches."""
+Tolerances (against an fp32 reference / an fp64 oracle): attention 2e-5 absolute on O(1) outputs for the fp32 kernel and 6e-5
+for the tcgen05 kernel (3-term split fp16 operands: 2^-22 per product, amplified by the softmax), transport 2e-4 on
+log-scores, full model 2e-3 on log-scores with identical matches."""
 import os
 
 import numpy as np
@@ -20,11 +21,15 @@ WEIGHT_PATHS = [os.path.join(ROOT, "oracle", "_ref", "weights", "superglue_outdo
                 "/root/reference/third_party/SuperGluePretrainedNetwork/models/weights/superglue_outdoor.pth"]
 
 
+ATT_TOL = {"fp32": 2e-5, "tensor": 6e-5}
+
+
+@pytest.mark.parametrize("mode", ["tensor", "fp32"])
 @pytest.mark.parametrize("name", ["a", "b", "c", "d"])
-def test_attention_matches_reference_outputs(name):
+def test_attention_matches_reference_outputs(name, mode):
     q, k, v, want = (torch.from_numpy(OPS["att_%s_%s" % (name, t)]) for t in ("q", "k", "v", "out"))
-    got = sg.attention(q.cuda(), k.cuda(), v.cuda()).cpu()
-    assert got.shape == want.shape and float((got - want).abs().max()) < 2e-5
+    got = sg.attention(q.cuda(), k.cuda(), v.cuda(), mode=mode).cpu()
+    assert got.shape == want.shape and float((got - want).abs().max()) < ATT_TOL[mode], float((got - want).abs().max())
 
 
 @pytest.mark.parametrize("name", ["a", "b", "c"])
@@ -42,11 +47,18 @@ def test_large_problem_properties():
     g = torch.Generator().manual_seed(1)
     n = m = 2048
     q, k, v = (torch.randn(1, 64, 4, s, generator=g).cuda() for s in (n, m, m))
-    o = sg.attention(q, k, v)
-    assert float(o.max()) <= float(v.max()) + 1e-5 and float(o.min()) >= float(v.min()) - 1e-5
-    idx = [0, 1, 63, 64, 1000, 2047]
+    idx = [0, 1, 63, 64, 127, 128, 1000, 2047]
     want = so.attention(q[0][:, :, idx].double().cpu().numpy(), k[0].double().cpu().numpy(), v[0].double().cpu().numpy())
-    assert np.abs(o[0][:, :, idx].cpu().numpy() - want).max() < 2e-5
+    for mode in ("tensor", "fp32"):
+        o = sg.attention(q, k, v, mode=mode)
+        assert float(o.max()) <= float(v.max()) + 1e-4 and float(o.min()) >= float(v.min()) - 1e-4
+        assert np.abs(o[0][:, :, idx].cpu().numpy() - want).max() < ATT_TOL[mode], mode
+        assert torch.equal(o, sg.attention(q, k, v, mode=mode))
+    # ragged sizes: 130 queries (two query tiles, the second almost empty) x 257 keys (three key chunks, the last with one key)
+    q2, k2, v2 = q[:, :, :, :130].contiguous(), k[:, :, :, :257].contiguous(), v[:, :, :, :257].contiguous()
+    want2 = so.attention(q2[0].double().cpu().numpy(), k2[0].double().cpu().numpy(), v2[0].double().cpu().numpy())
+    for mode in ("tensor", "fp32"):
+        assert np.abs(sg.attention(q2, k2, v2, mode=mode)[0].cpu().numpy() - want2).max() < ATT_TOL[mode], mode
     s = torch.randn(1, m, n, generator=g).cuda() * 2
     Z = sg.log_optimal_transport(s, torch.tensor(1.0), 100)
     P = (Z.double() - np.log(m + n)).exp()                   # undo the (m + n) scaling of :183

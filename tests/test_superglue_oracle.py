@@ -46,9 +46,9 @@ def test_full_forward_matches_reference():
 
 def test_superglue_abi_argument_errors_do_not_need_a_gpu():
     lib = cabi.load_library()
-    assert lib.oetr_sg_attention(None, None, None, None, 1, 4, 4, None) == cabi.OETR_E_ARG
+    assert lib.oetr_sg_attention(None, None, None, None, 1, 4, 4, 0, None) == cabi.OETR_E_ARG
     assert lib.oetr_sg_optimal_transport(None, 1.0, 10, None, 1, 4, 4, None, 0, None) == cabi.OETR_E_ARG
-    assert lib.oetr_sg_transport_workspace_bytes(2, 10, 20) == 2 * (32 + 200) * 4
+    assert lib.oetr_sg_transport_workspace_bytes(2, 10, 20) == 256 + 2 * (32 + 200) * 4
     import torch
     from oetr_b200 import superglue as sg
     model = sg.SuperGlue()

@@ -56,6 +56,7 @@ def main():
     s = (torch.randn(1, n, n, generator=g) * 2).cuda()
     res = {"keypoints": n, "sinkhorn_iterations": a.iters}
     res["attention_ms"] = timed(lambda: sg.attention(q, k, v))
+    res["attention_fp32_kernel_ms"] = timed(lambda: sg.attention(q, k, v, mode="fp32"))
     res["attention_torch_ms"] = timed(lambda: torch_attention(q, k, v))
     res["attention_max_diff"] = float((sg.attention(q, k, v) - torch_attention(q, k, v)).abs().max())
     res["attention_gflop"] = 4 * 2 * 2.0 * n * n * 64 / 1e9
