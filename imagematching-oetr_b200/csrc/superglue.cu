@@ -131,26 +131,31 @@ __global__ void __launch_bounds__(256) k_sg_attention(const float* __restrict__ 
 }
 
 // ---- attention on the tensor cores ----------------------------------------------------------------------------------
-// k_sg_attention_tc: one CTA per (128 queries, head, batch element); keys in chunks of 128.  Per chunk:
-//   row threads (one per query row = TMEM lane) transpose the chunk's K [key][dim] and V [dim][key] into 128-byte-swizzled
-//   K-major fp16 (hi, lo) operand slabs -> S = Q K^T on tcgen05 (M 128, N 128, K 64) into TMEM -> each row thread reads
-//   its S row twice (row maximum, then p = exp2(s - max) and the row sum), rescales its O row in TMEM when the maximum
-//   moved, writes P as the next A operand -> O += P V on tcgen05 (M 128, N 64, K 128).
+// k_sg_attention_tc: one CTA per (128 queries, head, batch element); keys in chunks of 128.  Warp roles: 8 loader warps
+// transpose chunk c + 1 of K [key][dim] and V [dim][key] into 128-byte-swizzled K-major fp16 (hi, lo) operand slabs (two
+// buffers) while chunk c is processed; one MMA-issuing warp; 4 row warps (one thread per query row = TMEM lane).  Per chunk:
+//   S = Q K^T on tcgen05 (M 128, N 128, K 64) into TMEM -> each row thread reads its S row twice (row maximum, then
+//   p = exp2(s - max) and the row sum), rescales its O row in TMEM when the maximum moved, writes P as the next A operand
+//   -> O += P V on tcgen05 (M 128, N 64, K 128).
 // Every product is the 3-term split (a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32 accumulation): 2^-22 relative, so the match
 // decisions downstream see fp32-grade attention.  Q is pre-scaled by log2(e) / 8.
 namespace tca {
 using namespace oetr::tc;
-constexpr int THREADS = 160;                       // warps 0-3: query rows; warp 4: MMA issue
+constexpr int THREADS = 416;                       // warps 0-3: query rows (softmax); warp 4: MMA issue; warps 5-12: K/V loaders
+constexpr int LOADERS = 256;
 constexpr uint32_t SLAB16 = 128 * 128;             // [128 rows x 64 fp16]
 constexpr uint32_t SLAB8 = 64 * 128;               // [64 rows x 64 fp16]
-constexpr uint32_t SM_QH = 0, SM_QL = SM_QH + SLAB16, SM_KH = SM_QL + SLAB16, SM_KL = SM_KH + SLAB16;
-constexpr uint32_t SM_VH = SM_KL + SLAB16, SM_VL = SM_VH + 2 * SLAB8;
-constexpr uint32_t SM_PH = SM_VL + 2 * SLAB8, SM_PL = SM_PH + 2 * SLAB16;
-constexpr uint32_t SM_BAR = SM_PL + 2 * SLAB16;    // 160 KB
+constexpr uint32_t SM_QH = 0, SM_QL = SM_QH + SLAB16;
+constexpr uint32_t SM_PH = SM_QL + SLAB16, SM_PL = SM_PH + 2 * SLAB16;
+constexpr uint32_t SM_KV = SM_PL + 2 * SLAB16;     // two buffers of {K hi, K lo (16 KB each), V hi, V lo (2 x 8 KB each)} = 64 KB
+constexpr uint32_t KV_BUF = 4 * SLAB16, KV_KH = 0, KV_KL = SLAB16, KV_VH = 2 * SLAB16, KV_VL = 3 * SLAB16;
+constexpr uint32_t SM_BAR = SM_KV + 2 * KV_BUF;    // 224 KB
 constexpr uint32_t SM_TOTAL = SM_BAR + 64;
-struct Bars { uint64_t kv, s, p, o; uint32_t tmem, pad; };
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+struct Bars { uint64_t kv_full[2], kv_free[2], q_full, s, p, o; uint32_t tmem, pad; };
 constexpr uint32_t IDESC_S = umma_idesc_f16(128, 128, 0, 0), IDESC_O = umma_idesc_f16(128, 64, 0, 0);
 constexpr float Q_SCALE = 0.125f * 1.4426950408889634f;
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
@@ -165,13 +170,13 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// 64 consecutive K-columns of row r of a (hi, lo) slab pair
-__device__ __forceinline__ void store_row64(uint8_t* hi, uint8_t* lo, uint32_t r, const float (&v)[64]) {
+// 32 consecutive K-columns (half 0 / 1 of the 64) of row r
+__device__ __forceinline__ void store_row32h(uint8_t* hi, uint8_t* lo, uint32_t r, uint32_t half, const float (&v)[32]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
         uint4 h, l;
         split8(&v[8 * j], h, l);
-        const uint32_t off = slab_chunk_off(r, j);
+        const uint32_t off = slab_chunk_off(r, half * 4 + j);
         *reinterpret_cast<uint4*>(hi + off) = h;
         *reinterpret_cast<uint4*>(lo + off) = l;
     }
@@ -187,7 +192,8 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
     const int h = blockIdx.y, b = blockIdx.z, n0 = blockIdx.x * 128;
     const uint32_t sb = smem_u32(smem);
     if (tid == 0) {
-        mbar_init(&bars->kv, 128); mbar_init(&bars->s, 1); mbar_init(&bars->p, 128); mbar_init(&bars->o, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->kv_full[i], LOADERS); mbar_init(&bars->kv_free[i], 1); }
+        mbar_init(&bars->q_full, 128); mbar_init(&bars->s, 1); mbar_init(&bars->p, 128); mbar_init(&bars->o, 1);
         fence_mbar_init();
     }
     if (warp == 4) tmem_alloc(&bars->tmem, 256);
@@ -196,17 +202,45 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
     tc_fence_after();
     const uint32_t tmem = bars->tmem, TS = tmem, TO = tmem + 128;
     const int chunks = (M + 127) / 128;
-    const float* kb = k + (size_t)b * SG_C * M;
-    const float* vb = v + (size_t)b * SG_C * M;
 
-    if (warp == 4) {
+    if (warp > 4) {
+        // loaders: chunk c -> buffer c & 1, transposed / split into K-major swizzled (hi, lo) slabs while the row warps and
+        // the tensor core work on chunk c - 1
+        const int t = tid - 160, row = t & 127, half = t >> 7;
+        const float* kb = k + (size_t)b * SG_C * M;
+        const float* vb = v + (size_t)b * SG_C * M;
+        for (int c = 0; c < chunks; ++c) {
+            const int m0 = c * 128, bs = c & 1;
+            uint8_t* buf = smem + SM_KV + bs * KV_BUF;
+            float x[32];
+            {   // K: key m0 + row, dims half * 32 ..
+                const int key = m0 + row;
+#pragma unroll
+                for (int d = 0; d < 32; ++d) x[d] = key < M ? __ldg(kb + (size_t)((half * 32 + d) * SG_H + h) * M + key) : 0.f;
+            }
+            if (c >= 2) mbar_wait(&bars->kv_free[bs], ((c >> 1) - 1) & 1, nullptr);
+            store_row32h(buf + KV_KH, buf + KV_KL, row, half, x);
+            {   // V: operand row = dim row >> 1, slab = row & 1 (keys m0 + 64 slab ..), keys half * 32 .. of the slab
+                const int d = row >> 1, sl = row & 1;
+                const float* src = vb + (size_t)(d * SG_H + h) * M;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const int key = m0 + sl * 64 + half * 32 + j; x[j] = key < M ? __ldg(src + key) : 0.f; }
+                store_row32h(buf + KV_VH + sl * SLAB8, buf + KV_VL + sl * SLAB8, d, half, x);
+            }
+            fence_async_smem();
+            mbar_arrive(&bars->kv_full[bs]);
+        }
+    } else if (warp == 4) {
         if (lane == 0) {
+            mbar_wait(&bars->q_full, 0, nullptr);
             for (int c = 0; c < chunks; ++c) {
-                mbar_wait(&bars->kv, c & 1, nullptr);
+                const int bs = c & 1;
+                const uint32_t kvb = sb + SM_KV + bs * KV_BUF;
+                mbar_wait(&bars->kv_full[bs], (c >> 1) & 1, nullptr);
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {                                   // Qhi.Khi, Qlo.Khi, Qhi.Klo
-                    const uint32_t a = sb + (t == 1 ? SM_QL : SM_QH), bb = sb + (t == 2 ? SM_KL : SM_KH);
+                    const uint32_t a = sb + (t == 1 ? SM_QL : SM_QH), bb = kvb + (t == 2 ? KV_KL : KV_KH);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                         umma_f16(TS, umma_desc(a + ks * 32, 16, ATOM_BYTES), umma_desc(bb + ks * 32, 16, ATOM_BYTES), IDESC_S,
@@ -217,7 +251,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {                                   // Phi.Vhi, Plo.Vhi, Phi.Vlo
-                    const uint32_t a = sb + (t == 1 ? SM_PL : SM_PH), bb = sb + (t == 2 ? SM_VL : SM_VH);
+                    const uint32_t a = sb + (t == 1 ? SM_PL : SM_PH), bb = kvb + (t == 2 ? KV_VL : KV_VH);
 #pragma unroll
                     for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
@@ -227,6 +261,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
                                      (c > 0 || t > 0 || sl > 0 || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(&bars->o);
+                umma_commit(&bars->kv_free[bs]);
             }
         }
         __syncwarp();
@@ -236,32 +271,19 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
         {
             const float* qb = q + (size_t)b * SG_C * N;
             const int n = n0 + r;
-            float x[64];
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float x[32];
 #pragma unroll
-            for (int d = 0; d < 64; ++d) x[d] = n < N ? __ldg(qb + (size_t)(d * SG_H + h) * N + n) * Q_SCALE : 0.f;
-            store_row64(smem + SM_QH, smem + SM_QL, r, x);
+                for (int d = 0; d < 32; ++d) x[d] = n < N ? __ldg(qb + (size_t)((half * 32 + d) * SG_H + h) * N + n) * Q_SCALE : 0.f;
+                store_row32h(smem + SM_QH, smem + SM_QL, r, half, x);
+            }
+            fence_async_smem();
         }
+        mbar_arrive(&bars->q_full);                                             // Q operand published to the MMA warp
         float m_run = -INFINITY, l_run = 0.f;
         for (int c = 0; c < chunks; ++c) {
             const int m0 = c * 128;
-            if (c > 0) { mbar_wait(&bars->o, (c - 1) & 1, nullptr); tc_fence_after(); }   // P, V and O of the previous chunk are free
-            {   // K chunk: key m0 + r -> row r
-                const int key = m0 + r;
-                float x[64];
-#pragma unroll
-                for (int d = 0; d < 64; ++d) x[d] = key < M ? __ldg(kb + (size_t)(d * SG_H + h) * M + key) : 0.f;
-                store_row64(smem + SM_KH, smem + SM_KL, r, x);
-            }
-            {   // V chunk: row = dim r >> 1, slab = r & 1 (keys m0 + 64 slab ..)
-                const int d = r >> 1, sl = r & 1;
-                const float* src = vb + (size_t)(d * SG_H + h) * M;
-                float x[64];
-#pragma unroll
-                for (int j = 0; j < 64; ++j) { const int key = m0 + sl * 64 + j; x[j] = key < M ? __ldg(src + key) : 0.f; }
-                store_row64(smem + SM_VH + sl * SLAB8, smem + SM_VL + sl * SLAB8, d, x);
-            }
-            fence_async_smem();
-            mbar_arrive(&bars->kv);
             mbar_wait(&bars->s, c & 1, nullptr);
             tc_fence_after();
             const int valid = M - m0 < 128 ? M - m0 : 128;
@@ -274,14 +296,15 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
                 for (int j = 0; j < 32; ++j) if (cc * 32 + j < valid) rmax = fmaxf(rmax, sv[j]);
             }
             const float m_new = fmaxf(m_run, rmax);
-            const float sc = exp2f(m_run - m_new);                              // 0 on the first chunk
+            const float sc = ex2(m_run - m_new);                                // 0 on the first chunk
+            if (c > 0) { mbar_wait(&bars->o, (c - 1) & 1, nullptr); tc_fence_after(); }   // P and O of the previous chunk are free
             float rsum = 0.f;
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {
                 float sv[32];
                 tmem_ld32(TS + lane_addr + cc * 32, sv);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { sv[j] = cc * 32 + j < valid ? exp2f(sv[j] - m_new) : 0.f; rsum += sv[j]; }
+                for (int j = 0; j < 32; ++j) { sv[j] = cc * 32 + j < valid ? ex2(sv[j] - m_new) : 0.f; rsum += sv[j]; }
                 uint8_t* ph = smem + SM_PH + (cc >> 1) * SLAB16;
                 uint8_t* pl = smem + SM_PL + (cc >> 1) * SLAB16;
 #pragma unroll
@@ -331,11 +354,15 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
 }
 
 // ---- log-space optimal transport ------------------------------------------------------------------------------------
+// All Sinkhorn arithmetic runs in the log2 domain (values scaled by log2(e) on the fly): exp is then one MUFU (ex2.approx,
+// 2 ulp) and the results are converted back by k_sg_finish; mathematically identical to the reference's natural-log form.
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 struct LSE { float m, s; };
 __device__ __forceinline__ void lse_merge(LSE& a, const LSE& b) {
     const float m = fmaxf(a.m, b.m);
     if (m == -INFINITY) return;
-    a.s = a.s * expf(a.m - m) + b.s * expf(b.m - m);
+    a.s = a.s * ex2a(a.m - m) + b.s * ex2a(b.m - m);
     a.m = m;
 }
 // one chunk of 8 independent elements: local maximum first, then 8 independent exponentials (no serial rescale chain)
@@ -347,35 +374,9 @@ __device__ __forceinline__ void lse_chunk(LSE& a, const float (&x)[8]) {
     const float m = fmaxf(a.m, cm);
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sum += expf(x[i] - m);
-    a.s = a.s * expf(a.m - m) + sum;
+    for (int i = 0; i < 8; ++i) sum += ex2a(x[i] - m);
+    a.s = a.s * ex2a(a.m - m) + sum;
     a.m = m;
-}
-
-// One row of a half-iteration: out[row] = log_marg[row] - logsumexp_c (Z[row][c] + in[c]) for the R+1 rows of the augmented
-// matrix whose inner part `mat` is [R][Cn] row-major (the scores for the u-update, their transpose for the v-update) and
-// whose dustbin row / column is the scalar alpha.  A warp per row: coalesced loads, 8 independent loads in flight per lane.
-// `in` was written by other CTAs of the same launch: read through L2 (ld.cg), never the non-coherent path.
-__device__ __forceinline__ void sg_row(const float* __restrict__ mr, bool inner, float alpha, const float* iv, float* out_row,
-                                       int Cn, float log_marg, int first, int lane) {
-    LSE a{-INFINITY, 0.f};
-    for (int c0 = 0; c0 <= Cn; c0 += 256) {
-        float x[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int c = c0 + t * 32 + lane;
-            float z = -INFINITY;
-            if (c <= Cn) z = ((inner && c < Cn) ? __ldg(mr + c) : alpha) + (first ? 0.f : __ldcg(iv + c));
-            x[t] = z;
-        }
-        lse_chunk(a, x);
-    }
-#pragma unroll
-    for (int w = 16; w > 0; w >>= 1) {
-        LSE o{__shfl_xor_sync(0xffffffffu, a.m, w), __shfl_xor_sync(0xffffffffu, a.s, w)};
-        lse_merge(a, o);
-    }
-    if (lane == 0) *out_row = log_marg - (a.m + logf(a.s));
 }
 // all CTAs of a cooperative launch: monotonic ticket barrier on a zero-initialised counter
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
@@ -390,26 +391,64 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     }
     __syncthreads();
 }
-// ALL Sinkhorn iterations in one persistent cooperative kernel: rows are strided over the warps of the grid, a grid barrier
-// separates the half-iterations (200 launches of a few microseconds each were bound by the host's launch rate)
+// One half-iteration over the rows of the augmented matrix whose inner part `mat` is [R][Cn] row-major (the scores for the
+// u-update, their transpose for the v-update) and whose dustbin row / column is the scalar alpha:
+//     out[row] = log2_marg[row] - log2 sum_c 2^(Z[row][c] log2e + in[c])          (in / out in the log2 domain)
+// A block handles two rows at a time, four warps per row (a quarter of the columns each, 8 independent coalesced loads in
+// flight per lane), merged through shared memory.  `in` was written by other CTAs of the same launch: read through L2 (ld.cg).
+__device__ __forceinline__ void sg_half(const float* __restrict__ mat, float alpha2, const float* in, float* out, int batch, int R,
+                                        int Cn, float marg_inner, float marg_bin, int first, LSE (*sh)[4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = warp >> 2, quarter = warp & 3;
+    const int rows = batch * (R + 1);
+    for (int base = blockIdx.x * 2; base < rows; base += gridDim.x * 2) {
+        const int r = base + grp;
+        LSE a{-INFINITY, 0.f};
+        bool inner = false;
+        if (r < rows) {
+            const int b = r / (R + 1), row = r - b * (R + 1);
+            inner = row < R;
+            const float* mr = mat + (size_t)b * R * Cn + (size_t)row * Cn;
+            const float* iv = in + (size_t)b * (Cn + 1);
+            for (int c0 = quarter * 256; c0 <= Cn; c0 += 1024) {
+                float x[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int c = c0 + t * 32 + lane;
+                    float z = -INFINITY;
+                    if (c <= Cn) z = ((inner && c < Cn) ? __ldg(mr + c) * LOG2E : alpha2) + (first ? 0.f : __ldcg(iv + c));
+                    x[t] = z;
+                }
+                lse_chunk(a, x);
+            }
+#pragma unroll
+            for (int w = 16; w > 0; w >>= 1) {
+                LSE o{__shfl_xor_sync(0xffffffffu, a.m, w), __shfl_xor_sync(0xffffffffu, a.s, w)};
+                lse_merge(a, o);
+            }
+            if (lane == 0) sh[grp][quarter] = a;
+        }
+        __syncthreads();
+        if (r < rows && quarter == 0 && lane == 0) {
+#pragma unroll
+            for (int t = 1; t < 4; ++t) lse_merge(a, sh[grp][t]);
+            out[r] = (inner ? marg_inner : marg_bin) - (a.m + log2f(a.s));
+        }
+        __syncthreads();
+    }
+}
+// ALL Sinkhorn iterations in one persistent cooperative kernel: a grid barrier separates the half-iterations (one launch
+// instead of 2 x iters: at <= 1024 keypoints the launches themselves were the cost)
 __global__ void __launch_bounds__(256) k_sg_sinkhorn(const float* __restrict__ scores, const float* __restrict__ scores_t, float alpha,
                                                      float* u, float* v, int batch, int m, int n, float norm, int iters,
                                                      unsigned int* counter) {
-    const int lane = threadIdx.x & 31, wid = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
-    const float log_m = logf((float)m), log_n = logf((float)n);
+    __shared__ LSE sh[2][4];
+    const float norm2 = norm * LOG2E, alpha2 = alpha * LOG2E;
+    const float bin_u = log2f((float)n) + norm2, bin_v = log2f((float)m) + norm2;
     unsigned int phase = 0;
     for (int it = 0; it < iters; ++it) {
-        for (int r = wid; r < batch * (m + 1); r += nw) {
-            const int b = r / (m + 1), row = r - b * (m + 1);
-            sg_row(scores + (size_t)b * m * n + (size_t)row * n, row < m, alpha, v + (size_t)b * (n + 1), u + r, n,
-                   row < m ? norm : log_n + norm, it == 0, lane);
-        }
+        sg_half(scores, alpha2, v, u, batch, m, n, norm2, bin_u, it == 0, sh);
         grid_barrier(counter, ++phase * gridDim.x);
-        for (int r = wid; r < batch * (n + 1); r += nw) {
-            const int b = r / (n + 1), row = r - b * (n + 1);
-            sg_row(scores_t + (size_t)b * m * n + (size_t)row * m, row < n, alpha, u + (size_t)b * (m + 1), v + r, m,
-                   row < n ? norm : log_m + norm, 0, lane);
-        }
+        sg_half(scores_t, alpha2, u, v, batch, n, m, norm2, bin_v, 0, sh);
         grid_barrier(counter, ++phase * gridDim.x);
     }
 }
@@ -425,13 +464,13 @@ __global__ void __launch_bounds__(256) k_sg_transpose(const float* __restrict__ 
     for (int r = ty; r < 32; r += 8)
         if (j0 + r < n && i0 + tx < m) d[(size_t)(j0 + r) * m + i0 + tx] = t[tx][r];
 }
-// out[i][j] = Z[i][j] + u[i] + v[j] - norm        ([m+1][n+1], the matrix the reference returns)
+// out[i][j] = Z[i][j] + (u2[i] + v2[j]) ln 2 - norm        ([m+1][n+1], the matrix the reference returns; u2, v2: log2 domain)
 __global__ void __launch_bounds__(256) k_sg_finish(const float* __restrict__ scores, float alpha, const float* __restrict__ uu,
                                                    const float* __restrict__ vv, float* __restrict__ out, int m, int n, float norm) {
     const int b = blockIdx.z, j = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
     if (j > n) return;
     const float z = (i < m && j < n) ? scores[(size_t)b * m * n + (size_t)i * n + j] : alpha;
-    out[(size_t)b * (m + 1) * (n + 1) + (size_t)i * (n + 1) + j] = z + uu[(size_t)b * (m + 1) + i] + vv[(size_t)b * (n + 1) + j] - norm;
+    out[(size_t)b * (m + 1) * (n + 1) + (size_t)i * (n + 1) + j] = z + (uu[(size_t)b * (m + 1) + i] + vv[(size_t)b * (n + 1) + j]) * LN2 - norm;
 }
 
 thread_local char g_serr[256] = "";
@@ -506,8 +545,8 @@ int oetr_sg_optimal_transport(const float* scores, float alpha, int iters, float
         if (e0 == cudaSuccess) e0 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sg_sinkhorn, 256, 0);
         if (e0 != cudaSuccess || per_sm < 1) return sfail(OETR_E_CUDA, "oetr_sg_optimal_transport: occupancy query failed");
         const long rows = (long)batch * ((m > n ? m : n) + 1);
-        long grid = (rows + 7) / 8;
-        if (grid > (long)sms * (per_sm > 2 ? 2 : per_sm)) grid = (long)sms * (per_sm > 2 ? 2 : per_sm);
+        long grid = (rows + 1) / 2;                              // two rows per block and step
+        if (grid > (long)sms * per_sm) grid = (long)sms * per_sm;
         const float* sc_ = scores; const float* st_ = st;
         void* kargs[] = {(void*)&sc_, (void*)&st_, (void*)&alpha, (void*)&u, (void*)&v, (void*)&batch, (void*)&m, (void*)&n,
                          (void*)&norm, (void*)&iters, (void*)&counter};
