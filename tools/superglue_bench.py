@@ -66,6 +66,26 @@ def main():
     res["transport_max_diff"] = float((sg.log_optimal_transport(s, 1.0, a.iters) - torch_transport(s, 1.0, a.iters)).abs().max())
     # one Sinkhorn half-iteration reads the n x n scores once: effective bandwidth (L2-resident at this size)
     res["transport_gbs"] = 2 * a.iters * n * n * 4 / res["transport_ms"] / 1e6
+    # the whole SuperGlue forward (mirror with the CUDA operators) against the same module with PyTorch operators
+    torch.manual_seed(0)
+    model = sg.SuperGlue({"sinkhorn_iterations": a.iters}).cuda().eval()
+    data = {"image0": torch.zeros(1, 1, 1200, 1600), "image1": torch.zeros(1, 1, 1200, 1600),
+            "keypoints0": (torch.rand(1, n, 2, generator=g) * torch.tensor([1600.0, 1200.0])).cuda(),
+            "keypoints1": (torch.rand(1, n, 2, generator=g) * torch.tensor([1600.0, 1200.0])).cuda(),
+            "scores0": torch.rand(1, n, generator=g).cuda(), "scores1": torch.rand(1, n, generator=g).cuda(),
+            "descriptors0": torch.nn.functional.normalize(torch.randn(1, 256, n, generator=g), dim=1).cuda(),
+            "descriptors1": torch.nn.functional.normalize(torch.randn(1, 256, n, generator=g), dim=1).cuda()}
+    out = model(data)
+    res["model_ms"] = timed(lambda: model(data), steps=5, warmup=2)
+    att, ot = sg.attention, sg.log_optimal_transport
+    sg.attention = lambda q_, k_, v_, mode="tensor": torch_attention(q_, k_, v_)
+    sg.log_optimal_transport = lambda s_, alpha, iters: torch_transport(s_, float(alpha), iters)
+    ref = model(data)
+    res["model_torch_ops_ms"] = timed(lambda: model(data), steps=3, warmup=1)
+    sg.attention, sg.log_optimal_transport = att, ot
+    res["model_matches_equal"] = bool(torch.equal(out["matches0"], ref["matches0"]))
+    res["model_matches"] = int((out["matches0"] > -1).sum())
+    res["model_scores_max_diff"] = float((out["scores"] - ref["scores"]).abs().max())
     print(json.dumps(res))
 
 
