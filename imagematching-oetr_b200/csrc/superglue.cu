@@ -131,28 +131,34 @@ __global__ void __launch_bounds__(256) k_sg_attention(const float* __restrict__ 
 }
 
 // ---- attention on the tensor cores ----------------------------------------------------------------------------------
-// k_sg_attention_tc: one CTA per (128 queries, head, batch element); keys in chunks of 128.  Warp roles: 8 loader warps
-// transpose chunk c + 1 of K [key][dim] and V [dim][key] into 128-byte-swizzled K-major fp16 (hi, lo) operand slabs (two
-// buffers) while chunk c is processed; one MMA-issuing warp; 4 row warps (one thread per query row = TMEM lane).  Per chunk:
-//   S = Q K^T on tcgen05 (M 128, N 128, K 64) into TMEM -> each row thread reads its S row twice (row maximum, then
-//   p = exp2(s - max) and the row sum), rescales its O row in TMEM when the maximum moved, writes P as the next A operand
-//   -> O += P V on tcgen05 (M 128, N 64, K 128).
+// k_sg_attention_tc: one CTA per (128 queries, head, batch element); keys in chunks of 128.  Warp roles (13 warps):
+//   warps 0-7   softmax: TWO threads per query row (warp w and w + 4 share TMEM lane quarter w % 4; each owns 64 of the 128
+//               key columns of a chunk and 32 of the 64 output dims)
+//   warp 8      MMA issue
+//   warps 9-12  loaders: transpose chunk c + 1 of K [key][dim] and V [dim][key] into 128-byte-swizzled K-major fp16 (hi, lo)
+//               operand slabs (two buffers) while chunk c is processed
+// Per chunk: S = Q K^T on tcgen05 (M 128, N 128, K 64) into one of TWO S accumulators in TMEM (S(c+1) is issued while the
+// softmax of chunk c runs) -> each softmax thread reads its half row twice (maximum, exchanged with its partner through
+// shared memory; then p = exp2(s - max) and its partial row sum), rescales its half of the O row in TMEM when the maximum
+// moved, writes P as the next A operand -> O += P V on tcgen05 (M 128, N 64, K 128).
 // Every product is the 3-term split (a_hi b_hi + a_lo b_hi + a_hi b_lo, fp32 accumulation): 2^-22 relative, so the match
 // decisions downstream see fp32-grade attention.  Q is pre-scaled by log2(e) / 8.
 namespace tca {
 using namespace oetr::tc;
-constexpr int THREADS = 416;                       // warps 0-3: query rows (softmax); warp 4: MMA issue; warps 5-12: K/V loaders
-constexpr int LOADERS = 256;
+constexpr int SOFTMAX = 256, WARP_MMA = 8, LOADERS = 128;
+constexpr int THREADS = SOFTMAX + 32 + LOADERS;    // 416 (13 warps: 128 registers per thread)
 constexpr uint32_t SLAB16 = 128 * 128;             // [128 rows x 64 fp16]
 constexpr uint32_t SLAB8 = 64 * 128;               // [64 rows x 64 fp16]
 constexpr uint32_t SM_QH = 0, SM_QL = SM_QH + SLAB16;
 constexpr uint32_t SM_PH = SM_QL + SLAB16, SM_PL = SM_PH + 2 * SLAB16;
 constexpr uint32_t SM_KV = SM_PL + 2 * SLAB16;     // two buffers of {K hi, K lo (16 KB each), V hi, V lo (2 x 8 KB each)} = 64 KB
 constexpr uint32_t KV_BUF = 4 * SLAB16, KV_KH = 0, KV_KL = SLAB16, KV_VH = 2 * SLAB16, KV_VL = 3 * SLAB16;
-constexpr uint32_t SM_BAR = SM_KV + 2 * KV_BUF;    // 224 KB
-constexpr uint32_t SM_TOTAL = SM_BAR + 64;
+constexpr uint32_t SM_X = SM_KV + 2 * KV_BUF;      // float[2 parities][2 halves][128 rows]: row-maximum exchange; then row sums
+constexpr uint32_t SM_BAR = SM_X + 2 * 2 * 128 * 4;
+constexpr uint32_t SM_TOTAL = SM_BAR + 128;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
-struct Bars { uint64_t kv_full[2], kv_free[2], q_full, s, p, o; uint32_t tmem, pad; };
+struct Bars { uint64_t kv_full[2], kv_free[2], q_full, s[2], p, o; uint32_t tmem, pad; };
+static_assert(sizeof(Bars) <= 128, "Bars");
 constexpr uint32_t IDESC_S = umma_idesc_f16(128, 128, 0, 0), IDESC_O = umma_idesc_f16(128, 64, 0, 0);
 constexpr float Q_SCALE = 0.125f * 1.4426950408889634f;
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -170,7 +176,7 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// 32 consecutive K-columns (half 0 / 1 of the 64) of row r
+// 32 consecutive K-columns (half 0 / 1 of the 64) of row r of a (hi, lo) slab pair
 __device__ __forceinline__ void store_row32h(uint8_t* hi, uint8_t* lo, uint32_t r, uint32_t half, const float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -192,61 +198,68 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
     const int h = blockIdx.y, b = blockIdx.z, n0 = blockIdx.x * 128;
     const uint32_t sb = smem_u32(smem);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->kv_full[i], LOADERS); mbar_init(&bars->kv_free[i], 1); }
-        mbar_init(&bars->q_full, 128); mbar_init(&bars->s, 1); mbar_init(&bars->p, 128); mbar_init(&bars->o, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->kv_full[i], LOADERS); mbar_init(&bars->kv_free[i], 1); mbar_init(&bars->s[i], 1); }
+        mbar_init(&bars->q_full, SOFTMAX); mbar_init(&bars->p, SOFTMAX); mbar_init(&bars->o, 1);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc(&bars->tmem, 256);
+    if (warp == WARP_MMA) tmem_alloc(&bars->tmem, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem, TS = tmem, TO = tmem + 128;
+    const uint32_t tmem = bars->tmem, TS = tmem, TO = tmem + 256;          // S0 | S1 | O
     const int chunks = (M + 127) / 128;
 
-    if (warp > 4) {
-        // loaders: chunk c -> buffer c & 1, transposed / split into K-major swizzled (hi, lo) slabs while the row warps and
-        // the tensor core work on chunk c - 1
-        const int t = tid - 160, row = t & 127, half = t >> 7;
+    if (warp > WARP_MMA) {
+        const int row = tid - (SOFTMAX + 32);                                   // 0..127
         const float* kb = k + (size_t)b * SG_C * M;
         const float* vb = v + (size_t)b * SG_C * M;
         for (int c = 0; c < chunks; ++c) {
             const int m0 = c * 128, bs = c & 1;
             uint8_t* buf = smem + SM_KV + bs * KV_BUF;
-            float x[32];
-            {   // K: key m0 + row, dims half * 32 ..
-                const int key = m0 + row;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float x[32];
+                {   // K: key m0 + row, dims half * 32 ..
+                    const int key = m0 + row;
 #pragma unroll
-                for (int d = 0; d < 32; ++d) x[d] = key < M ? __ldg(kb + (size_t)((half * 32 + d) * SG_H + h) * M + key) : 0.f;
-            }
-            if (c >= 2) mbar_wait(&bars->kv_free[bs], ((c >> 1) - 1) & 1, nullptr);
-            store_row32h(buf + KV_KH, buf + KV_KL, row, half, x);
-            {   // V: operand row = dim row >> 1, slab = row & 1 (keys m0 + 64 slab ..), keys half * 32 .. of the slab
-                const int d = row >> 1, sl = row & 1;
-                const float* src = vb + (size_t)(d * SG_H + h) * M;
+                    for (int d = 0; d < 32; ++d) x[d] = key < M ? __ldg(kb + (size_t)((half * 32 + d) * SG_H + h) * M + key) : 0.f;
+                }
+                if (half == 0 && c >= 2) mbar_wait(&bars->kv_free[bs], ((c >> 1) - 1) & 1, nullptr);
+                store_row32h(buf + KV_KH, buf + KV_KL, row, half, x);
+                {   // V: operand row = dim row >> 1, slab = row & 1 (keys m0 + 64 slab ..), keys half * 32 .. of the slab
+                    const int d = row >> 1, sl = row & 1;
+                    const float* src = vb + (size_t)(d * SG_H + h) * M;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { const int key = m0 + sl * 64 + half * 32 + j; x[j] = key < M ? __ldg(src + key) : 0.f; }
-                store_row32h(buf + KV_VH + sl * SLAB8, buf + KV_VL + sl * SLAB8, d, half, x);
+                    for (int j = 0; j < 32; ++j) { const int key = m0 + sl * 64 + half * 32 + j; x[j] = key < M ? __ldg(src + key) : 0.f; }
+                    store_row32h(buf + KV_VH + sl * SLAB8, buf + KV_VL + sl * SLAB8, d, half, x);
+                }
             }
             fence_async_smem();
             mbar_arrive(&bars->kv_full[bs]);
         }
-    } else if (warp == 4) {
+    } else if (warp == WARP_MMA) {
         if (lane == 0) {
-            mbar_wait(&bars->q_full, 0, nullptr);
-            for (int c = 0; c < chunks; ++c) {
-                const int bs = c & 1;
-                const uint32_t kvb = sb + SM_KV + bs * KV_BUF;
-                mbar_wait(&bars->kv_full[bs], (c >> 1) & 1, nullptr);
+            auto issue_s = [&](int c) {                                         // S(c) = Q K(c)^T: Qhi.Khi, Qlo.Khi, Qhi.Klo
+                const uint32_t kvb = sb + SM_KV + (c & 1) * KV_BUF;
+                mbar_wait(&bars->kv_full[c & 1], (c >> 1) & 1, nullptr);
                 tc_fence_after();
 #pragma unroll
-                for (int t = 0; t < 3; ++t) {                                   // Qhi.Khi, Qlo.Khi, Qhi.Klo
+                for (int t = 0; t < 3; ++t) {
                     const uint32_t a = sb + (t == 1 ? SM_QL : SM_QH), bb = kvb + (t == 2 ? KV_KL : KV_KH);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_f16(TS, umma_desc(a + ks * 32, 16, ATOM_BYTES), umma_desc(bb + ks * 32, 16, ATOM_BYTES), IDESC_S,
-                                 (t > 0 || ks > 0) ? 1u : 0u);
+                        umma_f16(TS + (c & 1) * 128, umma_desc(a + ks * 32, 16, ATOM_BYTES), umma_desc(bb + ks * 32, 16, ATOM_BYTES),
+                                 IDESC_S, (t > 0 || ks > 0) ? 1u : 0u);
                 }
-                umma_commit(&bars->s);
+                umma_commit(&bars->s[c & 1]);
+            };
+            mbar_wait(&bars->q_full, 0, nullptr);
+            issue_s(0);
+            for (int c = 0; c < chunks; ++c) {
+                // S(c+1) goes out while the softmax of chunk c runs: its accumulator was last read for chunk c - 1, whose
+                // readers arrived on p(c-1) (waited for below, in the previous iteration)
+                if (c + 1 < chunks) issue_s(c + 1);
+                const uint32_t kvb = sb + SM_KV + (c & 1) * KV_BUF;
                 mbar_wait(&bars->p, c & 1, nullptr);
                 tc_fence_after();
 #pragma unroll
@@ -261,96 +274,86 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
                                      (c > 0 || t > 0 || sl > 0 || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(&bars->o);
-                umma_commit(&bars->kv_free[bs]);
+                umma_commit(&bars->kv_free[c & 1]);
             }
         }
         __syncwarp();
     } else {
-        const int r = tid;                                                      // query row = TMEM lane
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const int quad = warp & 3, hf = warp >> 2;                              // TMEM lane quarter; column half of the row
+        const int r = quad * 32 + lane;                                         // query row = TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        float* xch = reinterpret_cast<float*>(smem + SM_X);
         {
             const float* qb = q + (size_t)b * SG_C * N;
             const int n = n0 + r;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                float x[32];
+            float x[32];
 #pragma unroll
-                for (int d = 0; d < 32; ++d) x[d] = n < N ? __ldg(qb + (size_t)((half * 32 + d) * SG_H + h) * N + n) * Q_SCALE : 0.f;
-                store_row32h(smem + SM_QH, smem + SM_QL, r, half, x);
-            }
+            for (int d = 0; d < 32; ++d) x[d] = n < N ? __ldg(qb + (size_t)((hf * 32 + d) * SG_H + h) * N + n) * Q_SCALE : 0.f;
+            store_row32h(smem + SM_QH, smem + SM_QL, r, hf, x);
             fence_async_smem();
         }
         mbar_arrive(&bars->q_full);                                             // Q operand published to the MMA warp
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_run = -INFINITY, l_part = 0.f;
         for (int c = 0; c < chunks; ++c) {
             const int m0 = c * 128;
-            mbar_wait(&bars->s, c & 1, nullptr);
+            const uint32_t ts = TS + (c & 1) * 128 + lane_addr + hf * 64;
+            mbar_wait(&bars->s[c & 1], (c >> 1) & 1, nullptr);
             tc_fence_after();
-            const int valid = M - m0 < 128 ? M - m0 : 128;
+            const int valid = (M - m0 < 128 ? M - m0 : 128) - hf * 64;          // valid columns of this thread's half (may be <= 0)
             float rmax = -INFINITY;
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < 2; ++cc) {
                 float sv[32];
-                tmem_ld32(TS + lane_addr + cc * 32, sv);
+                tmem_ld32(ts + cc * 32, sv);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) if (cc * 32 + j < valid) rmax = fmaxf(rmax, sv[j]);
             }
-            const float m_new = fmaxf(m_run, rmax);
+            xch[((c & 1) * 2 + hf) * 128 + r] = rmax;
+            named_bar_sync(1 + quad, 64);                                       // the two warps of this lane quarter
+            const float m_new = fmaxf(m_run, fmaxf(rmax, xch[((c & 1) * 2 + (hf ^ 1)) * 128 + r]));
             const float sc = ex2(m_run - m_new);                                // 0 on the first chunk
             if (c > 0) { mbar_wait(&bars->o, (c - 1) & 1, nullptr); tc_fence_after(); }   // P and O of the previous chunk are free
             float rsum = 0.f;
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < 2; ++cc) {
                 float sv[32];
-                tmem_ld32(TS + lane_addr + cc * 32, sv);
+                tmem_ld32(ts + cc * 32, sv);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { sv[j] = cc * 32 + j < valid ? ex2(sv[j] - m_new) : 0.f; rsum += sv[j]; }
-                uint8_t* ph = smem + SM_PH + (cc >> 1) * SLAB16;
-                uint8_t* pl = smem + SM_PL + (cc >> 1) * SLAB16;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 hh, ll;
-                    split8(&sv[8 * j], hh, ll);
-                    const uint32_t off = slab_chunk_off(r, (cc & 1) * 4 + j);
-                    *reinterpret_cast<uint4*>(ph + off) = hh;
-                    *reinterpret_cast<uint4*>(pl + off) = ll;
-                }
+                store_row32h(smem + SM_PH + hf * SLAB16, smem + SM_PL + hf * SLAB16, r, cc, sv);
             }
-            l_run = l_run * sc + rsum;
+            l_part = l_part * sc + rsum;
             m_run = m_new;
-            if (c > 0) {                                                        // rescale the O row in TMEM
-#pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    float ov[32];
-                    tmem_ld32(TO + lane_addr + cc * 32, ov);
+            if (c > 0) {                                                        // rescale this thread's half of the O row in TMEM
+                float ov[32];
+                tmem_ld32(TO + lane_addr + hf * 32, ov);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) ov[j] *= sc;
-                    tmem_st32(TO + lane_addr + cc * 32, ov);
-                }
+                for (int j = 0; j < 32; ++j) ov[j] *= sc;
+                tmem_st32(TO + lane_addr + hf * 32, ov);
                 tmem_st_wait();
             }
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(&bars->p);
         }
+        // row sum = the two partial sums (same running maximum in both threads)
+        xch[hf * 128 + r] = l_part;
+        named_bar_sync(1 + quad, 64);
+        const float inv = 1.f / (l_part + xch[(hf ^ 1) * 128 + r]);
         mbar_wait(&bars->o, (chunks - 1) & 1, nullptr);
         tc_fence_after();
-        const float inv = 1.f / l_run;
         float* ob = out + (size_t)b * SG_C * N;
         const int n = n0 + r;
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            float ov[32];
-            tmem_ld32(TO + lane_addr + cc * 32, ov);
-            if (n < N) {
+        float ov[32];
+        tmem_ld32(TO + lane_addr + hf * 32, ov);
+        if (n < N) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ob[(size_t)((cc * 32 + j) * SG_H + h) * N + n] = ov[j] * inv;
-            }
+            for (int j = 0; j < 32; ++j) ob[(size_t)((hf * 32 + j) * SG_H + h) * N + n] = ov[j] * inv;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 256);
+    if (warp == WARP_MMA) tmem_dealloc(tmem, 512);
 }
 
 // ---- log-space optimal transport ------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ def timed(fn, steps=20, warmup=3):
 
 def torch_attention(q, k, v):
     s = torch.einsum("bdhn,bdhm->bhnm", q, k) / 8.0
-    return torch.einsum("bhnm,bdhm->bdhn", torch.softmax(s, dim=-1), v)
+    return torch.einsum("bhnm,bdhm->bdhn", torch.softmax(s, dim=-1), v).contiguous()
 
 
 def torch_transport(scores, alpha, iters):
