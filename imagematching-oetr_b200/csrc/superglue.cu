@@ -213,26 +213,39 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
         const int row = tid - (SOFTMAX + 32);                                   // 0..127
         const float* kb = k + (size_t)b * SG_C * M;
         const float* vb = v + (size_t)b * SG_C * M;
+        const bool vec_ok = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(vb) & 15) == 0;
         for (int c = 0; c < chunks; ++c) {
             const int m0 = c * 128, bs = c & 1;
             uint8_t* buf = smem + SM_KV + bs * KV_BUF;
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < 2; ++half) {                              // K: key m0 + row, dims half * 32 .. (coalesced over keys)
                 float x[32];
-                {   // K: key m0 + row, dims half * 32 ..
-                    const int key = m0 + row;
+                const int key = m0 + row;
 #pragma unroll
-                    for (int d = 0; d < 32; ++d) x[d] = key < M ? __ldg(kb + (size_t)((half * 32 + d) * SG_H + h) * M + key) : 0.f;
-                }
+                for (int d = 0; d < 32; ++d) x[d] = key < M ? __ldg(kb + (size_t)((half * 32 + d) * SG_H + h) * M + key) : 0.f;
                 if (half == 0 && c >= 2) mbar_wait(&bars->kv_free[bs], ((c >> 1) - 1) & 1, nullptr);
                 store_row32h(buf + KV_KH, buf + KV_KL, row, half, x);
-                {   // V: operand row = dim row >> 1, slab = row & 1 (keys m0 + 64 slab ..), keys half * 32 .. of the slab
-                    const int d = row >> 1, sl = row & 1;
-                    const float* src = vb + (size_t)(d * SG_H + h) * M;
+            }
+            // V: operand rows = dims, 64 keys (128 B) per slab row.  One item = one 16-byte chunk (8 keys) of a row; the 8
+            // lanes of a row read 256 contiguous bytes (two 16-byte loads each when the row is 16-byte aligned)
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+                const int item = it * LOADERS + row, ci = item & 7, rid = item >> 3, d = rid >> 1, sl = rid & 1;
+                const int key0 = m0 + sl * 64 + ci * 8;
+                const float* src = vb + (size_t)(d * SG_H + h) * M + key0;
+                float x[8];
+                if (vec_ok && key0 + 8 <= M) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bq.x; x[5] = bq.y; x[6] = bq.z; x[7] = bq.w;
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { const int key = m0 + sl * 64 + half * 32 + j; x[j] = key < M ? __ldg(src + key) : 0.f; }
-                    store_row32h(buf + KV_VH + sl * SLAB8, buf + KV_VL + sl * SLAB8, d, half, x);
+                    for (int j = 0; j < 8; ++j) x[j] = key0 + j < M ? __ldg(src + j) : 0.f;
                 }
+                uint4 hh, ll;
+                split8(x, hh, ll);
+                const uint32_t off = sl * SLAB8 + slab_chunk_off(d, ci);
+                *reinterpret_cast<uint4*>(buf + KV_VH + off) = hh;
+                *reinterpret_cast<uint4*>(buf + KV_VL + off) = ll;
             }
             fence_async_smem();
             mbar_arrive(&bars->kv_full[bs]);
