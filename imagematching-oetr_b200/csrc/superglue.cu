@@ -229,23 +229,30 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
             // V: operand rows = dims, 64 keys (128 B) per slab row.  One item = one 16-byte chunk (8 keys) of a row; the 8
             // lanes of a row read 256 contiguous bytes (two 16-byte loads each when the row is 16-byte aligned)
 #pragma unroll 1
-            for (int it = 0; it < 8; ++it) {
-                const int item = it * LOADERS + row, ci = item & 7, rid = item >> 3, d = rid >> 1, sl = rid & 1;
-                const int key0 = m0 + sl * 64 + ci * 8;
-                const float* src = vb + (size_t)(d * SG_H + h) * M + key0;
-                float x[8];
-                if (vec_ok && key0 + 8 <= M) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bq.x; x[5] = bq.y; x[6] = bq.z; x[7] = bq.w;
-                } else {
+            for (int g4 = 0; g4 < 2; ++g4) {                                    // four items per step: 8 independent 16-byte loads in flight
+                float x[4][8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = key0 + j < M ? __ldg(src + j) : 0.f;
+                for (int u = 0; u < 4; ++u) {
+                    const int item = (g4 * 4 + u) * LOADERS + row, ci = item & 7, rid = item >> 3, d = rid >> 1, sl = rid & 1;
+                    const int key0 = m0 + sl * 64 + ci * 8;
+                    const float* src = vb + (size_t)(d * SG_H + h) * M + key0;
+                    if (vec_ok && key0 + 8 <= M) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), bq = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        x[u][0] = a.x; x[u][1] = a.y; x[u][2] = a.z; x[u][3] = a.w; x[u][4] = bq.x; x[u][5] = bq.y; x[u][6] = bq.z; x[u][7] = bq.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[u][j] = key0 + j < M ? __ldg(src + j) : 0.f;
+                    }
                 }
-                uint4 hh, ll;
-                split8(x, hh, ll);
-                const uint32_t off = sl * SLAB8 + slab_chunk_off(d, ci);
-                *reinterpret_cast<uint4*>(buf + KV_VH + off) = hh;
-                *reinterpret_cast<uint4*>(buf + KV_VL + off) = ll;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int item = (g4 * 4 + u) * LOADERS + row, ci = item & 7, rid = item >> 3, d = rid >> 1, sl = rid & 1;
+                    uint4 hh, ll;
+                    split8(x[u], hh, ll);
+                    const uint32_t off = sl * SLAB8 + slab_chunk_off(d, ci);
+                    *reinterpret_cast<uint4*>(buf + KV_VH + off) = hh;
+                    *reinterpret_cast<uint4*>(buf + KV_VL + off) = ll;
+                }
             }
             fence_async_smem();
             mbar_arrive(&bars->kv_full[bs]);
