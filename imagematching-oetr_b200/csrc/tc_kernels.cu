@@ -35,6 +35,7 @@
 #include "tc_tiles.cuh"
 #include "tc_enc.cuh"
 #include "tc_head.cuh"
+#include "tc_dec_cluster.cuh"
 #include "tc_full.cuh"
 
 #include <cmath>
@@ -78,7 +79,8 @@ int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, Tc
     if (cudaMalloc(&out.enc_img, N_ENC * ENC_LAYER_HALFS * sizeof(__half)) != cudaSuccess ||
         cudaMalloc(&out.dec_img, N_DEC * DEC_LAYER_HALFS * sizeof(__half)) != cudaSuccess ||
         cudaMalloc(&out.head_img, 9 * GEMM_HALFS * sizeof(__half)) != cudaSuccess ||
-        cudaMalloc(&out.dec_t, (N_DEC * DEC_T_FLOATS + (size_t)C * C) * sizeof(float)) != cudaSuccess) {
+        cudaMalloc(&out.dec_t, (N_DEC * DEC_T_FLOATS + (size_t)C * C) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&out.dec_ts, DCL_RANKS * DCL_RANK_FLOATS * sizeof(float)) != cudaSuccess) {
         snprintf(msg, msg_len, "weight image allocation failed");
         return -1;
     }
@@ -107,6 +109,21 @@ int tc_prepare_weights(const float* d_w, const float* d_w9, const WLayout& L, Tc
         k_transpose<<<dim3(C / 32, FF / 32), dim3(32, 8)>>>(d_w + d.w2, C, FF, t + (size_t)6 * C * C + (size_t)FF * C);
     }
     k_transpose<<<dim3(C / 32, C / 32), dim3(32, 8)>>>(d_w + L.tl_w0, C, C, out.dec_t + N_DEC * DEC_T_FLOATS);
+    {   // per-rank slices for k_decoder_cl, in consumption order: sa.wq | sa.wk | sa.wv | sa.wm | ca.wq | ca.wm | w1 | w2 per layer, tl_w0
+        size_t o = 0;
+        auto slice = [&](size_t src, int N, int K) {
+            const int NL = N / DCL_RANKS;
+            k_slice_t<<<(DCL_RANKS * K * NL + 255) / 256, 256>>>(d_w + src, K, NL, 0, K, out.dec_ts + o, DCL_RANK_FLOATS);
+            o += (size_t)K * NL;
+        };
+        for (int j = 0; j < N_DEC; ++j) {
+            const DecW& d = L.dec[j];
+            for (size_t src : {d.sa.wq, d.sa.wk, d.sa.wv, d.sa.wm, d.ca.wq, d.ca.wm}) slice(src, C, C);
+            slice(d.w1, FF, C);
+            slice(d.w2, C, FF);
+        }
+        slice(L.tl_w0, C, C);
+    }
     for (int tap = 0; tap < 9; ++tap) make_gemm_image(d_w9 + (size_t)tap * C * C, C, 0, 0, out.head_img + (size_t)tap * GEMM_HALFS);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -121,8 +138,9 @@ void tc_free_weights(TcWeights& w) {
     cudaFree(w.dec_img);
     cudaFree(w.head_img);
     cudaFree(w.dec_t);
+    cudaFree(w.dec_ts);
     w.enc_img = w.dec_img = w.head_img = nullptr;
-    w.dec_t = nullptr;
+    w.dec_t = w.dec_ts = nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -310,6 +328,7 @@ static int set_attrs(char* msg, size_t msg_len) {
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_proj_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_TOTAL);
     if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_decoder, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_decoder_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, DCL_SMEM);
     if (e1 != cudaSuccess) {
         snprintf(msg, msg_len, "cudaFuncSetAttribute(max dynamic smem %u): %s", SM_TOTAL, cudaGetErrorString(e1));
         return -1;
@@ -564,7 +583,16 @@ int tc_decoder_head(const TcWeights& tw, const float* d_w, const WLayout& L, con
     }
     dp.qe = d_w + L.qe1; dp.kvs = ws.dec_kvs; dp.hs = hs_out; dp.B = B;
     dp.wt = tw.dec_t; dp.tl_w2 = d_w + L.tl_w2; dp.tl_b2 = d_w + L.tl_b2; dp.tlbr = ws.tlbr;
-    k_decoder<<<(2 * B + DEC_R - 1) / DEC_R, DEC_THREADS, DEC_SMEM, s>>>(dp); lc.n++;
+    // OETR_DEC=1 (read once): the one-CTA-per-two-tokens decoder; default: clusters of 8 CTAs per 16 tokens
+    static const bool one_cta_decoder = getenv("OETR_DEC") && atoi(getenv("OETR_DEC")) == 1;
+    if (one_cta_decoder) {
+        k_decoder<<<(2 * B + DEC_R - 1) / DEC_R, DEC_THREADS, DEC_SMEM, s>>>(dp); lc.n++;
+    } else {
+        DecClParams cp{};
+        for (int j = 0; j < N_DEC; ++j) cp.layer[j] = dp.layer[j];
+        cp.qe = dp.qe; cp.kvs = dp.kvs; cp.hs = dp.hs; cp.wts = tw.dec_ts; cp.tl_w2 = dp.tl_w2; cp.tl_b2 = dp.tl_b2; cp.tlbr = dp.tlbr; cp.B = B;
+        k_decoder_cl<<<DCL_RANKS * ((2 * B + DCL_ROWS - 1) / DCL_ROWS), DCL_THREADS, DCL_SMEM, s>>>(cp); lc.n++;
+    }
     k_att<<<g.tiles(), 256, 0, s>>>(ws.xt, g, hs_out, ws.att); lc.n++;
     ConvParams cp{};
     cp.g = g; cp.hf1 = hg.hf1; cp.wf1 = hg.wf1; cp.hf2 = hg.hf2; cp.wf2 = hg.wf2; cp.xt = ws.xt; cp.att = ws.att;

@@ -12,6 +12,7 @@ struct TcWeights {
     __half* dec_img = nullptr;     // decoder cross-attention k/v projection chunk streams (2 layers)
     __half* head_img = nullptr;    // heatmap_conv.0: 9 tap GEMM images
     float* dec_t = nullptr;        // transposed fp32 decoder weights (k_decoder)
+    float* dec_ts = nullptr;       // the same, sliced per cluster rank (k_decoder_cl)
     size_t enc_layer_halfs = 0, dec_layer_halfs = 0;
 };
 
