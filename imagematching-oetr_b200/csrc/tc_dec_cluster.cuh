@@ -4,9 +4,9 @@
 // chain.  Here a cluster of 8 CTAs serves 16 query tokens: CTA `rank` owns output columns [32 rank, 32 rank + 32) of every
 // projection -- exactly attention head `rank` -- so it streams 1/8 of every weight matrix (a pre-sliced, contiguous
 // per-rank stream: 21 bulk copies of 32 KB), and the per-head arithmetic of both attentions is local to a CTA (and to a
-// warp: lanes = the head's 32 channels).  Only the inputs of the next projection are exchanged: each thread stores its
-// outputs into the shared memory of all 8 CTAs (st.shared::cluster over DSMEM) and the cluster synchronises
-// (barrier.cluster, 13 times per forward).  LayerNorms run redundantly in every CTA on the gathered rows.
+// warp: lanes = the head's 32 channels).  Only the inputs of the next projection are exchanged: each CTA writes its output
+// slice to its own shared memory, the cluster synchronises (barrier.cluster, 13 times per forward) and every CTA pulls the
+// 8 slices over DSMEM (ld.shared::cluster, 16 bytes per load).  LayerNorms run redundantly in every CTA on the gathered rows.
 // Part of the tcgen05 path's head; compiled into tc_kernels.cu.
 #pragma once
 #include "tc_head.cuh"
@@ -20,9 +20,11 @@ constexpr size_t DCL_LAYER_FLOATS = (size_t)6 * C * 32 + (size_t)C * 64 + (size_
 constexpr size_t DCL_RANK_FLOATS = N_DEC * DCL_LAYER_FLOATS + (size_t)C * 32;                    // + tlbr_reg.0 slice
 constexpr uint32_t DCL_TOTAL_CHUNKS = (uint32_t)(DCL_RANK_FLOATS * 4 / DCL_CHUNK);               // 21
 static_assert(DCL_RANK_FLOATS * 4 % DCL_CHUNK == 0, "whole chunks");
-// shared memory: ring | V[2][16][512] gather targets | u[16][256] | a[16][256] | barriers
+// shared memory: ring | V[16][512] the gathered vector | S[2][16][64] this CTA's own output slice (what peers pull) |
+// u[16][256] | a[16][256] | barriers
 constexpr uint32_t DCL_SM_V = DCL_STAGES * DCL_CHUNK;
-constexpr uint32_t DCL_SM_U = DCL_SM_V + 2 * DCL_ROWS * FF * 4;
+constexpr uint32_t DCL_SM_S = DCL_SM_V + DCL_ROWS * FF * 4;
+constexpr uint32_t DCL_SM_U = DCL_SM_S + 2 * DCL_ROWS * 64 * 4;
 constexpr uint32_t DCL_SM_A = DCL_SM_U + DCL_ROWS * C * 4;
 constexpr uint32_t DCL_SM_BAR = DCL_SM_A + DCL_ROWS * C * 4;
 constexpr uint32_t DCL_SMEM = DCL_SM_BAR + 64;
@@ -93,15 +95,23 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-// v -> the same shared-memory location of all 8 CTAs of the cluster
-__device__ __forceinline__ void dcl_scatter(const float* local_ptr, float v) {
-    const uint32_t la = smem_u32(local_ptr);
-#pragma unroll
-    for (uint32_t rk = 0; rk < DCL_RANKS; ++rk) {
+// All-gather by PULLING: every CTA has written its own output slice S[par][16][W] (W = 32 or 64 columns) to its own shared
+// memory and the cluster has synchronised; each CTA now copies the 8 slices into its local V[16][8 W] with 16-byte
+// ld.shared::cluster loads (scalar st.shared::cluster pushes -- 16 per thread -- made the first version no faster than the
+// one-CTA kernel).  S is double-buffered: a peer may still be pulling S[par] while this CTA already writes S[par ^ 1].
+template <int W>
+__device__ __forceinline__ void dcl_pull(float* V, const float* S_par) {
+    constexpr int F4_ROW = W / 4, ITEMS = DCL_RANKS * DCL_ROWS * F4_ROW;          // float4 items: (rank, row, quad)
+    const uint32_t la = smem_u32(S_par);
+    for (int it = threadIdx.x; it < ITEMS; it += DCL_THREADS) {
+        const int qd = it % F4_ROW, row = (it / F4_ROW) % DCL_ROWS, rk = it / (F4_ROW * DCL_ROWS);
         uint32_t ra;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rk));
-        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la + (uint32_t)(row * 64 + qd * 4) * 4u), "r"((uint32_t)rk));
+        float4 v;
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+        *reinterpret_cast<float4*>(V + row * FF + rk * W + qd * 4) = v;
     }
+    __syncthreads();
 }
 // u[row] = LN(src[row]) and a[row] = u[row] + qe(row) for this warp's two rows (src rows have stride FF)
 __device__ __forceinline__ void dcl_ln(const float* src, const float* __restrict__ g, const float* __restrict__ b, float* u, float* a,
@@ -131,7 +141,8 @@ __device__ __forceinline__ void dcl_ln(const float* src, const float* __restrict
 
 __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS, 1) k_decoder_cl(const DecClParams p) {
     extern __shared__ __align__(1024) uint8_t dsm[];
-    float* V = reinterpret_cast<float*>(dsm + DCL_SM_V);             // [2][16][512]
+    float* V = reinterpret_cast<float*>(dsm + DCL_SM_V);             // [16][512]: the gathered vector (every CTA has all of it)
+    float* S = reinterpret_cast<float*>(dsm + DCL_SM_S);             // [2][16][64]: this CTA's slice of the next gathered vector
     float* u = reinterpret_cast<float*>(dsm + DCL_SM_U);
     float* a = reinterpret_cast<float*>(dsm + DCL_SM_A);
     uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + DCL_SM_BAR);
@@ -143,9 +154,8 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
         for (int i = 0; i < DCL_STAGES; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[DCL_STAGES + i], 8); }
         fence_mbar_init();
     }
-    for (int i = tid; i < DCL_ROWS * FF; i += DCL_THREADS) V[i] = 0.f;            // tgt = zeros (transformer.py:361) in V[0]
+    for (int i = tid; i < DCL_ROWS * FF; i += DCL_THREADS) V[i] = 0.f;            // tgt = zeros (transformer.py:361)
     __syncthreads();
-    cluster_sync_all();                                              // every CTA's barriers and buffers exist before remote stores
     DclRing ring{bars, bars + DCL_STAGES, reinterpret_cast<const float*>(dsm),
                  reinterpret_cast<const uint8_t*>(p.wts + (size_t)rank * DCL_RANK_FLOATS), 0u, 0u};
     const int r0 = 2 * warp, r1 = r0 + 1;
@@ -153,13 +163,19 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
     const float* qe0 = p.qe + (g0 >= p.B ? C : 0);
     const float* qe1 = p.qe + (g1 >= p.B ? C : 0);
     float t_my[2] = {0.f, 0.f};
-    int par = 0;                                                     // V[par] holds the latest gathered vector
-    auto gather2 = [&](float v0, float v1, int col) {                // this thread's values of rows r0, r1 -> V[par ^ 1] everywhere
+    int par = 0;
+    // this thread's values of rows r0, r1 (output channel n) -> own slice -> cluster barrier -> every CTA pulls all slices
+    // into its V.  All local reads of V (the previous gathered vector) are complete before the pull overwrites it: the
+    // values being gathered were computed from it.
+    auto gather2 = [&](float v0, float v1) {
         par ^= 1;
-        dcl_scatter(V + (size_t)par * DCL_ROWS * FF + r0 * FF + col, v0);
-        dcl_scatter(V + (size_t)par * DCL_ROWS * FF + r1 * FF + col, v1);
+        float* Sp = S + par * DCL_ROWS * 64;
+        Sp[r0 * 64 + lane] = v0;
+        Sp[r1 * 64 + lane] = v1;
+        cluster_sync_all();
+        dcl_pull<32>(V, Sp);
     };
-    auto Vcur = [&]() { return V + (size_t)par * DCL_ROWS * FF; };
+    auto Vcur = [&]() { return V; };
     for (int j = 0; j < N_DEC; ++j) {
         const DecLayerT& w = p.layer[j];
         float acc[2][1], kk[2][1], vv[2][1], h2[2][2];
@@ -176,12 +192,10 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
             const float sden = warp_sum_f(qf * kf);                                   // warp lanes = the head's channels
             o2[i] = (vv[i][0] + w.sa_bv[n]) * sden / (sden + ATTN_EPS);
         }
-        gather2(o2[0], o2[1], n);
-        cluster_sync_all();
+        gather2(o2[0], o2[1]);
         dcl_matvec<C, 32>(ring, dsm, Vcur() + r0 * FF, Vcur() + r1 * FF, acc);
         t_my[0] += acc[0][0]; t_my[1] += acc[1][0];
-        gather2(t_my[0], t_my[1], n);
-        cluster_sync_all();
+        gather2(t_my[0], t_my[1]);
         // ---- cross-attention into the memory summaries (transformer.py:243-250)
         dcl_ln(Vcur(), w.ln2_g, w.ln2_b, u, a, qe0, qe1);
         __syncthreads();
@@ -196,27 +210,28 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
             for (int d = 0; d < HD; ++d) o = fmaf(__shfl_sync(0xffffffffu, qv, d), kv[(rank * HD + d) * HD + lane], o);
             o2[i] = o / (den + ATTN_EPS);
         }
-        gather2(o2[0], o2[1], n);
-        cluster_sync_all();
+        gather2(o2[0], o2[1]);
         dcl_matvec<C, 32>(ring, dsm, Vcur() + r0 * FF, Vcur() + r1 * FF, acc);
         t_my[0] += acc[0][0]; t_my[1] += acc[1][0];
-        gather2(t_my[0], t_my[1], n);
-        cluster_sync_all();
+        gather2(t_my[0], t_my[1]);
         // ---- feed-forward (transformer.py:252-254): hidden columns [64 rank, 64 rank + 64) here
         dcl_ln(Vcur(), w.ln3_g, w.ln3_b, u, a, qe0, qe1);
         __syncthreads();
         dcl_matvec<C, 64>(ring, dsm, u + r0 * C, u + r1 * C, h2);
-        par ^= 1;
+        {
+            par ^= 1;
+            float* Sp = S + par * DCL_ROWS * 64;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            dcl_scatter(V + (size_t)par * DCL_ROWS * FF + r0 * FF + rank * 64 + lane + 32 * c, fmaxf(h2[0][c], 0.f));
-            dcl_scatter(V + (size_t)par * DCL_ROWS * FF + r1 * FF + rank * 64 + lane + 32 * c, fmaxf(h2[1][c], 0.f));
+            for (int c = 0; c < 2; ++c) {
+                Sp[r0 * 64 + lane + 32 * c] = fmaxf(h2[0][c], 0.f);
+                Sp[r1 * 64 + lane + 32 * c] = fmaxf(h2[1][c], 0.f);
+            }
+            cluster_sync_all();
+            dcl_pull<64>(V, Sp);
         }
-        cluster_sync_all();
         dcl_matvec<FF, 32>(ring, dsm, Vcur() + r0 * FF, Vcur() + r1 * FF, acc);
         t_my[0] += acc[0][0]; t_my[1] += acc[1][0];
-        gather2(t_my[0], t_my[1], n);
-        cluster_sync_all();
+        gather2(t_my[0], t_my[1]);
     }
     if (row_base + r0 < rows) p.hs[(size_t)(row_base + r0) * C + n] = t_my[0];
     if (row_base + r1 < rows) p.hs[(size_t)(row_base + r1) * C + n] = t_my[1];
@@ -224,8 +239,7 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
     {
         float acc[2][1];
         dcl_matvec<C, 32>(ring, dsm, Vcur() + r0 * FF, Vcur() + r1 * FF, acc);
-        gather2(fmaxf(acc[0][0], 0.f), fmaxf(acc[1][0], 0.f), n);
-        cluster_sync_all();                                          // the last remote stores: CTAs may exit independently afterwards
+        gather2(fmaxf(acc[0][0], 0.f), fmaxf(acc[1][0], 0.f));
         if (rank < 4) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -239,6 +253,7 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
             }
         }
     }
+    cluster_sync_all();                                              // no CTA exits while a peer may still pull from its shared memory
 }
 
 }  // namespace oetr
