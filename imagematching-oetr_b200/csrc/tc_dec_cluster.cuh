@@ -26,7 +26,10 @@ constexpr uint32_t DCL_SM_V = DCL_STAGES * DCL_CHUNK;
 constexpr uint32_t DCL_SM_S = DCL_SM_V + DCL_ROWS * FF * 4;
 constexpr uint32_t DCL_SM_U = DCL_SM_S + 2 * DCL_ROWS * 64 * 4;
 constexpr uint32_t DCL_SM_A = DCL_SM_U + DCL_ROWS * C * 4;
-constexpr uint32_t DCL_SM_BAR = DCL_SM_A + DCL_ROWS * C * 4;
+// staged small vectors per layer: ln1_g ln1_b ln2_g ln2_b ln3_g ln3_b sa_bq sa_bk sa_bv ca_bq (10 x 256), then qe1 | qe2
+constexpr int DCL_PV = 10 * C;
+constexpr uint32_t DCL_SM_P = DCL_SM_A + DCL_ROWS * C * 4;
+constexpr uint32_t DCL_SM_BAR = DCL_SM_P + (N_DEC * DCL_PV + 2 * C) * 4;
 constexpr uint32_t DCL_SMEM = DCL_SM_BAR + 64;
 
 struct DecClParams {
@@ -155,13 +158,25 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
         fence_mbar_init();
     }
     for (int i = tid; i < DCL_ROWS * FF; i += DCL_THREADS) V[i] = 0.f;            // tgt = zeros (transformer.py:361)
+    // every small vector the layers read (LayerNorm parameters, projection biases, query embeddings) is staged in shared
+    // memory once, coalesced, under the first weight copies: the layer code then has no dependent global-load latencies
+    // (the decoder is a serial chain of 17 small products: those ~1 us stalls were most of the one-CTA kernel's 100 us)
+    float* P = reinterpret_cast<float*>(dsm + DCL_SM_P);
+    for (int j = 0; j < N_DEC; ++j) {
+        const DecLayerT& w = p.layer[j];
+        const float* src[10] = {w.ln1_g, w.ln1_b, w.ln2_g, w.ln2_b, w.ln3_g, w.ln3_b, w.sa_bq, w.sa_bk, w.sa_bv, w.ca_bq};
+#pragma unroll
+        for (int v = 0; v < 10; ++v) P[j * DCL_PV + v * C + tid] = src[v][tid];
+    }
+    P[N_DEC * DCL_PV + tid] = p.qe[tid];
+    P[N_DEC * DCL_PV + C + tid] = p.qe[C + tid];
     __syncthreads();
     DclRing ring{bars, bars + DCL_STAGES, reinterpret_cast<const float*>(dsm),
                  reinterpret_cast<const uint8_t*>(p.wts + (size_t)rank * DCL_RANK_FLOATS), 0u, 0u};
     const int r0 = 2 * warp, r1 = r0 + 1;
     const int g0 = min(row_base + r0, rows - 1), g1 = min(row_base + r1, rows - 1);      // clamped global rows (reads)
-    const float* qe0 = p.qe + (g0 >= p.B ? C : 0);
-    const float* qe1 = p.qe + (g1 >= p.B ? C : 0);
+    const float* qe0 = P + N_DEC * DCL_PV + (g0 >= p.B ? C : 0);
+    const float* qe1 = P + N_DEC * DCL_PV + (g1 >= p.B ? C : 0);
     float t_my[2] = {0.f, 0.f};
     int par = 0;
     // this thread's values of rows r0, r1 (output channel n) -> own slice -> cluster barrier -> every CTA pulls all slices
@@ -177,10 +192,19 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
     };
     auto Vcur = [&]() { return V; };
     for (int j = 0; j < N_DEC; ++j) {
-        const DecLayerT& w = p.layer[j];
+        const float* Pj = P + j * DCL_PV;
         float acc[2][1], kk[2][1], vv[2][1], h2[2][2];
+        // the cross-attention summaries of this thread's head and rows: in flight during the self-attention
+        float kvr[2][HD], ksr[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float* kv = p.kvs + ((size_t)j * rows + (i ? g1 : g0)) * KVS;
+            ksr[i] = __ldg(kv + NH * HD * HD + n);
+#pragma unroll
+            for (int d = 0; d < HD; ++d) kvr[i][d] = __ldg(kv + (rank * HD + d) * HD + lane);
+        }
         // ---- self-attention over the single query token (transformer.py:236-241, linear_attention.py:22-50)
-        dcl_ln(Vcur(), w.ln1_g, w.ln1_b, u, a, qe0, qe1);
+        dcl_ln(Vcur(), Pj + 0 * C, Pj + 1 * C, u, a, qe0, qe1);
         __syncthreads();
         dcl_matvec<C, 32>(ring, dsm, a + r0 * C, a + r1 * C, acc);
         dcl_matvec<C, 32>(ring, dsm, a + r0 * C, a + r1 * C, kk);
@@ -188,26 +212,25 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
         float o2[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float qf = elu1(acc[i][0] + w.sa_bq[n]), kf = elu1(kk[i][0] + w.sa_bk[n]);
+            const float qf = elu1(acc[i][0] + Pj[6 * C + n]), kf = elu1(kk[i][0] + Pj[7 * C + n]);
             const float sden = warp_sum_f(qf * kf);                                   // warp lanes = the head's channels
-            o2[i] = (vv[i][0] + w.sa_bv[n]) * sden / (sden + ATTN_EPS);
+            o2[i] = (vv[i][0] + Pj[8 * C + n]) * sden / (sden + ATTN_EPS);
         }
         gather2(o2[0], o2[1]);
         dcl_matvec<C, 32>(ring, dsm, Vcur() + r0 * FF, Vcur() + r1 * FF, acc);
         t_my[0] += acc[0][0]; t_my[1] += acc[1][0];
         gather2(t_my[0], t_my[1]);
         // ---- cross-attention into the memory summaries (transformer.py:243-250)
-        dcl_ln(Vcur(), w.ln2_g, w.ln2_b, u, a, qe0, qe1);
+        dcl_ln(Vcur(), Pj + 2 * C, Pj + 3 * C, u, a, qe0, qe1);
         __syncthreads();
         dcl_matvec<C, 32>(ring, dsm, a + r0 * C, a + r1 * C, acc);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float qv = elu1(acc[i][0] + w.ca_bq[n]);
-            const float* kv = p.kvs + ((size_t)j * rows + (i ? g1 : g0)) * KVS;
-            const float den = warp_sum_f(qv * kv[NH * HD * HD + n]);
+            const float qv = elu1(acc[i][0] + Pj[9 * C + n]);
+            const float den = warp_sum_f(qv * ksr[i]);
             float o = 0.f;
-#pragma unroll 8
-            for (int d = 0; d < HD; ++d) o = fmaf(__shfl_sync(0xffffffffu, qv, d), kv[(rank * HD + d) * HD + lane], o);
+#pragma unroll
+            for (int d = 0; d < HD; ++d) o = fmaf(__shfl_sync(0xffffffffu, qv, d), kvr[i][d], o);
             o2[i] = o / (den + ATTN_EPS);
         }
         gather2(o2[0], o2[1]);
@@ -215,7 +238,7 @@ __global__ void __cluster_dims__(DCL_RANKS, 1, 1) __launch_bounds__(DCL_THREADS,
         t_my[0] += acc[0][0]; t_my[1] += acc[1][0];
         gather2(t_my[0], t_my[1]);
         // ---- feed-forward (transformer.py:252-254): hidden columns [64 rank, 64 rank + 64) here
-        dcl_ln(Vcur(), w.ln3_g, w.ln3_b, u, a, qe0, qe1);
+        dcl_ln(Vcur(), Pj + 4 * C, Pj + 5 * C, u, a, qe0, qe1);
         __syncthreads();
         dcl_matvec<C, 64>(ring, dsm, u + r0 * C, u + r1 * C, h2);
         {
