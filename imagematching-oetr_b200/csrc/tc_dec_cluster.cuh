@@ -104,15 +104,23 @@ __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("m
 // one-CTA kernel).  S is double-buffered: a peer may still be pulling S[par] while this CTA already writes S[par ^ 1].
 template <int W>
 __device__ __forceinline__ void dcl_pull(float* V, const float* S_par) {
-    constexpr int F4_ROW = W / 4, ITEMS = DCL_RANKS * DCL_ROWS * F4_ROW;          // float4 items: (rank, row, quad)
+    constexpr int F4_ROW = W / 4, ITEMS = DCL_RANKS * DCL_ROWS * F4_ROW, PER = ITEMS / DCL_THREADS;     // float4 items: (rank, row, quad)
+    static_assert(ITEMS % DCL_THREADS == 0, "whole items per thread");
     const uint32_t la = smem_u32(S_par);
-    for (int it = threadIdx.x; it < ITEMS; it += DCL_THREADS) {
+    float4 v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {                                  // all remote loads in flight together
+        const int it = i * DCL_THREADS + threadIdx.x;
         const int qd = it % F4_ROW, row = (it / F4_ROW) % DCL_ROWS, rk = it / (F4_ROW * DCL_ROWS);
         uint32_t ra;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la + (uint32_t)(row * 64 + qd * 4) * 4u), "r"((uint32_t)rk));
-        float4 v;
-        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
-        *reinterpret_cast<float4*>(V + row * FF + rk * W + qd * 4) = v;
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la + (uint32_t)(row * 64 + qd * 4) * 4u), "r"((uint32_t)rk));
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(ra));
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int it = i * DCL_THREADS + threadIdx.x;
+        const int qd = it % F4_ROW, row = (it / F4_ROW) % DCL_ROWS, rk = it / (F4_ROW * DCL_ROWS);
+        *reinterpret_cast<float4*>(V + row * FF + rk * W + qd * 4) = v[i];
     }
     __syncthreads();
 }
