@@ -33,6 +33,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <queue>
 #include <vector>
 
 using namespace oetr::tc;
@@ -211,22 +212,30 @@ __global__ void __launch_bounds__(k1::N_THREADS, 1) k_neck_proj(const k1::Params
 namespace k2 {
 constexpr int N_THREADS = 192;                   // warp 0: TMA producer, warp 1: MMA issue, warps 2-5: epilogue
 constexpr int STAGES = 4;
-constexpr uint32_t A_BYTES = SLAB, STAGE = A_BYTES + WUNIT;       // 48 KB
+constexpr uint32_t A_BYTES = SLAB, STAGE = 3 * SLAB;              // 48 KB: {A0, A1, B 16 KB} or {A, B 32 KB}
 constexpr uint32_t SM_BAR = STAGES * STAGE;
 constexpr uint32_t SM_TOTAL = SM_BAR + 128;
 struct Bars {
     uint64_t full[STAGES], empty[STAGES], done;
     uint32_t tmem, pad;
 };
-// one (tap, channel slab) of the unified 16 x 16 tap grid.  kind 0: outer tap, k16 only (B tile 128 rows, TMEM columns
-// 0-127); kind 1: inner tap, k16 | k8 (256 rows, columns 0-255); kind 2: centre tap, k4 (256 rows, columns 256-511)
+// One unit = one (tap, 64-channel slab) step of an item.  The L2 -> SM operand stream bounds this kernel (a 16 KB A tile and
+// a 16 KB weight tile for 256 MMA cycles = 124 B/cycle against ~64 B/cycle of ingest), so the work is cut so that every
+// weight tile is used twice:
+//   kind 0  k16 (16 x 16 taps, 128 outputs): an item covers a PAIR of tiles; per unit two A tiles and ONE 128-row weight
+//           tile, two N=128 MMAs into TMEM columns [0,128) and [128,256)  (46 KB per 512 MMA cycles = 92 B/cycle)
+//   kind 1  k8 (the 8 x 8 centre taps, 128 outputs): one tile, 128-row weight tile, columns [0,128)
+//   kind 2  k4 (the 4 x 4 centre taps, 256 outputs): one tile, 256-row weight tile, columns [128,384)
+// Type-1 items hold kind-0 units, type-2 items kind-1 and kind-2 units; both are split over K into parts.
 struct Unit { int dx, dy, phase_slab_kind; uint32_t w_kb; };
 struct Params {
-    const Unit* units;
+    const Unit* units1;      // kind-0 units in the order of the chosen part count P1 (part p: [begin1[p], begin1[p+1]))
+    const Unit* units2;      // kind-1/2 units for P2
     const __half* w_img;
-    float* partial;          // [P][tiles][128][512]
-    int part_begin[MAX_PARTS + 1];
-    int P, tiles, YG, ny, nb, R;
+    float* partial1;         // [P1][tiles_pad][128][128]
+    float* partial2;         // [P2][tiles][128][384]
+    int begin1[MAX_PARTS + 1], begin2[MAX_PARTS + 1];
+    int P1, P2, pairs, tiles, YG, ny, nb, R, items1;
 };
 }  // namespace k2
 
@@ -244,8 +253,13 @@ __global__ void __launch_bounds__(k2::N_THREADS, 1) k_neck_conv(const __grid_con
     Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const int part = blockIdx.x / p.tiles, tile = blockIdx.x % p.tiles;
-    const int ub = p.part_begin[part], ue = p.part_begin[part + 1];
+    // items: type 1 first (the long ones), part-major so that neighbouring CTAs stream the same weights
+    const bool type1 = (int)blockIdx.x < p.items1;
+    const int local = type1 ? (int)blockIdx.x : (int)blockIdx.x - p.items1;
+    const int part = type1 ? local / p.pairs : local / p.tiles;
+    const int tile0 = type1 ? 2 * (local % p.pairs) : local % p.tiles;
+    const Unit* units = type1 ? p.units1 : p.units2;
+    const int ub = type1 ? p.begin1[part] : p.begin2[part], ue = type1 ? p.begin1[part + 1] : p.begin2[part + 1];
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
         mbar_init(&bars->done, 1);
@@ -259,37 +273,50 @@ __global__ void __launch_bounds__(k2::N_THREADS, 1) k_neck_conv(const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            const int y0 = (tile % p.YG) * p.ny, n0 = (tile / p.YG) * p.nb;
-            const uint32_t a_bytes = (uint32_t)p.R * 128u;
+            const int y0 = (tile0 % p.YG) * p.ny, n0 = (tile0 / p.YG) * p.nb;
+            const int y1 = ((tile0 + 1) % p.YG) * p.ny, n1 = ((tile0 + 1) / p.YG) * p.nb;      // second tile of a pair (may lie
+            const uint32_t a_bytes = (uint32_t)p.R * 128u;                                     // past the last image: zero fill)
             for (int u = ub; u < ue; ++u) {
                 const int i = u - ub, st = i % STAGES;
                 if (i >= STAGES) mbar_wait(&bars->empty[st], ((i / STAGES) - 1) & 1, nullptr);
-                const Unit un = p.units[u];
+                const Unit un = units[u];
                 const int phase = un.phase_slab_kind & 0xff, slab = (un.phase_slab_kind >> 8) & 0xff, kind = un.phase_slab_kind >> 16;
-                const uint32_t b_bytes = kind == 0 ? SLAB : WUNIT;
-                mbar_arrive_expect_tx(&bars->full[st], a_bytes + b_bytes);
-                tma_load_5d(smem_base + st * STAGE, &tmap, slab * 64, un.dx, y0 + un.dy, phase, n0, &bars->full[st]);
-                bulk_g2s(smem + st * STAGE + A_BYTES, p.w_img + (size_t)un.w_kb * 512, b_bytes, &bars->full[st]);
+                const uint32_t b_bytes = kind == 2 ? WUNIT : SLAB;
+                const uint32_t stage = smem_base + st * STAGE;
+                mbar_arrive_expect_tx(&bars->full[st], (kind == 0 ? 2 * a_bytes : a_bytes) + b_bytes);
+                tma_load_5d(stage, &tmap, slab * 64, un.dx, y0 + un.dy, phase, n0, &bars->full[st]);
+                if (kind == 0) tma_load_5d(stage + A_BYTES, &tmap, slab * 64, un.dx, y1 + un.dy, phase, n1, &bars->full[st]);
+                bulk_g2s(smem + st * STAGE + (kind == 0 ? 2 * A_BYTES : A_BYTES), p.w_img + (size_t)un.w_kb * 512, b_bytes, &bars->full[st]);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            bool init01 = false, init2 = false;
+            bool init0 = false, init1 = false;       // type 1: both tile accumulators together; type 2: k8 | k4
             for (int u = ub; u < ue; ++u) {
                 const int i = u - ub, st = i % STAGES;
-                const int kind = p.units[u].phase_slab_kind >> 16;
+                const int kind = units[u].phase_slab_kind >> 16;
                 mbar_wait(&bars->full[st], (i / STAGES) & 1, nullptr);
                 tc_fence_after();
-                const uint32_t a = smem_base + st * STAGE, b = a + A_BYTES;
-                const uint32_t d = tmem + (kind == 2 ? 256u : 0u);
-                const uint32_t idesc = kind == 0 ? IDESC_N128 : IDESC_N256;
-                const bool first = kind == 2 ? !init2 : !init01;
+                const uint32_t a = smem_base + st * STAGE;
+                if (kind == 0) {
+                    const uint32_t b = a + 2 * A_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_f16(d, umma_desc(a + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES), idesc,
-                             (first && k == 0) ? 0u : 1u);
-                if (kind == 2) init2 = true; else init01 = true;
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem + t * 128, umma_desc(a + t * A_BYTES + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                                     IDESC_N128, (!init0 && k == 0) ? 0u : 1u);
+                    init0 = true;
+                } else {
+                    const uint32_t b = a + A_BYTES;
+                    const bool first = kind == 1 ? !init0 : !init1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tmem + (kind == 2 ? 128u : 0u), umma_desc(a + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
+                                 kind == 2 ? IDESC_N256 : IDESC_N128, (first && k == 0) ? 0u : 1u);
+                    if (kind == 1) init0 = true; else init1 = true;
+                }
                 umma_commit(&bars->empty[st]);
             }
             umma_commit(&bars->done);
@@ -300,15 +327,32 @@ __global__ void __launch_bounds__(k2::N_THREADS, 1) k_neck_conv(const __grid_con
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         mbar_wait(&bars->done, 0, nullptr);
         tc_fence_after();
-        float* out = p.partial + ((size_t)blockIdx.x * TILE + r) * CM;
+        if (type1) {                                 // [part][tile][128][128] for the two tiles of the pair
 #pragma unroll 1
-        for (int cc = 0; cc < CM / 32; ++cc) {
-            float v[32];
-            tmem_ld32(tmem + lane_addr + cc * 32, v);
-            if (r < p.R) {
+            for (int t = 0; t < 2; ++t) {
+                float* out = p.partial1 + (((size_t)part * 2 * p.pairs + tile0 + t) * TILE + r) * 128;
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    float v[32];
+                    tmem_ld32(tmem + lane_addr + t * 128 + cc * 32, v);
+                    if (r < p.R) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(out + cc * 32 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(out + cc * 32 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+        } else {                                     // [part][tile][128][384]: k8 | k4
+            float* out = p.partial2 + (((size_t)part * p.tiles + tile0) * TILE + r) * 384;
+#pragma unroll 1
+            for (int cc = 0; cc < 12; ++cc) {
+                float v[32];
+                tmem_ld32(tmem + lane_addr + cc * 32, v);
+                if (r < p.R) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(out + cc * 32 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
             }
         }
     }
@@ -333,11 +377,12 @@ struct Bars {
     uint32_t tmem, pad;
 };
 struct Params {
-    const float* partial;    // [P][tiles][128][512]
-    const __half* w_img;     // [8 ks][256 n][64 k] swizzled, K in the TMEM column order (k16 | k8 | k4)
+    const float* partial1;   // [P1][tiles_pad][128][128]: k16
+    const float* partial2;   // [P2][tiles][128][384]: k8 | k4
+    const __half* w_img;     // [8 ks][256 n][64 k] swizzled, K in the order k16 | k8 | k4
     const float *bias_cat, *bias2;       // [512] in the same order; [256]
     float* feat;             // [n][256][ho][wo]
-    int P, tiles, YG, ny, nb, R, n, ho, wo;
+    int P1, P2, tiles_pad, tiles, YG, ny, nb, R, n, ho, wo;
 };
 }  // namespace k3
 
@@ -402,8 +447,12 @@ __global__ void __launch_bounds__(k3::N_THREADS, 1) k_neck_out(const k3::Params 
                 v[4 * j] = b4.x; v[4 * j + 1] = b4.y; v[4 * j + 2] = b4.z; v[4 * j + 3] = b4.w;
             }
             if (in_box) {
-                for (int part = 0; part < p.P; ++part) {
-                    const float4* src = reinterpret_cast<const float4*>(p.partial + (((size_t)part * p.tiles + tile) * TILE + r) * CM + c0);
+                // columns [0,128) = k16 from the type-1 parts, [128,512) = k8 | k4 from the type-2 parts
+                const int nparts = cq == 0 ? p.P1 : p.P2;
+                for (int part = 0; part < nparts; ++part) {
+                    const float4* src = cq == 0
+                        ? reinterpret_cast<const float4*>(p.partial1 + (((size_t)part * p.tiles_pad + tile) * TILE + r) * 128 + ch * 32)
+                        : reinterpret_cast<const float4*>(p.partial2 + (((size_t)part * p.tiles + tile) * TILE + r) * 384 + (c0 - 128));
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 t = __ldg(src + j);
@@ -483,12 +532,26 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct Geometry {
-    int n, h, w, T, tiles_per_img, Hh, Wh, ho, wo, ny, nb, YG, NG, tiles, R, P;
-    size_t xn_bytes, partial_bytes;
+    int n, h, w, T, tiles_per_img, Hh, Wh, ho, wo, ny, nb, YG, NG, tiles, pairs, R, P1, P2;
+    size_t xn_bytes, partial1_bytes, partial2_bytes;
 };
 
-// box rows of a conv tile = wo * ny * nb <= 128: the (ny, nb) with the fewest tiles; then the number of split-K parts
-// that fills whole waves of `sms` CTAs best
+// makespan (cycles) of n1 items of cost c1 followed by n2 items of cost c2 dispatched in order to `sms` SMs
+double makespan(long n1, double c1, long n2, double c2, int sms) {
+    std::priority_queue<double, std::vector<double>, std::greater<double>> q;
+    for (int i = 0; i < sms; ++i) q.push(0.0);
+    double end = 0.0;
+    auto run = [&](long n, double c) {
+        for (long i = 0; i < n; ++i) { const double t = q.top() + c; q.pop(); q.push(t); if (t > end) end = t; }
+    };
+    run(n1, c1);
+    run(n2, c2);
+    return end;
+}
+
+// box rows of a conv tile = wo * ny * nb <= 128: the (ny, nb) with the fewest tiles; then the split-K part counts of the two
+// item types (k16 on tile pairs; k8 + k4 per tile) that minimise the modelled makespan on `sms` SMs plus the round trip of
+// the partial sums through HBM.  Step costs (cycles) follow the measured L2 -> SM ingest of ~64 B/cycle per SM.
 int make_geometry(int n, int h, int w, int sms, Geometry& g) {
     if (n < 1 || h < 2 || w < 2 || h > 200 || w > 200) return -1;
     g.n = n; g.h = h; g.w = w; g.T = h * w;
@@ -502,17 +565,19 @@ int make_geometry(int n, int h, int w, int sms, Geometry& g) {
         }
     g.YG = (g.ho + g.ny - 1) / g.ny; g.NG = (n + g.nb - 1) / g.nb;
     g.tiles = g.YG * g.NG; g.R = g.wo * g.ny * g.nb;
-    // cost of P parts in units of one (tap, slab) step of a CTA: waves x (1408 / P steps + ~40 for the epilogue) plus the
-    // partial sums' round trip through HBM (512 KB per tile and part at ~7.7 TB/s ~ 0.27 steps, not divided by the SMs)
-    const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16};
+    g.pairs = (g.tiles + 1) / 2;
+    const double step16 = 720.0, step8 = 484.0, step4 = 734.0, fixed = 4000.0, hbm_bytes_per_cycle = 3500.0;
     double best_cost = -1.0;
-    for (int P : cand) {
-        const long items = (long)g.tiles * P;
-        const double cost = (double)((items + sms - 1) / sms) * (1408.0 / P + 40.0) + 0.27 * (double)items;
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; g.P = P; }
-    }
+    for (int P1 : {1, 2, 4, 8, 16})
+        for (int P2 : {1, 2, 4, 8}) {
+            const double c1 = 1024.0 / P1 * step16 + fixed, c2 = (256.0 * step8 + 64.0 * step4) / P2 + fixed;
+            const double bytes = 2.0 * ((double)P1 * 2 * g.pairs * TILE * 128 * 4 + (double)P2 * g.tiles * TILE * 384 * 4);
+            const double cost = makespan((long)g.pairs * P1, c1, (long)g.tiles * P2, c2, sms) + bytes / hbm_bytes_per_cycle;
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; g.P1 = P1; g.P2 = P2; }
+        }
     g.xn_bytes = (((size_t)n * 4 * g.Hh * g.Wh * C * sizeof(__half)) + 1023) & ~(size_t)1023;
-    g.partial_bytes = (size_t)g.P * g.tiles * TILE * CM * sizeof(float);
+    g.partial1_bytes = (size_t)g.P1 * 2 * g.pairs * TILE * 128 * sizeof(float);
+    g.partial2_bytes = (size_t)g.P2 * g.tiles * TILE * 384 * sizeof(float);
     return 0;
 }
 
@@ -525,13 +590,26 @@ struct oetr_neck {
     int device = 0, sms = 148;
     __half *w1_img = nullptr, *conv_img = nullptr, *w2_img = nullptr;
     float* vec = nullptr;            // b1[256] | ln_g[256] | ln_b[256] | bias_cat[512] | b2[256]
-    k2::Unit* units = nullptr;       // unit lists of every part count: [MAX_PARTS + 1][n_units]
-    std::vector<k2::Unit> h_units;   // the P = 1 order (inner, centre, outer)
-    int n_units = 0;
-    int part_begin[MAX_PARTS + 1][MAX_PARTS + 1] = {};
+    k2::Unit *units1 = nullptr, *units2 = nullptr;      // unit lists of every part count: [MAX_PARTS + 1][n_units]
+    int n_units1 = 0, n_units2 = 0;
+    int begin1[MAX_PARTS + 1][MAX_PARTS + 1] = {}, begin2[MAX_PARTS + 1][MAX_PARTS + 1] = {};
     EncodeTiledFn encode = nullptr;
     int last_launches = 0;
+    std::mutex mu;                   // geometry cache (the part-count search costs ~0.1 ms: once per problem size)
+    std::vector<Geometry> cache;
 };
+
+namespace {
+int cached_geometry(oetr_neck* h, int n, int height, int width, Geometry& g) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (const Geometry& c : h->cache)
+        if (c.n == n && c.h == height && c.w == width) { g = c; return 0; }
+    if (make_geometry(n, height, width, h->sms, g)) return -1;
+    if (h->cache.size() >= 64) h->cache.erase(h->cache.begin());
+    h->cache.push_back(g);
+    return 0;
+}
+}  // namespace
 
 extern "C" {
 
@@ -540,7 +618,7 @@ size_t oetr_neck_packed_weight_count(void) { return neck_layout().total; }
 
 int oetr_neck_destroy(oetr_neck* h) {
     if (!h) return OETR_OK;
-    cudaFree(h->w1_img); cudaFree(h->conv_img); cudaFree(h->w2_img); cudaFree(h->vec); cudaFree(h->units);
+    cudaFree(h->w1_img); cudaFree(h->conv_img); cudaFree(h->w2_img); cudaFree(h->vec); cudaFree(h->units1); cudaFree(h->units2);
     delete h;
     return OETR_OK;
 }
@@ -586,58 +664,59 @@ int oetr_neck_create(const float* weights_host, size_t n_floats, oetr_neck** out
     memcpy(&vec[0], W + L.b1, 256 * 4); memcpy(&vec[256], W + L.ln_g, 256 * 4); memcpy(&vec[512], W + L.ln_b, 256 * 4);
     memcpy(&vec[768], W + L.b16, 128 * 4); memcpy(&vec[768 + 128], W + L.b8, 128 * 4); memcpy(&vec[768 + 256], W + L.b4, 256 * 4);
     memcpy(&vec[768 + 512], W + L.b2, 256 * 4);
-    // convolution units: weight tiles in list order (inner, centre, outer); every unit's tile starts on a 1 KB boundary
-    std::vector<k2::Unit> inner, centre, outer;
+    // convolution units; every unit's weight tile starts on a 1 KB boundary.  kind 0: k16 over all 256 taps (128 rows);
+    // kind 1: k8 over its 64 taps (128 rows); kind 2: k4 over its 16 taps (256 rows)
+    std::vector<k2::Unit> u16, u8, u4;
     size_t kb = 0;
-    for (int pass = 0; pass < 3; ++pass)
+    for (int kind = 0; kind < 3; ++kind)
         for (int ky = 0; ky < 16; ++ky)
             for (int kx = 0; kx < 16; ++kx) {
                 const bool in8 = ky >= 4 && ky < 12 && kx >= 4 && kx < 12, in4 = ky >= 6 && ky < 10 && kx >= 6 && kx < 10;
-                if ((pass == 0 && !in8) || (pass == 1 && !in4) || (pass == 2 && in8)) continue;
+                if ((kind == 1 && !in8) || (kind == 2 && !in4)) continue;
                 const int py = (ky - 7) & 1, px = (kx - 7) & 1;
                 for (int slab = 0; slab < 4; ++slab) {
                     k2::Unit u;
                     u.dy = (ky - 7 - py) / 2; u.dx = (kx - 7 - px) / 2;
-                    const int kind = pass == 0 ? 1 : (pass == 1 ? 2 : 0);
                     u.phase_slab_kind = (py * 2 + px) | (slab << 8) | (kind << 16);
                     u.w_kb = (uint32_t)kb;
-                    kb += kind == 0 ? 16 : 32;
-                    (pass == 0 ? inner : (pass == 1 ? centre : outer)).push_back(u);
+                    kb += kind == 2 ? 32 : 16;
+                    (kind == 0 ? u16 : (kind == 1 ? u8 : u4)).push_back(u);
                 }
             }
     std::vector<__half> conv(kb * 512);
-    auto fill = [&](const k2::Unit& u, int ky, int kx) {
-        const int slab = (u.phase_slab_kind >> 8) & 0xff, kind = u.phase_slab_kind >> 16;
-        __half* t = conv.data() + (size_t)u.w_kb * 512;
-        const int rows = kind == 0 ? 128 : 256;
-        for (int n = 0; n < rows; ++n)
-            for (int k = 0; k < 64; ++k) {
-                const int c = slab * 64 + k;
-                float v;
-                if (kind == 2) v = W[L.w4 + (((size_t)n * C + c) * 4 + (ky - 6)) * 4 + (kx - 6)];
-                else if (n < 128) v = W[L.w16 + (((size_t)n * C + c) * 16 + ky) * 16 + kx];
-                else v = W[L.w8 + (((size_t)(n - 128) * C + c) * 8 + (ky - 4)) * 8 + (kx - 4)];
-                t[tile_half_index(n, k)] = __float2half_rn(v);
-            }
-    };
-    for (auto* lst : {&inner, &centre, &outer})
+    for (auto* lst : {&u16, &u8, &u4})
         for (const k2::Unit& u : *lst) {
             const int py = (u.phase_slab_kind & 0xff) >> 1, px = u.phase_slab_kind & 1;
-            fill(u, 2 * u.dy + py + 7, 2 * u.dx + px + 7);
+            const int ky = 2 * u.dy + py + 7, kx = 2 * u.dx + px + 7;
+            const int slab = (u.phase_slab_kind >> 8) & 0xff, kind = u.phase_slab_kind >> 16;
+            __half* t = conv.data() + (size_t)u.w_kb * 512;
+            const int rows = kind == 2 ? 256 : 128;
+            for (int n = 0; n < rows; ++n)
+                for (int k = 0; k < 64; ++k) {
+                    const int c = slab * 64 + k;
+                    float v;
+                    if (kind == 2) v = W[L.w4 + (((size_t)n * C + c) * 4 + (ky - 6)) * 4 + (kx - 6)];
+                    else if (kind == 0) v = W[L.w16 + (((size_t)n * C + c) * 16 + ky) * 16 + kx];
+                    else v = W[L.w8 + (((size_t)n * C + c) * 8 + (ky - 4)) * 8 + (kx - 4)];
+                    t[tile_half_index(n, k)] = __float2half_rn(v);
+                }
         }
-    h->n_units = (int)(inner.size() + centre.size() + outer.size());
-    // the unit list of every part count P: part p takes every P-th unit of each class, inner first (its first MMA
-    // initialises TMEM columns 0-255), then centre (columns 256-511), then outer
-    std::vector<k2::Unit> all((size_t)(MAX_PARTS + 1) * h->n_units);
+    h->n_units1 = (int)u16.size();
+    h->n_units2 = (int)(u8.size() + u4.size());
+    // the unit list of every part count P: part p takes every P-th unit of each kind (type 2: k8 units first, then k4)
+    std::vector<k2::Unit> all1((size_t)(MAX_PARTS + 1) * h->n_units1), all2((size_t)(MAX_PARTS + 1) * h->n_units2);
     for (int P = 1; P <= MAX_PARTS; ++P) {
-        size_t o = (size_t)P * h->n_units;
-        const size_t base = o;
+        size_t o1 = (size_t)P * h->n_units1, o2 = (size_t)P * h->n_units2;
+        const size_t b1 = o1, b2 = o2;
         for (int part = 0; part < P; ++part) {
-            h->part_begin[P][part] = (int)(o - base);
-            for (auto* lst : {&inner, &centre, &outer})
-                for (size_t i = part; i < lst->size(); i += P) all[o++] = (*lst)[i];
+            h->begin1[P][part] = (int)(o1 - b1);
+            h->begin2[P][part] = (int)(o2 - b2);
+            for (size_t i = part; i < u16.size(); i += P) all1[o1++] = u16[i];
+            for (size_t i = part; i < u8.size(); i += P) all2[o2++] = u8[i];
+            for (size_t i = part; i < u4.size(); i += P) all2[o2++] = u4[i];
         }
-        h->part_begin[P][P] = (int)(o - base);
+        h->begin1[P][P] = (int)(o1 - b1);
+        h->begin2[P][P] = (int)(o2 - b2);
     }
     cudaError_t e = cudaSuccess;
     auto up = [&](void** d, const void* src, size_t bytes) {
@@ -648,7 +727,8 @@ int oetr_neck_create(const float* weights_host, size_t n_floats, oetr_neck** out
     up((void**)&h->w2_img, w2.data(), w2.size() * 2);
     up((void**)&h->conv_img, conv.data(), conv.size() * 2);
     up((void**)&h->vec, vec.data(), vec.size() * 4);
-    up((void**)&h->units, all.data(), all.size() * sizeof(k2::Unit));
+    up((void**)&h->units1, all1.data(), all1.size() * sizeof(k2::Unit));
+    up((void**)&h->units2, all2.data(), all2.size() * sizeof(k2::Unit));
     if (e == cudaSuccess) {
         std::lock_guard<std::mutex> lk(g_attr_mu);
         if (dev < 64 && !g_attr_done[dev]) {
@@ -669,18 +749,19 @@ int oetr_neck_create(const float* weights_host, size_t n_floats, oetr_neck** out
 int oetr_neck_workspace_bytes(const oetr_neck* h, int n_images, int height, int width, size_t* out) {
     if (!h || !out) return nfail(OETR_E_ARG, "oetr_neck_workspace_bytes: null argument");
     Geometry g;
-    if (make_geometry(n_images, height, width, h->sms, g)) return nfail(OETR_E_SHAPE, "oetr_neck_workspace_bytes: %d images of %d x %d", n_images, height, width);
-    *out = g.xn_bytes + g.partial_bytes + 1024;
+    if (cached_geometry(const_cast<oetr_neck*>(h), n_images, height, width, g)) return nfail(OETR_E_SHAPE, "oetr_neck_workspace_bytes: %d images of %d x %d", n_images, height, width);
+    *out = g.xn_bytes + g.partial1_bytes + g.partial2_bytes + 1024;
     return OETR_OK;
 }
 
 int oetr_neck_last_launch_count(const oetr_neck* h) { return h ? h->last_launches : 0; }
 
-// host-only: the conv tiling chosen for a problem (tests): out = {tiles, rows per tile, ny, nb, parts}
+// host-only: the conv tiling chosen for a problem (tests): out = {tiles, rows per tile, ny, nb, parts of the k16 items
+// (on tile pairs) * 100 + parts of the k8 + k4 items}
 int oetr_neck_geometry(int n_images, int height, int width, int sms, int* out5) {
     Geometry g;
     if (!out5 || make_geometry(n_images, height, width, sms > 0 ? sms : 148, g)) return nfail(OETR_E_SHAPE, "oetr_neck_geometry: bad problem");
-    out5[0] = g.tiles; out5[1] = g.R; out5[2] = g.ny; out5[3] = g.nb; out5[4] = g.P;
+    out5[0] = g.tiles; out5[1] = g.R; out5[2] = g.ny; out5[3] = g.nb; out5[4] = g.P1 * 100 + g.P2;
     return OETR_OK;
 }
 
@@ -691,13 +772,15 @@ int oetr_neck_forward(oetr_neck* h, const float* backbone_out, int n_images, int
     NCU(cudaGetDevice(&dev));
     if (dev != h->device) return nfail(OETR_E_ARG, "oetr_neck_forward: handle belongs to device %d, current device is %d", h->device, dev);
     Geometry g;
-    if (make_geometry(n_images, height, width, h->sms, g)) return nfail(OETR_E_SHAPE, "oetr_neck_forward: %d images of %d x %d", n_images, height, width);
+    if (cached_geometry(h, n_images, height, width, g)) return nfail(OETR_E_SHAPE, "oetr_neck_forward: %d images of %d x %d", n_images, height, width);
     const uintptr_t base = ((uintptr_t)workspace + 1023) & ~(uintptr_t)1023;
-    if (base + g.xn_bytes + g.partial_bytes > (uintptr_t)workspace + workspace_bytes)
-        return nfail(OETR_E_NOMEM, "oetr_neck_forward: workspace of %zu bytes, %zu needed", workspace_bytes, g.xn_bytes + g.partial_bytes + 1024);
+    if (base + g.xn_bytes + g.partial1_bytes + g.partial2_bytes > (uintptr_t)workspace + workspace_bytes)
+        return nfail(OETR_E_NOMEM, "oetr_neck_forward: workspace of %zu bytes, %zu needed", workspace_bytes,
+                     g.xn_bytes + g.partial1_bytes + g.partial2_bytes + 1024);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     __half* xn = reinterpret_cast<__half*>(base);
-    float* partial = reinterpret_cast<float*>(base + g.xn_bytes);
+    float* partial1 = reinterpret_cast<float*>(base + g.xn_bytes);
+    float* partial2 = reinterpret_cast<float*>(base + g.xn_bytes + g.partial1_bytes);
     int launches = 0;
     if ((height & 1) || (width & 1)) NCU(cudaMemsetAsync(xn, 0, g.xn_bytes, s));     // the missing last row / column of the odd planes
     {
@@ -719,17 +802,22 @@ int oetr_neck_forward(oetr_neck* h, const float* backbone_out, int n_images, int
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return nfail(OETR_E_CUDA, "oetr_neck_forward: cuTensorMapEncodeTiled failed (%d)", (int)r);
         k2::Params p;
-        p.units = h->units + (size_t)g.P * h->n_units; p.w_img = h->conv_img; p.partial = partial;
-        for (int i = 0; i <= MAX_PARTS; ++i) p.part_begin[i] = h->part_begin[g.P][i < g.P ? i : g.P];
-        p.P = g.P; p.tiles = g.tiles; p.YG = g.YG; p.ny = g.ny; p.nb = g.nb; p.R = g.R;
-        k_neck_conv<<<g.tiles * g.P, k2::N_THREADS, k2::SM_TOTAL, s>>>(tmap, p);
+        p.units1 = h->units1 + (size_t)g.P1 * h->n_units1; p.units2 = h->units2 + (size_t)g.P2 * h->n_units2;
+        p.w_img = h->conv_img; p.partial1 = partial1; p.partial2 = partial2;
+        for (int i = 0; i <= MAX_PARTS; ++i) {
+            p.begin1[i] = h->begin1[g.P1][i < g.P1 ? i : g.P1];
+            p.begin2[i] = h->begin2[g.P2][i < g.P2 ? i : g.P2];
+        }
+        p.P1 = g.P1; p.P2 = g.P2; p.pairs = g.pairs; p.tiles = g.tiles; p.YG = g.YG; p.ny = g.ny; p.nb = g.nb; p.R = g.R;
+        p.items1 = g.pairs * g.P1;
+        k_neck_conv<<<p.items1 + g.tiles * g.P2, k2::N_THREADS, k2::SM_TOTAL, s>>>(tmap, p);
         NCU(cudaGetLastError());
         ++launches;
     }
     {
         k3::Params p;
-        p.partial = partial; p.w_img = h->w2_img; p.bias_cat = h->vec + 768; p.bias2 = h->vec + 768 + 512; p.feat = feat_out;
-        p.P = g.P; p.tiles = g.tiles; p.YG = g.YG; p.ny = g.ny; p.nb = g.nb; p.R = g.R; p.n = g.n; p.ho = g.ho; p.wo = g.wo;
+        p.partial1 = partial1; p.partial2 = partial2; p.w_img = h->w2_img; p.bias_cat = h->vec + 768; p.bias2 = h->vec + 768 + 512; p.feat = feat_out;
+        p.P1 = g.P1; p.P2 = g.P2; p.tiles_pad = 2 * g.pairs; p.tiles = g.tiles; p.YG = g.YG; p.ny = g.ny; p.nb = g.nb; p.R = g.R; p.n = g.n; p.ho = g.ho; p.wo = g.wo;
         k_neck_out<<<g.tiles, k3::N_THREADS, k3::SM_TOTAL, s>>>(p);
         NCU(cudaGetLastError());
         ++launches;

@@ -234,7 +234,7 @@ OETR_API int oetr_neck_forward(oetr_neck* h, const float* backbone_out, int n_im
                                void* workspace, size_t workspace_bytes, void* stream);
 OETR_API int oetr_neck_last_launch_count(const oetr_neck* h);
 /* host-only: the convolution tiling of a problem on a GPU of `sms` SMs: out5 = {tiles, rows per tile (<= 128), output rows
- * per tile, images per tile, split-K parts} */
+ * per tile, images per tile, 100 * split-K parts of the k16 items (tile pairs) + split-K parts of the k8 + k4 items} */
 OETR_API int oetr_neck_geometry(int n_images, int height, int width, int sms, int* out5);
 OETR_API const char* oetr_neck_last_error(void);
 

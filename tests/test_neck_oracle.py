@@ -62,16 +62,17 @@ def test_packed_neck_weights():
 
 
 def test_neck_conv_tiling_host_logic():
-    """oetr_neck_geometry (host only): box rows <= 128, every output position covered, split-K parts fill the waves."""
+    """oetr_neck_geometry (host only): box rows <= 128, every output position covered, split-K part counts of the two item
+    types (k16 on tile pairs: out[4] // 100; k8 + k4 per tile: out[4] % 100) in range."""
     lib = cabi.load_library()
     out = (ctypes.c_int * 5)()
-    expect = {(64, 40, 40): (220, 120, 2, 3, 2), (2, 40, 40): (7, 120, 3, 2, 16), (32, 52, 52): (208, 104, 2, 2, 2)}
+    expect = {(64, 40, 40): (220, 120, 2, 3, 102), (2, 40, 40): (7, 120, 3, 2, 1604), (32, 52, 52): (208, 104, 2, 2, 202)}
     for n in (1, 2, 3, 7, 32, 64):
         for h, w in ((40, 40), (52, 52), (30, 38), (39, 37), (8, 12), (2, 2), (200, 200), (3, 120)):
             assert lib.oetr_neck_geometry(n, h, w, 148, out) == 0, lib.oetr_neck_last_error()
             tiles, rows, ny, nb, parts = list(out)
             ho, wo = h // 2, w // 2
-            assert rows == wo * ny * nb <= 128 and 1 <= parts <= 16
+            assert rows == wo * ny * nb <= 128 and parts // 100 in (1, 2, 4, 8, 16) and parts % 100 in (1, 2, 4, 8)
             assert tiles == -(-ho // ny) * -(-n // nb)
             assert ny * -(-ho // ny) >= ho and nb * -(-n // nb) >= n
             if (n, h, w) in expect:
