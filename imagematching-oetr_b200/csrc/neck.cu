@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -300,13 +301,15 @@ __global__ void __launch_bounds__(k2::N_THREADS, 1) k_neck_conv(const __grid_con
                 tc_fence_after();
                 const uint32_t a = smem_base + st * STAGE;
                 if (kind == 0) {
-                    const uint32_t b = a + 2 * A_BYTES;
+                    // swapped roles: the WEIGHT tile is the M operand (128 output channels = TMEM lanes), the two
+                    // activation tiles, adjacent in the stage, are ONE N = 256 operand (positions = TMEM columns):
+                    // an N=256 MMA fetches 12 KB of operands per 128 cycles, two N=128 MMAs 16 KB -- this kernel is bound
+                    // by shared-memory bandwidth (TMA writes + MMA operand fetch), measured
+                    const uint32_t w = a + 2 * A_BYTES;
 #pragma unroll
-                    for (int t = 0; t < 2; ++t)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(tmem + t * 128, umma_desc(a + t * A_BYTES + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                     IDESC_N128, (!init0 && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tmem, umma_desc(w + k * 32, 16, ATOM_BYTES), umma_desc(a + k * 32, 16, ATOM_BYTES), IDESC_N256,
+                                 (!init0 && k == 0) ? 0u : 1u);
                     init0 = true;
                 } else {
                     const uint32_t b = a + A_BYTES;
@@ -327,19 +330,18 @@ __global__ void __launch_bounds__(k2::N_THREADS, 1) k_neck_conv(const __grid_con
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         mbar_wait(&bars->done, 0, nullptr);
         tc_fence_after();
-        if (type1) {                                 // [part][tile][128][128] for the two tiles of the pair
+        if (type1) {                                 // TMEM lane = output channel, column = position: [part][tile][pos][128 oc]
+            const int oc = r;
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
-                float* out = p.partial1 + (((size_t)part * 2 * p.pairs + tile0 + t) * TILE + r) * 128;
+                float* out = p.partial1 + ((size_t)part * 2 * p.pairs + tile0 + t) * TILE * 128 + oc;
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     float v[32];
                     tmem_ld32(tmem + lane_addr + t * 128 + cc * 32, v);
-                    if (r < p.R) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(out + cc * 32 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (cc * 32 + j < p.R) out[(size_t)(cc * 32 + j) * 128] = v[j];          // a warp: 32 channels of one position
                 }
             }
         } else {                                     // [part][tile][128][384]: k8 | k4
@@ -566,10 +568,13 @@ int make_geometry(int n, int h, int w, int sms, Geometry& g) {
     g.YG = (g.ho + g.ny - 1) / g.ny; g.NG = (n + g.nb - 1) / g.nb;
     g.tiles = g.YG * g.NG; g.R = g.wo * g.ny * g.nb;
     g.pairs = (g.tiles + 1) / 2;
-    const double step16 = 720.0, step8 = 484.0, step4 = 734.0, fixed = 4000.0, hbm_bytes_per_cycle = 3500.0;
+    const double step16 = 800.0, step8 = 500.0, step4 = 750.0, fixed = 4000.0, hbm_bytes_per_cycle = 3500.0;
     double best_cost = -1.0;
+    static const int force1 = getenv("OETR_NECK_P1") ? atoi(getenv("OETR_NECK_P1")) : 0;      // experiments
+    static const int force2 = getenv("OETR_NECK_P2") ? atoi(getenv("OETR_NECK_P2")) : 0;
     for (int P1 : {1, 2, 4, 8, 16})
         for (int P2 : {1, 2, 4, 8}) {
+            if ((force1 && P1 != force1) || (force2 && P2 != force2)) continue;
             const double c1 = 1024.0 / P1 * step16 + fixed, c2 = (256.0 * step8 + 64.0 * step4) / P2 + fixed;
             const double bytes = 2.0 * ((double)P1 * 2 * g.pairs * TILE * 128 * 4 + (double)P2 * g.tiles * TILE * 384 * 4);
             const double cost = makespan((long)g.pairs * P1, c1, (long)g.tiles * P2, c2, sms) + bytes / hbm_bytes_per_cycle;
