@@ -568,7 +568,7 @@ int make_geometry(int n, int h, int w, int sms, Geometry& g) {
     g.YG = (g.ho + g.ny - 1) / g.ny; g.NG = (n + g.nb - 1) / g.nb;
     g.tiles = g.YG * g.NG; g.R = g.wo * g.ny * g.nb;
     g.pairs = (g.tiles + 1) / 2;
-    const double step16 = 800.0, step8 = 500.0, step4 = 750.0, fixed = 4000.0, hbm_bytes_per_cycle = 3500.0;
+    const double step16 = 1000.0, step8 = 500.0, step4 = 750.0, fixed = 40000.0, hbm_bytes_per_cycle = 2000.0;   // fitted to a sweep on B200
     double best_cost = -1.0;
     static const int force1 = getenv("OETR_NECK_P1") ? atoi(getenv("OETR_NECK_P1")) : 0;      // experiments
     static const int force2 = getenv("OETR_NECK_P2") ? atoi(getenv("OETR_NECK_P2")) : 0;
