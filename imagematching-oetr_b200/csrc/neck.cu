@@ -10,13 +10,13 @@
 //                [128 x 256] in TMEM, the epilogue adds the bias, applies the LayerNorm (two-pass statistics) and writes
 //                fp16 tokens in a PHASE-PLANAR layout xn[image][py][px][Y][X][256] (input pixel (2Y+py, 2X+px)), so that
 //                every tap of a stride-2 convolution is a dense, stride-1 box of one plane.
-//   k_neck_conv  the three convolutions as ONE implicit GEMM over the 16 x 16 tap grid of the largest kernel (the 8 x 8
-//                and 4 x 4 kernels are its centre taps): per (tap, 64-channel slab) the A operand is ONE TMA tensor load
-//                (cp.async.bulk.tensor.5d, SWIZZLE_128B, zero fill outside the plane = the convolution's padding) of the
-//                shifted box, the B operand one bulk copy of the tap's pre-swizzled weight tile; accumulators of the
-//                three convolutions sit side by side in TMEM (k16 | k8 | k4 = 128 + 128 + 256 columns).  Split-K: the
-//                units of a tile are dealt to P parts (P chosen so that tiles x P fills whole waves of 148 SMs); every
-//                part writes its fp32 partial sums.
+//   k_neck_conv  the three convolutions as implicit GEMMs over the 16 x 16 tap grid of the largest kernel (the 8 x 8
+//                and 4 x 4 kernels are its centre taps): per (tap, 64-channel slab) the activation operand is ONE TMA tensor
+//                load (cp.async.bulk.tensor.5d, SWIZZLE_128B, zero fill outside the plane = the convolution's padding) of
+//                the shifted box, the weight operand one bulk copy of the tap's pre-swizzled tile.  Items are cut by
+//                convolution (see k2::Unit): k16 on tile pairs with the weights as the M operand and both activation tiles
+//                as one N = 256 operand; k8 + k4 per tile.  Split-K parts per item type; every item writes its fp32
+//                partial sums.
 //   k_neck_out   sums the parts in fixed order (deterministic), adds the convolution biases, rounds to fp16 and runs the
 //                512 -> 256 projection on the tensor cores; writes feat [n,256,h/2,w/2] fp32 NCHW (the reference's
 //                feature_extraction output, and what oetr_forward reads).
