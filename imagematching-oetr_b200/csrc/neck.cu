@@ -57,16 +57,16 @@ constexpr int MAX_PARTS = 16;
 // ---------------------------------------------------------------------------------------------------------
 namespace k1 {
 // persistent CTAs (one per SM), warp-specialised so that the HBM stream never stops:
-//   warps 0-7   loaders: 128 tokens x 64 channels of the NCHW fp32 features per k-slab, transposed on the fly into a K-major
-//               fp16 operand slab (thread = token row x 32 channels; a warp's lanes read 32 consecutive tokens of one
-//               channel: 128 B, coalesced); the loads of the next slab are in flight while the current one is stored, and
-//               the slab sequence runs on across tile boundaries
-//   warps 8-11  epilogue: one thread per token row (TMEM lane): bias, LayerNorm (exact two-pass statistics over the 256
+//   warps 0-15  loaders: 128 tokens x 64 channels of the NCHW fp32 features per k-slab, transposed on the fly into a K-major
+//               fp16 operand slab (thread = token row x 16 channels; a warp's lanes read 32 consecutive tokens of one
+//               channel: 128 B, coalesced); the loads of two slabs ahead are in flight while the current one is stored
+//               (64 KB per SM; a third slab would spill at 704 threads), and the slab sequence runs on across tile boundaries
+//   warps 16-19 epilogue: one thread per token row (TMEM lane): bias, LayerNorm (exact two-pass statistics over the 256
 //               channels of the row: three reads of the accumulator), fp16 tokens to the phase-planar layout
-//   warp 12     MMA issue; the [128 x 256] accumulator is double-buffered in TMEM, so tile i + 1 is multiplied while tile i
+//   warp 20     MMA issue; the [128 x 256] accumulator is double-buffered in TMEM, so tile i + 1 is multiplied while tile i
 //               is normalised and stored
-//   warp 13     weight stream (the same 16 k-slabs of 32 KB for every tile, L2-resident)
-constexpr int N_LOAD = 256, N_EPI = 128, W_EPI0 = 8, W_MMA = 12, W_PROD = 13, N_THREADS = 448;
+//   warp 21     weight stream (the same 16 k-slabs of 32 KB for every tile, L2-resident)
+constexpr int N_LOAD = 512, N_EPI = 128, W_EPI0 = 16, W_MMA = 20, W_PROD = 21, N_THREADS = 704;
 constexpr int KS = CB / 64;                      // 16 k-slabs
 constexpr int A_SLOTS = 4, W_SLOTS = 3;
 constexpr uint32_t SM_A = 0;
@@ -140,38 +140,35 @@ __global__ void __launch_bounds__(k1::N_THREADS, 1) k_neck_proj(const k1::Params
         __syncwarp();
     } else if (warp < W_EPI0) {
         // ---- loaders
-        const int r = tid & 127, half = tid >> 7;                // token row of the tile, channels half * 32 .. of the slab
+        const int r = tid & 127, cq = tid >> 7;                  // token row of the tile, channels cq * 16 .. of the slab
         const size_t T = (size_t)p.T;
-        float cur[32], nxt[32];
-        auto src_of = [&](int g, bool& valid) {                  // first of this thread's 32 channel values of slab g
+        const int total = my_tiles * KS;
+        float buf[3][16];
+        auto load = [&](float (&dst)[16], int g) {               // this thread's 16 channel values of slab g
             const int tile = (int)blockIdx.x + (g / KS) * (int)gridDim.x, ks = g % KS;
             const int img = tile / p.tiles_per_img, l = (tile % p.tiles_per_img) * TILE + r;
-            valid = l < p.T;
-            return p.X + ((size_t)img * CB + ks * 64 + half * 32) * T + (valid ? l : 0);
+            const bool valid = l < p.T;
+            const float* src = p.X + ((size_t)img * CB + ks * 64 + cq * 16) * T + (valid ? l : 0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = valid ? __ldg(src + (size_t)j * T) : 0.f;
         };
-        const int total = my_tiles * KS;
-        if (total > 0) {
-            bool v;
-            const float* s0 = src_of(0, v);
+        if (total > 0) load(buf[0], 0);
+        if (total > 1) load(buf[1], 1);
+        for (int g0 = 0; g0 < total; g0 += 3) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = v ? __ldg(s0 + (size_t)j * T) : 0.f;
-        }
-        for (int g = 0; g < total; ++g) {
-            if (g + 1 < total) {
-                bool v;
-                const float* s1 = src_of(g + 1, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) nxt[j] = v ? __ldg(s1 + (size_t)j * T) : 0.f;
+            for (int u = 0; u < 3; ++u) {
+                const int g = g0 + u;
+                if (g < total) {
+                    if (g + 2 < total) load(buf[(u + 2) % 3], g + 2);
+                    const int sa = g % A_SLOTS;
+                    if (g >= A_SLOTS) mbar_wait(&bars->a_free[sa], ((g / A_SLOTS) - 1) & 1, nullptr);
+                    uint8_t* slab = smem + SM_A + sa * SLAB;
+                    *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2)) = pack8_f16(&buf[u][0]);
+                    *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2 + 1)) = pack8_f16(&buf[u][8]);
+                    fence_async_smem();
+                    mbar_arrive(&bars->a_full[sa]);
+                }
             }
-            const int sa = g % A_SLOTS;
-            if (g >= A_SLOTS) mbar_wait(&bars->a_free[sa], ((g / A_SLOTS) - 1) & 1, nullptr);
-            uint8_t* slab = smem + SM_A + sa * SLAB;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, half * 4 + j)) = pack8_f16(&cur[8 * j]);
-            fence_async_smem();
-            mbar_arrive(&bars->a_full[sa]);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
         }
     } else {
         // ---- epilogue: thread = token row (TMEM lane), all 256 channels in chunks of 32
