@@ -5,10 +5,10 @@
 //     concatenated                                       src/models/backbone.py:28-67
 //     input_proj2 (1x1, 512 -> 256)                      src/model.py:48-50,123-124
 // as three kernels:
-//   k_neck_proj  persistent CTAs over tiles of 128 tokens: loader warps transpose the NCHW fp32 backbone features on the fly
-//                into K-major fp16 operand slabs (4-slot ring), the 1x1 weights stream through a bulk-copy ring, tcgen05
-//                accumulates [128 x 256] in a double-buffered TMEM accumulator, epilogue warps add the bias, apply the
-//                LayerNorm (two-pass statistics) and write fp16 tokens in a PHASE-PLANAR layout xn[image][py][px][Y][X][256] (input pixel (2Y+py, 2X+px)), so that
+//   k_neck_proj  one CTA per 128 tokens: the NCHW fp32 backbone features are transposed on the fly into K-major fp16
+//                operand slabs (4-slot ring), the 1x1 weights stream through a bulk-copy ring, tcgen05 accumulates
+//                [128 x 256] in TMEM, the epilogue adds the bias, applies the LayerNorm (two-pass statistics) and writes
+//                fp16 tokens in a PHASE-PLANAR layout xn[image][py][px][Y][X][256] (input pixel (2Y+py, 2X+px)), so that
 //                every tap of a stride-2 convolution is a dense, stride-1 box of one plane.
 //   k_neck_conv  the three convolutions as implicit GEMMs over the 16 x 16 tap grid of the largest kernel (the 8 x 8
 //                and 4 x 4 kernels are its centre taps): per (tap, 64-channel slab) the activation operand is ONE TMA tensor
@@ -56,25 +56,16 @@ constexpr int MAX_PARTS = 16;
 // k_neck_proj
 // ---------------------------------------------------------------------------------------------------------
 namespace k1 {
-// persistent CTAs (one per SM), warp-specialised so that the HBM stream never stops:
-//   warps 0-15  loaders: 128 tokens x 64 channels of the NCHW fp32 features per k-slab, transposed on the fly into a K-major
-//               fp16 operand slab (thread = token row x 16 channels; a warp's lanes read 32 consecutive tokens of one
-//               channel: 128 B, coalesced); the loads of two slabs ahead are in flight while the current one is stored
-//               (64 KB per SM; a third slab would spill at 704 threads), and the slab sequence runs on across tile boundaries
-//   warps 16-19 epilogue: one thread per token row (TMEM lane): bias, LayerNorm (exact two-pass statistics over the 256
-//               channels of the row: three reads of the accumulator), fp16 tokens to the phase-planar layout
-//   warp 20     MMA issue; the [128 x 256] accumulator is double-buffered in TMEM, so tile i + 1 is multiplied while tile i
-//               is normalised and stored
-//   warp 21     weight stream (the same 16 k-slabs of 32 KB for every tile, L2-resident)
-constexpr int N_LOAD = 512, N_EPI = 128, W_EPI0 = 16, W_MMA = 20, W_PROD = 21, N_THREADS = 704;
+constexpr int N_ROW = 512, N_THREADS = 576, W_PROD = 16, W_MMA = 17;
 constexpr int KS = CB / 64;                      // 16 k-slabs
 constexpr int A_SLOTS = 4, W_SLOTS = 3;
 constexpr uint32_t SM_A = 0;
 constexpr uint32_t SM_W = SM_A + A_SLOTS * SLAB;
-constexpr uint32_t SM_BAR = SM_W + W_SLOTS * WUNIT;
+constexpr uint32_t SM_RED = SM_W + W_SLOTS * WUNIT;             // float[2][128][4]: LayerNorm partial sums
+constexpr uint32_t SM_BAR = SM_RED + 2 * 128 * 4 * 4;
 constexpr uint32_t SM_TOTAL = SM_BAR + 256;
 struct Bars {
-    uint64_t a_full[A_SLOTS], a_free[A_SLOTS], w_full[W_SLOTS], w_empty[W_SLOTS], acc_full[2], acc_free[2];
+    uint64_t a_full[A_SLOTS], a_free[A_SLOTS], w_full[W_SLOTS], w_empty[W_SLOTS], s_full;
     uint32_t tmem, pad;
 };
 static_assert(sizeof(Bars) <= 256, "Bars");
@@ -83,9 +74,14 @@ struct Params {
     const __half* w_img;     // [16 ks][256 n][64 k] swizzled
     const float *bias, *gamma, *beta;
     __half* xn;              // [n][4][Hh][Wh][256]
-    int n, h, w, T, tiles_per_img, Hh, Wh, tiles;
+    int n, h, w, T, tiles_per_img, Hh, Wh;
 };
 }  // namespace k1
+
+__device__ __forceinline__ void load16(const float* __restrict__ src, size_t cstride, bool valid, float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = valid ? __ldg(src + (size_t)j * cstride) : 0.f;
+}
 
 __global__ void __launch_bounds__(k1::N_THREADS, 1) k_neck_proj(const k1::Params p) {
     using namespace k1;
@@ -93,139 +89,122 @@ __global__ void __launch_bounds__(k1::N_THREADS, 1) k_neck_proj(const k1::Params
     Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = smem_u32(smem);
+    const int img = blockIdx.x / p.tiles_per_img, l0 = (blockIdx.x % p.tiles_per_img) * TILE;
     if (tid == 0) {
-        for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&bars->a_full[i], N_LOAD); mbar_init(&bars->a_free[i], 1); }
+        for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&bars->a_full[i], N_ROW); mbar_init(&bars->a_free[i], 1); }
         for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_free[i], N_EPI); }
+        mbar_init(&bars->s_full, 1);
         fence_mbar_init();
     }
-    if (warp == W_MMA) tmem_alloc(&bars->tmem, 512);
+    if (warp == W_PROD) tmem_alloc(&bars->tmem, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem;
-    const int my_tiles = ((int)blockIdx.x < p.tiles) ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == W_PROD) {
         if (lane == 0) {
-            for (int g = 0; g < my_tiles * KS; ++g) {
-                const int st = g % W_SLOTS;
-                if (g >= W_SLOTS) mbar_wait(&bars->w_empty[st], ((g / W_SLOTS) - 1) & 1, nullptr);
+            for (int ks = 0; ks < KS; ++ks) {
+                const int st = ks % W_SLOTS;
+                if (ks >= W_SLOTS) mbar_wait(&bars->w_empty[st], ((ks / W_SLOTS) - 1) & 1, nullptr);
                 mbar_arrive_expect_tx(&bars->w_full[st], WUNIT);
-                bulk_g2s(smem + SM_W + st * WUNIT, p.w_img + (size_t)(g % KS) * (WUNIT / 2), WUNIT, &bars->w_full[st]);
+                bulk_g2s(smem + SM_W + st * WUNIT, p.w_img + (size_t)ks * (WUNIT / 2), WUNIT, &bars->w_full[st]);
             }
         }
         __syncwarp();
     } else if (warp == W_MMA) {
         if (lane == 0) {
-            for (int it = 0; it < my_tiles; ++it) {
-                const int par = it & 1;
-                if (it >= 2) { mbar_wait(&bars->acc_free[par], ((it >> 1) - 1) & 1, nullptr); tc_fence_after(); }
-                for (int ks = 0; ks < KS; ++ks) {
-                    const int g = it * KS + ks, sa = g % A_SLOTS, sw = g % W_SLOTS;
-                    mbar_wait(&bars->a_full[sa], (g / A_SLOTS) & 1, nullptr);
-                    mbar_wait(&bars->w_full[sw], (g / W_SLOTS) & 1, nullptr);
-                    tc_fence_after();
-                    const uint32_t a = smem_base + SM_A + sa * SLAB, b = smem_base + SM_W + sw * WUNIT;
+            for (int ks = 0; ks < KS; ++ks) {
+                const int sa = ks % A_SLOTS, sw = ks % W_SLOTS;
+                mbar_wait(&bars->a_full[sa], (ks / A_SLOTS) & 1, nullptr);
+                mbar_wait(&bars->w_full[sw], (ks / W_SLOTS) & 1, nullptr);
+                tc_fence_after();
+                const uint32_t a = smem_base + SM_A + sa * SLAB, b = smem_base + SM_W + sw * WUNIT;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem + par * 256, umma_desc(a + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES),
-                                 IDESC_N256, (ks > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&bars->a_free[sa]);
-                    umma_commit(&bars->w_empty[sw]);
-                }
-                umma_commit(&bars->acc_full[par]);
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tmem, umma_desc(a + k * 32, 16, ATOM_BYTES), umma_desc(b + k * 32, 16, ATOM_BYTES), IDESC_N256,
+                             (ks > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&bars->a_free[sa]);
+                umma_commit(&bars->w_empty[sw]);
             }
+            umma_commit(&bars->s_full);
         }
         __syncwarp();
-    } else if (warp < W_EPI0) {
-        // ---- loaders
-        const int r = tid & 127, cq = tid >> 7;                  // token row of the tile, channels cq * 16 .. of the slab
-        const size_t T = (size_t)p.T;
-        const int total = my_tiles * KS;
-        float buf[3][16];
-        auto load = [&](float (&dst)[16], int g) {               // this thread's 16 channel values of slab g
-            const int tile = (int)blockIdx.x + (g / KS) * (int)gridDim.x, ks = g % KS;
-            const int img = tile / p.tiles_per_img, l = (tile % p.tiles_per_img) * TILE + r;
-            const bool valid = l < p.T;
-            const float* src = p.X + ((size_t)img * CB + ks * 64 + cq * 16) * T + (valid ? l : 0);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) dst[j] = valid ? __ldg(src + (size_t)j * T) : 0.f;
-        };
-        if (total > 0) load(buf[0], 0);
-        if (total > 1) load(buf[1], 1);
-        for (int g0 = 0; g0 < total; g0 += 3) {
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int g = g0 + u;
-                if (g < total) {
-                    if (g + 2 < total) load(buf[(u + 2) % 3], g + 2);
-                    const int sa = g % A_SLOTS;
-                    if (g >= A_SLOTS) mbar_wait(&bars->a_free[sa], ((g / A_SLOTS) - 1) & 1, nullptr);
-                    uint8_t* slab = smem + SM_A + sa * SLAB;
-                    *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2)) = pack8_f16(&buf[u][0]);
-                    *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2 + 1)) = pack8_f16(&buf[u][8]);
-                    fence_async_smem();
-                    mbar_arrive(&bars->a_full[sa]);
-                }
-            }
-        }
     } else {
-        // ---- epilogue: thread = token row (TMEM lane), all 256 channels in chunks of 32
-        const int q = warp - W_EPI0, r = q * 32 + lane;
+        const int q = warp & 3, cq = warp >> 2;
+        const int r = q * 32 + lane;
+        const int l = l0 + r;
+        const bool valid = l < p.T;
+        // operand slabs: this thread converts 16 channels (cq*16 ..) of token row r per k-slab; a warp's 32 lanes read 32
+        // consecutive tokens of one channel (128 B, coalesced).  Loads run two slabs ahead of the stores.
+        const float* src = p.X + ((size_t)img * CB + cq * 16) * p.T + (valid ? l : 0);
+        const size_t T = (size_t)p.T;
+        float buf[3][16];
+        load16(src, T, valid, buf[0]);
+        load16(src + 64 * T, T, valid, buf[1]);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            if (ks + 2 < KS) load16(src + (size_t)(ks + 2) * 64 * T, T, valid, buf[(ks + 2) % 3]);
+            const int sa = ks % A_SLOTS;
+            if (ks >= A_SLOTS) mbar_wait(&bars->a_free[sa], ((ks / A_SLOTS) - 1) & 1, nullptr);
+            uint8_t* slab = smem + SM_A + sa * SLAB;
+            *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2)) = pack8_f16(&buf[ks % 3][0]);
+            *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2 + 1)) = pack8_f16(&buf[ks % 3][8]);
+            fence_async_smem();
+            mbar_arrive(&bars->a_full[sa]);
+        }
+        // epilogue: bias, LayerNorm over the 256 channels of the token (this thread: channels cq*64 .. +64)
+        mbar_wait(&bars->s_full, 0, nullptr);
+        tc_fence_after();
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int par = it & 1, tile = (int)blockIdx.x + it * (int)gridDim.x;
-            const int img = tile / p.tiles_per_img, l = (tile % p.tiles_per_img) * TILE + r;
-            const bool valid = l < p.T;
-            const uint32_t acc = tmem + par * 256 + lane_addr;
-            mbar_wait(&bars->acc_full[par], (it >> 1) & 1, nullptr);
-            tc_fence_after();
-            float s = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < 8; ++cc) {
-                float v[32];
-                tmem_ld32(acc + cc * 32, v);
+        float v0[32], v1[32];
+        tmem_ld32x2_adj(tmem + lane_addr + cq * 64, v0, v1);
+        tc_fence_before();
+        float* red_s = reinterpret_cast<float*>(smem + SM_RED);
+        float* red_m = red_s + 128 * 4;
+        float s = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s += v[i] + __ldg(p.bias + cc * 32 + i);
-            }
-            const float mean = s * (1.f / C);
-            float m2 = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < 8; ++cc) {
-                float v[32];
-                tmem_ld32(acc + cc * 32, v);
+        for (int i = 0; i < 32; ++i) {
+            v0[i] += __ldg(p.bias + cq * 64 + i);
+            v1[i] += __ldg(p.bias + cq * 64 + 32 + i);
+            s += v0[i] + v1[i];
+        }
+        red_s[r * 4 + cq] = s;
+        named_bar_sync(1, N_ROW);
+        const float4 s4 = *reinterpret_cast<const float4*>(red_s + r * 4);
+        const float mean = (s4.x + s4.y + s4.z + s4.w) * (1.f / C);
+        float m2 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { const float d = v[i] + __ldg(p.bias + cc * 32 + i) - mean; m2 = fmaf(d, d, m2); }
-            }
-            const float rstd = rsqrtf(m2 * (1.f / C) + LN_EPS);
-            __half* dst = nullptr;
-            if (valid) {
-                const int iy = l / p.w, ix = l - iy * p.w;
-                const int ph = (iy & 1) * 2 + (ix & 1);
-                dst = p.xn + ((((size_t)img * 4 + ph) * p.Hh + (iy >> 1)) * p.Wh + (ix >> 1)) * C;
-            }
-#pragma unroll 1
-            for (int cc = 0; cc < 8; ++cc) {
-                float v[32];
-                tmem_ld32(acc + cc * 32, v);
+        for (int i = 0; i < 32; ++i) {
+            const float d0 = v0[i] - mean, d1 = v1[i] - mean;
+            m2 = fmaf(d0, d0, m2);
+            m2 = fmaf(d1, d1, m2);
+        }
+        red_m[r * 4 + cq] = m2;
+        named_bar_sync(1, N_ROW);
+        const float4 m4 = *reinterpret_cast<const float4*>(red_m + r * 4);
+        const float rstd = rsqrtf((m4.x + m4.y + m4.z + m4.w) * (1.f / C) + LN_EPS);
+        if (valid) {
+            const int iy = l / p.w, ix = l - iy * p.w;
+            const int ph = (iy & 1) * 2 + (ix & 1);
+            __half* dst = p.xn + ((((size_t)img * 4 + ph) * p.Hh + (iy >> 1)) * p.Wh + (ix >> 1)) * C + cq * 64;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float y[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int c = cc * 32 + i;
-                    v[i] = fmaf((v[i] + __ldg(p.bias + c) - mean) * rstd, __ldg(p.gamma + c), __ldg(p.beta + c));
+                    const int c = cq * 64 + half * 32 + i;
+                    const float x = half ? v1[i] : v0[i];
+                    y[i] = fmaf((x - mean) * rstd, __ldg(p.gamma + c), __ldg(p.beta + c));
                 }
-                if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + cc * 32 + j * 8) = pack8_f16(&v[j * 8]);
-                }
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + half * 32 + j * 8) = pack8_f16(&y[j * 8]);
             }
-            tc_fence_before();
-            mbar_arrive(&bars->acc_free[par]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA) tmem_dealloc(tmem, 512);
+    if (warp == W_PROD) tmem_dealloc(tmem, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -813,8 +792,7 @@ int oetr_neck_forward(oetr_neck* h, const float* backbone_out, int n_images, int
         k1::Params p;
         p.X = backbone_out; p.w_img = h->w1_img; p.bias = h->vec; p.gamma = h->vec + 256; p.beta = h->vec + 512; p.xn = xn;
         p.n = g.n; p.h = g.h; p.w = g.w; p.T = g.T; p.tiles_per_img = g.tiles_per_img; p.Hh = g.Hh; p.Wh = g.Wh;
-        p.tiles = g.n * g.tiles_per_img;
-        k_neck_proj<<<p.tiles < h->sms ? p.tiles : h->sms, k1::N_THREADS, k1::SM_TOTAL, s>>>(p);
+        k_neck_proj<<<g.n * g.tiles_per_img, k1::N_THREADS, k1::SM_TOTAL, s>>>(p);
         NCU(cudaGetLastError());
         ++launches;
     }
