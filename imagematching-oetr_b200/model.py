@@ -219,16 +219,18 @@ class OETR(nn.Module):
     def feature_extraction(self, image1, image2, mask1=None, mask2=None):
         """backbone -> input_proj -> patchmerging -> input_proj2 for both images and the position encodings: the
         reference's 8-tuple (feat1, feat2, pos1, pos2, hf1, wf1, hf2, wf2), model.py:109-130."""
-        x1, x2 = self.backbone(image1), self.backbone(image2)
         if self.neck_mode == "cuda" and not (torch.is_grad_enabled() and self.training):
-            if x1.shape == x2.shape:                         # one launch sequence for both image sets
-                f = self.neck_path.forward(torch.cat([x1, x2], dim=0))
-                feat1, feat2 = f[: x1.shape[0]], f[x1.shape[0]:]
+            if image1.shape == image2.shape:
+                # both image sets through the trunk and the neck as ONE batch (eval-mode BatchNorm: samples are independent);
+                # concatenating the images (157 MB at batch 32) is cheap, concatenating the 1024-channel features is not
+                n = image1.shape[0]
+                f = self.neck_path.forward(self.backbone(torch.cat([image1, image2], dim=0)))
+                feat1, feat2 = f[:n], f[n:]
             else:
-                feat1, feat2 = self.neck_path.forward(x1), self.neck_path.forward(x2)
+                feat1, feat2 = self.neck_path.forward(self.backbone(image1)), self.neck_path.forward(self.backbone(image2))
         else:
-            feat1 = self.input_proj2(self.patchmerging(self.input_proj(x1)))
-            feat2 = self.input_proj2(self.patchmerging(self.input_proj(x2)))
+            feat1 = self.input_proj2(self.patchmerging(self.input_proj(self.backbone(image1))))
+            feat2 = self.input_proj2(self.patchmerging(self.input_proj(self.backbone(image2))))
         hf1, wf1 = feat1.shape[2:]
         hf2, wf2 = feat2.shape[2:]
         return feat1, feat2, self.pos_encoding(feat1), self.pos_encoding(feat2), hf1, wf1, hf2, wf2
