@@ -120,12 +120,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             if (p.do_kv) {
                 if (!dec_mode) {
                     gemm(T, false, true, T_ALL);            umma_commit(&bars->s_full[0]);   // v
-                    if (p.do_q && p.store_x) {              // the row warps re-read the residual stream from XA for the
-                        const long long t0 = clock64();     // global store while v is multiplied: XA is free once they have
-                        mbar_wait(&bars->s_free, 1, p.flag);
-                        ms.t_a += clock64() - t0;
-                        tc_fence_after();
-                    }
                     gemm(XA, false, false, T_HH | T_LH);    umma_commit(&bars->s_full[1]);   // k (same image)
                 } else {
                     gemm(T, false, true, T_HH | T_HL);      umma_commit(&bars->s_full[0]);   // v = x Wv^T
@@ -436,22 +430,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             load_acc(XA, x);
             stamp(10);
         }
-        // With a query phase before and a source phase after, the store of the residual stream leaves the critical path:
-        // the LN_kv image goes out first (the v GEMM starts), then the row is re-read from XA -- still intact: the k GEMM that
-        // overwrites XA waits for s_free -- and stored to global memory while the tensor core works.
-        const bool late_store = p.store_x && p.do_q && p.do_kv && !dec_mode;
-        if (p.store_x && !late_store) store_x(x);
+        if (p.store_x) store_x(x);
         stamp(11);
         if (p.do_kv) {
             if (!dec_mode) {
                 ln_image(x, p.lnkv_g, p.lnkv_b, true, true);   // k and v share LN_kv(x)+pos (transformer.py:119-126)
                 stamp(12);
-                if (late_store) {
-                    load_acc(XA, x);
-                    tc_fence_before();
-                    mbar_arrive(&bars->s_free);
-                    store_x(x);
-                }
                 wait_s(0);
                 wait_s(1);
             } else {
