@@ -135,73 +135,23 @@ __global__ void __launch_bounds__(k1::N_THREADS, 1) k_neck_proj(const k1::Params
         const int r = q * 32 + lane;
         const int l = l0 + r;
         const bool valid = l < p.T;
+        // operand slabs: this thread converts 16 channels (cq*16 ..) of token row r per k-slab; a warp's 32 lanes read 32
+        // consecutive tokens of one channel (128 B, coalesced).  Loads run two slabs ahead of the stores.
+        const float* src = p.X + ((size_t)img * CB + cq * 16) * p.T + (valid ? l : 0);
         const size_t T = (size_t)p.T;
-        if ((p.T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0) {
-            // operand slabs, 16-byte loads along the token axis.  Lane = (token quad tq_l = lane & 7, channel quad cql =
-            // lane >> 3), warp = (token block tb = warp & 3: 32 tokens, channel block cb = warp >> 2: 16 channels): a load
-            // instruction reads four channels x 128 contiguous bytes, and a slab takes 4 instructions per thread instead of
-            // 16 (the 4-byte version ran into lg_throttle).  Each thread then holds 4 tokens x 4 channels; lane pairs
-            // (cql, cql ^ 1) swap halves so that each ends up with 2 tokens x 8 channels = two 16-byte chunks of the
-            // K-major slab (4-way bank conflicts, the minimum for 16-byte stores).
-            const int tq_l = lane & 7, cql = lane >> 3, tb = warp & 3, cb = warp >> 2;
-            const int tok0 = tb * 32 + tq_l * 4;                         // first of this thread's four token rows
-            const bool ok = l0 + tok0 < p.T;                             // T % 4 == 0: a quad is all valid or all invalid
-            const float* src4 = p.X + ((size_t)img * CB + cb * 16 + cql * 4) * T + (ok ? l0 + tok0 : 0);
-            float4 buf4[3][4];
-            auto load4 = [&](float4 (&dst)[4], int ks) {
+        float buf[3][16];
+        load16(src, T, valid, buf[0]);
+        load16(src + 64 * T, T, valid, buf[1]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    dst[j] = ok ? __ldg(reinterpret_cast<const float4*>(src4 + ((size_t)ks * 64 + j) * T)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            load4(buf4[0], 0);
-            load4(buf4[1], 1);
-            const bool odd = cql & 1;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                if (ks + 2 < KS) load4(buf4[(ks + 2) % 3], ks + 2);
-                const float4(&b)[4] = buf4[ks % 3];                      // b[j] = channel j, tokens 0..3 (x, y, z, w)
-                // even lane keeps tokens 0,1 and receives the partner's channels for them; odd lane keeps tokens 2,3
-                float mine[2][4], theirs[2][4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float k0 = odd ? b[j].z : b[j].x, k1 = odd ? b[j].w : b[j].y;     // kept tokens
-                    const float s0 = odd ? b[j].x : b[j].z, s1 = odd ? b[j].y : b[j].w;     // sent tokens
-                    mine[0][j] = k0; mine[1][j] = k1;
-                    theirs[0][j] = __shfl_xor_sync(0xffffffffu, s0, 8);
-                    theirs[1][j] = __shfl_xor_sync(0xffffffffu, s1, 8);
-                }
-                const int sa = ks % A_SLOTS;
-                if (ks >= A_SLOTS) mbar_wait(&bars->a_free[sa], ((ks / A_SLOTS) - 1) & 1, nullptr);
-                uint8_t* slab = smem + SM_A + sa * SLAB;
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    float v8[8];                                         // channels (cql & ~1) * 4 .. + 8 of this token, in order
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { v8[j] = odd ? theirs[t][j] : mine[t][j]; v8[4 + j] = odd ? mine[t][j] : theirs[t][j]; }
-                    const int row = tok0 + (odd ? 2 : 0) + t;
-                    *reinterpret_cast<uint4*>(slab + slab_chunk_off(row, cb * 2 + (cql >> 1))) = pack8_f16(v8);
-                }
-                fence_async_smem();
-                mbar_arrive(&bars->a_full[sa]);
-            }
-        } else {
-            // operand slabs, general path: this thread converts 16 channels (cq*16 ..) of token row r per k-slab; a warp's 32
-            // lanes read 32 consecutive tokens of one channel (128 B, coalesced).  Loads run two slabs ahead of the stores.
-            const float* src = p.X + ((size_t)img * CB + cq * 16) * p.T + (valid ? l : 0);
-            float buf[3][16];
-            load16(src, T, valid, buf[0]);
-            load16(src + 64 * T, T, valid, buf[1]);
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                if (ks + 2 < KS) load16(src + (size_t)(ks + 2) * 64 * T, T, valid, buf[(ks + 2) % 3]);
-                const int sa = ks % A_SLOTS;
-                if (ks >= A_SLOTS) mbar_wait(&bars->a_free[sa], ((ks / A_SLOTS) - 1) & 1, nullptr);
-                uint8_t* slab = smem + SM_A + sa * SLAB;
-                *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2)) = pack8_f16(&buf[ks % 3][0]);
-                *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2 + 1)) = pack8_f16(&buf[ks % 3][8]);
-                fence_async_smem();
-                mbar_arrive(&bars->a_full[sa]);
-            }
+        for (int ks = 0; ks < KS; ++ks) {
+            if (ks + 2 < KS) load16(src + (size_t)(ks + 2) * 64 * T, T, valid, buf[(ks + 2) % 3]);
+            const int sa = ks % A_SLOTS;
+            if (ks >= A_SLOTS) mbar_wait(&bars->a_free[sa], ((ks / A_SLOTS) - 1) & 1, nullptr);
+            uint8_t* slab = smem + SM_A + sa * SLAB;
+            *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2)) = pack8_f16(&buf[ks % 3][0]);
+            *reinterpret_cast<uint4*>(slab + slab_chunk_off(r, cq * 2 + 1)) = pack8_f16(&buf[ks % 3][8]);
+            fence_async_smem();
+            mbar_arrive(&bars->a_full[sa]);
         }
         // epilogue: bias, LayerNorm over the 256 channels of the token (this thread: channels cq*64 .. +64)
         mbar_wait(&bars->s_full, 0, nullptr);
