@@ -163,17 +163,25 @@ class SuperGlue(nn.Module):
         mdesc0, mdesc1 = self.final_proj(desc0), self.final_proj(desc1)
         scores = torch.einsum("bdn,bdm->bnm", mdesc0, mdesc1) / 256 ** 0.5
         scores = log_optimal_transport(scores, self.bin_score, iters=self.config["sinkhorn_iterations"])
-        max0, max1 = scores[:, :-1, :-1].max(2), scores[:, :-1, :-1].max(1)
-        indices0, indices1 = max0.indices, max1.indices
-        ar0 = torch.arange(indices0.shape[1], device=indices0.device)[None]
-        ar1 = torch.arange(indices1.shape[1], device=indices1.device)[None]
-        mutual0 = ar0 == indices1.gather(1, indices0)
-        mutual1 = ar1 == indices0.gather(1, indices1)
-        zero = scores.new_tensor(0)
-        mscores0 = torch.where(mutual0, max0.values.exp(), zero)
-        mscores1 = torch.where(mutual1, mscores0.gather(1, indices1), zero)
-        valid0 = mutual0 & (mscores0 > self.config["match_threshold"])
-        valid1 = mutual1 & valid0.gather(1, indices1)
-        return {"matches0": torch.where(valid0, indices0, indices0.new_tensor(-1)),
-                "matches1": torch.where(valid1, indices1, indices1.new_tensor(-1)),
-                "matching_scores0": mscores0, "matching_scores1": mscores1, "scores": scores}
+        m0, m1, s0, s1 = mutual_matches(scores, self.config["match_threshold"])
+        return {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1, "scores": scores}
+
+
+def mutual_matches(log_assignment, threshold):
+    """The decision rule of reference superglue.py:268-282 on the [b, m+1, n+1] log assignment matrix: keypoint i of image
+    0 and j of image 1 match when each is the other's arg-max over the non-dustbin block and exp(score) exceeds the
+    threshold; -1 marks unmatched keypoints.  Returns (matches0 [b,m], matches1 [b,n], scores0, scores1)."""
+    block = log_assignment[:, :-1, :-1]
+    best_for_0 = block.max(dim=2)                     # per keypoint of image 0: best partner in image 1
+    best_for_1 = block.max(dim=1)
+    j_of_i, i_of_j = best_for_0.indices, best_for_1.indices
+    rows = torch.arange(j_of_i.shape[1], device=block.device).expand_as(j_of_i)
+    cols = torch.arange(i_of_j.shape[1], device=block.device).expand_as(i_of_j)
+    agree0 = i_of_j.gather(1, j_of_i) == rows          # i -> j -> back to i
+    agree1 = j_of_i.gather(1, i_of_j) == cols
+    conf0 = best_for_0.values.exp() * agree0
+    conf1 = conf0.gather(1, i_of_j) * agree1
+    keep0 = agree0 & (conf0 > threshold)
+    keep1 = agree1 & keep0.gather(1, i_of_j)
+    unmatched = j_of_i.new_full((), -1)
+    return torch.where(keep0, j_of_i, unmatched), torch.where(keep1, i_of_j, unmatched), conf0, conf1
