@@ -112,17 +112,32 @@ class AttentionalPropagation(nn.Module):
 
 
 class AttentionalGNN(nn.Module):
+    """reference superglue.py:123-140.  Every layer's Conv1d / BatchNorm1d is pointwise along the keypoint axis and both
+    images use the same weights, so the two descriptor sets travel as ONE tensor [b, 256, n0 + n1]: per layer three
+    projections, one merge and one MLP call instead of twice as many (the forward is launch-bound: ~10 small kernels per
+    layer instead of ~24), and only the attention itself runs per image (self: own keys; cross: the other image's keys)."""
+
     def __init__(self, feature_dim, layer_names):
         super().__init__()
         self.layers = nn.ModuleList([AttentionalPropagation(feature_dim, 4) for _ in layer_names])
         self.names = list(layer_names)
 
     def forward(self, desc0, desc1):
+        b, n0 = desc0.size(0), desc0.size(2)
+        x = torch.cat([desc0, desc1], dim=2)
         for layer, name in zip(self.layers, self.names):
-            src0, src1 = (desc1, desc0) if name == "cross" else (desc0, desc1)
-            delta0, delta1 = layer(desc0, src0), layer(desc1, src1)
-            desc0, desc1 = desc0 + delta0, desc1 + delta1
-        return desc0, desc1
+            att = layer.attn
+            q, k, v = [proj(x).view(b, att.dim, att.num_heads, -1) for proj in att.proj]
+            q0, q1 = q[..., :n0].contiguous(), q[..., n0:].contiguous()
+            k0, k1 = k[..., :n0].contiguous(), k[..., n0:].contiguous()
+            v0, v1 = v[..., :n0].contiguous(), v[..., n0:].contiguous()
+            if name == "cross":
+                m0, m1 = attention(q0, k1, v1), attention(q1, k0, v0)
+            else:
+                m0, m1 = attention(q0, k0, v0), attention(q1, k1, v1)
+            message = att.merge(torch.cat([m0, m1], dim=3).view(b, att.dim * att.num_heads, -1))
+            x = x + layer.mlp(torch.cat([x, message], dim=1))
+        return x[..., :n0], x[..., n0:]
 
 
 class SuperGlue(nn.Module):
