@@ -34,14 +34,6 @@ struct EncParams {
     int dec_mode;               // decoder: k = (x+pos) Wk^T + bk, v = x Wv^T + bv, no LayerNorm (transformer.py:243-249)
     const __half* w_kv;         // Wv | Wk
     float* kv_part;             // [tiles][ppt][PART_FLOATS] per-tile partial summaries
-    // fused fold (nullable fold_wm = off, a separate k_fold launch does it): the LAST tile CTA of an image to finish its
-    // source phase sums the image's partial summaries and folds them into the NEXT layer's merge weights (what k_fold
-    // does), written to the other half of the double-buffered (mimg, ksum) -- tiles of this launch still read the current one
-    const float* fold_wm;       // merge.weight [256][256] fp32 of the layer the source phase belongs to
-    __half* mimg_out;
-    float* ksum_out;
-    int* fold_cnt;              // [2B] arrival counters, zero between launches
-    int ppt;
     int* flag;
     unsigned long long* dbg_acc;   // nullable: global cycle accumulators (OETR_TIMING=1), see DBG_* in tc_tiles.cuh
     // L2 prefetch: every layer's weights are read once per forward, so without it each stage is a DRAM-latency
@@ -53,77 +45,6 @@ struct EncParams {
     float lnq_g[C], lnq_b[C], ln2_g[C], ln2_b[C];
     float lnkv_g[C], lnkv_b[C];     // dec_mode: bv | bk
 };
-
-// One (image, head) of the fold by a group of 256 threads (tg = thread in the group): KV_h = sum of the image's partials
-// (fixed order), scaled by 1/S; M_img[n][h*32+d] = sum_e Wm[n][h*32+e] KV_h[d][e] as (hi, lo) stage images; Ksum.  Same
-// arithmetic and summation order as k_fold (tc_kernels.cu).  wT [32][C+4] and kvT [32][36] floats are the group's scratch.
-__device__ __forceinline__ void fold_image_head(const float* part, const TileGeom& g, const EncGeom& eg, int ppt, int img, int h,
-                                                const float* __restrict__ Wm, __half* mimg, float* ksum, float* wT, float* kvT,
-                                                int tg, int bar_id) {
-    constexpr int WP = C + 4, KP = HD + 4;
-    const int set = img / g.B, b = img % g.B;
-    const int T = enc_parts(g, eg, ppt, set, b);
-    const int warp = tg >> 5, lane = tg & 31;
-    const float inv_s = 1.f / (float)(set == 0 ? g.L1 : g.L2);
-    {
-        const int i = tg * 4, d = i >> 5, e0 = i & 31;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = 0; t < T; ++t) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * PART_FLOATS + h * HD * HD + i));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        kvT[e0 * KP + d] = acc.x * inv_s; kvT[(e0 + 1) * KP + d] = acc.y * inv_s;
-        kvT[(e0 + 2) * KP + d] = acc.z * inv_s; kvT[(e0 + 3) * KP + d] = acc.w * inv_s;
-    }
-    if (tg < HD) {
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) {
-            const float* ks = part + (size_t)enc_part_index(g, eg, ppt, set, b, t) * PART_FLOATS + NH * HD * HD + h * HD + tg;
-            acc += (__ldcg(ks) + __ldcg(ks + C)) + (__ldcg(ks + 2 * C) + __ldcg(ks + 3 * C));
-        }
-        ksum[(size_t)img * C + h * HD + tg] = acc * inv_s;
-    }
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-        const int n = warp * 32 + i;
-        wT[lane * WP + n] = __ldg(Wm + (size_t)n * C + h * HD + lane);
-    }
-    named_bar_sync(bar_id, 256);
-    const int tn = tg >> 3, td = tg & 7;
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < HD; ++e) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&wT[e * WP + 8 * tn]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&wT[e * WP + 8 * tn + 4]);
-        const float4 k4 = *reinterpret_cast<const float4*>(&kvT[e * KP + 4 * td]);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            acc[i][0] = fmaf(a[i], k4.x, acc[i][0]); acc[i][1] = fmaf(a[i], k4.y, acc[i][1]);
-            acc[i][2] = fmaf(a[i], k4.z, acc[i][2]); acc[i][3] = fmaf(a[i], k4.w, acc[i][3]);
-        }
-    }
-    __half* dst = mimg + (size_t)img * GEMM_HALFS;
-    const int ks = h >> 1, col = (h & 1) * 32 + 4 * td;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int n = 8 * tn + i, nh = n >> 7, r = n & 127;
-        const __half2 h0 = __floats2half2_rn(acc[i][0], acc[i][1]), h1 = __floats2half2_rn(acc[i][2], acc[i][3]);
-        const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
-        const __half2 l0 = __floats2half2_rn(acc[i][0] - b0.x, acc[i][1] - b0.y), l1 = __floats2half2_rn(acc[i][2] - b1.x, acc[i][3] - b1.y);
-        const uint32_t off = slab_chunk_off(r, col >> 3) + (col & 7) * 2;
-        uint2 hv, lv;
-        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
-        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 0, nh)) + off) = hv;
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dst + gemm_stage_off(ks, 1, nh)) + off) = lv;
-    }
-    named_bar_sync(bar_id, 256);             // the group's scratch may be overwritten by its next head
-}
 
 __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ EncParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -596,32 +517,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_enc(const __grid_constant__ En
             }
             tc_fence_before();
             stamp(16);
-            if (p.fold_wm && !dec_mode) {
-                // ---- fused fold: is this the last tile of one of its images?  (threadFenceReduction pattern: every writer
-                // fences its partial-summary stores, one thread counts the tile in; the last arrival sees all partials)
-                __threadfence();
-                named_bar_sync(1, N_ROW_THREADS);
-                int* last = reinterpret_cast<int*>(X);
-                if (tid == 0) {
-                    for (int im = 0; im < (two ? 2 : 1); ++im) {
-                        const int img = et.set * p.g.B + et.b0 + im;
-                        const int expected = enc_parts(p.g, p.eg, p.ppt, et.set, et.b0 + im);
-                        last[im] = atomicAdd(p.fold_cnt + img, 1) == expected - 1 ? 1 : 0;
-                    }
-                    __threadfence();
-                }
-                named_bar_sync(1, N_ROW_THREADS);
-                for (int im = 0; im < (two ? 2 : 1); ++im) {
-                    if (!last[im]) continue;
-                    const int img = et.set * p.g.B + et.b0 + im;
-                    const int grp = tid >> 8, tg = tid & 255;
-                    float* wT = reinterpret_cast<float*>(smem + SM_AHI) + grp * (HD * (C + 4) + HD * (HD + 4));
-                    float* kvT = wT + HD * (C + 4);
-                    for (int h = grp; h < NH; h += 2)
-                        fold_image_head(p.kv_part, p.g, p.eg, p.ppt, img, h, p.fold_wm, p.mimg_out, p.ksum_out, wT, kvT, tg, 6 + grp);
-                    if (tid == 0) p.fold_cnt[img] = 0;                       // ready for the next launch
-                }
-            }
         }
     }
     // teardown

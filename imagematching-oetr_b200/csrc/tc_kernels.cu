@@ -303,9 +303,8 @@ void tc_carve(size_t& off, void* base, int B, int L1, int L2, TcWorkspace& w, bo
     w.xt_enc = static_cast<float*>(take((size_t)g.tiles() * TILE * C * sizeof(float)));      // flat tiles <= per-image tiles
     w.kv_part = static_cast<float*>(take((size_t)g.tiles() * 2 * PART_FLOATS * sizeof(float)));   // flat tiling: one partial per (tile, image)
     w.dec_kvs = static_cast<float*>(take((size_t)N_DEC * 2 * B * KVS * sizeof(float)));
-    w.mimg = static_cast<__half*>(take((size_t)2 * 2 * B * GEMM_HALFS * sizeof(__half)));      // double-buffered (fused fold)
-    w.ksum = static_cast<float*>(take((size_t)2 * 2 * B * C * sizeof(float)));
-    w.fold_cnt = static_cast<int*>(take((size_t)2 * B * sizeof(int)));
+    w.mimg = static_cast<__half*>(take((size_t)2 * B * GEMM_HALFS * sizeof(__half)));
+    w.ksum = static_cast<float*>(take((size_t)2 * B * C * sizeof(float)));
     w.att = static_cast<float*>(take((size_t)g.tiles() * TILE * sizeof(float)));
     w.gstat = static_cast<float*>(take((size_t)g.tiles() * 64 * sizeof(float)));
     w.z = static_cast<float*>(take((size_t)g.tiles() * TILE * sizeof(float)));
@@ -466,17 +465,6 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WL
             p.pf_ptr[1] = tw.head_img; p.pf_bytes[1] = 9 * G;
         }
     };
-    // The fold of the partial summaries into the next layer's merge weights runs in the tail of k_enc (the last tile CTA of
-    // an image); (mimg, ksum) are double-buffered: launch i reads half i & 1 and writes the other.  OETR_FOLD=1 (read once):
-    // the separate k_fold launches of round 1.
-    static const bool separate_fold = getenv("OETR_FOLD") && atoi(getenv("OETR_FOLD")) == 1;
-    const size_t mimg_half = (size_t)2 * B * GEMM_HALFS, ksum_half = (size_t)2 * B * C;
-    if (!separate_fold) cudaMemsetAsync(ws.fold_cnt, 0, (size_t)2 * B * sizeof(int), s);
-    auto set_fold = [&](EncParams& p, int next_layer, int out_half) {
-        if (separate_fold) return;
-        p.fold_wm = d_w + L.enc[next_layer].wm; p.fold_cnt = ws.fold_cnt; p.ppt = ppt;
-        p.mimg_out = ws.mimg + out_half * mimg_half; p.ksum_out = ws.ksum + out_half * ksum_half;
-    };
     // source phase of layer 0 straight from the NCHW features
     {
         EncParams p = base;
@@ -484,24 +472,22 @@ int tc_encoder(const TcWeights& tw, const float* d_w, const float* h_w, const WL
         set_kv_enc(p, 0);
         set_prefetch_for(p, 0);
         p.pf_ptr[2] = p.w_kv; p.pf_bytes[2] = 2 * G;          // its own weights: nobody ran before it
-        set_fold(p, 0, 0);
         launch_enc(p);
-        if (separate_fold) { k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, eg, ppt, d_w + L.enc[0].wm, ws.mimg, ws.ksum); lc.n++; }
+        k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, eg, ppt, d_w + L.enc[0].wm, ws.mimg, ws.ksum); lc.n++;
     }
     for (int i = 0; i < N_ENC; ++i) {
         const EncW& e = L.enc[i];
         const __half* img = tw.enc_img + (size_t)i * ENC_LAYER_HALFS;
         EncParams p = base;
         p.store_x = 1; p.do_q = 1; p.cross = i & 1;
-        if (!separate_fold) { p.mimg = ws.mimg + (i & 1) * mimg_half; p.ksum = ws.ksum + (i & 1) * ksum_half; }
         vec(p.lnq_g, e.lnq_g); vec(p.lnq_b, e.lnq_b); vec(p.ln2_g, e.ln2_g); vec(p.ln2_b, e.ln2_b);
         p.w_q = img; p.w_mlp = img + GEMM_HALFS;
-        if (i + 1 < N_ENC) { set_kv_enc(p, i + 1); set_fold(p, i + 1, (i + 1) & 1); } else set_kv_dec(p, 0);
+        if (i + 1 < N_ENC) set_kv_enc(p, i + 1); else set_kv_dec(p, 0);
         set_prefetch_for(p, i + 1);
         if (prof) prof->mark(s);
         launch_enc(p);
         if (prof) prof->mark(s);
-        if (i + 1 < N_ENC) { if (separate_fold) { k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, eg, ppt, d_w + L.enc[i + 1].wm, ws.mimg, ws.ksum); lc.n++; } }
+        if (i + 1 < N_ENC) { k_fold<<<2 * B * NH, 256, 0, s>>>(ws.kv_part, g, eg, ppt, d_w + L.enc[i + 1].wm, ws.mimg, ws.ksum); lc.n++; }
         else { k_sum_partials<<<dim3(2 * B, (KVS / 4 + 255) / 256), 256, 0, s>>>(ws.kv_part, g, eg, ppt, ws.dec_kvs); lc.n++; }
     }
     // decoder layer 1 cross-attention summaries: k = (memory+pos) Wk^T + bk, v = memory Wv^T + bv

@@ -22,8 +22,7 @@ struct TcWorkspace {
     float* kv_part = nullptr;      // per-tile linear-attention partial summaries [tiles][KVS]
     float* dec_kvs = nullptr;      // [2 decoder layers][2B][KVS] cross-attention summaries
     __half* mimg = nullptr;        // [2B images] folded merge weights (hi/lo stage images, 256 KB each)
-    float* ksum = nullptr;         // [2][2B][256] Ksum of every image for the current layer (double-buffered)
-    int* fold_cnt = nullptr;       // [2B] tile arrival counters of the fused fold
+    float* ksum = nullptr;         // [2B][256] Ksum of every image for the current layer
     float* att = nullptr;          // [tiles][128] per-token <memory, hs> (head)
     float* gstat = nullptr;        // [tiles][32][2] per-tile GroupNorm partials (mean, M2)
     float* z = nullptr;            // [tiles][128] heat-map logits
