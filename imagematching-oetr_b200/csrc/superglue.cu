@@ -195,7 +195,12 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars* bars = reinterpret_cast<Bars*>(smem + SM_BAR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int h = blockIdx.y, b = blockIdx.z, n0 = blockIdx.x * 128;
+    // key split: the CTAs of a cluster (1, 2 or 4 along x) share a query tile and take consecutive ranges of key chunks;
+    // rank 0 merges the partial (max, sum, O) of its peers at the end
+    uint32_t crank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    const int h = blockIdx.y, b = blockIdx.z, n0 = (int)(blockIdx.x / csize) * 128;
     const uint32_t sb = smem_u32(smem);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->kv_full[i], LOADERS); mbar_init(&bars->kv_free[i], 1); mbar_init(&bars->s[i], 1); }
@@ -207,7 +212,9 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem, TS = tmem, TO = tmem + 256;          // S0 | S1 | O
-    const int chunks = (M + 127) / 128;
+    const int all_chunks = (M + 127) / 128, per = (all_chunks + (int)csize - 1) / (int)csize;
+    const int c_begin = (int)crank * per;
+    const int chunks = max(0, min(all_chunks, c_begin + per) - c_begin);       // this CTA's chunks (the host keeps csize <= all_chunks)
 
     if (warp > WARP_MMA) {
         const int row = tid - (SOFTMAX + 32);                                   // 0..127
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
         const float* vb = v + (size_t)b * SG_C * M;
         const bool vec_ok = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(vb) & 15) == 0;
         for (int c = 0; c < chunks; ++c) {
-            const int m0 = c * 128, bs = c & 1;
+            const int m0 = (c_begin + c) * 128, bs = c & 1;
             uint8_t* buf = smem + SM_KV + bs * KV_BUF;
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {                              // K: key m0 + row, dims half * 32 .. (coalesced over keys)
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
                 umma_commit(&bars->s[c & 1]);
             };
             mbar_wait(&bars->q_full, 0, nullptr);
-            issue_s(0);
+            if (chunks > 0) issue_s(0);
             for (int c = 0; c < chunks; ++c) {
                 // S(c+1) goes out while the softmax of chunk c runs: its accumulator was last read for chunk c - 1, whose
                 // readers arrived on p(c-1) (waited for below, in the previous iteration)
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
         mbar_arrive(&bars->q_full);                                             // Q operand published to the MMA warp
         float m_run = -INFINITY, l_part = 0.f;
         for (int c = 0; c < chunks; ++c) {
-            const int m0 = c * 128;
+            const int m0 = (c_begin + c) * 128;
             const uint32_t ts = TS + (c & 1) * 128 + lane_addr + hf * 64;
             mbar_wait(&bars->s[c & 1], (c >> 1) & 1, nullptr);
             tc_fence_after();
@@ -359,17 +366,67 @@ __global__ void __launch_bounds__(tca::THREADS, 1) k_sg_attention_tc(const float
         // row sum = the two partial sums (same running maximum in both threads)
         xch[hf * 128 + r] = l_part;
         named_bar_sync(1 + quad, 64);
-        const float inv = 1.f / (l_part + xch[(hf ^ 1) * 128 + r]);
-        mbar_wait(&bars->o, (chunks - 1) & 1, nullptr);
-        tc_fence_after();
-        float* ob = out + (size_t)b * SG_C * N;
-        const int n = n0 + r;
+        float l_tot = l_part + xch[(hf ^ 1) * 128 + r];
         float ov[32];
-        tmem_ld32(TO + lane_addr + hf * 32, ov);
-        if (n < N) {
+        if (chunks > 0) {
+            mbar_wait(&bars->o, (chunks - 1) & 1, nullptr);
+            tc_fence_after();
+            tmem_ld32(TO + lane_addr + hf * 32, ov);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ob[(size_t)((hf * 32 + j) * SG_H + h) * N + n] = ov[j] * inv;
+            for (int j = 0; j < 32; ++j) ov[j] = 0.f;
         }
+        // merge buffer in rank 0's (now idle) K/V area, per peer p = 1 .. csize-1: M[128] | L[128] | O[128][64]
+        float* mb = reinterpret_cast<float*>(smem + SM_KV);
+        constexpr int PEER_FLOATS = 128 * 2 + 128 * 64;
+        if (csize > 1) {
+            tc_fence_before();
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");      // every CTA is done with its own shared memory
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            if (crank != 0) {
+                const uint32_t base = smem_u32(mb + (size_t)(crank - 1) * PEER_FLOATS);
+                uint32_t ra;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(base), "r"(0u));
+                if (hf == 0) {
+                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra + (uint32_t)r * 4u), "f"(m_run) : "memory");
+                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra + (uint32_t)(128 + r) * 4u), "f"(l_tot) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra + (uint32_t)(256 + r * 64 + hf * 32 + j) * 4u),
+                                 "f"(ov[j]), "f"(ov[j + 1]), "f"(ov[j + 2]), "f"(ov[j + 3]) : "memory");
+            }
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        if (crank == 0) {
+            float m_all = m_run;
+            for (uint32_t pe = 1; pe < csize; ++pe) m_all = fmaxf(m_all, mb[(pe - 1) * PEER_FLOATS + r]);
+            const float s0 = ex2(m_run - m_all);
+            l_tot *= s0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ov[j] *= s0;
+            for (uint32_t pe = 1; pe < csize; ++pe) {
+                const float* pb = mb + (pe - 1) * PEER_FLOATS;
+                const float sp = ex2(pb[r] - m_all);
+                l_tot = fmaf(pb[128 + r], sp, l_tot);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ov[j] = fmaf(pb[256 + r * 64 + hf * 32 + j], sp, ov[j]);
+            }
+            const float inv = 1.f / l_tot;
+            float* ob = out + (size_t)b * SG_C * N;
+            const int n = n0 + r;
+            if (n < N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ob[(size_t)((hf * 32 + j) * SG_H + h) * N + n] = ov[j] * inv;
+            }
+        }
+    }
+    if (warp >= WARP_MMA && csize > 1) {         // the loader and MMA warps take part in the two cluster barriers
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -529,9 +586,22 @@ int oetr_sg_attention(const float* query, const float* key, const float* value, 
     }
     if (e != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_attention: %s", cudaGetErrorString(e));
     if (mode != OETR_SG_TENSOR && mode != OETR_SG_FP32) return sfail(OETR_E_ARG, "oetr_sg_attention: mode %d", mode);
-    if (mode == OETR_SG_TENSOR)
-        k_sg_attention_tc<<<dim3((n + 127) / 128, SG_H, batch), tca::THREADS, tca::SM_TOTAL, static_cast<cudaStream_t>(stream)>>>(query, key, value, out, n, m);
-    else
+    if (mode == OETR_SG_TENSOR) {
+        // key split over a cluster of 1, 2 or 4 CTAs so that small problems still fill the GPU (2048 keypoints: 64 query
+        // tile x head CTAs on 148 SMs)
+        const int qt = (n + 127) / 128, chunks = (m + 127) / 128, base = qt * SG_H * batch;
+        int split = 1;
+        while (split < 4 && base * split * 2 <= 160 && split * 2 <= chunks) split *= 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(qt * split, SG_H, batch); cfg.blockDim = dim3(tca::THREADS); cfg.dynamicSmemBytes = tca::SM_TOTAL;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = split; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, k_sg_attention_tc, query, key, value, out, n, m);
+        if (e != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_attention: %s", cudaGetErrorString(e));
+    } else
         k_sg_attention<<<dim3((n + BQ - 1) / BQ, SG_H, batch), 256, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(query, key, value, out, n, m);
     e = cudaGetLastError();
     if (e != cudaSuccess) return sfail(OETR_E_CUDA, "oetr_sg_attention: %s", cudaGetErrorString(e));

@@ -54,6 +54,11 @@ def test_large_problem_properties():
         assert float(o.max()) <= float(v.max()) + 1e-4 and float(o.min()) >= float(v.min()) - 1e-4
         assert np.abs(o[0][:, :, idx].cpu().numpy() - want).max() < ATT_TOL[mode], mode
         assert torch.equal(o, sg.attention(q, k, v, mode=mode))
+    # key split over CTA clusters: 128 queries x 600 keys -> 5 chunks over 4 CTAs (one peer gets none); 256 x 1024 -> 2 x 4 CTAs
+    for nq, nk in ((128, 600), (256, 1024), (100, 129)):
+        qs, ks, vs = q[:, :, :, :nq].contiguous(), k[:, :, :, :nk].contiguous(), v[:, :, :, :nk].contiguous()
+        wants = so.attention(qs[0].double().cpu().numpy(), ks[0].double().cpu().numpy(), vs[0].double().cpu().numpy())
+        assert np.abs(sg.attention(qs, ks, vs)[0].cpu().numpy() - wants).max() < ATT_TOL["tensor"], (nq, nk)
     # ragged sizes: 130 queries (two query tiles, the second almost empty) x 257 keys (three key chunks, the last with one key)
     q2, k2, v2 = q[:, :, :, :130].contiguous(), k[:, :, :, :257].contiguous(), v[:, :, :, :257].contiguous()
     want2 = so.attention(q2[0].double().cpu().numpy(), k2[0].double().cpu().numpy(), v2[0].double().cpu().numpy())
